@@ -1,0 +1,173 @@
+/* vqb.h — C ABI of libvqvae_b200.so: the B200 (sm_100a) kernels under the Keras-style layer API of the
+ * VQ-VAE audio hot path.
+ *
+ * The reference (sunzeyucmu/VAE-based-Music--Deep-Generative-Models) has no FFI of its own: the hot path sits
+ * behind Keras Layer/Model classes whose arithmetic is dispatched, op by op, to TensorFlow kernels.  Each entry
+ * point below replaces one such group of TF op dispatches; the reference call site it replaces is cited as
+ * (file:line) into the reference tree.
+ *
+ * Conventions
+ *   - every function returns 0 (VQB_OK) or a negative VQB_ERR_* code; nothing throws; the message of the last
+ *     error on the calling thread is returned by vqb_last_error().
+ *   - all pointers are DEVICE pointers owned by the caller (fp32 unless stated), alive until `stream` has passed
+ *     the call; functions never allocate device memory, never synchronise and only enqueue work on `stream`
+ *     (a cudaStream_t passed as void*), so every call is CUDA-graph capturable.
+ *   - activations are channels-last [B, L, C] fp32 (Keras layout); Conv1D kernels are [k, Cin, Cout],
+ *     Conv1DTranspose kernels [k, Cout, Cin] (Keras layouts); the codebook is [D, K] column-per-code
+ *     (VectorQuantizer.py:38-44); code indices are int64 (tf.argmin default).
+ *   - padding is TF "SAME": out = ceil(L/stride), pad = max((out-1)*stride + (k-1)*dilation + 1 - L, 0),
+ *     left = pad/2.  Conv1DTranspose output length is L*stride, left crop (k-stride)/2.
+ *   - there is no CPU fallback: on a device that is not sm_100 every compute entry point returns VQB_ERR_ARCH.
+ */
+#ifndef VQB_H_
+#define VQB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQB_VERSION 100
+
+enum {
+  VQB_OK = 0,
+  VQB_ERR_INVALID = -1,       /* bad argument (shape, null pointer, unsupported size) */
+  VQB_ERR_ARCH = -2,          /* device is not compute capability 10.x */
+  VQB_ERR_CUDA = -3,          /* a CUDA runtime call failed; see vqb_last_error() */
+  VQB_ERR_WORKSPACE = -4,     /* workspace too small */
+  VQB_ERR_UNIMPLEMENTED = -5
+};
+
+/* arithmetic used for the contraction */
+enum {
+  VQB_PREC_FP32 = 0, /* fp32 FMA on CUDA cores, exact fp32 accumulation */
+  VQB_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
+  VQB_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+};
+
+int vqb_version(void);
+const char* vqb_last_error(void);
+/* 0 if `device` is a compute-capability-10.x GPU, VQB_ERR_ARCH otherwise (also caches the answer). */
+int vqb_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Conv1D / Conv1DTranspose   (replace layers.Conv1D: resnet.py:13,17; encdec.py:33,38,60,148 and
+ *                             layers.Conv1DTranspose: encdec.py:67-68, plus their tape.gradient kernels,
+ *                             vqvae.py:143)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct vqb_conv_desc {
+  int32_t B;         /* batch */
+  int32_t L;         /* INPUT length of the forward op */
+  int32_t C_in;      /* forward input channels */
+  int32_t C_out;     /* forward output channels */
+  int32_t k;         /* taps */
+  int32_t stride;    /* forward stride (Conv1D: decimation; Conv1DTranspose: upsampling) */
+  int32_t dilation;  /* Conv1D only; must be 1 for Conv1DTranspose */
+  int32_t relu_in;   /* 1: the op consumes ReLU(x) (fused pre-activation, resnet.py:12,16) */
+  int32_t precision; /* VQB_PREC_* */
+} vqb_conv_desc;
+
+/* y[B, ceil(L/stride), C_out] = conv(act(x)) + bias (+ residual, same shape as y; may be NULL) */
+int vqb_conv1d_fwd(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
+                   const float* residual, float* y, void* stream);
+/* dx[B, L, C_in] = conv^T(dy) (* (x > 0) if d->relu_in; x may be NULL otherwise) (+ dx_add, may be NULL) */
+int vqb_conv1d_dgrad(const vqb_conv_desc* d, const float* dy, const float* w, const float* x,
+                     const float* dx_add, float* dx, void* stream);
+/* dw[k, C_in, C_out] = sum_{b,t} act(x)[..] dy[..];  dbias[C_out] = sum dy (dbias may be NULL) */
+size_t vqb_conv1d_wgrad_workspace_bytes(const vqb_conv_desc* d);
+int vqb_conv1d_wgrad(const vqb_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* y[B, L*stride, C_out] = convT(x) + bias ; w is [k, C_out, C_in] */
+int vqb_conv1d_transpose_fwd(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
+                             float* y, void* stream);
+int vqb_conv1d_transpose_dgrad(const vqb_conv_desc* d, const float* dy, const float* w, float* dx,
+                               void* stream);
+size_t vqb_conv1d_transpose_wgrad_workspace_bytes(const vqb_conv_desc* d);
+int vqb_conv1d_transpose_wgrad(const vqb_conv_desc* d, const float* x, const float* dy, float* dw,
+                               float* dbias, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused pre-activation residual block  (replaces ResnetConv1DBlock.call, resnet.py:11-18,29:
+ *   y = x + Conv1D_k3(ReLU(Conv1D_k3,dil(ReLU(x)))), both SAME, C -> F -> C channels)
+ * h [B,L,F] receives the first conv's output (pre-ReLU); the backward pass needs it, so it is always written.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct vqb_resblock_desc {
+  int32_t B, L, C, F, dilation;
+  int32_t precision;
+} vqb_resblock_desc;
+
+int vqb_resblock_fwd(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1,
+                     const float* w2, const float* b2, float* h, float* y, void* stream);
+/* given dy: dx = dy + (x>0)*conv1^T((h>0)*conv2^T(dy)); dh ([B,L,F] scratch, also an output) holds
+ * (h>0)*conv2^T(dy), the gradient at conv1's output, for the weight gradients. */
+int vqb_resblock_bwd_data(const vqb_resblock_desc* d, const float* x, const float* h, const float* dy,
+                          const float* w1, const float* w2, float* dh, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * VectorQuantizer  (replaces VectorQuantizer.call / get_code_indices, VectorQuantizer.py:75-186)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct vqb_vq_desc {
+  int64_t N;         /* latents (B * T/hop) */
+  int32_t D;         /* embedding_dim */
+  int32_t K;         /* num_embeddings */
+  float beta;        /* commitment weight (VectorQuantizer.py:97) */
+  int32_t precision; /* VQB_PREC_FP32: exact fp32 search; VQB_PREC_BF16 / TF32: tensor-core search with exact
+                        fp32 re-ranking of the best candidates */
+} vqb_vq_desc;
+
+size_t vqb_vq_fwd_workspace_bytes(const vqb_vq_desc* d);
+/* x [N,D], E [D,K] ->
+ *   idx    [N] int64            nearest code, first minimum (VectorQuantizer.py:173-185)
+ *   q_st   [N,D]                x + (E[:,idx] - x)          (:86-90,114), may be NULL
+ *   q      [N,D]                E[:,idx]                    (:88) may be NULL
+ *   loss   [1]                  beta * mean((q - x)^2)      (:97-99)
+ *   m_batch[D,K], n_batch[K]    X^T onehot, sum(onehot)     (:123-124); both may be NULL (inference)
+ * m_batch / n_batch are OVERWRITTEN (zeroed inside the call). */
+int vqb_vq_fwd(const vqb_vq_desc* d, const float* x, const float* E, int64_t* idx, float* q_st, float* q,
+               float* loss, float* m_batch, float* n_batch, void* workspace, size_t workspace_bytes,
+               void* stream);
+/* straight-through + commitment gradient (VectorQuantizer.py:97-99,114):
+ *   dx = dq_out + loss_scale * (2*beta/(N*D)) * (x - q)   (loss_scale: d total / d commitment loss) */
+int vqb_vq_bwd(const vqb_vq_desc* d, const float* dq_out, const float* x, const float* q, float loss_scale,
+               float* dx, void* stream);
+/* EMA codebook update with dead-code restart (VectorQuantizer.py:128-159), in place on E, m_t, N_t.
+ *   restart_rows [K,D]: the first K rows of shuffle(_tile(flattened)) (:137) chosen by the caller.
+ *   metrics [3] = {batch usage (:151), running usage (:153), entropy (:157-158)}.
+ * Every multiply and add is separately rounded (no FMA contraction), as in eager TF.  gamma is a double because
+ * the reference forms (1. - gamma) in Python double arithmetic before TF casts it to fp32 (:128,131). */
+int vqb_vq_ema_update(int32_t D, int32_t K, double gamma, float threshold, const float* m_batch,
+                      const float* n_batch, const float* restart_rows, float* E, float* m_t, float* N_t,
+                      float* metrics, void* stream);
+/* rows[i,:] = x[(ids[i] mod N), :]  i < n_ids   (the `_tile` + shuffle[:K] row pick, VectorQuantizer.py:137,191-199) */
+int vqb_gather_rows(const float* x, int64_t N, int32_t D, const int64_t* ids, int32_t n_ids, float* rows,
+                    void* stream);
+/* ids[i] = (a*i + c) mod Nt, i < K, with (a, c) hashed from (seed, *step_counter): K distinct pseudo-random
+ * row numbers of the tiled batch, identical on every rank that shares seed and step.  Nt = max(N, K rounded up
+ * to a multiple of N) as `_tile` produces. */
+int vqb_restart_ids(int64_t N, int32_t K, uint64_t seed, const int64_t* step_counter, int64_t* ids,
+                    void* stream);
+/* out[i,:] = E[:, idx[i]]   (decode path gather, vqvae.py:248) */
+int vqb_gather_codes(const float* E, int32_t D, int32_t K, const int64_t* idx, int64_t n, float* out,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * loss head + optimiser pieces of VQVAE.train_step (vqvae.py:125,143-144)
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t vqb_reduce_workspace_bytes(int64_t n);
+/* loss[0] = mean((x - r)^2); if dr != NULL: dr = loss_scale * 2 (r - x) / n  (+ dr_add if non-NULL) */
+int vqb_mse(const float* x, const float* r, int64_t n, float loss_scale, const float* dr_add, float* loss,
+            float* dr, void* workspace, size_t workspace_bytes, void* stream);
+/* Keras-2.7 Adam on a flat buffer, step taken from *step_counter (device int64, 1-based step = counter+1; the
+ * kernel does NOT increment it): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m += (g*gs - m)(1-b1); v += ((g*gs)^2 - v)(1-b2);
+ * p -= lr_t*m/(sqrt(v)+eps) */
+int vqb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
+                  float eps, float grad_scale, const int64_t* step_counter, void* stream);
+int vqb_increment(int64_t* counter, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQB_H_ */

@@ -1,0 +1,69 @@
+// common.cuh — error plumbing and small device helpers shared by the libvqvae_b200 translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "vqb.h"
+
+namespace vqb {
+
+// thread-local last-error text (vqb_last_error)
+char* err_buf();
+int set_err(int code, const char* fmt, ...);
+// VQB_OK if the current device is sm_100-class (cached per device)
+int require_arch();
+
+#define VQB_REQUIRE(cond, ...)                                   \
+  do {                                                           \
+    if (!(cond)) return ::vqb::set_err(VQB_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define VQB_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return ::vqb::set_err(VQB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                            \
+  } while (0)
+
+#define VQB_LAUNCH_CHECK()                                                                       \
+  do {                                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                                        \
+    if (e__ != cudaSuccess)                                                                      \
+      return ::vqb::set_err(VQB_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                                 \
+  } while (0)
+
+#define VQB_ARCH()                        \
+  do {                                    \
+    int a__ = ::vqb::require_arch();      \
+    if (a__ != VQB_OK) return a__;        \
+  } while (0)
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// deterministic block sum (fixed tree); result valid in thread 0.  `red` has >= 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = 0.f;
+  if (wid == 0) {
+    r = lane < nw ? red[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+}  // namespace vqb

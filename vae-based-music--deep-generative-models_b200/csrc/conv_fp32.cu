@@ -1,0 +1,553 @@
+// conv_fp32.cu — exact-fp32 (CUDA-core FFMA) Conv1D / Conv1DTranspose forward, data-gradient and
+// weight-gradient kernels behind vqb_conv1d_* / vqb_conv1d_transpose_* (include/vqb.h).
+//
+// Every one of those ops is a "tap-gather contraction"
+//     out[b, t*out_step + out_off, o] = sum_n sum_i act(in[b, t*in_step + off[n], i]) * W_{wj[n]}[i, o]
+// over a small host-built tap table:
+//   Conv1D forward            (encdec.py:33,38,60,148; resnet.py:13,17)  in_step = stride, off = j*dil - padL
+//   Conv1D data gradient      one launch per output phase r < stride: off = (r + padL - j*dil)/stride
+//   Conv1DTranspose forward   (encdec.py:67-68) same phase form with dil = 1, padL = (k - stride)/2
+//   Conv1DTranspose data grad Conv1D-forward form over dy
+// so one kernel (tgc_kernel) serves all four; tgc_narrow_kernel covers C_out <= 4 (the final 64->1 conv),
+// wgrad_kernel the weight gradients (split over time chunks, reduced in a fixed order => deterministic).
+#include "common.cuh"
+
+namespace vqb {
+
+constexpr int MAX_TAPS = 16;
+struct TapTable {
+  int ntaps;
+  int wj[MAX_TAPS];
+  int off[MAX_TAPS];
+};
+
+struct TgcParams {
+  const float* in;
+  const float* w;
+  const float* bias;  // [COUT] or null
+  const float* res;   // added before masking (forward residual) or null
+  const float* mask;  // out *= (mask > 0) or null     (ReLU backward)
+  const float* add;   // out += add after masking or null (skip-path gradient)
+  float* out;
+  int B, L_in, CIN, COUT, L_out;  // L_out: rows per batch item of out/res/mask/add
+  int Lt, in_step, out_step, out_off;
+  int relu_in;
+  int w_sj, w_si, w_so;  // W_j[i,o] = w[j*w_sj + i*w_si + o*w_so]
+  int ci_ch, rows, minoff;
+  TapTable taps;
+};
+
+constexpr int TGC_TT = 128;
+
+// 256 threads; tile = 128 time positions x 32 output channels; thread = 4 positions x 4 channels.
+__global__ void __launch_bounds__(256) tgc_kernel(const TgcParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* in_s = smem;                            // [rows][ci_ch]
+  float* w_s = smem + (size_t)p.rows * p.ci_ch;  // [ntaps][ci_ch][32]
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  const int t0 = blockIdx.x * TGC_TT, b = blockIdx.y, co0 = blockIdx.z * 32;
+  const int cch = p.ci_ch;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+
+  const float* inb = p.in + (size_t)b * p.L_in * p.CIN;
+  const long g0 = (long)t0 * p.in_step + p.minoff;
+  const int ntaps = p.taps.ntaps;
+
+  for (int c0 = 0; c0 < p.CIN && ntaps > 0; c0 += cch) {
+    if ((p.CIN & 3) == 0) {
+      const int v4 = cch >> 2;
+      for (int e = tid; e < p.rows * v4; e += 256) {
+        const int r = e / v4, c = (e - r * v4) * 4;
+        const long g = g0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g >= 0 && g < p.L_in && c0 + c < p.CIN) v = *(const float4*)(inb + g * p.CIN + c0 + c);
+        if (p.relu_in) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        *(float4*)(in_s + r * cch + c) = v;
+      }
+    } else {
+      for (int e = tid; e < p.rows * cch; e += 256) {
+        const int r = e / cch, c = e - r * cch;
+        const long g = g0 + r;
+        float v = 0.f;
+        if (g >= 0 && g < p.L_in && c0 + c < p.CIN) v = inb[g * p.CIN + c0 + c];
+        if (p.relu_in) v = fmaxf(v, 0.f);
+        in_s[r * cch + c] = v;
+      }
+    }
+    for (int e = tid; e < ntaps * cch * 32; e += 256) {
+      const int o = e & 31, c = (e >> 5) % cch, n = (e >> 5) / cch;
+      const int ci = c0 + c, co = co0 + o;
+      float v = 0.f;
+      if (ci < p.CIN && co < p.COUT) v = p.w[(size_t)p.taps.wj[n] * p.w_sj + (size_t)ci * p.w_si + (size_t)co * p.w_so];
+      w_s[e] = v;
+    }
+    __syncthreads();
+    const int rstride = 32 * p.in_step * cch;
+    for (int n = 0; n < ntaps; ++n) {
+      const float* a0 = in_s + (size_t)(ty * p.in_step + p.taps.off[n] - p.minoff) * cch;
+      const float* wn = w_s + n * cch * 32 + tx * 4;
+      for (int c = 0; c < cch; c += 4) {
+        float4 a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = *(const float4*)(a0 + i * rstride + c);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float4 wv = *(const float4*)(wn + (c + cc) * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float av = cc == 0 ? a[i].x : cc == 1 ? a[i].y : cc == 2 ? a[i].z : a[i].w;
+            acc[i][0] = fmaf(av, wv.x, acc[i][0]);
+            acc[i][1] = fmaf(av, wv.y, acc[i][1]);
+            acc[i][2] = fmaf(av, wv.z, acc[i][2]);
+            acc[i][3] = fmaf(av, wv.w, acc[i][3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const int co = co0 + tx * 4;
+  if (co >= p.COUT) return;
+  const bool vec = ((p.COUT & 3) == 0);
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.bias) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (co + c < p.COUT) bv[c] = p.bias[co + c];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = t0 + ty + 32 * i;
+    if (t >= p.Lt) continue;
+    const size_t row = (size_t)b * p.L_out + (size_t)t * p.out_step + p.out_off;
+    const size_t base = row * p.COUT + co;
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = acc[i][c] + bv[c];
+    if (vec) {
+      if (p.res) { const float4 r = *(const float4*)(p.res + base); v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w; }
+      if (p.mask) {
+        const float4 m = *(const float4*)(p.mask + base);
+        v[0] = m.x > 0.f ? v[0] : 0.f; v[1] = m.y > 0.f ? v[1] : 0.f;
+        v[2] = m.z > 0.f ? v[2] : 0.f; v[3] = m.w > 0.f ? v[3] : 0.f;
+      }
+      if (p.add) { const float4 r = *(const float4*)(p.add + base); v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w; }
+      *(float4*)(p.out + base) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (co + c >= p.COUT) break;
+        float x = v[c];
+        if (p.res) x += p.res[base + c];
+        if (p.mask) x = p.mask[base + c] > 0.f ? x : 0.f;
+        if (p.add) x += p.add[base + c];
+        p.out[base + c] = x;
+      }
+    }
+  }
+}
+
+// C_out <= 4 (e.g. the final Conv1D(1, 3), encdec.py:148): one thread per output position, weights in smem.
+__global__ void __launch_bounds__(256) tgc_narrow_kernel(const TgcParams p) {
+  extern __shared__ __align__(16) float w_s[];  // [ntaps][CIN][COUT]
+  const int ntaps = p.taps.ntaps;
+  for (int e = threadIdx.x; e < ntaps * p.CIN * p.COUT; e += blockDim.x) {
+    const int o = e % p.COUT, ci = (e / p.COUT) % p.CIN, n = e / (p.COUT * p.CIN);
+    w_s[e] = p.w[(size_t)p.taps.wj[n] * p.w_sj + (size_t)ci * p.w_si + (size_t)o * p.w_so];
+  }
+  __syncthreads();
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)p.B * p.Lt) return;
+  const int b = (int)(idx / p.Lt), t = (int)(idx - (long)b * p.Lt);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* inb = p.in + (size_t)b * p.L_in * p.CIN;
+  for (int n = 0; n < ntaps; ++n) {
+    const long g = (long)t * p.in_step + p.taps.off[n];
+    if (g < 0 || g >= p.L_in) continue;
+    const float* row = inb + g * p.CIN;
+    const float* wn = w_s + (size_t)n * p.CIN * p.COUT;
+    if ((p.CIN & 3) == 0) {
+      for (int ci = 0; ci < p.CIN; ci += 4) {
+        float4 a = *(const float4*)(row + ci);
+        if (p.relu_in) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+        for (int o = 0; o < p.COUT; ++o) {
+          acc[o] = fmaf(a.x, wn[(ci + 0) * p.COUT + o], acc[o]);
+          acc[o] = fmaf(a.y, wn[(ci + 1) * p.COUT + o], acc[o]);
+          acc[o] = fmaf(a.z, wn[(ci + 2) * p.COUT + o], acc[o]);
+          acc[o] = fmaf(a.w, wn[(ci + 3) * p.COUT + o], acc[o]);
+        }
+      }
+    } else {
+      for (int ci = 0; ci < p.CIN; ++ci) {
+        float a = row[ci];
+        if (p.relu_in) a = fmaxf(a, 0.f);
+        for (int o = 0; o < p.COUT; ++o) acc[o] = fmaf(a, wn[ci * p.COUT + o], acc[o]);
+      }
+    }
+  }
+  const size_t base = ((size_t)b * p.L_out + (size_t)t * p.out_step + p.out_off) * p.COUT;
+  for (int o = 0; o < p.COUT; ++o) {
+    float x = acc[o] + (p.bias ? p.bias[o] : 0.f);
+    if (p.res) x += p.res[base + o];
+    if (p.mask) x = p.mask[base + o] > 0.f ? x : 0.f;
+    if (p.add) x += p.add[base + o];
+    p.out[base + o] = x;
+  }
+}
+
+static int launch_tgc(TgcParams& p, cudaStream_t st) {
+  int minoff = 0, maxoff = 0;
+  for (int n = 0; n < p.taps.ntaps; ++n) {
+    if (n == 0 || p.taps.off[n] < minoff) minoff = p.taps.off[n];
+    if (n == 0 || p.taps.off[n] > maxoff) maxoff = p.taps.off[n];
+  }
+  if (p.Lt <= 0 || p.B <= 0) return VQB_OK;
+  if (p.COUT <= 4) {
+    const size_t smem = (size_t)p.taps.ntaps * p.CIN * p.COUT * sizeof(float);
+    VQB_REQUIRE(smem <= 48 * 1024, "narrow conv: weights (%zu B) exceed 48 KB of shared memory", smem);
+    const long n = (long)p.B * p.Lt;
+    tgc_narrow_kernel<<<cdiv(n, 256), 256, smem, st>>>(p);
+    VQB_LAUNCH_CHECK();
+    return VQB_OK;
+  }
+  p.minoff = minoff;
+  p.ci_ch = p.CIN >= 32 ? 32 : ((p.CIN + 3) & ~3);
+  p.rows = (TGC_TT - 1) * p.in_step + (maxoff - minoff) + 1;
+  size_t smem = ((size_t)p.rows * p.ci_ch + (size_t)p.taps.ntaps * p.ci_ch * 32) * sizeof(float);
+  while (smem > 200 * 1024 && p.ci_ch > 4) {  // very large dilation: narrow the channel chunk
+    p.ci_ch >>= 1;
+    smem = ((size_t)p.rows * p.ci_ch + (size_t)p.taps.ntaps * p.ci_ch * 32) * sizeof(float);
+  }
+  VQB_REQUIRE(smem <= 200 * 1024, "conv: receptive field of one tile (%d rows) does not fit shared memory", p.rows);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    VQB_CUDA(cudaFuncSetAttribute(tgc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    smem_set = 200 * 1024;
+  }
+  dim3 grid(cdiv(p.Lt, TGC_TT), p.B, cdiv(p.COUT, 32));
+  tgc_kernel<<<grid, 256, smem, st>>>(p);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient: dW[j][cg][co] = sum_{b,t} act(ga[b, t*g_step + off[j], cg]) * ot[b, t, co]
+// ---------------------------------------------------------------------------------------------------------
+struct WgParams {
+  const float* ga;
+  const float* ot;
+  float* partial;  // [B*nchunk][ntaps*Cg*Co]
+  int B, Lg, Cg, Lo, Co, Lt, g_step, relu_ga, tch, nchunk;
+  TapTable taps;
+};
+
+constexpr int WG_TCH = 1024;
+
+// grid (B*nchunk, ntaps*ceil(Cg/32), ceil(Co/32)); 64 threads; thread = 4 gather channels x 4 other channels.
+// Operands are read straight from global memory (every load is a 16-byte contiguous piece shared by 8 lanes).
+__global__ void __launch_bounds__(64) wgrad_kernel(const WgParams p) {
+  const int tid = threadIdx.x;
+  const int ncgt = (p.Cg + 31) >> 5;
+  const int j = blockIdx.y / ncgt, cgt = blockIdx.y - j * ncgt;
+  const int cg = cgt * 32 + (tid >> 3) * 4, co = blockIdx.z * 32 + (tid & 7) * 4;
+  const int b = blockIdx.x / p.nchunk, ch = blockIdx.x - b * p.nchunk;
+  const int tb = ch * p.tch, te = min(tb + p.tch, p.Lt);
+  const int off = p.taps.off[j];
+  const float* gab = p.ga + (size_t)b * p.Lg * p.Cg;
+  const float* otb = p.ot + (size_t)b * p.Lo * p.Co;
+  const bool gvec = (p.Cg & 3) == 0, ovec = (p.Co & 3) == 0;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+#pragma unroll 4
+  for (int t = tb; t < te; ++t) {
+    const long gr = (long)t * p.g_step + off;
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gr >= 0 && gr < p.Lg && cg < p.Cg) {
+      const float* r = gab + gr * p.Cg + cg;
+      if (gvec) { const float4 v = *(const float4*)r; a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+      else { for (int i = 0; i < 4; ++i) if (cg + i < p.Cg) a[i] = r[i]; }
+      if (p.relu_ga) { for (int i = 0; i < 4; ++i) a[i] = fmaxf(a[i], 0.f); }
+    }
+    if (co < p.Co) {
+      const float* r = otb + (size_t)t * p.Co + co;
+      if (ovec) { const float4 v = *(const float4*)r; g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w; }
+      else { for (int i = 0; i < 4; ++i) if (co + i < p.Co) g[i] = r[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(a[i], g[c], acc[i][c]);
+  }
+  float* out = p.partial + (size_t)blockIdx.x * p.taps.ntaps * p.Cg * p.Co + (size_t)j * p.Cg * p.Co;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (cg + i < p.Cg && co + c < p.Co) out[(size_t)(cg + i) * p.Co + co + c] = acc[i][c];
+}
+
+// out[e] = sum_{c < nchunk} partial[c][e], fixed order
+__global__ void reduce_chunks_kernel(const float* __restrict__ partial, int nchunk, int n, float* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = 0;
+  for (; c + 4 <= nchunk; c += 4) {
+    s0 += partial[(size_t)(c + 0) * n + e];
+    s1 += partial[(size_t)(c + 1) * n + e];
+    s2 += partial[(size_t)(c + 2) * n + e];
+    s3 += partial[(size_t)(c + 3) * n + e];
+  }
+  for (; c < nchunk; ++c) s0 += partial[(size_t)c * n + e];
+  out[e] = (s0 + s1) + (s2 + s3);
+}
+
+// column sums of a [rows, C] matrix (bias gradient): partial[block][c]
+constexpr int COLSUM_ROWS = 2048;
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long rows, int C, float* __restrict__ partial) {
+  __shared__ float red[256];
+  const long r0 = (long)blockIdx.x * COLSUM_ROWS, r1 = min(r0 + (long)COLSUM_ROWS, rows);
+  if (C <= 256) {
+    const int lanes = 256 / C, nt = lanes * C;
+    const int c = threadIdx.x % C, rl = threadIdx.x / C;
+    float s = 0.f;
+    if (threadIdx.x < nt)
+      for (long r = r0 + rl; r < r1; r += lanes) s += x[r * C + c];
+    red[threadIdx.x] = threadIdx.x < nt ? s : 0.f;
+    __syncthreads();
+    if (threadIdx.x < C) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += red[l * C + threadIdx.x];
+      partial[(size_t)blockIdx.x * C + threadIdx.x] = t;
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float s = 0.f;
+      for (long r = r0; r < r1; ++r) s += x[r * C + c];
+      partial[(size_t)blockIdx.x * C + c] = s;
+    }
+  }
+}
+
+static size_t wgrad_ws_floats(int B, int Lt, int ntaps, int Cg, int Co, long bias_rows, int Cb) {
+  const size_t nchunk = (size_t)B * cdiv(Lt, WG_TCH);
+  return nchunk * ntaps * Cg * Co + (size_t)cdiv(bias_rows, COLSUM_ROWS) * Cb;
+}
+
+static int run_wgrad(WgParams& p, float* dw, const float* bias_src, long bias_rows, int Cb, float* dbias,
+                     void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int ntaps = p.taps.ntaps;
+  p.tch = WG_TCH;
+  p.nchunk = cdiv(p.Lt, WG_TCH);
+  const size_t need = wgrad_ws_floats(p.B, p.Lt, ntaps, p.Cg, p.Co, dbias ? bias_rows : 0, Cb) * sizeof(float);
+  if (ws_bytes < need || !ws) return set_err(VQB_ERR_WORKSPACE, "wgrad workspace: need %zu bytes, got %zu", need, ws_bytes);
+  p.partial = (float*)ws;
+  const int nchunks = p.B * p.nchunk;
+  const int n = ntaps * p.Cg * p.Co;
+  dim3 grid(nchunks, ntaps * cdiv(p.Cg, 32), cdiv(p.Co, 32));
+  wgrad_kernel<<<grid, 64, 0, st>>>(p);
+  VQB_LAUNCH_CHECK();
+  reduce_chunks_kernel<<<cdiv(n, 128), 128, 0, st>>>(p.partial, nchunks, n, dw);
+  VQB_LAUNCH_CHECK();
+  if (dbias) {
+    float* bp = p.partial + (size_t)nchunks * n;
+    const int nb = cdiv(bias_rows, COLSUM_ROWS);
+    colsum_kernel<<<nb, 256, 0, st>>>(bias_src, bias_rows, Cb, bp);
+    VQB_LAUNCH_CHECK();
+    reduce_chunks_kernel<<<cdiv(Cb, 128), 128, 0, st>>>(bp, nb, Cb, dbias);
+    VQB_LAUNCH_CHECK();
+  }
+  return VQB_OK;
+}
+
+static inline int floordiv(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+static inline int floormod(int a, int b) { return a - floordiv(a, b) * b; }
+
+static int check_desc(const vqb_conv_desc* d, bool transpose) {
+  VQB_REQUIRE(d != nullptr, "conv desc is NULL");
+  VQB_REQUIRE(d->B >= 0 && d->L >= 0 && d->C_in > 0 && d->C_out > 0, "conv desc: bad shape B=%d L=%d Cin=%d Cout=%d",
+              d->B, d->L, d->C_in, d->C_out);
+  VQB_REQUIRE(d->k >= 1 && d->k <= MAX_TAPS, "conv desc: k=%d outside [1,%d]", d->k, MAX_TAPS);
+  VQB_REQUIRE(d->stride >= 1 && d->dilation >= 1, "conv desc: stride=%d dilation=%d", d->stride, d->dilation);
+  if (transpose) VQB_REQUIRE(d->dilation == 1, "Conv1DTranspose: dilation must be 1");
+  return VQB_OK;
+}
+
+static void same_pad(int L, int k, int s, int dil, int* out, int* left) {
+  *out = (L + s - 1) / s;
+  int pad = (*out - 1) * s + (k - 1) * dil + 1 - L;
+  if (pad < 0) pad = 0;
+  *left = pad / 2;
+}
+
+// the "phase" form shared by Conv1D data-gradient and Conv1DTranspose forward
+static int run_phases(TgcParams base, int k, int s, int dil, int padL, int L_full, cudaStream_t st) {
+  for (int r = 0; r < s; ++r) {
+    TgcParams p = base;
+    p.taps.ntaps = 0;
+    for (int j = 0; j < k; ++j) {
+      const int num = r + padL - j * dil;
+      if (floormod(num, s) != 0) continue;
+      p.taps.wj[p.taps.ntaps] = j;
+      p.taps.off[p.taps.ntaps] = floordiv(num, s);
+      ++p.taps.ntaps;
+    }
+    p.in_step = 1;
+    p.out_step = s;
+    p.out_off = r;
+    p.Lt = L_full > r ? (L_full - r + s - 1) / s : 0;
+    int rc = launch_tgc(p, st);
+    if (rc != VQB_OK) return rc;
+  }
+  return VQB_OK;
+}
+
+int conv1d_fwd_fp32(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
+                    const float* residual, float* y, cudaStream_t st) {
+  int Lo, padL;
+  same_pad(d->L, d->k, d->stride, d->dilation, &Lo, &padL);
+  TgcParams p{};
+  p.in = x; p.w = w; p.bias = bias; p.res = residual; p.out = y;
+  p.B = d->B; p.L_in = d->L; p.CIN = d->C_in; p.COUT = d->C_out; p.L_out = Lo;
+  p.Lt = Lo; p.in_step = d->stride; p.out_step = 1; p.out_off = 0; p.relu_in = d->relu_in;
+  p.w_sj = d->C_in * d->C_out; p.w_si = d->C_out; p.w_so = 1;
+  p.taps.ntaps = d->k;
+  for (int j = 0; j < d->k; ++j) { p.taps.wj[j] = j; p.taps.off[j] = j * d->dilation - padL; }
+  return launch_tgc(p, st);
+}
+
+int conv1d_dgrad_fp32(const vqb_conv_desc* d, const float* dy, const float* w, const float* x,
+                      const float* dx_add, float* dx, cudaStream_t st) {
+  int Lo, padL;
+  same_pad(d->L, d->k, d->stride, d->dilation, &Lo, &padL);
+  TgcParams p{};
+  p.in = dy; p.w = w; p.mask = d->relu_in ? x : nullptr; p.add = dx_add; p.out = dx;
+  p.B = d->B; p.L_in = Lo; p.CIN = d->C_out; p.COUT = d->C_in; p.L_out = d->L;
+  p.w_sj = d->C_in * d->C_out; p.w_si = 1; p.w_so = d->C_out;  // W_j[i=co][o=ci] = w[j][ci][co]
+  return run_phases(p, d->k, d->stride, d->dilation, padL, d->L, st);
+}
+
+int conv1d_transpose_fwd_fp32(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
+                              float* y, cudaStream_t st) {
+  const int padL = (d->k > d->stride ? d->k - d->stride : 0) / 2;
+  TgcParams p{};
+  p.in = x; p.w = w; p.bias = bias; p.out = y;
+  p.B = d->B; p.L_in = d->L; p.CIN = d->C_in; p.COUT = d->C_out; p.L_out = d->L * d->stride;
+  p.relu_in = d->relu_in;
+  p.w_sj = d->C_out * d->C_in; p.w_si = 1; p.w_so = d->C_in;  // W_j[i=ci][o=co] = w[j][co][ci]
+  return run_phases(p, d->k, d->stride, 1, padL, d->L * d->stride, st);
+}
+
+int conv1d_transpose_dgrad_fp32(const vqb_conv_desc* d, const float* dy, const float* w, float* dx,
+                                cudaStream_t st) {
+  const int padL = (d->k > d->stride ? d->k - d->stride : 0) / 2;
+  TgcParams p{};
+  p.in = dy; p.w = w; p.out = dx;
+  p.B = d->B; p.L_in = d->L * d->stride; p.CIN = d->C_out; p.COUT = d->C_in; p.L_out = d->L;
+  p.Lt = d->L; p.in_step = d->stride; p.out_step = 1; p.out_off = 0;
+  p.w_sj = d->C_out * d->C_in; p.w_si = d->C_in; p.w_so = 1;  // W_j[i=co][o=ci] = w[j][co][ci]
+  p.taps.ntaps = d->k;
+  for (int j = 0; j < d->k; ++j) { p.taps.wj[j] = j; p.taps.off[j] = j - padL; }
+  return launch_tgc(p, st);
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" {
+
+int vqb_conv1d_fwd(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
+                   const float* residual, float* y, void* stream) {
+  VQB_ARCH();
+  int rc = check_desc(d, false);
+  if (rc) return rc;
+  VQB_REQUIRE(x && w && y, "vqb_conv1d_fwd: NULL pointer");
+  VQB_REQUIRE(d->precision == VQB_PREC_FP32, "vqb_conv1d_fwd: precision %d not available for this op", d->precision);
+  return conv1d_fwd_fp32(d, x, w, bias, residual, y, (cudaStream_t)stream);
+}
+
+int vqb_conv1d_dgrad(const vqb_conv_desc* d, const float* dy, const float* w, const float* x,
+                     const float* dx_add, float* dx, void* stream) {
+  VQB_ARCH();
+  int rc = check_desc(d, false);
+  if (rc) return rc;
+  VQB_REQUIRE(dy && w && dx, "vqb_conv1d_dgrad: NULL pointer");
+  VQB_REQUIRE(!d->relu_in || x, "vqb_conv1d_dgrad: relu_in needs x for the ReLU mask");
+  return conv1d_dgrad_fp32(d, dy, w, x, dx_add, dx, (cudaStream_t)stream);
+}
+
+size_t vqb_conv1d_wgrad_workspace_bytes(const vqb_conv_desc* d) {
+  if (!d || d->k < 1 || d->k > MAX_TAPS) return 0;
+  int Lo, padL;
+  same_pad(d->L, d->k, d->stride, d->dilation, &Lo, &padL);
+  return wgrad_ws_floats(d->B, Lo, d->k, d->C_in, d->C_out, (long)d->B * Lo, d->C_out) * sizeof(float);
+}
+
+int vqb_conv1d_wgrad(const vqb_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  VQB_ARCH();
+  int rc = check_desc(d, false);
+  if (rc) return rc;
+  VQB_REQUIRE(x && dy && dw, "vqb_conv1d_wgrad: NULL pointer");
+  int Lo, padL;
+  same_pad(d->L, d->k, d->stride, d->dilation, &Lo, &padL);
+  WgParams p{};
+  p.ga = x; p.ot = dy;
+  p.B = d->B; p.Lg = d->L; p.Cg = d->C_in; p.Lo = Lo; p.Co = d->C_out; p.Lt = Lo;
+  p.g_step = d->stride; p.relu_ga = d->relu_in;
+  p.taps.ntaps = d->k;
+  for (int j = 0; j < d->k; ++j) { p.taps.wj[j] = j; p.taps.off[j] = j * d->dilation - padL; }
+  return run_wgrad(p, dw, dy, (long)d->B * Lo, d->C_out, dbias, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int vqb_conv1d_transpose_fwd(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
+                             float* y, void* stream) {
+  VQB_ARCH();
+  int rc = check_desc(d, true);
+  if (rc) return rc;
+  VQB_REQUIRE(x && w && y, "vqb_conv1d_transpose_fwd: NULL pointer");
+  return conv1d_transpose_fwd_fp32(d, x, w, bias, y, (cudaStream_t)stream);
+}
+
+int vqb_conv1d_transpose_dgrad(const vqb_conv_desc* d, const float* dy, const float* w, float* dx, void* stream) {
+  VQB_ARCH();
+  int rc = check_desc(d, true);
+  if (rc) return rc;
+  VQB_REQUIRE(dy && w && dx, "vqb_conv1d_transpose_dgrad: NULL pointer");
+  return conv1d_transpose_dgrad_fp32(d, dy, w, dx, (cudaStream_t)stream);
+}
+
+size_t vqb_conv1d_transpose_wgrad_workspace_bytes(const vqb_conv_desc* d) {
+  if (!d || d->k < 1 || d->k > MAX_TAPS) return 0;
+  return wgrad_ws_floats(d->B, d->L, d->k, d->C_out, d->C_in, (long)d->B * d->L * d->stride, d->C_out) * sizeof(float);
+}
+
+int vqb_conv1d_transpose_wgrad(const vqb_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  VQB_ARCH();
+  int rc = check_desc(d, true);
+  if (rc) return rc;
+  VQB_REQUIRE(x && dy && dw, "vqb_conv1d_transpose_wgrad: NULL pointer");
+  const int padL = (d->k > d->stride ? d->k - d->stride : 0) / 2;
+  WgParams p{};
+  p.ga = dy; p.ot = x;  // dW[j][co][ci] = sum dy[m*s + j - padL][co] * x[m][ci]
+  p.B = d->B; p.Lg = d->L * d->stride; p.Cg = d->C_out; p.Lo = d->L; p.Co = d->C_in; p.Lt = d->L;
+  p.g_step = d->stride; p.relu_ga = 0;
+  p.taps.ntaps = d->k;
+  for (int j = 0; j < d->k; ++j) { p.taps.wj[j] = j; p.taps.off[j] = j - padL; }
+  return run_wgrad(p, dw, dy, (long)d->B * d->L * d->stride, d->C_out, dbias, workspace, workspace_bytes,
+                   (cudaStream_t)stream);
+}
+
+}  // extern "C"

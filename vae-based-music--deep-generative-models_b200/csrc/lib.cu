@@ -1,0 +1,55 @@
+// lib.cu — version, error text and the architecture gate of libvqvae_b200.so.
+#include "common.cuh"
+
+namespace vqb {
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int require_arch() {
+  static thread_local int cached_dev = -1, cached_rc = 0;
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_err(VQB_ERR_CUDA, "cudaGetDevice failed: %s", cudaGetErrorString(e));
+  if (dev == cached_dev) return cached_rc;
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return set_err(VQB_ERR_CUDA, "cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
+  cached_dev = dev;
+  cached_rc = major == 10 ? VQB_OK
+                          : set_err(VQB_ERR_ARCH, "device %d has compute capability %d.x; libvqvae_b200 is sm_100a only", dev, major);
+  return cached_rc;
+}
+
+}  // namespace vqb
+
+extern "C" {
+
+int vqb_version(void) { return VQB_VERSION; }
+
+const char* vqb_last_error(void) { return vqb::err_buf(); }
+
+int vqb_device_check(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || device < 0 || device >= n)
+    return vqb::set_err(VQB_ERR_ARCH, "no CUDA device %d (%s)", device, e != cudaSuccess ? cudaGetErrorString(e) : "out of range");
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e != cudaSuccess) return vqb::set_err(VQB_ERR_CUDA, "cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
+  if (major != 10)
+    return vqb::set_err(VQB_ERR_ARCH, "device %d has compute capability %d.x; libvqvae_b200 is sm_100a only", device, major);
+  return VQB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+// resblock.cu — vqb_resblock_fwd / vqb_resblock_bwd_data: the pre-activation residual block of
+// ResnetConv1DBlock.call (resnet.py:11-18,29).  VQB_PREC_FP32 runs the exact CUDA-core contraction
+// kernels of conv_fp32.cu (two launches, ReLU / bias / residual fused into load and epilogue);
+// VQB_PREC_BF16 / TF32 run the fused tcgen05 kernel of resblock_tc.cu for the shapes it supports.
+#include "common.cuh"
+
+namespace vqb {
+int conv1d_fwd_fp32(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
+                    const float* residual, float* y, cudaStream_t st);
+int conv1d_dgrad_fp32(const vqb_conv_desc* d, const float* dy, const float* w, const float* x,
+                      const float* dx_add, float* dx, cudaStream_t st);
+int resblock_fwd_tc(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1,
+                    const float* w2, const float* b2, float* h, float* y, cudaStream_t st);
+}  // namespace vqb
+
+using namespace vqb;
+
+static int check_rb(const vqb_resblock_desc* d) {
+  VQB_REQUIRE(d != nullptr, "resblock desc is NULL");
+  VQB_REQUIRE(d->B >= 0 && d->L >= 0 && d->C > 0 && d->F > 0 && d->dilation >= 1,
+              "resblock desc: bad shape B=%d L=%d C=%d F=%d dil=%d", d->B, d->L, d->C, d->F, d->dilation);
+  return VQB_OK;
+}
+
+extern "C" {
+
+int vqb_resblock_fwd(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1,
+                     const float* w2, const float* b2, float* h, float* y, void* stream) {
+  VQB_ARCH();
+  int rc = check_rb(d);
+  if (rc) return rc;
+  VQB_REQUIRE(x && w1 && w2 && h && y, "vqb_resblock_fwd: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->precision != VQB_PREC_FP32) return resblock_fwd_tc(d, x, w1, b1, w2, b2, h, y, st);
+  vqb_conv_desc c1{d->B, d->L, d->C, d->F, 3, 1, d->dilation, 1, VQB_PREC_FP32};
+  rc = conv1d_fwd_fp32(&c1, x, w1, b1, nullptr, h, st);
+  if (rc) return rc;
+  vqb_conv_desc c2{d->B, d->L, d->F, d->C, 3, 1, 1, 1, VQB_PREC_FP32};
+  return conv1d_fwd_fp32(&c2, h, w2, b2, x, y, st);
+}
+
+int vqb_resblock_bwd_data(const vqb_resblock_desc* d, const float* x, const float* h, const float* dy,
+                          const float* w1, const float* w2, float* dh, float* dx, void* stream) {
+  VQB_ARCH();
+  int rc = check_rb(d);
+  if (rc) return rc;
+  VQB_REQUIRE(x && h && dy && w1 && w2 && dh && dx, "vqb_resblock_bwd_data: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  vqb_conv_desc c2{d->B, d->L, d->F, d->C, 3, 1, 1, 1, VQB_PREC_FP32};
+  rc = conv1d_dgrad_fp32(&c2, dy, w2, h, nullptr, dh, st);  // dh = (h>0) * conv2^T(dy)
+  if (rc) return rc;
+  vqb_conv_desc c1{d->B, d->L, d->C, d->F, 3, 1, d->dilation, 1, VQB_PREC_FP32};
+  return conv1d_dgrad_fp32(&c1, dh, w1, x, dy, dx, st);     // dx = (x>0) * conv1^T(dh) + dy
+}
+
+}  // extern "C"

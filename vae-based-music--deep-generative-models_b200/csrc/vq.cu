@@ -1,0 +1,461 @@
+// vq.cu — VectorQuantizer kernels (exact-fp32 search path) behind vqb_vq_* (include/vqb.h).
+//
+//   vq_prep_kernel     Et[K,D] = E^T, ee[k] = sum_d E[d,k]^2                 (VectorQuantizer.py:180)
+//   vq_search_kernel   dist = (xx + ee) - 2 x.E, first-min argmin            (VectorQuantizer.py:173-185)
+//   vq_finish_kernel   gather E[:,idx], straight-through output, commitment partial sums, per-code
+//                      count / sum statistics                                 (:86-99,114,123-124)
+//   vq_ema_kernel      EMA + dead-code restart, separately rounded ops        (:128-145)
+//   vq_metrics_kernel  batch usage, running usage, entropy                    (:151-159)
+#include "common.cuh"
+
+namespace vqb {
+
+// implemented in vq_tc.cu (tcgen05 search); returns VQB_ERR_UNIMPLEMENTED for unsupported shapes
+int vq_search_tc(const vqb_vq_desc* d, const float* x, const float* E, const float* Et, const float* ee,
+                 int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t vq_search_tc_workspace_bytes(const vqb_vq_desc* d);
+
+__global__ void vq_prep_kernel(const float* __restrict__ E, int D, int K, float* __restrict__ Et,
+                               float* __restrict__ ee) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float v = E[(size_t)d * K + k];
+    Et[(size_t)k * D + d] = v;
+    s = fmaf(v, v, s);
+  }
+  ee[k] = s;
+}
+
+constexpr int VQ_RT = 32;   // rows per CTA
+constexpr int VQ_CT = 128;  // codes per tile
+constexpr int VQ_DC = 64;   // depth chunk
+
+// 256 threads: tx = tid % 32 -> 4 codes, ty = tid / 32 -> 4 rows.
+__global__ void __launch_bounds__(256) vq_search_kernel(const float* __restrict__ x, const float* __restrict__ E,
+                                                        const float* __restrict__ ee, long N, int D, int K,
+                                                        int64_t* __restrict__ idx) {
+  __shared__ __align__(16) float Xs[VQ_DC][VQ_RT + 4];   // transposed rows (+4: fewer store conflicts)
+  __shared__ __align__(16) float Es[VQ_DC][VQ_CT];
+  __shared__ float xx_s[VQ_RT];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const long n0 = (long)blockIdx.x * VQ_RT;
+  const int ndc = (D + VQ_DC - 1) / VQ_DC;
+
+  // ||x||^2 per row (sequential in d, one thread per row)
+  if (tid < VQ_RT) {
+    float s = 0.f;
+    const long n = n0 + tid;
+    if (n < N)
+      for (int d = 0; d < D; ++d) { const float v = x[n * D + d]; s = fmaf(v, v, s); }
+    xx_s[tid] = s;
+  }
+  float best[4];
+  int bidx[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { best[r] = INFINITY; bidx[r] = 0; }
+
+  for (int k0 = 0; k0 < K; k0 += VQ_CT) {
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    for (int dc = 0; dc < ndc; ++dc) {
+      const int d0 = dc * VQ_DC;
+      __syncthreads();
+      if (ndc > 1 || k0 == 0) {
+        for (int e = tid; e < VQ_RT * VQ_DC; e += 256) {
+          const int r = e / VQ_DC, d = e - r * VQ_DC;  // coalesced over d
+          const long n = n0 + r;
+          Xs[d][r] = (n < N && d0 + d < D) ? x[n * D + d0 + d] : 0.f;
+        }
+      }
+      for (int e = tid; e < VQ_DC * VQ_CT; e += 256) {
+        const int d = e / VQ_CT, c = e - d * VQ_CT;
+        Es[d][c] = (d0 + d < D && k0 + c < K) ? E[(size_t)(d0 + d) * K + k0 + c] : 0.f;
+      }
+      __syncthreads();
+      const int dmax = min(VQ_DC, D - d0);
+#pragma unroll 4
+      for (int d = 0; d < dmax; ++d) {
+        const float4 xv = *(const float4*)&Xs[d][ty * 4];
+        const float4 ev = *(const float4*)&Es[d][tx * 4];
+        const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          acc[r][0] = fmaf(xr[r], ev.x, acc[r][0]);
+          acc[r][1] = fmaf(xr[r], ev.y, acc[r][1]);
+          acc[r][2] = fmaf(xr[r], ev.z, acc[r][2]);
+          acc[r][3] = fmaf(xr[r], ev.w, acc[r][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int k = k0 + tx * 4 + c;
+      if (k < K) {
+        const float e2 = ee[k];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float dist = __fsub_rn(__fadd_rn(xx_s[ty * 4 + r], e2), 2.f * acc[r][c]);
+          if (dist < best[r]) { best[r] = dist; bidx[r] = k; }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float bd = best[r];
+    int bi = bidx[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    const long n = n0 + ty * 4 + r;
+    if (tx == 0 && n < N) idx[n] = bi;
+  }
+}
+
+// one warp per row, 8 warps x VQ_FR rows per CTA
+constexpr int VQ_FR = 4;
+__global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict__ x, const float* __restrict__ Et,
+                                                        const int64_t* __restrict__ idx, long N, int D, int K,
+                                                        float* __restrict__ q_st, float* __restrict__ q,
+                                                        float* __restrict__ m_batch, float* __restrict__ n_batch,
+                                                        float* __restrict__ loss_partial) {
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float ls = 0.f;
+  for (int i = 0; i < VQ_FR; ++i) {
+    const long n = ((long)blockIdx.x * 8 + wid) * VQ_FR + i;
+    if (n >= N) break;
+    const int k = (int)idx[n];
+    for (int d = lane; d < D; d += 32) {
+      const float xv = x[n * D + d];
+      const float qv = Et[(size_t)k * D + d];
+      const float diff = __fsub_rn(qv, xv);
+      if (q) q[n * D + d] = qv;
+      if (q_st) q_st[n * D + d] = __fadd_rn(xv, diff);
+      ls = fmaf(diff, diff, ls);
+      if (m_batch) atomicAdd(&m_batch[(size_t)d * K + k], xv);
+    }
+    if (n_batch && lane == 0) atomicAdd(&n_batch[k], 1.0f);
+  }
+  const float s = block_sum(ls, red);
+  if (threadIdx.x == 0) loss_partial[blockIdx.x] = s;
+}
+
+// out[0] = scale * sum(partial[0..n))  — single block, fixed order
+__global__ void __launch_bounds__(256) final_sum_kernel(const float* __restrict__ partial, long n, float scale,
+                                                        float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long i = threadIdx.x; i < n; i += 256) s += partial[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+
+__global__ void vq_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ x, const float* __restrict__ q,
+                              long n, float c, float* __restrict__ dx) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dx[i] = fmaf(c, x[i] - q[i], dq ? dq[i] : 0.f);
+}
+
+// block (32, 8): x -> code, y strides the embedding dimension
+__global__ void __launch_bounds__(256) vq_ema_kernel(int D, int K, float g, float omg, float thr,
+                                                     const float* __restrict__ m_batch,
+                                                     const float* __restrict__ n_batch,
+                                                     const float* __restrict__ rows, float* __restrict__ E,
+                                                     float* __restrict__ m_t, float* __restrict__ N_t) {
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  float Nn = 0.f;
+  if (k < K) {
+    Nn = __fadd_rn(__fmul_rn(g, N_t[k]), __fmul_rn(omg, n_batch[k]));  // VectorQuantizer.py:131
+    const float usage = Nn >= thr ? 1.f : 0.f;                         // :133 (uses the updated N_t)
+    const float den = fminf(fmaxf(Nn, 1e-8f), 1e8f);                   // :144 clip_by_value
+    for (int d = threadIdx.y; d < D; d += 8) {
+      const size_t o = (size_t)d * K + k;
+      const float mn = __fadd_rn(__fmul_rn(g, m_t[o]), __fmul_rn(omg, m_batch[o]));  // :128
+      m_t[o] = mn;
+      const float reset = __fmul_rn(__fsub_rn(1.f, usage), rows[(size_t)k * D + d]);  // :138
+      E[o] = __fadd_rn(__fmul_rn(usage, __fdiv_rn(mn, den)), reset);                  // :144-145
+    }
+  }
+  __syncthreads();
+  if (k < K && threadIdx.y == 0) N_t[k] = Nn;
+}
+
+__global__ void __launch_bounds__(256) vq_metrics_kernel(int K, float thr, const float* __restrict__ n_batch,
+                                                         const float* __restrict__ N_t, float* __restrict__ metrics) {
+  __shared__ float red[32];
+  __shared__ float tot_s;
+  float tot = 0.f, bu = 0.f, u = 0.f;
+  for (int k = threadIdx.x; k < K; k += 256) {
+    tot += n_batch[k];
+    bu += n_batch[k] >= thr ? 1.f : 0.f;
+    u += N_t[k] >= thr ? 1.f : 0.f;
+  }
+  tot = block_sum(tot, red);
+  if (threadIdx.x == 0) tot_s = tot;
+  bu = block_sum(bu, red);
+  u = block_sum(u, red);
+  __syncthreads();
+  const float total = tot_s;
+  float ent = 0.f;
+  for (int k = threadIdx.x; k < K; k += 256) {
+    const float p = __fdiv_rn(n_batch[k], total);
+    ent += p * logf(p + 1e-8f);
+  }
+  ent = block_sum(ent, red);
+  if (threadIdx.x == 0) { metrics[0] = bu; metrics[1] = u; metrics[2] = -ent; }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ x, long N, int D, const int64_t* __restrict__ ids, int n_ids,
+                                   float* __restrict__ rows) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long)n_ids * D) return;
+  const int i = (int)(e / D), d = (int)(e - (long)i * D);
+  long r = ids[i] % N;
+  if (r < 0) r += N;
+  rows[e] = x[r * D + d];
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void restart_ids_kernel(long N, int K, uint64_t seed, const int64_t* __restrict__ step, int64_t* __restrict__ ids) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const uint64_t Nt = N >= K ? (uint64_t)N : (uint64_t)N * (uint64_t)((K + N - 1) / N);
+  const uint64_t h1 = splitmix64(seed ^ splitmix64((uint64_t)(step ? step[0] : 0)));
+  const uint64_t h2 = splitmix64(h1);
+  uint64_t a = Nt > 1 ? 1 + h1 % (Nt - 1) : 1;
+  for (;;) {  // smallest a' >= a coprime with Nt
+    uint64_t u = a, v = Nt;
+    while (v) { const uint64_t t = u % v; u = v; v = t; }
+    if (u == 1) break;
+    a = a + 1 >= Nt ? 1 : a + 1;
+  }
+  const uint64_t c = h2 % Nt;
+  ids[i] = (int64_t)((a % Nt * ((uint64_t)i % Nt) + c) % Nt);
+}
+
+__global__ void gather_codes_kernel(const float* __restrict__ E, int D, int K, const int64_t* __restrict__ idx, long n,
+                                    float* __restrict__ out) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * D) return;
+  const long i = e / D;
+  const int d = (int)(e - i * D);
+  long k = idx[i];
+  k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+  out[e] = E[(size_t)d * K + k];
+}
+
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ x, const float* __restrict__ r, long n, float gscale,
+                                                  const float* __restrict__ dr_add, float* __restrict__ dr,
+                                                  float* __restrict__ partial) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const long base = (long)blockIdx.x * 256 * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long e = base + i * 256 + threadIdx.x;
+    if (e < n) {
+      const float df = r[e] - x[e];
+      s = fmaf(df, df, s);
+      if (dr) dr[e] = fmaf(gscale, df, dr_add ? dr_add[e] : 0.f);
+    }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long n, float lr, float b1, float b2, float eps,
+                                                   float gs, const int64_t* __restrict__ step) {
+  __shared__ float lr_s;
+  if (threadIdx.x == 0) {
+    const double t = (double)(step[0] + 1);
+    lr_s = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  }
+  __syncthreads();
+  const float lr_t = lr_s;
+  const float omb1 = 1.f - b1, omb2 = 1.f - b2;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+    const float gg = g[i] * gs;
+    const float mm = m[i] + (gg - m[i]) * omb1;
+    const float vv = v[i] + (gg * gg - v[i]) * omb2;
+    m[i] = mm;
+    v[i] = vv;
+    p[i] = p[i] - lr_t * mm / (sqrtf(vv) + eps);
+  }
+}
+
+__global__ void increment_kernel(int64_t* c) { c[0] += 1; }
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" {
+
+size_t vqb_reduce_workspace_bytes(int64_t n) { return (size_t)cdiv(n, 2048) * sizeof(float) + 16; }
+
+static size_t vq_base_ws_floats(const vqb_vq_desc* d) {
+  const size_t nfin = (size_t)cdiv(d->N, 8 * VQ_FR);
+  return (size_t)d->K * d->D + d->K + nfin + 64;
+}
+
+size_t vqb_vq_fwd_workspace_bytes(const vqb_vq_desc* d) {
+  if (!d || d->N < 0 || d->D <= 0 || d->K <= 0) return 0;
+  size_t b = vq_base_ws_floats(d) * sizeof(float);
+  b = (b + 1023) & ~(size_t)1023;
+  if (d->precision != VQB_PREC_FP32) b += vq_search_tc_workspace_bytes(d);
+  return b;
+}
+
+int vqb_vq_fwd(const vqb_vq_desc* d, const float* x, const float* E, int64_t* idx, float* q_st, float* q,
+               float* loss, float* m_batch, float* n_batch, void* workspace, size_t workspace_bytes, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(d && d->N >= 0 && d->D > 0 && d->K > 0, "vqb_vq_fwd: bad descriptor");
+  VQB_REQUIRE(x && E && idx, "vqb_vq_fwd: NULL pointer");
+  VQB_REQUIRE((m_batch == nullptr) == (n_batch == nullptr), "vqb_vq_fwd: m_batch and n_batch go together");
+  const size_t need = vqb_vq_fwd_workspace_bytes(d);
+  if (!workspace || workspace_bytes < need)
+    return set_err(VQB_ERR_WORKSPACE, "vqb_vq_fwd workspace: need %zu bytes, got %zu", need, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* Et = (float*)workspace;
+  float* ee = Et + (size_t)d->K * d->D;
+  float* part = ee + d->K;
+  const long N = d->N;
+  const int D = d->D, K = d->K;
+  vq_prep_kernel<<<cdiv(K, 128), 128, 0, st>>>(E, D, K, Et, ee);
+  VQB_LAUNCH_CHECK();
+  if (m_batch) {
+    VQB_CUDA(cudaMemsetAsync(m_batch, 0, (size_t)D * K * sizeof(float), st));
+    VQB_CUDA(cudaMemsetAsync(n_batch, 0, (size_t)K * sizeof(float), st));
+  }
+  if (N == 0) {
+    if (loss) VQB_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    return VQB_OK;
+  }
+  if (d->precision == VQB_PREC_FP32) {
+    vq_search_kernel<<<cdiv(N, VQ_RT), 256, 0, st>>>(x, E, ee, N, D, K, idx);
+    VQB_LAUNCH_CHECK();
+  } else {
+    size_t off = (vq_base_ws_floats(d) * sizeof(float) + 1023) & ~(size_t)1023;
+    int rc = vq_search_tc(d, x, E, Et, ee, idx, (char*)workspace + off, workspace_bytes - off, st);
+    if (rc != VQB_OK) return rc;
+  }
+  const int nfin = cdiv(N, 8 * VQ_FR);
+  vq_finish_kernel<<<nfin, 256, 0, st>>>(x, Et, idx, N, D, K, q_st, q, m_batch, n_batch, part);
+  VQB_LAUNCH_CHECK();
+  if (loss) {
+    final_sum_kernel<<<1, 256, 0, st>>>(part, nfin, d->beta / ((float)N * (float)D), loss);
+    VQB_LAUNCH_CHECK();
+  }
+  return VQB_OK;
+}
+
+int vqb_vq_bwd(const vqb_vq_desc* d, const float* dq_out, const float* x, const float* q, float loss_scale,
+               float* dx, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(d && x && q && dx, "vqb_vq_bwd: NULL pointer");
+  const long n = d->N * d->D;
+  if (n == 0) return VQB_OK;
+  const float c = loss_scale * 2.f * d->beta / ((float)d->N * (float)d->D);
+  vq_bwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(dq_out, x, q, n, c, dx);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+int vqb_vq_ema_update(int32_t D, int32_t K, double gamma, float threshold, const float* m_batch,
+                      const float* n_batch, const float* restart_rows, float* E, float* m_t, float* N_t,
+                      float* metrics, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(D > 0 && K > 0, "vqb_vq_ema_update: bad shape");
+  VQB_REQUIRE(m_batch && n_batch && restart_rows && E && m_t && N_t, "vqb_vq_ema_update: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float g = (float)gamma, omg = (float)(1.0 - gamma);  // python-float arithmetic, then cast (VectorQuantizer.py:128)
+  vq_ema_kernel<<<cdiv(K, 32), dim3(32, 8), 0, st>>>(D, K, g, omg, threshold, m_batch, n_batch, restart_rows, E, m_t, N_t);
+  VQB_LAUNCH_CHECK();
+  if (metrics) {
+    vq_metrics_kernel<<<1, 256, 0, st>>>(K, threshold, n_batch, N_t, metrics);
+    VQB_LAUNCH_CHECK();
+  }
+  return VQB_OK;
+}
+
+int vqb_gather_rows(const float* x, int64_t N, int32_t D, const int64_t* ids, int32_t n_ids, float* rows, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(x && ids && rows && N > 0 && D > 0 && n_ids >= 0, "vqb_gather_rows: bad argument");
+  const long n = (long)n_ids * D;
+  if (n == 0) return VQB_OK;
+  gather_rows_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, N, D, ids, n_ids, rows);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+int vqb_restart_ids(int64_t N, int32_t K, uint64_t seed, const int64_t* step_counter, int64_t* ids, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(N > 0 && K > 0 && ids, "vqb_restart_ids: bad argument");
+  restart_ids_kernel<<<cdiv(K, 128), 128, 0, (cudaStream_t)stream>>>(N, K, seed, step_counter, ids);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+int vqb_gather_codes(const float* E, int32_t D, int32_t K, const int64_t* idx, int64_t n, float* out, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(E && idx && out && D > 0 && K > 0 && n >= 0, "vqb_gather_codes: bad argument");
+  if (n == 0) return VQB_OK;
+  gather_codes_kernel<<<cdiv(n * D, 256), 256, 0, (cudaStream_t)stream>>>(E, D, K, idx, n, out);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+int vqb_mse(const float* x, const float* r, int64_t n, float loss_scale, const float* dr_add, float* loss,
+            float* dr, void* workspace, size_t workspace_bytes, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(x && r && loss && n > 0, "vqb_mse: bad argument");
+  const size_t need = vqb_reduce_workspace_bytes(n);
+  if (!workspace || workspace_bytes < need)
+    return set_err(VQB_ERR_WORKSPACE, "vqb_mse workspace: need %zu bytes, got %zu", need, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = cdiv(n, 2048);
+  mse_kernel<<<nb, 256, 0, st>>>(x, r, n, loss_scale * 2.f / (float)n, dr_add, dr, (float*)workspace);
+  VQB_LAUNCH_CHECK();
+  final_sum_kernel<<<1, 256, 0, st>>>((const float*)workspace, nb, 1.f / (float)n, loss);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+int vqb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
+                  float eps, float grad_scale, const int64_t* step_counter, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(p && g && m && v && step_counter && n >= 0, "vqb_adam_step: bad argument");
+  if (n == 0) return VQB_OK;
+  int nb = cdiv(n, 256);
+  if (nb > 148 * 16) nb = 148 * 16;
+  adam_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps, grad_scale, step_counter);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+int vqb_increment(int64_t* counter, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(counter, "vqb_increment: NULL pointer");
+  increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+}  // extern "C"
