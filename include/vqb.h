@@ -141,9 +141,11 @@ int vqb_vq_bwd(const vqb_vq_desc* d, const float* dq_out, const float* x, const 
 int vqb_vq_ema_update(int32_t D, int32_t K, double gamma, float threshold, const float* m_batch,
                       const float* n_batch, const float* restart_rows, float* E, float* m_t, float* N_t,
                       float* metrics, void* stream);
-/* rows[i,:] = x[(ids[i] mod N), :]  i < n_ids   (the `_tile` + shuffle[:K] row pick, VectorQuantizer.py:137,191-199) */
-int vqb_gather_rows(const float* x, int64_t N, int32_t D, const int64_t* ids, int32_t n_ids, float* rows,
-                    void* stream);
+/* the `_tile` + shuffle[:K] row pick (VectorQuantizer.py:137,191-199) for a batch that may be sharded over ranks:
+ *   r = ids[i] mod N_total;  rows[i,:] = x[r - row_offset, :] if row_offset <= r < row_offset + N_local else 0
+ * (single GPU: N_total = N_local, row_offset = 0; under data parallelism the per-rank results are summed). */
+int vqb_gather_rows(const float* x, int64_t N_local, int32_t D, const int64_t* ids, int32_t n_ids,
+                    int64_t N_total, int64_t row_offset, float* rows, void* stream);
 /* ids[i] = (a*i + c) mod Nt, i < K, with (a, c) hashed from (seed, *step_counter): K distinct pseudo-random
  * row numbers of the tiled batch, identical on every rank that shares seed and step.  Nt = max(N, K rounded up
  * to a multiple of N) as `_tile` produces. */

@@ -1,0 +1,229 @@
+"""TEST DOUBLE for libvqvae_b200.so: the same `vqb_*` entry points (include/vqb.h) evaluated on CPU memory with the
+oracle, so that the package's HOST logic (tape, variable packing, Keras `training` resolution, metric plumbing,
+data-parallel sharding arithmetic over gloo) can be unit-tested in a container without a GPU.
+
+It is installed only by tests (`vqvae_b200._lib.set_backend(FakeBackend(), "cpu")`); the product never imports it
+and raises without the CUDA library.  No parity claim is made from tests that use it."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from oracle import vqvae_oracle as O
+
+
+def _t(ptr, shape, dtype=np.float32):
+    if ptr is None:
+        return None
+    n = int(np.prod(shape)) if len(shape) else 1
+    ct = {np.float32: C.c_float, np.int64: C.c_int64, np.uint8: C.c_uint8}[dtype]
+    a = np.frombuffer((ct * max(n, 1)).from_address(int(ptr)), dtype=dtype)[:n].reshape(shape)
+    return torch.from_numpy(a)
+
+
+def _d(ref):
+    return ref._obj
+
+
+def _mix(z):
+    m = (1 << 64) - 1
+    z = (z + 0x9E3779B97F4A7C15) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    return z ^ (z >> 31)
+
+
+class FakeBackend:
+    def __init__(self):
+        self.calls = []
+        self._err = b""
+
+    # ---- misc
+    def vqb_version(self):
+        return 100
+
+    def vqb_last_error(self):
+        return self._err
+
+    def vqb_device_check(self, dev):
+        return 0
+
+    # ---- conv
+    @staticmethod
+    def _act(x, d):
+        return torch.relu(x) if d.relu_in else x
+
+    def vqb_conv1d_fwd(self, dref, x, w, b, res, y, stream):
+        d = _d(dref)
+        Lo = -(-d.L // d.stride)
+        X = _t(x, (d.B, d.L, d.C_in)); W = _t(w, (d.k, d.C_in, d.C_out)); Bv = _t(b, (d.C_out,))
+        out = O.conv1d(self._act(X, d), W, Bv, d.stride, d.dilation)
+        if res is not None:
+            out = out + _t(res, (d.B, Lo, d.C_out))
+        _t(y, (d.B, Lo, d.C_out)).copy_(out)
+        return 0
+
+    def vqb_conv1d_dgrad(self, dref, dy, w, x, dx_add, dx, stream):
+        d = _d(dref)
+        Lo = -(-d.L // d.stride)
+        W = _t(w, (d.k, d.C_in, d.C_out)); DY = _t(dy, (d.B, Lo, d.C_out))
+        xr = torch.zeros(d.B, d.L, d.C_in, requires_grad=True)
+        (g,) = torch.autograd.grad(O.conv1d(xr, W, None, d.stride, d.dilation), xr, DY)
+        if d.relu_in:
+            g = g * (_t(x, (d.B, d.L, d.C_in)) > 0)
+        if dx_add is not None:
+            g = g + _t(dx_add, (d.B, d.L, d.C_in))
+        _t(dx, (d.B, d.L, d.C_in)).copy_(g)
+        return 0
+
+    def vqb_conv1d_wgrad_workspace_bytes(self, dref):
+        return 64
+
+    def vqb_conv1d_wgrad(self, dref, x, dy, dw, db, ws, wsn, stream):
+        d = _d(dref)
+        Lo = -(-d.L // d.stride)
+        X = self._act(_t(x, (d.B, d.L, d.C_in)), d); DY = _t(dy, (d.B, Lo, d.C_out))
+        wr = torch.zeros(d.k, d.C_in, d.C_out, requires_grad=True)
+        (g,) = torch.autograd.grad(O.conv1d(X, wr, None, d.stride, d.dilation), wr, DY)
+        _t(dw, (d.k, d.C_in, d.C_out)).copy_(g)
+        if db is not None:
+            _t(db, (d.C_out,)).copy_(DY.sum((0, 1)))
+        return 0
+
+    def vqb_conv1d_transpose_fwd(self, dref, x, w, b, y, stream):
+        d = _d(dref)
+        X = _t(x, (d.B, d.L, d.C_in)); W = _t(w, (d.k, d.C_out, d.C_in)); Bv = _t(b, (d.C_out,))
+        _t(y, (d.B, d.L * d.stride, d.C_out)).copy_(O.conv1d_transpose(X, W, Bv, d.stride))
+        return 0
+
+    def vqb_conv1d_transpose_dgrad(self, dref, dy, w, dx, stream):
+        d = _d(dref)
+        W = _t(w, (d.k, d.C_out, d.C_in)); DY = _t(dy, (d.B, d.L * d.stride, d.C_out))
+        xr = torch.zeros(d.B, d.L, d.C_in, requires_grad=True)
+        (g,) = torch.autograd.grad(O.conv1d_transpose(xr, W, None, d.stride), xr, DY)
+        _t(dx, (d.B, d.L, d.C_in)).copy_(g)
+        return 0
+
+    def vqb_conv1d_transpose_wgrad_workspace_bytes(self, dref):
+        return 64
+
+    def vqb_conv1d_transpose_wgrad(self, dref, x, dy, dw, db, ws, wsn, stream):
+        d = _d(dref)
+        X = _t(x, (d.B, d.L, d.C_in)); DY = _t(dy, (d.B, d.L * d.stride, d.C_out))
+        wr = torch.zeros(d.k, d.C_out, d.C_in, requires_grad=True)
+        (g,) = torch.autograd.grad(O.conv1d_transpose(X, wr, None, d.stride), wr, DY)
+        _t(dw, (d.k, d.C_out, d.C_in)).copy_(g)
+        if db is not None:
+            _t(db, (d.C_out,)).copy_(DY.sum((0, 1)))
+        return 0
+
+    # ---- resblock
+    def vqb_resblock_fwd(self, dref, x, w1, b1, w2, b2, h, y, stream):
+        d = _d(dref)
+        X = _t(x, (d.B, d.L, d.C))
+        H = O.conv1d(torch.relu(X), _t(w1, (3, d.C, d.F)), _t(b1, (d.F,)), 1, d.dilation)
+        _t(h, (d.B, d.L, d.F)).copy_(H)
+        _t(y, (d.B, d.L, d.C)).copy_(X + O.conv1d(torch.relu(H), _t(w2, (3, d.F, d.C)), _t(b2, (d.C,)), 1, 1))
+        return 0
+
+    def vqb_resblock_bwd_data(self, dref, x, h, dy, w1, w2, dh, dx, stream):
+        d = _d(dref)
+        X = _t(x, (d.B, d.L, d.C)); H = _t(h, (d.B, d.L, d.F)); DY = _t(dy, (d.B, d.L, d.C))
+        W1 = _t(w1, (3, d.C, d.F)); W2 = _t(w2, (3, d.F, d.C))
+        hr = torch.zeros(d.B, d.L, d.F, requires_grad=True)
+        (g2,) = torch.autograd.grad(O.conv1d(hr, W2, None, 1, 1), hr, DY)
+        DH = g2 * (H > 0)
+        xr = torch.zeros(d.B, d.L, d.C, requires_grad=True)
+        (g1,) = torch.autograd.grad(O.conv1d(xr, W1, None, 1, d.dilation), xr, DH)
+        _t(dh, (d.B, d.L, d.F)).copy_(DH)
+        _t(dx, (d.B, d.L, d.C)).copy_(g1 * (X > 0) + DY)
+        return 0
+
+    # ---- VQ
+    def vqb_vq_fwd_workspace_bytes(self, dref):
+        return 64
+
+    def vqb_vq_fwd(self, dref, x, E, idx, q_st, q, loss, m_batch, n_batch, ws, wsn, stream):
+        d = _d(dref)
+        X = _t(x, (d.N, d.D)); Ev = _t(E, (d.D, d.K))
+        I = O.vq_code_indices(X, Ev)
+        _t(idx, (d.N,), np.int64).copy_(I)
+        Q = Ev.t()[I]
+        if q is not None:
+            _t(q, (d.N, d.D)).copy_(Q)
+        if q_st is not None:
+            _t(q_st, (d.N, d.D)).copy_(X + (Q - X))
+        if loss is not None:
+            _t(loss, (1,)).copy_((d.beta * ((Q - X) ** 2).mean()).reshape(1))
+        if m_batch is not None:
+            mb, nb = O.vq_batch_stats(X, I, d.K)
+            _t(m_batch, (d.D, d.K)).copy_(mb)
+            _t(n_batch, (d.K,)).copy_(nb)
+        return 0
+
+    def vqb_vq_bwd(self, dref, dq, x, q, scale, dx, stream):
+        d = _d(dref)
+        X = _t(x, (d.N, d.D)); Q = _t(q, (d.N, d.D))
+        g = scale * 2.0 * d.beta / (d.N * d.D) * (X - Q)
+        if dq is not None:
+            g = g + _t(dq, (d.N, d.D))
+        _t(dx, (d.N, d.D)).copy_(g)
+        return 0
+
+    def vqb_vq_ema_update(self, D, K, gamma, thr, m_batch, n_batch, rows, E, m_t, N_t, metrics, stream):
+        st = O.VQState(_t(E, (D, K)), _t(m_t, (D, K)), _t(N_t, (K,)))
+        new, met = O.vq_ema_update(st, _t(m_batch, (D, K)), _t(n_batch, (K,)), _t(rows, (K, D)), gamma, thr)
+        st.E.copy_(new.E); st.m_t.copy_(new.m_t); st.N_t.copy_(new.N_t)
+        if metrics is not None:
+            _t(metrics, (3,)).copy_(torch.stack([met["batch_usage"], met["usage"], met["entropy"]]))
+        return 0
+
+    def vqb_gather_rows(self, x, N, D, ids, n_ids, n_total, off, rows, stream):
+        X = _t(x, (N, D)); I = _t(ids, (n_ids,), np.int64)
+        r = (I % n_total) - off
+        ok = (r >= 0) & (r < N)
+        out = torch.zeros(n_ids, D)
+        out[ok] = X[r[ok]]
+        _t(rows, (n_ids, D)).copy_(out)
+        return 0
+
+    def vqb_restart_ids(self, N, K, seed, step, ids, stream):
+        s = int(_t(step, (1,), np.int64)[0]) if step is not None else 0
+        Nt = N if N >= K else N * (-(-K // N))
+        h1 = _mix(seed ^ _mix(s)); h2 = _mix(h1)
+        a = 1 + h1 % (Nt - 1) if Nt > 1 else 1
+        while np.gcd(a, Nt) != 1:
+            a = 1 if a + 1 >= Nt else a + 1
+        c = h2 % Nt
+        _t(ids, (K,), np.int64).copy_(torch.tensor([(a * i + c) % Nt for i in range(K)], dtype=torch.int64))
+        return 0
+
+    def vqb_gather_codes(self, E, D, K, idx, n, out, stream):
+        _t(out, (n, D)).copy_(_t(E, (D, K)).t()[_t(idx, (n,), np.int64).clamp(0, K - 1)])
+        return 0
+
+    # ---- loss / optimiser
+    def vqb_reduce_workspace_bytes(self, n):
+        return 64
+
+    def vqb_mse(self, x, r, n, scale, dr_add, loss, dr, ws, wsn, stream):
+        X = _t(x, (n,)); R = _t(r, (n,))
+        _t(loss, (1,)).copy_(((X - R) ** 2).mean().reshape(1))
+        if dr is not None:
+            g = scale * 2.0 / n * (R - X)
+            if dr_add is not None:
+                g = g + _t(dr_add, (n,))
+            _t(dr, (n,)).copy_(g)
+        return 0
+
+    def vqb_adam_step(self, p, g, m, v, n, lr, b1, b2, eps, gs, step, stream):
+        t = int(_t(step, (1,), np.int64)[0]) + 1
+        P, G, M, V = _t(p, (n,)), _t(g, (n,)), _t(m, (n,)), _t(v, (n,))
+        O.adam_step([P], [G * gs], [M], [V], t, lr, b1, b2, eps)
+        return 0
+
+    def vqb_increment(self, c, stream):
+        _t(c, (1,), np.int64).add_(1)
+        return 0

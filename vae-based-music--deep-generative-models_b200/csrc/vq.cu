@@ -216,13 +216,14 @@ __global__ void __launch_bounds__(256) vq_metrics_kernel(int K, float thr, const
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ x, long N, int D, const int64_t* __restrict__ ids, int n_ids,
-                                   float* __restrict__ rows) {
+                                   long Ntot, long off, float* __restrict__ rows) {
   const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long)n_ids * D) return;
   const int i = (int)(e / D), d = (int)(e - (long)i * D);
-  long r = ids[i] % N;
-  if (r < 0) r += N;
-  rows[e] = x[r * D + d];
+  long r = ids[i] % Ntot;
+  if (r < 0) r += Ntot;
+  r -= off;
+  rows[e] = (r >= 0 && r < N) ? x[r * D + d] : 0.f;
 }
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
@@ -395,12 +396,13 @@ int vqb_vq_ema_update(int32_t D, int32_t K, double gamma, float threshold, const
   return VQB_OK;
 }
 
-int vqb_gather_rows(const float* x, int64_t N, int32_t D, const int64_t* ids, int32_t n_ids, float* rows, void* stream) {
+int vqb_gather_rows(const float* x, int64_t N, int32_t D, const int64_t* ids, int32_t n_ids, int64_t N_total,
+                    int64_t row_offset, float* rows, void* stream) {
   VQB_ARCH();
-  VQB_REQUIRE(x && ids && rows && N > 0 && D > 0 && n_ids >= 0, "vqb_gather_rows: bad argument");
+  VQB_REQUIRE(x && ids && rows && N > 0 && D > 0 && n_ids >= 0 && N_total > 0, "vqb_gather_rows: bad argument");
   const long n = (long)n_ids * D;
   if (n == 0) return VQB_OK;
-  gather_rows_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, N, D, ids, n_ids, rows);
+  gather_rows_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, N, D, ids, n_ids, N_total, row_offset, rows);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

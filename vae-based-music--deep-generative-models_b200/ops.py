@@ -1,0 +1,210 @@
+"""Thin tensor-level wrappers over the C ABI (include/vqb.h).  torch is used only to own device memory and to
+name the stream; every computation below is one or more `vqb_*` calls into libvqvae_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, ResblockDesc, VQDesc, call, ptr
+
+F32 = torch.float32
+
+
+def empty(*shape, dtype=F32):
+    return torch.empty(*shape, dtype=dtype, device=_lib.device())
+
+
+def zeros(*shape, dtype=F32):
+    return torch.zeros(*shape, dtype=dtype, device=_lib.device())
+
+
+def _ws(nbytes: int):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=_lib.device())
+
+
+def _chk(t, name):
+    if t is None:
+        return
+    if t.dtype != F32 or not t.is_contiguous() or t.device != _lib.device():
+        raise ValueError(f"{name}: expected a contiguous float32 tensor on {_lib.device()}, got {t.dtype} "
+                         f"contiguous={t.is_contiguous()} on {t.device}")
+
+
+def out_len(L, stride):
+    return -(-L // stride)
+
+
+# ----------------------------------------------------------------------------------------------- conv
+def _cdesc(B, L, cin, cout, k, stride, dilation, relu_in, precision=0):
+    return ConvDesc(B, L, cin, cout, k, stride, dilation, int(bool(relu_in)), precision)
+
+
+def conv1d_fwd(x, w, b, stride=1, dilation=1, relu_in=False, residual=None, precision=0):
+    _chk(x, "x"); _chk(w, "w"); _chk(b, "b"); _chk(residual, "residual")
+    B, L, cin = x.shape
+    k, wcin, cout = w.shape
+    if wcin != cin:
+        raise ValueError(f"Conv1D: input has {cin} channels, kernel expects {wcin}")
+    y = empty(B, out_len(L, stride), cout)
+    d = _cdesc(B, L, cin, cout, k, stride, dilation, relu_in, precision)
+    call("vqb_conv1d_fwd", C.byref(d), ptr(x), ptr(w), ptr(b), ptr(residual), ptr(y), _lib.stream())
+    return y
+
+
+def conv1d_dgrad(dy, w, x_shape, x=None, stride=1, dilation=1, relu_in=False, dx_add=None):
+    _chk(dy, "dy"); _chk(w, "w"); _chk(x, "x"); _chk(dx_add, "dx_add")
+    B, L, cin = x_shape
+    k, _, cout = w.shape
+    dx = empty(B, L, cin)
+    d = _cdesc(B, L, cin, cout, k, stride, dilation, relu_in)
+    call("vqb_conv1d_dgrad", C.byref(d), ptr(dy), ptr(w), ptr(x), ptr(dx_add), ptr(dx), _lib.stream())
+    return dx
+
+
+def conv1d_wgrad(x, dy, dw, db, stride=1, dilation=1, relu_in=False):
+    _chk(x, "x"); _chk(dy, "dy"); _chk(dw, "dw"); _chk(db, "db")
+    B, L, cin = x.shape
+    k, _, cout = dw.shape
+    d = _cdesc(B, L, cin, cout, k, stride, dilation, relu_in)
+    n = _lib.lib().vqb_conv1d_wgrad_workspace_bytes(C.byref(d))
+    ws = _ws(n)
+    call("vqb_conv1d_wgrad", C.byref(d), ptr(x), ptr(dy), ptr(dw), ptr(db), ptr(ws), ws.numel(), _lib.stream())
+
+
+def conv1d_transpose_fwd(x, w, b, stride=2):
+    _chk(x, "x"); _chk(w, "w"); _chk(b, "b")
+    B, L, cin = x.shape
+    k, cout, wcin = w.shape
+    if wcin != cin:
+        raise ValueError(f"Conv1DTranspose: input has {cin} channels, kernel expects {wcin}")
+    y = empty(B, L * stride, cout)
+    d = _cdesc(B, L, cin, cout, k, stride, 1, 0)
+    call("vqb_conv1d_transpose_fwd", C.byref(d), ptr(x), ptr(w), ptr(b), ptr(y), _lib.stream())
+    return y
+
+
+def conv1d_transpose_dgrad(dy, w, x_shape, stride=2):
+    _chk(dy, "dy"); _chk(w, "w")
+    B, L, cin = x_shape
+    k, cout, _ = w.shape
+    dx = empty(B, L, cin)
+    d = _cdesc(B, L, cin, cout, k, stride, 1, 0)
+    call("vqb_conv1d_transpose_dgrad", C.byref(d), ptr(dy), ptr(w), ptr(dx), _lib.stream())
+    return dx
+
+
+def conv1d_transpose_wgrad(x, dy, dw, db, stride=2):
+    _chk(x, "x"); _chk(dy, "dy"); _chk(dw, "dw"); _chk(db, "db")
+    B, L, cin = x.shape
+    k, cout, _ = dw.shape
+    d = _cdesc(B, L, cin, cout, k, stride, 1, 0)
+    n = _lib.lib().vqb_conv1d_transpose_wgrad_workspace_bytes(C.byref(d))
+    ws = _ws(n)
+    call("vqb_conv1d_transpose_wgrad", C.byref(d), ptr(x), ptr(dy), ptr(dw), ptr(db), ptr(ws), ws.numel(),
+         _lib.stream())
+
+
+# ------------------------------------------------------------------------------------------- resblock
+def resblock_fwd(x, w1, b1, w2, b2, dilation, precision=0):
+    for t, n in ((x, "x"), (w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2")):
+        _chk(t, n)
+    B, L, Cc = x.shape
+    Fc = w1.shape[2]
+    if w1.shape[1] != Cc or w2.shape[1] != Fc or w2.shape[2] != Cc:
+        raise ValueError(f"ResnetConv1DBlock: kernel shapes {tuple(w1.shape)}, {tuple(w2.shape)} do not fit input {tuple(x.shape)}")
+    h, y = empty(B, L, Fc), empty(B, L, Cc)
+    d = ResblockDesc(B, L, Cc, Fc, dilation, precision)
+    call("vqb_resblock_fwd", C.byref(d), ptr(x), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(h), ptr(y), _lib.stream())
+    return y, h
+
+
+def resblock_bwd_data(x, h, dy, w1, w2, dilation, precision=0):
+    _chk(dy, "dy")
+    B, L, Cc = x.shape
+    Fc = h.shape[2]
+    dh, dx = empty(B, L, Fc), empty(B, L, Cc)
+    d = ResblockDesc(B, L, Cc, Fc, dilation, precision)
+    call("vqb_resblock_bwd_data", C.byref(d), ptr(x), ptr(h), ptr(dy), ptr(w1), ptr(w2), ptr(dh), ptr(dx),
+         _lib.stream())
+    return dx, dh
+
+
+# ------------------------------------------------------------------------------------------------- VQ
+def vq_fwd(flat, E, beta, want_q_st=True, want_q=True, m_batch=None, n_batch=None, precision=0):
+    """flat [N,D], E [D,K] -> idx int64 [N], q_st, q, loss[1]"""
+    _chk(flat, "x"); _chk(E, "embeddings")
+    N, D = flat.shape
+    if E.shape[0] != D:
+        raise ValueError(f"VectorQuantizer: input depth {D} != embedding_dim {E.shape[0]}")
+    K = E.shape[1]
+    idx = empty(N, dtype=torch.int64)
+    q_st = empty(N, D) if want_q_st else None
+    q = empty(N, D) if want_q else None
+    loss = empty(1)
+    d = VQDesc(N, D, K, beta, precision)
+    ws = _ws(_lib.lib().vqb_vq_fwd_workspace_bytes(C.byref(d)))
+    call("vqb_vq_fwd", C.byref(d), ptr(flat), ptr(E), ptr(idx), ptr(q_st), ptr(q), ptr(loss), ptr(m_batch),
+         ptr(n_batch), ptr(ws), ws.numel(), _lib.stream())
+    return idx, q_st, q, loss
+
+
+def vq_bwd(dq, flat, q, beta, loss_scale):
+    N, D = flat.shape
+    dx = empty(N, D)
+    d = VQDesc(N, D, 0, beta, 0)
+    call("vqb_vq_bwd", C.byref(d), ptr(dq), ptr(flat), ptr(q), float(loss_scale), ptr(dx), _lib.stream())
+    return dx
+
+
+def vq_ema_update(E, m_t, N_t, m_batch, n_batch, restart_rows, gamma, threshold, metrics=None):
+    D, K = E.shape
+    call("vqb_vq_ema_update", D, K, float(gamma), float(threshold), ptr(m_batch), ptr(n_batch), ptr(restart_rows),
+         ptr(E), ptr(m_t), ptr(N_t), ptr(metrics), _lib.stream())
+
+
+def gather_rows(flat, ids, n_total=None, row_offset=0, out=None):
+    N, D = flat.shape
+    rows = out if out is not None else empty(ids.numel(), D)
+    call("vqb_gather_rows", ptr(flat), N, D, ptr(ids), ids.numel(), int(n_total if n_total is not None else N),
+         int(row_offset), ptr(rows), _lib.stream())
+    return rows
+
+
+def restart_ids(N, K, seed, step_counter):
+    ids = empty(K, dtype=torch.int64)
+    call("vqb_restart_ids", int(N), int(K), int(seed), ptr(step_counter), ptr(ids), _lib.stream())
+    return ids
+
+
+def gather_codes(E, idx):
+    D, K = E.shape
+    idx = idx.contiguous()
+    out = empty(*idx.shape, D)
+    call("vqb_gather_codes", ptr(E), D, K, ptr(idx), idx.numel(), ptr(out), _lib.stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------- loss / optimiser
+def mse(x, r, loss_scale=None, dr_add=None):
+    """returns (loss[1], dr or None).  dr = loss_scale * 2 (r - x)/n (+ dr_add) when loss_scale is given."""
+    _chk(x, "x"); _chk(r, "r")
+    if x.shape != r.shape:
+        raise ValueError(f"mse: shapes differ {tuple(x.shape)} vs {tuple(r.shape)}")
+    n = x.numel()
+    loss = empty(1)
+    dr = empty(r.shape) if loss_scale is not None else None
+    ws = _ws(_lib.lib().vqb_reduce_workspace_bytes(n))
+    call("vqb_mse", ptr(x), ptr(r), n, float(loss_scale or 0.0), ptr(dr_add), ptr(loss), ptr(dr), ptr(ws),
+         ws.numel(), _lib.stream())
+    return loss, dr
+
+
+def adam_step(p, g, m, v, lr, b1, b2, eps, grad_scale, step_counter):
+    call("vqb_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(b1), float(b2), float(eps),
+         float(grad_scale), ptr(step_counter), _lib.stream())
+
+
+def increment(counter):
+    call("vqb_increment", ptr(counter), _lib.stream())

@@ -1,0 +1,70 @@
+"""resnet — drop-in for the reference's `resnet.py`: `ResnetConv1DBlock` (:7-29) and `DilatedResnet1D` (:40-59).
+
+`ResnetConv1DBlock.model` is still the `Sequential([ReLU, Conv1D(dil), ReLU, Conv1D])` the reference builds (callers
+walk it: encdec.py:7-14, src/conditioner/conditioners.py:108-118), but `call` runs the whole pre-activation block
+as ONE fused operation (`vqb_resblock_fwd`), and its backward as `vqb_resblock_bwd_data` + two weight-gradient calls.
+"""
+from __future__ import annotations
+
+from . import _lib, ops
+from .keras_compat import KerasTensor, Sequential, _is_symbolic, grad_buffer, layers, record, write_grad
+
+
+class ResnetConv1DBlock(layers.Layer):
+    def __init__(self, input_dim, filters, dilation=1, **kwargs):
+        super(ResnetConv1DBlock, self).__init__(**kwargs)
+        self.input_dim, self.filters, self.dilation = input_dim, filters, dilation
+        self.model = Sequential([
+            layers.ReLU(),
+            layers.Conv1D(filters, 3, dilation_rate=dilation, padding="same",
+                          name="dilated_cov1d_dr-{}".format(dilation)),  # resnet.py:13-15 (name kept, typo included)
+            layers.ReLU(),
+            layers.Conv1D(input_dim, 3, dilation_rate=1, padding="same"),
+        ])
+        self.precision = _lib.PREC_FP32
+
+    def call(self, input_tensor, **kwargs):
+        x = input_tensor
+        if _is_symbolic(x):
+            y = self.model(x)  # builds the four sub-layers
+            return KerasTensor(x.shape)
+        conv1, conv2 = self.model.layers[1], self.model.layers[3]
+        if not conv1.built:
+            conv1.build(tuple(x.shape)); conv1.built = True
+            conv2.build(tuple(x.shape[:-1]) + (self.filters,)); conv2.built = True
+        if x.shape[-1] != self.input_dim:
+            raise ValueError(f"{self.name}: input has {x.shape[-1]} channels, block was built for {self.input_dim}")
+        x = x if x.is_contiguous() else x.contiguous()
+        d, prec = self.dilation, self.precision
+        # y = x + conv2(relu(conv1(relu(x))))   (resnet.py:11-18,29)
+        y, h = ops.resblock_fwd(x, conv1.kernel.value, conv1.bias.value, conv2.kernel.value, conv2.bias.value, d, prec)
+
+        def bwd(g, needs):
+            dy = g[0].contiguous()
+            dx, dh = ops.resblock_bwd_data(x, h, dy, conv1.kernel.value, conv2.kernel.value, d)
+            write_grad(conv2.kernel, lambda buf: ops.conv1d_wgrad(h, dy, buf, grad_buffer(conv2.bias), 1, 1, True))
+            conv2.bias._grad_written = True
+            write_grad(conv1.kernel, lambda buf: ops.conv1d_wgrad(x, dh, buf, grad_buffer(conv1.bias), 1, d, True))
+            conv1.bias._grad_written = True
+            return [dx if needs[0] else None]
+
+        record([input_tensor], [y], bwd)
+        return y
+
+
+class DilatedResnet1D(layers.Layer):
+    def __init__(self, input_dim, depth, dilation_factor=1, reverse_dilation=False, dilation_cycle=None, **kwargs):
+        super(DilatedResnet1D, self).__init__(**kwargs)
+
+        def _get_dilation(cur_depth):
+            if dilation_cycle is None:
+                return dilation_factor ** cur_depth
+            return dilation_factor ** (cur_depth % dilation_cycle)  # cyclic dilation (resnet.py:44-48)
+
+        blocks = [ResnetConv1DBlock(input_dim, input_dim, dilation=_get_dilation(d)) for d in range(depth)]
+        if reverse_dilation:  # decoder stacks contract the dilation down to 1 (resnet.py:54-55)
+            blocks = blocks[::-1]
+        self.model = Sequential(blocks)
+
+    def call(self, input, **kwargs):
+        return self.model(input)

@@ -1,0 +1,341 @@
+"""vqvae — drop-in for the reference's `vqvae.py`: `get_vqvae` (:15-21) and `VQVAE` (:24-326) with the same
+constructor, attributes (`vqvaes`, `encoders`, `decoders`, `vqs`, `levels`, ...) and methods (`train_step`,
+`test_step`, `call`, `encode`, `decode`, `update_metrics`, `get_quantizer`, `_multispectral_loss`, `compile`, `fit`,
+`evaluate`).  Every level is an independent VQ-VAE on the same input (Jukebox style).
+
+What is different underneath:
+  * all trainable variables of all levels live in ONE packed parameter buffer / ONE gradient buffer, so the data-
+    parallel gradient all-reduce and the Adam step are single launches;
+  * `train_step` is captured into CUDA graphs after its first eager execution for a given batch shape (the reference
+    runs ~1500 eager TF kernels per step, vqvae.py:110 has @tf.function commented out) — graph A = forward + backward
+    of every level, [NCCL all-reduce of gradients + EMA statistics + loss scalars under data parallelism],
+    graph B = EMA codebook update + Adam;
+  * `train_step_training` controls the `training` flag the VectorQuantizer sees inside train_step.  Strict Keras-2.7
+    resolution of the reference's `self.vqvaes[level](x)` gives training=False (the functional model's `call` default is
+    None -> False, and the nested layer inherits it), i.e. the reference as written never runs its EMA update during
+    `fit`; the benchmark configurations ask for "training with codebook EMA", so the default here is True.  Set it to
+    None for the literal Keras resolution.
+"""
+from __future__ import annotations
+
+from itertools import chain
+
+import torch
+
+from . import _lib, dist as vdist, ops
+from .VectorQuantizer import VectorQuantizer
+from .data_utils import STFT_ARGS, MultiSpectralLoss, norm, spectral  # noqa: F401
+from .encdec import Decoder, Encoder, print_dec_layer  # noqa: F401
+from .keras_compat import (GradientTape, Input, MeanSquaredError, Model, Packed, Scalar, convert_to_tensor, metrics,
+                           reduce_mean)
+
+
+def get_vqvae(input_shape, encoder, decoder, vq, level=0):
+    inputs = Input(shape=input_shape)
+    encoder_outputs = encoder(inputs)
+    quantized_latents, _ = vq(encoder_outputs)
+    reconstructions = decoder(quantized_latents)
+    return Model(inputs, reconstructions, name="vq_vae_{}".format(level))
+
+
+class VQVAE(Model):
+    """@levels: number of independent VQ-VAEs, bottom (finest) to top."""
+
+    def __init__(self, input_shape, levels, latent_dim, down_depth, strides, num_embeddings=128, residual_width=64,
+                 residual_depth=4, dilation_factor=1, train_variance=1.0, **kwargs):
+        super(VQVAE, self).__init__(**kwargs)
+        self.levels = levels
+        self.train_variance = train_variance
+        self.latent_dim = latent_dim
+        self.num_embeddings = num_embeddings
+        self.vqs = [VectorQuantizer(num_embeddings, latent_dim, level=level, name="vector_quantizer_{}".format(level))
+                    for level in range(levels)]
+        self.encoders = [Encoder(output_dim=latent_dim, residual_width=residual_width, residual_depth=residual_depth,
+                                 depth=level + 1, down_depth=down_depth[:level + 1], strides=strides[:level + 1],
+                                 dilation_factor=dilation_factor, name="encoder_{}".format(level))
+                         for level in range(levels)]
+        self.decoders = [Decoder(output_dim=input_shape[-1], embed_width=latent_dim, residual_width=residual_width,
+                                 residual_depth=residual_depth, depth=level + 1, down_depth=down_depth[:level + 1],
+                                 strides=strides[:level + 1], dilation_factor=dilation_factor,
+                                 name="decoder_{}".format(level)) for level in range(levels)]
+        self.vqvaes = [get_vqvae(input_shape, self.encoders[level], self.decoders[level], self.vqs[level], level)
+                       for level in range(levels)]
+
+        self.total_loss_tracker = metrics.Mean(name="total_loss")
+        self.reconstruction_loss_tracker = metrics.Mean(name="reconstruction_loss")
+        self.vq_loss_tracker = metrics.Mean(name="vq_loss")
+        self.spectral_loss_tracker = metrics.Mean(name="spectral_loss")
+        self.level_loss_trackers = [metrics.Mean(name="[{}]level_loss".format(level)) for level in range(levels)]
+        self.recon_loss_trackers = [metrics.Mean(name="[{}]recon_loss".format(level)) for level in range(levels)]
+        self.vq_loss_trackers = [metrics.Mean(name="[{}]vq_loss".format(level)) for level in range(levels)]
+        self.spectral_loss_trackers = [metrics.Mean(name="[{}]spectral_loss".format(level)) for level in range(levels)]
+        self.loss_fn = MeanSquaredError(reduction="none")
+        self.built = True
+
+        # ---- implementation state --------------------------------------------------------------------------
+        self.train_step_training = True   # see module docstring
+        self.use_cuda_graph = _lib.is_native() or _lib._BACKEND is None
+        self.spectral_weight = 1.0        # parity tests may switch the torch-side loss head off (0.0)
+        self._graphs = {}
+        self._pack_variables()
+
+    # ------------------------------------------------------------------------------------------------------
+    def _pack_variables(self):
+        tv = list(chain.from_iterable(m.trainable_variables for m in self.vqvaes))
+        D, K = self.latent_dim, self.num_embeddings
+        per_level = D * K + K + K * D
+        n_scalars = 3 * self.levels
+        self._packed = Packed(tv, extra_floats=self.levels * per_level + n_scalars)
+        ex = self._packed.extra
+        for l, vq in enumerate(self.vqs):
+            o = l * per_level
+            vq.bind_stats(ex[o:o + D * K].view(D, K), ex[o + D * K:o + D * K + K],
+                          ex[o + D * K + K:o + per_level].view(K, D))
+        self._comm_scalars = ex[self.levels * per_level:]
+        # metric totals of every tracker in one vector (one add per step)
+        trackers = self._all_trackers()
+        self._metric_totals = ops.zeros(len(trackers))
+        for i, m in enumerate(trackers):
+            m._bind(self._metric_totals[i:i + 1])
+
+    def _all_trackers(self):
+        return self.metrics + list(chain.from_iterable(vq.metrics for vq in self.vqs))
+
+    @property
+    def metrics(self):
+        return [
+            self.total_loss_tracker,
+            self.reconstruction_loss_tracker,
+            self.vq_loss_tracker,
+            self.spectral_loss_tracker,
+            *self.level_loss_trackers,
+            *self.recon_loss_trackers,
+            *self.vq_loss_trackers,
+            *self.spectral_loss_trackers,
+        ]
+
+    def reset_metrics(self):
+        for m in self._all_trackers():
+            m.reset_state()
+
+    @property
+    def trainable_variables(self):
+        return list(chain.from_iterable(m.trainable_variables for m in self.vqvaes))
+
+    @property
+    def variables(self):
+        out = []
+        for l in range(self.levels):
+            out += self.vqvaes[l].variables
+        return out
+
+    # ------------------------------------------------------------------------------------------------------
+    def _level_losses(self, level, x, training):
+        """One level of the loss computation shared by train_step / test_step / call (vqvae.py:121-131)."""
+        reconstructions = self.vqvaes[level](x) if training is None else self.vqvaes[level](x, training=training)
+        reconstruction_loss = reduce_mean(self.loss_fn(x, reconstructions))
+        spectral_loss = reduce_mean(self._multispectral_loss(x, reconstructions)) if self.spectral_weight else Scalar()
+        commit_loss = sum(self.vqvaes[level].losses)
+        return reconstructions, reconstruction_loss, spectral_loss, commit_loss
+
+    def _forward_backward(self, x):
+        """The tape part of train_step (vqvae.py:113-143)."""
+        commit_losses, recon_losses, spectral_losses, level_losses = [], [], [], []
+        total_loss = Scalar()
+        with GradientTape() as tape:
+            for level in range(self.levels):  # bottom to top
+                _, reconstruction_loss, spectral_loss, commit_loss = self._level_losses(
+                    level, x, self.train_step_training)
+                level_loss = reconstruction_loss + commit_loss + spectral_loss
+                commit_losses.append(commit_loss)
+                recon_losses.append(reconstruction_loss)
+                spectral_losses.append(spectral_loss)
+                level_losses.append(level_loss)
+                total_loss += level_loss
+        trainable_vars = self.trainable_variables
+        grads = tape.gradient(total_loss, trainable_vars)
+        return grads, trainable_vars, (level_losses, recon_losses, commit_losses, spectral_losses)
+
+    def train_step(self, data):
+        x = convert_to_tensor(data[0] if isinstance(data, (tuple, list)) else data)
+        if self.optimizer is None:
+            raise RuntimeError("VQVAE.train_step: call compile(optimizer=...) first")
+        world = vdist.world_size()
+        for vq in self.vqs:
+            vq.defer_ema = world > 1
+            vq.shard = (world, vdist.rank())
+        self.optimizer.grad_scale = 1.0 / world
+        if self.use_cuda_graph and _lib.device().type == "cuda":
+            return self._graph_train_step(x)
+        grads, tvars, losses = self._forward_backward(x)
+        losses = self._exchange(losses, world)
+        for vq in self.vqs:
+            vq.apply_ema()
+        self.optimizer.apply_gradients(zip(grads, tvars))
+        return self.update_metrics(*losses)
+
+    def _exchange(self, losses, world):
+        """Data parallelism: ONE all-reduce of [gradients | EMA statistics + restart rows | loss scalars]."""
+        if world == 1:
+            return losses
+        level_losses, recon_losses, commit_losses, spectral_losses = losses
+        L = self.levels
+        vec = torch.cat([s.tensor().reshape(1) for s in (*recon_losses, *commit_losses, *spectral_losses)])
+        self._comm_scalars.copy_(vec)
+        vdist.all_reduce_sum(self._packed.comm)
+        sc = self._comm_scalars / world
+        rec = [Scalar.leaf(sc[i:i + 1]) for i in range(L)]
+        com = [Scalar.leaf(sc[L + i:L + i + 1]) for i in range(L)]
+        spe = [Scalar.leaf(sc[2 * L + i:2 * L + i + 1]) for i in range(L)]
+        lev = [rec[i] + com[i] + spe[i] for i in range(L)]
+        return lev, rec, com, spe
+
+    # ---- CUDA-graph path ------------------------------------------------------------------------------------
+    def _step_vector(self, losses):
+        """All per-step metric increments, in `_all_trackers()` order, as one device vector."""
+        level_losses, recon_losses, commit_losses, spectral_losses = losses
+        parts = [sum(level_losses), sum(recon_losses), sum(commit_losses), sum(spectral_losses),
+                 *level_losses, *recon_losses, *commit_losses, *spectral_losses]
+        vec = [p.tensor().reshape(1) for p in parts]
+        for vq in self.vqs:
+            vec.append(vq._metrics_buf if vq._metrics_buf is not None else ops.zeros(3))
+        return torch.cat(vec)
+
+    def _graph_train_step(self, x):
+        key = (tuple(x.shape), vdist.world_size(), self.train_step_training, self.spectral_weight)
+        st = self._graphs.get(key)
+        world = vdist.world_size()
+        if st is None:
+            # first step for this shape: run it eagerly (it is a real training step and doubles as warm-up)
+            self._graphs[key] = {"graph": None, "x": x.clone()}
+            for vq in self.vqs:
+                vq.skip_metric_update = True
+            grads, tvars, losses = self._forward_backward(x)
+            losses = self._exchange(losses, world)
+            for vq in self.vqs:
+                vq.apply_ema()
+            self.optimizer.apply_gradients(zip(grads, tvars))
+            vec = self._step_vector(losses)
+            return self._accumulate(vec)
+        if st["graph"] is None:
+            st["x"].copy_(x)
+            torch.cuda.synchronize()
+            pool = torch.cuda.graph_pool_handle()
+            ga = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga, pool=pool):
+                grads, tvars, losses = self._forward_backward(st["x"])
+                if world > 1:
+                    level_losses, recon_losses, commit_losses, spectral_losses = losses
+                    self._comm_scalars.copy_(torch.cat(
+                        [s.tensor().reshape(1) for s in (*recon_losses, *commit_losses, *spectral_losses)]))
+            st["ga"] = ga
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb, pool=pool):
+                if world > 1:
+                    L = self.levels
+                    sc = self._comm_scalars / world
+                    rec = [Scalar.leaf(sc[i:i + 1]) for i in range(L)]
+                    com = [Scalar.leaf(sc[L + i:L + i + 1]) for i in range(L)]
+                    spe = [Scalar.leaf(sc[2 * L + i:2 * L + i + 1]) for i in range(L)]
+                    losses = ([rec[i] + com[i] + spe[i] for i in range(L)], rec, com, spe)
+                for vq in self.vqs:
+                    vq.apply_ema()
+                self.optimizer.apply_gradients(zip(grads, tvars))
+                st["vec"] = self._step_vector(losses)
+            st["gb"] = gb
+            st["graph"] = True
+        else:
+            st["x"].copy_(x, non_blocking=True)
+        st["ga"].replay()
+        if world > 1:
+            vdist.all_reduce_sum(self._packed.comm)
+        st["gb"].replay()
+        return self._accumulate(st["vec"])
+
+    def _accumulate(self, vec):
+        self._metric_totals += vec
+        for m in self._all_trackers():
+            m._count += 1
+        return self._metric_dict()
+
+    # ------------------------------------------------------------------------------------------------------
+    def test_step(self, data):
+        x = convert_to_tensor(data[0] if isinstance(data, (tuple, list)) else data)
+        commit_losses, recon_losses, spectral_losses, level_losses = [], [], [], []
+        for level in range(self.levels):  # bottom to top
+            # the reference calls self.vqvaes[level](x) (vqvae.py:158); Keras resolves that to training=False
+            _, reconstruction_loss, spectral_loss, commit_loss = self._level_losses(level, x, None)
+            level_loss = reconstruction_loss + commit_loss + spectral_loss
+            commit_losses.append(commit_loss)
+            recon_losses.append(reconstruction_loss)
+            spectral_losses.append(spectral_loss)
+            level_losses.append(level_loss)
+        return self.update_metrics(level_losses, recon_losses, commit_losses, spectral_losses)
+
+    def call(self, x, training=False):
+        """For callback model calls (vqvae.py:178-206): returns (recons, dict of per-level loss lists)."""
+        if isinstance(x, tuple):
+            x, _ = x
+        x = convert_to_tensor(x)
+        commit_losses, recon_losses, spectral_losses, level_losses, recons = [], [], [], [], []
+        for level in range(self.levels):
+            reconstructions, reconstruction_loss, spectral_loss, commit_loss = self._level_losses(level, x, training)
+            recons.append(reconstructions)
+            level_loss = reconstruction_loss + commit_loss + spectral_loss
+            commit_losses.append(commit_loss)
+            recon_losses.append(reconstruction_loss)
+            spectral_losses.append(spectral_loss)
+            level_losses.append(level_loss)
+        return recons, {"level_losses": level_losses, "recon_losses": recon_losses, "commit_losses": commit_losses,
+                        "spec_losses": spectral_losses}
+
+    def encode_level(self, x, level, chunk=1):
+        enc_outputs = self.encoders[level](convert_to_tensor(x), training=False)
+        latent_output, latent_codes = self.vqs[level](enc_outputs, training=False)
+        return latent_codes.view(enc_outputs.shape[:-1])  # (N, T_downsampled) int64
+
+    def encode(self, x, start_level=0, end_level=None):
+        """list of code tensors for levels [start_level, end_level)  (vqvae.py:221-236)"""
+        if end_level is None:
+            end_level = self.levels
+        return [self.encode_level(x, i) for i in range(start_level, end_level)]
+
+    def decode_level(self, zq, level, chunk=1):
+        """zq (N, T) int64 codes -> (N, T * hop, 1)  (vqvae.py:238-251): codebook gather + decoder."""
+        level_vq = self.vqs[level]
+        quantized = ops.gather_codes(level_vq.embeddings.value, convert_to_tensor(zq, torch.int64))
+        return self.decoders[level](quantized, training=False)
+
+    def decode(self, zq, level=0):
+        return self.decode_level(zq, level)
+
+    def update_metrics(self, level_losses, recon_losses, commit_losses, spectral_losses):
+        self.total_loss_tracker.update_state(sum(level_losses))
+        self.reconstruction_loss_tracker.update_state(sum(recon_losses))
+        self.vq_loss_tracker.update_state(sum(commit_losses))
+        self.spectral_loss_tracker.update_state(sum(spectral_losses))
+        for level in range(self.levels):
+            self.level_loss_trackers[level].update_state(level_losses[level])
+            self.recon_loss_trackers[level].update_state(recon_losses[level])
+            self.vq_loss_trackers[level].update_state(commit_losses[level])
+            self.spectral_loss_trackers[level].update_state(spectral_losses[level])
+        return self._metric_dict()
+
+    def _metric_dict(self):
+        """The flat dict `update_metrics` returns (vqvae.py:276-304), same key order."""
+        ret_metrics = dict(loss=self.total_loss_tracker.result(),
+                           recon_loss=self.reconstruction_loss_tracker.result(),
+                           vqvae_loss=self.vq_loss_tracker.result(),
+                           spectral_loss=self.spectral_loss_tracker.result())
+        for level in range(self.levels):
+            for t in (self.level_loss_trackers, self.recon_loss_trackers, self.vq_loss_trackers,
+                      self.spectral_loss_trackers):
+                ret_metrics[t[level].name] = t[level].result()
+            ret_metrics.update({m.name: m.result() for m in self.vqs[level].metrics})
+        return ret_metrics
+
+    def get_quantizer(self):
+        return self.vqs[0]
+
+    def _multispectral_loss(self, target, recon, **kwargs):
+        return MultiSpectralLoss(target, recon)
