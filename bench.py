@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline workload on B200: SMALL_VQ_VAE training step (forward + backward of both levels,
+codebook EMA, Adam), batch 32 windows of 28160 samples per GPU, fp32 (BASELINE.json configs[1]; weak scaling under
+torchrun).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's CUDA path
+  python bench.py --impl reference [...]                       the CPU restatement of the reference (oracle port)
+
+Prints ONE JSON line (rank 0).  `value` = audio samples/s of the whole job with the batch resident in HBM (CUDA-graph
+replays, CUDA-event timing, max over ranks); `e2e` = the same metric through the public API (model.train_step on a
+pinned HOST batch: H2D copy in, loss scalar D2H out, every step); `roofline` = the dominant kernel timed alone with
+CUDA events; `cpu_baseline` = the oracle timed on the host cores on a bounded sample of the same workload."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_WINDOW = 28160
+FLOP_PER_SAMPLE_FWD_BWD = 691680.0  # SURVEY.md section 8d (both levels; conv + VQ distance, bwd = 2x fwd)
+METRIC = "VQ-VAE fwd+bwd audio samples/sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons every 100 ms during the timed region (pynvml; nvidia-smi semantics)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop, self._th = [], set(), None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._th = threading.Thread(target=self._run, daemon=True)
+            self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._th:
+            self._th.join()
+
+    def summary(self):
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(steps, warmup, batch):
+    """The reference's arithmetic on the host cores: oracle train_step (fwd, bwd, Adam, EMA), all threads."""
+    import numpy as np
+    import torch
+    from oracle import vqvae_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = O.ModelSpec(T=T_WINDOW, **O.SMALL_VQ_VAE)
+    weights, vq = O.init_model(spec, 0)
+    rng = np.random.Generator(np.random.PCG64(0))
+    x = torch.tensor(rng.uniform(0, 1, size=(batch, T_WINDOW, 1)).astype(np.float32))
+    tr = O.OracleTrainer(spec, weights, vq)
+    for _ in range(warmup):
+        tr.train_step(x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.train_step(x)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dict(value=batch * T_WINDOW / dt, ms_per_step=1e3 * dt, cores=cores,
+                sample=f"{steps} oracle train_step(s) (fwd+bwd+Adam+EMA, both levels) on {batch} windows of {T_WINDOW} "
+                       f"samples, torch CPU fp32, {cores} threads")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="windows per GPU")
+    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": f"SMALL_VQ_VAE train_step (fwd+bwd both levels, codebook EMA, Adam), {args.batch} windows x "
+                          f"{T_WINDOW} samples per GPU, fp32 (BASELINE.json configs[1]; configs[2] when gpus > 1)",
+              "levels": 2, "latent_dim": 64, "num_embeddings": 512, "window": T_WINDOW,
+              "global_batch": args.batch * world, "parallelism": f"dp{world}",
+              "l2_policy": "working set per step (~5 GB of activations) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warm = min(args.steps, 3), min(args.warmup, 1)
+        r = cpu_reference_run(steps, warm, args.cpu_batch)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"] + " (TensorFlow 2.7 is not installable offline: this is the "
+                                                         "oracle port of the reference's CPU path)"},
+                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import vqvae_b200 as V
+    V.dist.init_from_env("nccl")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    lib = V._lib.lib()
+    assert V._lib.is_native()
+
+    V.set_seed(0)
+    model = V.VQVAE((T_WINDOW, 1), **V.SMALL_VQ_VAE)
+    if world > 1:  # identical initial weights / codebooks on every rank
+        V.dist.broadcast(model._packed.params, 0)
+        for vq in model.vqs:
+            for v in (vq.embeddings, vq.m_t, vq.N_t):
+                V.dist.broadcast(v.value, 0)
+    model.compile(optimizer=V.keras.optimizers.Adam())
+    rng = np.random.Generator(np.random.PCG64(1000 + rank))
+    x_host = torch.from_numpy(rng.uniform(0, 1, size=(args.batch, T_WINDOW, 1)).astype(np.float32)).pin_memory()
+    x_dev = x_host.cuda(non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # eager step (counts kernels) + graph capture + warm-up replays
+    n0 = lib.vqb_kernel_launch_count()
+    model.train_step((x_dev, None))
+    torch.cuda.synchronize()
+    launches_per_step = lib.vqb_kernel_launch_count() - n0
+    for _ in range(max(args.warmup, 3)):
+        logs = model.train_step((x_dev, None))
+    barrier()
+
+    # ---- device-resident timing
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            logs = model.train_step((x_dev, None))
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    # ---- end to end: pinned host batch in, loss scalar out, every step
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss_host = 0.0
+    for _ in range(args.steps):
+        logs = model.train_step((x_host, None))
+        loss_host = float(logs["loss"])  # D2H read of the step's result
+    e1.record()
+    barrier()
+    ms_e2e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / args.steps
+    t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    samples = args.batch * T_WINDOW * world
+    pk = peaks()
+    line = {"metric": METRIC, "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
+            "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+            "clocks": clk.summary(), "final_loss": loss_host,
+            "step_tflops": FLOP_PER_SAMPLE_FWD_BWD * samples / (ms * 1e-3) / 1e12,
+            "step_frac_of_bf16_sustained": FLOP_PER_SAMPLE_FWD_BWD * samples / (ms * 1e-3) / 1e12 / (pk["tf_sust"] * world)}
+    if not args.no_roofline:
+        line.update(roofline_section(V, pk))
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(1, 1, args.cpu_batch)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def roofline_section(V, pk):
+    """The dominant kernel timed ALONE with CUDA events on its launch stream: the residual-block forward at the
+    largest stage of the model ([32, 14080, 32], dilation 1) — 80 of level 0's 93 and 128 of level 1's 149 forward
+    convolutions are inside such blocks.  Two buffer sets (231 MB) are alternated so that inputs do not sit in L2."""
+    import torch
+    ops = V.ops
+    B, L, C, d = 32, 14080, 32, 1
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xs = [torch.randn(B, L, C, device="cuda", generator=g) for _ in range(2)]
+    w1 = torch.randn(3, C, C, device="cuda", generator=g) * 0.1
+    w2 = torch.randn(3, C, C, device="cuda", generator=g) * 0.1
+    b1 = torch.zeros(C, device="cuda"); b2 = torch.zeros(C, device="cuda")
+    for i in range(4):
+        ops.resblock_fwd(xs[i % 2], w1, b1, w2, b2, d)
+    torch.cuda.synchronize()
+    n = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        ops.resblock_fwd(xs[i % 2], w1, b1, w2, b2, d)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops = 2.0 * B * L * (3 * C * C) * 2          # two k=3 C->C convolutions
+    bytes_alg = B * L * C * 4 * 3.0                # read x, write h (kept for backward), write y
+    tf = flops / (ms * 1e-3) / 1e12
+    gbs = bytes_alg / (ms * 1e-3) / 1e9
+    return {"roofline": {"kernel": "vqb_resblock_fwd [32,14080,32] dil 1 (fp32 path: 2 x tgc_kernel)", "bound": "tensor",
+                         "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tf / pk["tf_burst"],
+                         "traffic": None, "peak_source": pk["src"] + " bf16 burst", "ms_per_launch": ms,
+                         "flop_per_launch": flops},
+            "roofline_hbm": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                             "algorithmic_bytes_per_launch": bytes_alg}}
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,8 @@ enum {
 
 int vqb_version(void);
 const char* vqb_last_error(void);
+/* number of CUDA kernels this library has enqueued in this process (diagnostics; bench.py's gpu_launches) */
+int64_t vqb_kernel_launch_count(void);
 /* 0 if `device` is a compute-capability-10.x GPU, VQB_ERR_ARCH otherwise (also caches the answer). */
 int vqb_device_check(int device);
 

@@ -44,6 +44,9 @@ class FakeBackend:
     def vqb_version(self):
         return 100
 
+    def vqb_kernel_launch_count(self):
+        return 0
+
     def vqb_last_error(self):
         return self._err
 

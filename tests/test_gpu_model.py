@@ -1,0 +1,184 @@
+"""Whole-path parity on the GPU: the Keras-style model (vqvae_b200.VQVAE) against the oracle / committed golden vectors
+— reconstructions, losses, gradients, weights after training steps (eager and CUDA-graph), code indices — plus
+size-independent properties at BASELINE.json's full sizes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vqvae_oracle as O
+from oracle.make_golden import TINY, tiny_case
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL = 1e-3  # north-star tolerance for reconstructions / losses / gradients in fp32
+
+
+def rel_err(got, want):
+    got = got.detach().cpu().double().numpy() if torch.is_tensor(got) else np.asarray(got, np.float64)
+    want = want.detach().cpu().double().numpy() if torch.is_tensor(want) else np.asarray(want, np.float64)
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-12))
+
+
+def load_into(m, weights, vq):
+    for l in range(m.levels):
+        for v, w in zip(m.vqvaes[l].trainable_variables, weights[l]):
+            v.assign(w)
+        m.vqs[l].embeddings.assign(vq[l]["E"]); m.vqs[l].m_t.assign(vq[l]["m_t"]); m.vqs[l].N_t.assign(vq[l]["N_t"])
+
+
+def tiny_model(V, graph=False):
+    spec, weights, vq, x = tiny_case()
+    kw = {k: (list(v) if isinstance(v, tuple) else v) for k, v in TINY.items() if k != "T"}
+    m = V.VQVAE((TINY["T"], 1), **kw)
+    m.use_cuda_graph = graph
+    load_into(m, weights, vq)
+    for l in range(spec.levels):
+        m.vqs[l].restart_ids = torch.arange(TINY["num_embeddings"], dtype=torch.int64, device="cuda")
+    return m, spec, weights, vq, x
+
+
+def test_tiny_model_against_golden(gpu):
+    V = gpu
+    m, spec, weights, vq, x = tiny_model(V)
+    t = np.load(os.path.join(GOLD, "tiny_model.npz"))
+    recons, losses = m(x, training=False)
+    for l in range(spec.levels):
+        assert rel_err(recons[l], t[f"recon{l}"]) < REL
+        assert np.array_equal(m.encode(x)[l].reshape(-1).cpu().numpy(), t[f"idx{l}"])
+        got = [float(losses[k][l]) for k in ("recon_losses", "commit_losses", "spec_losses")]
+        np.testing.assert_allclose(got, t[f"losses{l}"], rtol=REL)
+    with V.GradientTape() as tape:
+        total = V.keras.Scalar()
+        for l in range(spec.levels):
+            _, r, s, c = m._level_losses(l, V.keras.convert_to_tensor(x), False)
+            total += r + c + s
+    grads = tape.gradient(total, m.trainable_variables)
+    i = 0
+    for l in range(spec.levels):
+        for j in range(len(weights[l])):
+            want = t[f"g{l}_{j:03d}"]
+            assert rel_err(grads[i], want) < REL or np.abs(want).max() < 1e-7, (l, j)
+            i += 1
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_tiny_model_training_steps(gpu, graph):
+    V = gpu
+    m, spec, weights, vq, x = tiny_model(V, graph)
+    m.compile(optimizer=V.keras.optimizers.Adam())
+    t = np.load(os.path.join(GOLD, "tiny_model.npz"))
+    for _ in range(2):
+        logs = m.train_step((x, None))
+    assert m.optimizer.iterations == 2
+    for l in range(spec.levels):
+        for j, v in enumerate(m.vqvaes[l].trainable_variables):
+            # Adam's first steps move every weight by ~lr regardless of gradient scale: compare the UPDATE
+            upd, want = v.numpy() - weights[l][j], t[f"w2_{l}_{j:03d}"] - weights[l][j]
+            assert np.abs(upd - want).max() <= 2e-2 * np.abs(want).max() + 1e-7, (l, j)
+        np.testing.assert_allclose(m.vqs[l].N_t.numpy(), t[f"vq2_{l}_N_t"], rtol=1e-6)
+        assert rel_err(m.vqs[l].embeddings.value, t[f"vq2_{l}_E"]) < REL
+    assert float(logs["loss"]) > 0
+
+
+def test_graph_and_eager_training_agree(gpu):
+    V = gpu
+    res = []
+    for graph in (False, True):
+        m, spec, weights, vq, x = tiny_model(V, graph)
+        m.compile(optimizer=V.keras.optimizers.Adam())
+        for _ in range(4):
+            logs = m.train_step((x, None))
+        res.append((m._packed.params.clone(), [vq_.embeddings.value.clone() for vq_ in m.vqs], float(logs["loss"])))
+    assert rel_err(res[1][0], res[0][0]) < 1e-4
+    for a, b in zip(res[0][1], res[1][1]):
+        assert rel_err(b, a) < 1e-4
+    assert abs(res[0][2] - res[1][2]) < 1e-4 * abs(res[0][2])
+
+
+def test_small_vqvae_forward_and_gradients(gpu):
+    """BASELINE config 1/2 shapes (SMALL_VQ_VAE, T = 28160) at batch 2 against the fp32 oracle."""
+    V = gpu
+    spec = O.ModelSpec(T=28160, **O.SMALL_VQ_VAE)
+    weights, vq = O.init_model(spec, 0, bias_scale=0.02)
+    rng = np.random.Generator(np.random.PCG64(0))
+    x = rng.uniform(0, 1, size=(2, 28160, 1)).astype(np.float32)
+    m = V.VQVAE((28160, 1), **V.SMALL_VQ_VAE)
+    m.use_cuda_graph = False
+    load_into(m, weights, vq)
+    res, grads = O.loss_and_grads(spec, weights, vq, torch.tensor(x))
+    with V.GradientTape() as tape:
+        total = V.keras.Scalar()
+        outs = []
+        for l in range(2):
+            rec, r, s, c = m._level_losses(l, V.keras.convert_to_tensor(x), False)
+            outs.append((rec, r, c, s))
+            total += r + c + s
+    g = tape.gradient(total, m.trainable_variables)
+    i = 0
+    for l in range(2):
+        rec, r, c, s = outs[l]
+        assert rel_err(rec, res[l]["recon"]) < REL
+        for got, key in ((r, "recon_loss"), (c, "commit_loss"), (s, "spec_loss")):
+            assert abs(float(got) - float(res[l][key])) < REL * abs(float(res[l][key]))
+        idx = m.encode(x)[l].reshape(-1).cpu()
+        d64 = O.vq_distances(res[l]["z"].reshape(-1, 64).double(), torch.tensor(vq[l]["E"]).double())
+        srt = torch.sort(d64, 1).values
+        ok = (srt[:, 1] - srt[:, 0]) > 1e-5 * srt[:, 0].abs()
+        assert int(((idx != res[l]["idx"]) & ok).sum()) == 0
+        gmax = max(float(t.abs().max()) for t in grads[l])
+        for want in grads[l]:
+            err = float((g[i].cpu() - want).abs().max())
+            assert err <= REL * max(float(want.abs().max()), 1e-3 * gmax), (l, i, err)
+            i += 1
+
+
+def test_full_size_properties(gpu):
+    """BASELINE config 2 size (batch 32 x 28160): properties that need no oracle run."""
+    V = gpu
+    m = V.VQVAE((28160, 1), **V.SMALL_VQ_VAE)
+    m.compile(optimizer=V.keras.optimizers.Adam())
+    rng = np.random.Generator(np.random.PCG64(1))
+    x = rng.uniform(0, 1, size=(32, 28160, 1)).astype(np.float32)
+    zs = m.encode(x)
+    assert [tuple(z.shape) for z in zs] == [(32, 880), (32, 110)]
+    for l, z in enumerate(zs):
+        assert int(z.min()) >= 0 and int(z.max()) < 512
+        y = m.decode(z, level=l)
+        assert tuple(y.shape) == (32, 28160, 1) and bool(torch.isfinite(y).all())
+        # batch independence: encoding a sub-batch gives the same codes (every op is per-example)
+        assert torch.equal(m.encode(x[5:9])[l], z[5:9])
+    logs0 = {k: float(v) for k, v in m.train_step((x, None)).items()}
+    for vq in m.vqs:
+        n_batch = vq._stats[1]
+        assert float(n_batch.sum()) == 32 * 28160 / (32 if vq is m.vqs[0] else 256)  # counts sum to N
+    for _ in range(3):
+        logs = m.train_step((x, None))
+    logs = {k: float(v) for k, v in logs.items()}
+    assert all(np.isfinite(v) for v in logs.values())
+    assert m.optimizer.iterations == 4
+    assert 1 <= logs["[0]batch_codebook_usage"] <= 512 and 0 <= logs["[0]codebook_entropy"] <= np.log(512) + 1e-3
+
+
+def test_vq_full_size_properties(gpu):
+    """BASELINE config 4 size: 2^20 latents x K in {512, 2048} x D = 64."""
+    ops = gpu.ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    N, D = 1 << 20, 64
+    x = torch.randn(N, D, device="cuda", generator=g)
+    for K in (512, 2048):
+        E = torch.randn(D, K, device="cuda", generator=g)
+        m_batch, n_batch = ops.empty(D, K), ops.empty(K)
+        idx, q_st, q, loss = ops.vq_fwd(x, E, 0.25, True, True, m_batch, n_batch)
+        assert float(n_batch.sum()) == N
+        assert torch.equal(torch.bincount(idx, minlength=K).float(), n_batch)
+        assert torch.equal(q, E.t()[idx])
+        colsum = x.double().sum(0)
+        assert float((m_batch.double().sum(1) - colsum).abs().max()) < 1e-3 * float(colsum.abs().max() + N ** 0.5)
+        # optimality: no other code is closer (checked with an independent fp32 GEMM on a slice)
+        sl = slice(12345, 12345 + 8192)
+        d = (x[sl] ** 2).sum(1, keepdim=True) + (E ** 2).sum(0) - 2 * x[sl] @ E
+        best = d.min(1).values
+        chosen = d.gather(1, idx[sl, None])[:, 0]
+        assert float(((chosen - best) / best).max()) < 1e-5

@@ -1,0 +1,228 @@
+"""Host-side logic of the package (Keras-style API, tape, packed buffers, training-flag resolution, metric plumbing,
+data-parallel sharding) exercised on CPU through the test double of the C ABI (tests/fake_backend.py).
+No numerical-parity claim is made here — the kernels are checked by the gpu-marked tests."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+from oracle import vqvae_oracle as O
+from oracle.make_golden import TINY, tiny_case
+
+
+def build_tiny(V, seed=0):
+    spec, weights, vq, x = tiny_case(seed)
+    kw = {k: (list(v) if isinstance(v, tuple) else v) for k, v in TINY.items() if k != "T"}
+    m = V.VQVAE((TINY["T"], 1), **kw)
+    m.use_cuda_graph = False
+    for l in range(spec.levels):
+        m.vqvaes[l].set_weights_trainable = None
+        for v, w in zip(m.vqvaes[l].trainable_variables, weights[l]):
+            v.assign(w)
+        m.vqs[l].embeddings.assign(vq[l]["E"]); m.vqs[l].m_t.assign(vq[l]["m_t"]); m.vqs[l].N_t.assign(vq[l]["N_t"])
+        m.vqs[l].restart_ids = np.arange(max(TINY["num_embeddings"], 1))
+    return m, spec, weights, vq, x
+
+
+def test_structure_names_and_variable_order(cpu_backend):
+    V = cpu_backend
+    m = V.VQVAE((28160, 1), **V.SMALL_VQ_VAE)
+    spec = O.ModelSpec(T=28160, **O.SMALL_VQ_VAE)
+    for l in range(2):
+        want = [s for op in spec.level_ops(l) for s in op.param_shapes()]
+        assert [v.shape for v in m.vqvaes[l].trainable_variables] == want
+    assert len(m.trainable_variables) == 484
+    assert sum(int(np.prod(v.shape)) for v in m.trainable_variables) == 799042
+    assert m.vqvaes[0].name == "vq_vae_0" and m.encoders[1].name == "encoder_1" and m.vqs[0].name == "vector_quantizer_0"
+    enc0 = m.encoders[0].model.layers[0]  # EncoderConvBlock
+    assert type(enc0).__name__ == "EncoderConvBlock" and len(enc0.model.layers) == 11
+    stack = enc0.model.layers[1]
+    assert "dilated_resnet1d" in stack.name
+    block = stack.model.layers[2]
+    assert [type(l).__name__ for l in block.model.layers] == ["ReLU", "Conv1D", "ReLU", "Conv1D"]
+    assert block.model.layers[1].name == "dilated_cov1d_dr-9" and block.model.layers[1].dilation_rate == 9
+    dec_stack = m.decoders[0].model.layers[0].model.layers[1]
+    assert [b.dilation for b in dec_stack.model.layers] == [27, 9, 3, 1]  # reversed for decoders (resnet.py:54-55)
+    # every trainable variable is a view of ONE parameter buffer, in order
+    base = m._packed.params.data_ptr()
+    off = 0
+    for v in m.trainable_variables:
+        assert v.value.data_ptr() == base + 4 * off and v.grad.data_ptr() == m._packed.grads.data_ptr() + 4 * off
+        off += v.value.numel()
+    # VQ state: non-trainable [D,K], m_t = E, N_t = ones (VectorQuantizer.py:38-60)
+    vq = m.get_quantizer()
+    assert vq.embeddings.shape == (64, 512) and not vq.embeddings.trainable
+    assert torch.equal(vq.m_t.value, vq.embeddings.value) and float(vq.N_t.value.sum()) == 512
+    assert float(vq.embeddings.value.abs().max()) <= 0.05
+    assert [t.name for t in vq.metrics] == ["[0]batch_codebook_usage", "[0]codebook_usage", "[0]codebook_entropy"]
+    V.print_dec_layer(m.decoders[0])
+
+
+def test_bad_arguments_raise(cpu_backend):
+    V = cpu_backend
+    with pytest.raises(AssertionError, match="not Legit"):  # encdec.py:84-85
+        V.Encoder(8, 8, 2, depth=2, down_depth=[2], strides=[2, 2])
+    with pytest.raises(AssertionError, match="not Legit"):
+        V.Decoder(1, 8, 8, 2, depth=1, down_depth=[2], strides=[2, 2])
+    blk = V.ResnetConv1DBlock(8, 8, dilation=3)
+    with pytest.raises(ValueError):
+        blk(np.zeros((1, 16, 4), np.float32))
+    vq = V.VectorQuantizer(6, 2)
+    with pytest.raises(ValueError):
+        vq(np.zeros((2, 5, 3), np.float32))
+    with pytest.raises(NotImplementedError):
+        V.keras.layers.Conv1D(4, 3, padding="valid")
+
+
+def test_training_flag_resolution(cpu_backend):
+    """Keras-2.7 rules: top-level VQ call defaults to training=True (signature default, VectorQuantizer.py:75);
+    inside the functional model it inherits the outer value (False when nothing is passed)."""
+    V = cpu_backend
+    m, spec, weights, vq, x = build_tiny(V)
+    E0 = m.vqs[0].embeddings.numpy().copy()
+    z = m.encoders[0](x)
+    m.vqs[0](z)  # top level: EMA runs
+    assert not np.array_equal(m.vqs[0].embeddings.numpy(), E0)
+    E1 = m.vqs[0].embeddings.numpy().copy()
+    m.vqvaes[0](x)  # functional model, nothing passed -> False
+    assert np.array_equal(m.vqs[0].embeddings.numpy(), E1)
+    m.vqvaes[0](x, training=True)
+    assert not np.array_equal(m.vqs[0].embeddings.numpy(), E1)
+    E2 = m.vqs[0].embeddings.numpy().copy()
+    m(x)  # VQVAE.call default training=False (vqvae.py:178)
+    m.test_step((x, None))
+    assert np.array_equal(m.vqs[0].embeddings.numpy(), E2)
+    assert len(m.vqvaes[0].losses) == 1  # exactly the commitment loss of the last call (add_loss, :107)
+
+
+def test_forward_and_train_steps_match_oracle(cpu_backend):
+    V = cpu_backend
+    m, spec, weights, vq, x = build_tiny(V)
+    recons, losses = m(x, training=False)
+    ref = O.forward_losses(spec, weights, vq, torch.tensor(x))
+    for l in range(spec.levels):
+        np.testing.assert_allclose(recons[l].numpy(), ref[l]["recon"].numpy(), rtol=1e-5, atol=1e-6)
+        for key, rk in (("recon_losses", "recon_loss"), ("commit_losses", "commit_loss"), ("spec_losses", "spec_loss")):
+            assert abs(float(losses[key][l]) - float(ref[l][rk])) < 1e-5
+    m.compile(optimizer=V.keras.optimizers.Adam())
+    tr = O.OracleTrainer(spec, weights, vq)
+    for step in range(2):
+        logs = m.train_step((x, np.zeros(len(x))))
+        tr.train_step(torch.tensor(x))
+    assert m.optimizer.iterations == 2
+    for l in range(spec.levels):
+        for a, b in zip(m.vqvaes[l].trainable_variables, tr.w[l]):
+            np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(m.vqs[l].embeddings.numpy(), tr.vq[l].E.numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(m.vqs[l].N_t.numpy(), tr.vq[l].N_t.numpy(), rtol=1e-6)
+    want_keys = ["loss", "recon_loss", "vqvae_loss", "spectral_loss"]
+    for l in range(spec.levels):
+        want_keys += [f"[{l}]level_loss", f"[{l}]recon_loss", f"[{l}]vq_loss", f"[{l}]spectral_loss",
+                      f"[{l}]batch_codebook_usage", f"[{l}]codebook_usage", f"[{l}]codebook_entropy"]
+    assert list(logs) == want_keys  # vqvae.py:276-304
+    assert abs(float(logs["loss"]) - sum(float(logs[f"[{l}]level_loss"]) for l in range(spec.levels))) < 1e-5
+
+
+def test_encode_decode_roundtrip_shapes(cpu_backend):
+    V = cpu_backend
+    m, spec, weights, vq, x = build_tiny(V)
+    zs = m.encode(x)
+    assert [tuple(z.shape) for z in zs] == [(3, 2048 // 8), (3, 2048 // 32)] and zs[0].dtype == torch.int64
+    assert [tuple(z.shape) for z in m.encode(x, start_level=1)] == [(3, 64)]
+    ref = O.forward_losses(spec, weights, vq, torch.tensor(x))
+    for l in range(2):
+        assert torch.equal(zs[l].reshape(-1), ref[l]["idx"])
+        y = m.decode(zs[l], level=l)
+        # decode(gather(E, idx)) equals the decoder applied to the raw (not straight-through) quantised latents
+        want = O.run_ops(spec.dec_ops[l], [torch.tensor(w) for w in weights[l][spec.n_enc_params(l):]], ref[l]["q"])
+        np.testing.assert_allclose(y.numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_fit_evaluate_and_checkpoint(cpu_backend, tmp_path):
+    V = cpu_backend
+    m, spec, weights, vq, x = build_tiny(V)
+    m.compile(optimizer=V.keras.optimizers.Adam())
+    xs = np.concatenate([x, x[:2]])  # 5 windows, batch 2 -> ragged last batch
+    h = m.fit(xs, np.zeros(5), batch_size=2, epochs=2, verbose=0, shuffle=False)
+    assert len(h.history["loss"]) == 2 and m.optimizer.iterations == 6
+    ev = m.evaluate(xs, None, batch_size=2, verbose=0, return_dict=True)
+    assert ev["loss"] > 0 and "[1]codebook_entropy" in ev
+    m.save_weights(str(tmp_path / "ck"))
+    m2, *_ = build_tiny(V, seed=3)
+    m2.load_weights(str(tmp_path / "ck"))
+    for a, b in zip(m.variables, m2.variables):
+        assert np.array_equal(a.numpy(), b.numpy())
+
+
+def test_generic_tape_with_plain_layers(cpu_backend):
+    """Conv1D / ReLU / add used directly (the reference's un-fused formulation of the residual block, resnet.py:29)
+    give the same result and gradients as the fused block."""
+    V = cpu_backend
+    K = V.keras
+    rng = np.random.default_rng(0)
+    x = torch.tensor(rng.normal(size=(2, 40, 8)).astype(np.float32))
+    blk = V.ResnetConv1DBlock(8, 8, dilation=3)
+    pre = K.layers.Conv1D(8, 3, padding="same")
+    with V.GradientTape() as tape:
+        h0 = pre(x)
+        y_fused = blk(h0)
+        loss = K.reduce_mean(K.losses.MeanSquaredError()(np.zeros((2, 40, 8), np.float32), y_fused))
+    vars_ = pre.trainable_variables + blk.trainable_variables
+    g_fused = [g.clone() for g in tape.gradient(loss, vars_)]
+    with V.GradientTape() as tape:
+        h0 = pre(x)
+        y_plain = K.layers.add([h0, blk.model(h0)])
+        loss2 = K.reduce_mean(K.losses.MeanSquaredError()(np.zeros((2, 40, 8), np.float32), y_plain))
+    g_plain = tape.gradient(loss2, vars_)
+    np.testing.assert_allclose(y_fused.numpy(), y_plain.numpy(), rtol=1e-5, atol=1e-6)
+    for a, b in zip(g_fused, g_plain):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _dp_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import vqvae_b200 as V
+    from tests.fake_backend import FakeBackend
+    V._lib.set_backend(FakeBackend(), "cpu")
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    m, spec, weights, vq, x = build_tiny(V)
+    xs = np.concatenate([x, x[::-1]])[:4]  # global batch 4
+    m.compile(optimizer=V.keras.optimizers.Adam())
+    per = len(xs) // world
+    for _ in range(2):
+        logs = m.train_step((xs[rank * per:(rank + 1) * per], None))
+    out = {f"w{i}": v.numpy() for i, v in enumerate(m.trainable_variables)}
+    for l in range(spec.levels):
+        out[f"E{l}"] = m.vqs[l].embeddings.numpy(); out[f"N{l}"] = m.vqs[l].N_t.numpy()
+    out["loss"] = np.float32(float(logs["loss"]))
+    np.savez(os.path.join(tmp, f"rank{rank}.npz"), **out)
+    td.destroy_process_group()
+
+
+def test_data_parallel_two_ranks_equal_unsharded(cpu_backend, tmp_path):
+    """world_size 2 over gloo: batch-sharded training (one flat all-reduce of gradients + EMA statistics + restart
+    rows + loss scalars) must reproduce the un-sharded step, and leave both ranks bit-identical."""
+    V = cpu_backend
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    for k in r0.files:
+        assert np.array_equal(r0[k], r1[k]), f"ranks differ in {k}"
+    m, spec, weights, vq, x = build_tiny(V)
+    xs = np.concatenate([x, x[::-1]])[:4]
+    m.compile(optimizer=V.keras.optimizers.Adam())
+    for _ in range(2):
+        logs = m.train_step((xs, None))
+    for i, v in enumerate(m.trainable_variables):
+        np.testing.assert_allclose(r0[f"w{i}"], v.numpy(), rtol=2e-4, atol=2e-6)
+    for l in range(spec.levels):
+        np.testing.assert_allclose(r0[f"E{l}"], m.vqs[l].embeddings.numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(r0[f"N{l}"], m.vqs[l].N_t.numpy(), rtol=1e-6)
+    assert abs(float(r0["loss"]) - float(logs["loss"])) < 1e-4

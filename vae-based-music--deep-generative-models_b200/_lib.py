@@ -43,6 +43,7 @@ _CD, _RD, _VD = C.POINTER(ConvDesc), C.POINTER(ResblockDesc), C.POINTER(VQDesc)
 SIGNATURES = {
     "vqb_version": (C.c_int, []),
     "vqb_last_error": (C.c_char_p, []),
+    "vqb_kernel_launch_count": (C.c_int64, []),
     "vqb_device_check": (C.c_int, [C.c_int]),
     "vqb_conv1d_fwd": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P]),
     "vqb_conv1d_dgrad": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P]),

@@ -14,6 +14,8 @@ char* err_buf();
 int set_err(int code, const char* fmt, ...);
 // VQB_OK if the current device is sm_100-class (cached per device)
 int require_arch();
+// bumps the process-wide kernel-launch counter (vqb_kernel_launch_count)
+void count_launch();
 
 #define VQB_REQUIRE(cond, ...)                                   \
   do {                                                           \
@@ -30,6 +32,7 @@ int require_arch();
 
 #define VQB_LAUNCH_CHECK()                                                                       \
   do {                                                                                           \
+    ::vqb::count_launch();                                                                       \
     cudaError_t e__ = cudaGetLastError();                                                        \
     if (e__ != cudaSuccess)                                                                      \
       return ::vqb::set_err(VQB_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \

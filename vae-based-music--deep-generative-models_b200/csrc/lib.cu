@@ -1,7 +1,11 @@
 // lib.cu — version, error text and the architecture gate of libvqvae_b200.so.
 #include "common.cuh"
+#include <atomic>
 
 namespace vqb {
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 char* err_buf() {
   static thread_local char buf[512] = {0};
@@ -36,6 +40,8 @@ int require_arch() {
 extern "C" {
 
 int vqb_version(void) { return VQB_VERSION; }
+
+int64_t vqb_kernel_launch_count(void) { return (int64_t)vqb::g_launches.load(); }
 
 const char* vqb_last_error(void) { return vqb::err_buf(); }
 

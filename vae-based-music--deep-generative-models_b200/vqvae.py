@@ -20,6 +20,7 @@ from __future__ import annotations
 
 from itertools import chain
 
+import numpy as np
 import torch
 
 from . import _lib, dist as vdist, ops
@@ -157,7 +158,7 @@ class VQVAE(Model):
         return grads, trainable_vars, (level_losses, recon_losses, commit_losses, spectral_losses)
 
     def train_step(self, data):
-        x = convert_to_tensor(data[0] if isinstance(data, (tuple, list)) else data)
+        raw = data[0] if isinstance(data, (tuple, list)) else data
         if self.optimizer is None:
             raise RuntimeError("VQVAE.train_step: call compile(optimizer=...) first")
         world = vdist.world_size()
@@ -166,7 +167,8 @@ class VQVAE(Model):
             vq.shard = (world, vdist.rank())
         self.optimizer.grad_scale = 1.0 / world
         if self.use_cuda_graph and _lib.device().type == "cuda":
-            return self._graph_train_step(x)
+            return self._graph_train_step(raw)
+        x = convert_to_tensor(raw)
         grads, tvars, losses = self._forward_backward(x)
         losses = self._exchange(losses, world)
         for vq in self.vqs:
@@ -201,11 +203,16 @@ class VQVAE(Model):
             vec.append(vq._metrics_buf if vq._metrics_buf is not None else ops.zeros(3))
         return torch.cat(vec)
 
-    def _graph_train_step(self, x):
-        key = (tuple(x.shape), vdist.world_size(), self.train_step_training, self.spectral_weight)
+    def _graph_train_step(self, raw):
+        key = (tuple(raw.shape), vdist.world_size(), self.train_step_training, self.spectral_weight)
         st = self._graphs.get(key)
         world = vdist.world_size()
+        if st is not None:
+            # straight into the graph's static input buffer (pinned host memory -> one asynchronous H2D copy)
+            src = raw if isinstance(raw, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(raw, dtype=np.float32))
+            st["x"].copy_(src.reshape(st["x"].shape), non_blocking=True)
         if st is None:
+            x = convert_to_tensor(raw)
             # first step for this shape: run it eagerly (it is a real training step and doubles as warm-up)
             self._graphs[key] = {"graph": None, "x": x.clone()}
             for vq in self.vqs:
@@ -218,7 +225,6 @@ class VQVAE(Model):
             vec = self._step_vector(losses)
             return self._accumulate(vec)
         if st["graph"] is None:
-            st["x"].copy_(x)
             torch.cuda.synchronize()
             pool = torch.cuda.graph_pool_handle()
             ga = torch.cuda.CUDAGraph()
@@ -244,8 +250,6 @@ class VQVAE(Model):
                 st["vec"] = self._step_vector(losses)
             st["gb"] = gb
             st["graph"] = True
-        else:
-            st["x"].copy_(x, non_blocking=True)
         st["ga"].replay()
         if world > 1:
             vdist.all_reduce_sum(self._packed.comm)
