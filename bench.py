@@ -119,6 +119,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run train_step eagerly (profiling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -161,6 +162,7 @@ def main():
             for v in (vq.embeddings, vq.m_t, vq.N_t):
                 V.dist.broadcast(v.value, 0)
     model.compile(optimizer=V.keras.optimizers.Adam())
+    model.use_cuda_graph = not args.no_graph
     rng = np.random.Generator(np.random.PCG64(1000 + rank))
     x_host = torch.from_numpy(rng.uniform(0, 1, size=(args.batch, T_WINDOW, 1)).astype(np.float32)).pin_memory()
     x_dev = x_host.cuda(non_blocking=True)

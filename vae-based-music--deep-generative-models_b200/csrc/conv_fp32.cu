@@ -239,80 +239,141 @@ static int launch_tgc(TgcParams& p, cudaStream_t st) {
 
 // ---------------------------------------------------------------------------------------------------------
 // weight gradient: dW[j][cg][co] = sum_{b,t} act(ga[b, t*g_step + off[j], cg]) * ot[b, t, co]
+// (Conv1D: ga = x, ot = dy;  Conv1DTranspose: ga = dy, ot = x  =>  both give the Keras kernel layout directly.)
+// One CTA = one batch item x WG_TCH time positions x up to 4 taps x a 32x32 channel tile; the two operand tiles
+// are staged through shared memory in sub-chunks of WG_SUB positions (coalesced float4 loads, ReLU fused into the
+// load), each thread owns NT x 4 x 2 accumulators.  Per-CTA partial sums go to a workspace and are reduced in a fixed
+// order (deterministic, no atomics).  When `bias_partial` is set the column sums of `ot` (the Conv1D bias gradient)
+// are produced by the same pass.
 // ---------------------------------------------------------------------------------------------------------
 struct WgParams {
   const float* ga;
   const float* ot;
-  float* partial;  // [B*nchunk][ntaps*Cg*Co]
-  int B, Lg, Cg, Lo, Co, Lt, g_step, relu_ga, tch, nchunk;
+  float* partial;       // [B*nchunk][ntaps*Cg*Co]
+  float* bias_partial;  // [B*nchunk][Co] or null
+  int B, Lg, Cg, Lo, Co, Lt, g_step, relu_ga, nchunk, sub, rows;
   TapTable taps;
 };
 
 constexpr int WG_TCH = 1024;
+constexpr int WG_SUB = 128;
 
-// grid (B*nchunk, ntaps*ceil(Cg/32), ceil(Co/32)); 64 threads; thread = 4 gather channels x 4 other channels.
-// Operands are read straight from global memory (every load is a 16-byte contiguous piece shared by 8 lanes).
-__global__ void __launch_bounds__(64) wgrad_kernel(const WgParams p) {
+template <int NT>
+__global__ void __launch_bounds__(128) wgrad_kernel(const WgParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* g_s = smem;                            // [rows][32]  gather-side tile
+  float* o_s = smem + (size_t)p.rows * 32;      // [sub][32]   other-side tile
   const int tid = threadIdx.x;
   const int ncgt = (p.Cg + 31) >> 5;
-  const int j = blockIdx.y / ncgt, cgt = blockIdx.y - j * ncgt;
-  const int cg = cgt * 32 + (tid >> 3) * 4, co = blockIdx.z * 32 + (tid & 7) * 4;
+  const int tg = blockIdx.y / ncgt, cgt = blockIdx.y - tg * ncgt;  // tap group (4 taps), gather-channel tile
+  const int j0 = tg * 4;
+  const int cg0 = cgt * 32, co0 = blockIdx.z * 32;
   const int b = blockIdx.x / p.nchunk, ch = blockIdx.x - b * p.nchunk;
-  const int tb = ch * p.tch, te = min(tb + p.tch, p.Lt);
-  const int off = p.taps.off[j];
+  const int tb = ch * WG_TCH, te = min(tb + WG_TCH, p.Lt);
+  int off[NT], minoff = 1 << 30;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { off[j] = p.taps.off[j0 + j]; minoff = min(minoff, off[j]); }
   const float* gab = p.ga + (size_t)b * p.Lg * p.Cg;
   const float* otb = p.ot + (size_t)b * p.Lo * p.Co;
   const bool gvec = (p.Cg & 3) == 0, ovec = (p.Co & 3) == 0;
-  float acc[4][4];
+  const int cq = tid >> 4, c2 = tid & 15;  // 4 gather channels cq*4.., 2 other channels c2*2..
+  float acc[NT][4][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int j = 0; j < NT; ++j)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
-#pragma unroll 4
-  for (int t = tb; t < te; ++t) {
-    const long gr = (long)t * p.g_step + off;
-    float a[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f};
-    if (gr >= 0 && gr < p.Lg && cg < p.Cg) {
-      const float* r = gab + gr * p.Cg + cg;
-      if (gvec) { const float4 v = *(const float4*)r; a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
-      else { for (int i = 0; i < 4; ++i) if (cg + i < p.Cg) a[i] = r[i]; }
-      if (p.relu_ga) { for (int i = 0; i < 4; ++i) a[i] = fmaxf(a[i], 0.f); }
+    for (int i = 0; i < 4; ++i) acc[j][i][0] = acc[j][i][1] = 0.f;
+  float bs0 = 0.f, bs1 = 0.f;
+  const bool do_bias = p.bias_partial != nullptr && blockIdx.y == 0 && cq == 0;
+
+  for (int t0 = tb; t0 < te; t0 += p.sub) {
+    const int nt = min(p.sub, te - t0);
+    const long gr0 = (long)t0 * p.g_step + minoff;
+    const int nrows = (nt - 1) * p.g_step + (p.rows - (p.sub - 1) * p.g_step);
+    __syncthreads();
+    for (int e = tid; e < nrows * 8; e += 128) {
+      const int r = e >> 3, c = (e & 7) * 4;
+      const long gr = gr0 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr >= 0 && gr < p.Lg) {
+        const float* src = gab + gr * p.Cg + cg0 + c;
+        if (gvec) { if (cg0 + c < p.Cg) v = *(const float4*)src; }
+        else {
+          if (cg0 + c + 0 < p.Cg) v.x = src[0];
+          if (cg0 + c + 1 < p.Cg) v.y = src[1];
+          if (cg0 + c + 2 < p.Cg) v.z = src[2];
+          if (cg0 + c + 3 < p.Cg) v.w = src[3];
+        }
+        if (p.relu_ga) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      }
+      *(float4*)(g_s + r * 32 + c) = v;
     }
-    if (co < p.Co) {
-      const float* r = otb + (size_t)t * p.Co + co;
-      if (ovec) { const float4 v = *(const float4*)r; g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w; }
-      else { for (int i = 0; i < 4; ++i) if (co + i < p.Co) g[i] = r[i]; }
+    for (int e = tid; e < nt * 8; e += 128) {
+      const int r = e >> 3, c = (e & 7) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* src = otb + (size_t)(t0 + r) * p.Co + co0 + c;
+      if (ovec) { if (co0 + c < p.Co) v = *(const float4*)src; }
+      else {
+        if (co0 + c + 0 < p.Co) v.x = src[0];
+        if (co0 + c + 1 < p.Co) v.y = src[1];
+        if (co0 + c + 2 < p.Co) v.z = src[2];
+        if (co0 + c + 3 < p.Co) v.w = src[3];
+      }
+      *(float4*)(o_s + r * 32 + c) = v;
     }
+    __syncthreads();
+    const float* gp = g_s + cq * 4;
+    const float* op = o_s + c2 * 2;
+#pragma unroll 2
+    for (int t = 0; t < nt; ++t) {
+      const float2 g2 = *(const float2*)(op + t * 32);
+      if (do_bias) { bs0 += g2.x; bs1 += g2.y; }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const float4 a = *(const float4*)(gp + (t * p.g_step + off[j] - minoff) * 32);
+        acc[j][0][0] = fmaf(a.x, g2.x, acc[j][0][0]); acc[j][0][1] = fmaf(a.x, g2.y, acc[j][0][1]);
+        acc[j][1][0] = fmaf(a.y, g2.x, acc[j][1][0]); acc[j][1][1] = fmaf(a.y, g2.y, acc[j][1][1]);
+        acc[j][2][0] = fmaf(a.z, g2.x, acc[j][2][0]); acc[j][2][1] = fmaf(a.z, g2.y, acc[j][2][1]);
+        acc[j][3][0] = fmaf(a.w, g2.x, acc[j][3][0]); acc[j][3][1] = fmaf(a.w, g2.y, acc[j][3][1]);
+      }
+    }
+  }
+  float* out = p.partial + (size_t)blockIdx.x * p.taps.ntaps * p.Cg * p.Co;
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(a[i], g[c], acc[i][c]);
+      for (int c = 0; c < 2; ++c) {
+        const int cg = cg0 + cq * 4 + i, co = co0 + c2 * 2 + c;
+        if (cg < p.Cg && co < p.Co) out[((size_t)(j0 + j) * p.Cg + cg) * p.Co + co] = acc[j][i][c];
+      }
+  if (do_bias) {
+    const int co = co0 + c2 * 2;
+    if (co < p.Co) p.bias_partial[(size_t)blockIdx.x * p.Co + co] = bs0;
+    if (co + 1 < p.Co) p.bias_partial[(size_t)blockIdx.x * p.Co + co + 1] = bs1;
   }
-  float* out = p.partial + (size_t)blockIdx.x * p.taps.ntaps * p.Cg * p.Co + (size_t)j * p.Cg * p.Co;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (cg + i < p.Cg && co + c < p.Co) out[(size_t)(cg + i) * p.Co + co + c] = acc[i][c];
 }
 
-// out[e] = sum_{c < nchunk} partial[c][e], fixed order
-__global__ void reduce_chunks_kernel(const float* __restrict__ partial, int nchunk, int n, float* __restrict__ out) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int c = 0;
-  for (; c + 4 <= nchunk; c += 4) {
-    s0 += partial[(size_t)(c + 0) * n + e];
-    s1 += partial[(size_t)(c + 1) * n + e];
-    s2 += partial[(size_t)(c + 2) * n + e];
-    s3 += partial[(size_t)(c + 3) * n + e];
+// out[e] = sum_{c < nchunk} partial[c][e]; block = 32 elements x 8 chunk lanes, fixed summation tree
+__global__ void __launch_bounds__(256) reduce_chunks_kernel(const float* __restrict__ partial, int nchunk, int n,
+                                                            float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int ex = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + ex;
+  float s = 0.f;
+  if (e < n)
+    for (int c = ly; c < nchunk; c += 8) s += partial[(size_t)c * n + e];
+  red[ly][ex] = s;
+  __syncthreads();
+  if (ly == 0 && e < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += red[l][ex];
+    out[e] = t;
   }
-  for (; c < nchunk; ++c) s0 += partial[(size_t)c * n + e];
-  out[e] = (s0 + s1) + (s2 + s3);
 }
 
-// column sums of a [rows, C] matrix (bias gradient): partial[block][c]
+// column sums of a [rows, C] matrix (Conv1DTranspose bias gradient): partial[block][c]
 constexpr int COLSUM_ROWS = 2048;
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long rows, int C, float* __restrict__ partial) {
   __shared__ float red[256];
@@ -339,33 +400,89 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   }
 }
 
+// workspace: [B*nchunk][ntaps*Cg*Co] weight partials, then the bias partials
 static size_t wgrad_ws_floats(int B, int Lt, int ntaps, int Cg, int Co, long bias_rows, int Cb) {
   const size_t nchunk = (size_t)B * cdiv(Lt, WG_TCH);
-  return nchunk * ntaps * Cg * Co + (size_t)cdiv(bias_rows, COLSUM_ROWS) * Cb;
+  const size_t nb = (size_t)cdiv(bias_rows, COLSUM_ROWS);
+  return nchunk * ntaps * Cg * Co + (nchunk > nb ? nchunk : nb) * Cb + 64;
 }
 
-static int run_wgrad(WgParams& p, float* dw, const float* bias_src, long bias_rows, int Cb, float* dbias,
-                     void* ws, size_t ws_bytes, cudaStream_t st) {
+template <int NT>
+static int launch_wgrad(const WgParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    static bool set = false;
+    if (!set) { VQB_CUDA(cudaFuncSetAttribute(wgrad_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set = true; }
+  }
+  wgrad_kernel<NT><<<grid, 128, smem, st>>>(p);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+// bias_from_ot: the bias gradient is the column sum of `ot` (Conv1D) and is fused; otherwise it is the column sum of
+// `bias_src` (Conv1DTranspose: all rows of dy) through colsum_kernel.
+static int run_wgrad(WgParams& p, float* dw, bool bias_from_ot, const float* bias_src, long bias_rows, int Cb,
+                     float* dbias, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int ntaps = p.taps.ntaps;
-  p.tch = WG_TCH;
   p.nchunk = cdiv(p.Lt, WG_TCH);
-  const size_t need = wgrad_ws_floats(p.B, p.Lt, ntaps, p.Cg, p.Co, dbias ? bias_rows : 0, Cb) * sizeof(float);
+  const size_t need = wgrad_ws_floats(p.B, p.Lt, ntaps, p.Cg, p.Co, bias_rows, Cb) * sizeof(float);
   if (ws_bytes < need || !ws) return set_err(VQB_ERR_WORKSPACE, "wgrad workspace: need %zu bytes, got %zu", need, ws_bytes);
-  p.partial = (float*)ws;
   const int nchunks = p.B * p.nchunk;
   const int n = ntaps * p.Cg * p.Co;
-  dim3 grid(nchunks, ntaps * cdiv(p.Cg, 32), cdiv(p.Co, 32));
-  wgrad_kernel<<<grid, 64, 0, st>>>(p);
-  VQB_LAUNCH_CHECK();
-  reduce_chunks_kernel<<<cdiv(n, 128), 128, 0, st>>>(p.partial, nchunks, n, dw);
+  p.partial = (float*)ws;
+  float* bp = p.partial + (size_t)nchunks * n;
+  p.bias_partial = (dbias && bias_from_ot) ? bp : nullptr;
+  if (nchunks == 0) {
+    VQB_CUDA(cudaMemsetAsync(dw, 0, (size_t)n * sizeof(float), st));
+    if (dbias) VQB_CUDA(cudaMemsetAsync(dbias, 0, (size_t)Cb * sizeof(float), st));
+    return VQB_OK;
+  }
+  // taps are processed 4 per CTA; pad the table so that every group is full (padding taps repeat the last offset and
+  // write to a scratch slot that is never read: handled by giving them weight index ntaps.. < 4*ngroups)
+  int span = 0;
+  for (int g0 = 0; g0 < ntaps; g0 += 4) {
+    int lo = 1 << 30, hi = -(1 << 30);
+    for (int j = g0; j < g0 + 4 && j < ntaps; ++j) { lo = p.taps.off[j] < lo ? p.taps.off[j] : lo; hi = p.taps.off[j] > hi ? p.taps.off[j] : hi; }
+    span = hi - lo > span ? hi - lo : span;
+  }
+  p.sub = WG_SUB;
+  size_t smem;
+  for (;;) {
+    p.rows = (p.sub - 1) * p.g_step + span + 1;
+    smem = ((size_t)p.rows * 32 + (size_t)p.sub * 32) * sizeof(float);
+    if (smem <= 160 * 1024 || p.sub <= 8) break;
+    p.sub >>= 1;
+  }
+  VQB_REQUIRE(smem <= 160 * 1024, "wgrad: tap span %d does not fit shared memory", span);
+  const int full = ntaps / 4, rem = ntaps % 4;
+  const int ncgt = cdiv(p.Cg, 32);
+  if (full > 0) {
+    dim3 grid(nchunks, full * ncgt, cdiv(p.Co, 32));
+    int rc = launch_wgrad<4>(p, grid, smem, st);
+    if (rc) return rc;
+  }
+  if (rem > 0) {
+    WgParams q = p;  // remaining taps: shift them to the front of a private table
+    for (int j = 0; j < rem; ++j) { q.taps.off[j] = p.taps.off[full * 4 + j]; }
+    q.partial = p.partial + (size_t)full * 4 * p.Cg * p.Co;  // tap index offset inside each chunk's block
+    q.bias_partial = full > 0 ? nullptr : p.bias_partial;
+    dim3 grid(nchunks, ncgt, cdiv(p.Co, 32));
+    int rc = rem == 1 ? launch_wgrad<1>(q, grid, smem, st) : rem == 2 ? launch_wgrad<2>(q, grid, smem, st)
+                                                                      : launch_wgrad<3>(q, grid, smem, st);
+    if (rc) return rc;
+  }
+  reduce_chunks_kernel<<<cdiv(n, 32), 256, 0, st>>>(p.partial, nchunks, n, dw);
   VQB_LAUNCH_CHECK();
   if (dbias) {
-    float* bp = p.partial + (size_t)nchunks * n;
-    const int nb = cdiv(bias_rows, COLSUM_ROWS);
-    colsum_kernel<<<nb, 256, 0, st>>>(bias_src, bias_rows, Cb, bp);
-    VQB_LAUNCH_CHECK();
-    reduce_chunks_kernel<<<cdiv(Cb, 128), 128, 0, st>>>(bp, nb, Cb, dbias);
-    VQB_LAUNCH_CHECK();
+    if (bias_from_ot) {
+      reduce_chunks_kernel<<<cdiv(Cb, 32), 256, 0, st>>>(bp, nchunks, Cb, dbias);
+      VQB_LAUNCH_CHECK();
+    } else {
+      const int nb = cdiv(bias_rows, COLSUM_ROWS);
+      colsum_kernel<<<nb, 256, 0, st>>>(bias_src, bias_rows, Cb, bp);
+      VQB_LAUNCH_CHECK();
+      reduce_chunks_kernel<<<cdiv(Cb, 32), 256, 0, st>>>(bp, nb, Cb, dbias);
+      VQB_LAUNCH_CHECK();
+    }
   }
   return VQB_OK;
 }
@@ -508,7 +625,7 @@ int vqb_conv1d_wgrad(const vqb_conv_desc* d, const float* x, const float* dy, fl
   p.g_step = d->stride; p.relu_ga = d->relu_in;
   p.taps.ntaps = d->k;
   for (int j = 0; j < d->k; ++j) { p.taps.wj[j] = j; p.taps.off[j] = j * d->dilation - padL; }
-  return run_wgrad(p, dw, dy, (long)d->B * Lo, d->C_out, dbias, workspace, workspace_bytes, (cudaStream_t)stream);
+  return run_wgrad(p, dw, true, dy, (long)d->B * Lo, d->C_out, dbias, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int vqb_conv1d_transpose_fwd(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
@@ -546,7 +663,7 @@ int vqb_conv1d_transpose_wgrad(const vqb_conv_desc* d, const float* x, const flo
   p.g_step = d->stride; p.relu_ga = 0;
   p.taps.ntaps = d->k;
   for (int j = 0; j < d->k; ++j) { p.taps.wj[j] = j; p.taps.off[j] = j - padL; }
-  return run_wgrad(p, dw, dy, (long)d->B * d->L * d->stride, d->C_out, dbias, workspace, workspace_bytes,
+  return run_wgrad(p, dw, false, dy, (long)d->B * d->L * d->stride, d->C_out, dbias, workspace, workspace_bytes,
                    (cudaStream_t)stream);
 }
 

@@ -328,7 +328,7 @@ int vqb_vq_fwd(const vqb_vq_desc* d, const float* x, const float* E, int64_t* id
                float* loss, float* m_batch, float* n_batch, void* workspace, size_t workspace_bytes, void* stream) {
   VQB_ARCH();
   VQB_REQUIRE(d && d->N >= 0 && d->D > 0 && d->K > 0, "vqb_vq_fwd: bad descriptor");
-  VQB_REQUIRE(x && E && idx, "vqb_vq_fwd: NULL pointer");
+  VQB_REQUIRE(E && (d->N == 0 || (x && idx)), "vqb_vq_fwd: NULL pointer");
   VQB_REQUIRE((m_batch == nullptr) == (n_batch == nullptr), "vqb_vq_fwd: m_batch and n_batch go together");
   const size_t need = vqb_vq_fwd_workspace_bytes(d);
   if (!workspace || workspace_bytes < need)
