@@ -101,6 +101,9 @@ typedef struct vqb_resblock_desc {
   int32_t precision;
 } vqb_resblock_desc;
 
+/* 1 if the (shape, precision) combination has a kernel (fp32: always; bf16/tf32 tensor-core path: C = F = 32,
+ * dilation <= 32), else 0 — callers pick VQB_PREC_FP32 for the rest. */
+int vqb_resblock_supports(const vqb_resblock_desc* d);
 int vqb_resblock_fwd(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1,
                      const float* w2, const float* b2, float* h, float* y, void* stream);
 /* given dy: dx = dy + (x>0)*conv1^T((h>0)*conv2^T(dy)); dh ([B,L,F] scratch, also an output) holds

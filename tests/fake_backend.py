@@ -123,6 +123,9 @@ class FakeBackend:
         return 0
 
     # ---- resblock
+    def vqb_resblock_supports(self, dref):
+        return 1
+
     def vqb_resblock_fwd(self, dref, x, w1, b1, w2, b2, h, y, stream):
         d = _d(dref)
         X = _t(x, (d.B, d.L, d.C))

@@ -53,6 +53,7 @@ SIGNATURES = {
     "vqb_conv1d_transpose_dgrad": (C.c_int, [_CD, _P, _P, _P, _P]),
     "vqb_conv1d_transpose_wgrad_workspace_bytes": (C.c_size_t, [_CD]),
     "vqb_conv1d_transpose_wgrad": (C.c_int, [_CD, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vqb_resblock_supports": (C.c_int, [_RD]),
     "vqb_resblock_fwd": (C.c_int, [_RD, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vqb_resblock_bwd_data": (C.c_int, [_RD, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vqb_vq_fwd_workspace_bytes": (C.c_size_t, [_VD]),

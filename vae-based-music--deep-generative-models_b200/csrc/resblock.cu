@@ -11,6 +11,9 @@ int conv1d_dgrad_fp32(const vqb_conv_desc* d, const float* dy, const float* w, c
                       const float* dx_add, float* dx, cudaStream_t st);
 int resblock_fwd_tc(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1,
                     const float* w2, const float* b2, float* h, float* y, cudaStream_t st);
+int resblock_bwd_tc(const vqb_resblock_desc* d, const float* x, const float* h, const float* dy, const float* w1,
+                    const float* w2, float* dh, float* dx, cudaStream_t st);
+bool resblock_tc_supported(const vqb_resblock_desc* d);
 }  // namespace vqb
 
 using namespace vqb;
@@ -23,6 +26,12 @@ static int check_rb(const vqb_resblock_desc* d) {
 }
 
 extern "C" {
+
+int vqb_resblock_supports(const vqb_resblock_desc* d) {
+  if (!d) return 0;
+  if (d->precision == VQB_PREC_FP32) return 1;
+  return resblock_tc_supported(d) ? 1 : 0;
+}
 
 int vqb_resblock_fwd(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1,
                      const float* w2, const float* b2, float* h, float* y, void* stream) {
@@ -46,6 +55,7 @@ int vqb_resblock_bwd_data(const vqb_resblock_desc* d, const float* x, const floa
   if (rc) return rc;
   VQB_REQUIRE(x && h && dy && w1 && w2 && dh && dx, "vqb_resblock_bwd_data: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (d->precision != VQB_PREC_FP32) return resblock_bwd_tc(d, x, h, dy, w1, w2, dh, dx, st);
   vqb_conv_desc c2{d->B, d->L, d->F, d->C, 3, 1, 1, 1, VQB_PREC_FP32};
   rc = conv1d_dgrad_fp32(&c2, dy, w2, h, nullptr, dh, st);  // dh = (h>0) * conv2^T(dy)
   if (rc) return rc;

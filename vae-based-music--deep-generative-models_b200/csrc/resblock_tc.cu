@@ -1,0 +1,281 @@
+// resblock_tc.cu — the pre-activation residual block (resnet.py:11-18,29) and its data gradient as ONE fused tcgen05
+// kernel each: a chain of two k=3 32->32 convolutions whose intermediate never leaves the SM.
+//
+//   stage 1:  out1 = conv_{d1}(act1(in1)) + bias1          (* (mask1 > 0))           -> stored (h / dh)
+//   stage 2:  out2 = conv_{d2}(act2(out1)) + bias2         (* (mask2 > 0)) (+ add2)  -> stored (y / dx)
+//   forward : in1 = x, act1 = ReLU, d1 = dilation, act2 = ReLU, d2 = 1, add2 = x
+//   backward: in1 = dy, d1 = 1, W = conv2^T (taps flipped), mask1 = h, d2 = dilation, W = conv1^T, mask2 = x, add2 = dy
+//
+// Each convolution is an implicit GEMM on the 5th-gen tensor cores: M = 128 time positions per MMA (two M blocks per
+// CTA), N = 32 output channels, K = 32 input channels per tap; the three taps are three accumulating groups of MMAs
+// whose A descriptors are the SAME shared-memory tile shifted by (tap-1)*dilation rows (tc.cuh, "plane layout").
+// Operands are bf16 (kind::f16) or tf32 (kind::tf32), accumulation is fp32 in TMEM; bias, ReLU / masks, the fp32
+// residual add and the conversion of the intermediate to the next A operand happen in the TMEM->register epilogue.
+// Activations are converted on the fly while being staged (fp32 global -> act -> bf16/tf32 shared), which is why the
+// A tile is written by threads rather than by TMA.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace vqb {
+
+using namespace tc;
+
+struct RbTcParams {
+  const float* in1;
+  const float* mask1;
+  float* out1;
+  const float* mask2;
+  const float* add2;
+  float* out2;
+  const float* w1;  // conv of stage 1: element (tap j, in-channel k, out-channel n) at w1[jj*sj1 + k*si1 + n*so1], jj = flip ? 2-j : j
+  const float* w2;
+  const float* bias1;
+  const float* bias2;
+  int sj1, si1, so1, flip1;
+  int sj2, si2, so2, flip2;
+  int B, L, d1, d2, relu1, relu2;
+};
+
+template <bool TF32>
+struct RbCfg {
+  static constexpr int R = 256;     // stage-1 rows per CTA (2 x M128)
+  static constexpr int DMAX = 32;   // largest supported dilation
+  static constexpr int C = 32;
+  static constexpr int ES = TF32 ? 4 : 2;
+  static constexpr int T = 16 / ES;
+  static constexpr int NP = C / T;          // planes per operand tile
+  static constexpr int KSTEPS = NP / 2;     // one MMA consumes 32 bytes of K = 2 planes
+  static constexpr int PLANE = (R + 2 * DMAX) * 16 + (TF32 ? 16 : 32);  // bytes; padding de-aliases the planes' banks
+  static constexpr int WPLANE = 32 * 16;
+  static constexpr int WTAP = NP * WPLANE;
+  static constexpr int WCONV = 3 * WTAP;
+  static constexpr int SMEM = 2 * NP * PLANE + 2 * WCONV + 64;
+};
+
+template <bool TF32>
+__device__ __forceinline__ void pack_weights(uint8_t* dst, const float* __restrict__ w, int sj, int si, int so, int flip) {
+  using Cfg = RbCfg<TF32>;
+  for (int e = threadIdx.x; e < 3 * 32 * 32; e += blockDim.x) {
+    const int n = e & 31, k = (e >> 5) & 31, j = e >> 10;
+    const int jj = flip ? 2 - j : j;
+    const float v = w[(size_t)jj * sj + (size_t)k * si + (size_t)n * so];
+    uint8_t* a = dst + j * Cfg::WTAP + (k / Cfg::T) * Cfg::WPLANE + n * 16 + (k % Cfg::T) * Cfg::ES;
+    if (TF32) *reinterpret_cast<float*>(a) = to_tf32(v);
+    else *reinterpret_cast<__nv_bfloat16*>(a) = __float2bfloat16_rn(v);
+  }
+}
+
+// 3 taps x KSTEPS accumulating MMAs for both M blocks of one stage (issued by a single thread)
+template <bool TF32>
+__device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int row_shift0, int dil, uint32_t w_base) {
+  using Cfg = RbCfg<TF32>;
+  const uint32_t idesc = instr_desc(TF32 ? FMT_TF32 : FMT_BF16, 128, 32, false, false);
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int kk = 0; kk < Cfg::KSTEPS; ++kk) {
+        const uint32_t a = a_base + (uint32_t)((mb * 128 + row_shift0 + j * dil) * 16) + kk * 2 * Cfg::PLANE;
+        const uint32_t b = w_base + j * Cfg::WTAP + kk * 2 * Cfg::WPLANE;
+        mma<TF32>(tmem + mb * 32, smem_desc(a, Cfg::PLANE, 128), smem_desc(b, Cfg::WPLANE, 128), idesc, (j | kk) != 0);
+      }
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(256, 2) rb_tc_kernel(const RbTcParams p) {
+  using Cfg = RbCfg<TF32>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* A1 = smem;
+  uint8_t* A2 = A1 + Cfg::NP * Cfg::PLANE;
+  uint8_t* W1 = A2 + Cfg::NP * Cfg::PLANE;
+  uint8_t* W2 = W1 + Cfg::WCONV;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(W2 + Cfg::WCONV);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, L = p.L;
+  const int Rout = Cfg::R - 2 * p.d2;
+  const int t0 = blockIdx.x * Rout;  // first out2 row of this CTA
+  const int s0 = t0 - p.d2;          // out1 row held by A2 row DMAX (A2 has DMAX guard rows in front)
+  const int g1 = s0 - p.d1;          // in1 row held by A1 row 0
+  const int rows1 = Cfg::R + 2 * p.d1;
+
+  if (warp == 0) tmem_alloc(tslot, 128);
+  if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
+  pack_weights<TF32>(W1, p.w1, p.sj1, p.si1, p.so1, p.flip1);
+  pack_weights<TF32>(W2, p.w2, p.sj2, p.si2, p.so2, p.flip2);
+
+  // stage in1 rows [g1, g1 + rows1) as the A operand of stage 1 (zero outside [0, L): SAME padding)
+  const float* inb = p.in1 + (size_t)b * L * 32;
+  for (int e = tid; e < rows1 * 8; e += 256) {
+    const int r = e >> 3, q = e & 7;
+    const int g = g1 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g >= 0 && g < L) v = *reinterpret_cast<const float4*>(inb + (size_t)g * 32 + q * 4);
+    if (p.relu1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (TF32) {
+      *reinterpret_cast<float4*>(A1 + q * Cfg::PLANE + r * 16) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    } else {
+      *reinterpret_cast<uint2*>(A1 + (q >> 1) * Cfg::PLANE + r * 16 + (q & 1) * 8) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tslot;
+
+  if (tid == 32) {
+    issue_stage<TF32>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1));
+    commit(bar);
+  }
+  __syncwarp();
+
+  // ---- epilogue 1: TMEM -> (+bias, mask) -> out1 (global, owned rows) and act2(out1) -> A2 (shared)
+  const int i = (warp >> 2) * 128 + (warp & 3) * 32 + lane;          // tile row handled by this thread
+  const uint32_t taddr = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 32u;
+  float v[32];
+  mbar_wait(bar, 0);
+  fence_after_sync();
+  tmem_ld32(taddr, v);
+  {
+    const int g = s0 + i;
+    const bool inrange = g >= 0 && g < L;
+    if (p.bias1) {
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        const float4 bv = *reinterpret_cast<const float4*>(p.bias1 + c);
+        v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
+      }
+    }
+    if (inrange) {
+      const size_t ro = ((size_t)b * L + g) * 32;
+      if (p.mask1) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 m = *reinterpret_cast<const float4*>(p.mask1 + ro + c);
+          v[c] = m.x > 0.f ? v[c] : 0.f; v[c + 1] = m.y > 0.f ? v[c + 1] : 0.f;
+          v[c + 2] = m.z > 0.f ? v[c + 2] : 0.f; v[c + 3] = m.w > 0.f ? v[c + 3] : 0.f;
+        }
+      }
+      if (p.out1 && i >= p.d2 && i < Cfg::R - p.d2) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          *reinterpret_cast<float4*>(p.out1 + ro + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      }
+    }
+    uint8_t* a2row = A2 + (Cfg::DMAX + i) * 16;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      float a = inrange ? v[c] : 0.f;  // rows outside [0, L) are conv2's zero padding
+      if (p.relu2) a = fmaxf(a, 0.f);
+      v[c] = a;
+    }
+    if (TF32) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(a2row + q * Cfg::PLANE) =
+            make_float4(to_tf32(v[4 * q]), to_tf32(v[4 * q + 1]), to_tf32(v[4 * q + 2]), to_tf32(v[4 * q + 3]));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(a2row + q * Cfg::PLANE) =
+            make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                       pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+    }
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+
+  if (tid == 32) {
+    // out2 tile row i uses A2 rows DMAX + i + (j-1)*d2
+    issue_stage<TF32>(tmem + 64, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2));
+    commit(bar);
+  }
+  __syncwarp();
+
+  // ---- epilogue 2: TMEM -> (+bias, mask, + add) -> out2
+  mbar_wait(bar, 1);
+  fence_after_sync();
+  tmem_ld32(taddr + 64, v);
+  {
+    const int g = s0 + i;
+    if (i >= p.d2 && i < Cfg::R - p.d2 && g < L) {
+      const size_t ro = ((size_t)b * L + g) * 32;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        if (p.bias2) {
+          const float4 bv = *reinterpret_cast<const float4*>(p.bias2 + c);
+          o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+        }
+        if (p.mask2) {
+          const float4 m = *reinterpret_cast<const float4*>(p.mask2 + ro + c);
+          o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
+        }
+        if (p.add2) {
+          const float4 a = *reinterpret_cast<const float4*>(p.add2 + ro + c);
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        }
+        *reinterpret_cast<float4*>(p.out2 + ro + c) = o;
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+template <bool TF32>
+static int launch_rb(const RbTcParams& p, cudaStream_t st) {
+  using Cfg = RbCfg<TF32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VQB_CUDA(cudaFuncSetAttribute(rb_tc_kernel<TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  const int Rout = Cfg::R - 2 * p.d2;
+  dim3 grid(cdiv(p.L, Rout), p.B);
+  rb_tc_kernel<TF32><<<grid, 256, Cfg::SMEM, st>>>(p);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+bool resblock_tc_supported(const vqb_resblock_desc* d) {
+  return d->C == 32 && d->F == 32 && d->dilation >= 1 && d->dilation <= 32 &&
+         (d->precision == VQB_PREC_BF16 || d->precision == VQB_PREC_TF32);
+}
+
+int resblock_fwd_tc(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float* h, float* y, cudaStream_t st) {
+  if (!resblock_tc_supported(d))
+    return set_err(VQB_ERR_UNIMPLEMENTED, "tensor-core residual block: C=F=32, dilation<=32, precision bf16|tf32 only (got C=%d F=%d dil=%d prec=%d)",
+                   d->C, d->F, d->dilation, d->precision);
+  if (d->B == 0 || d->L == 0) return VQB_OK;
+  RbTcParams p{};
+  p.in1 = x; p.out1 = h; p.add2 = x; p.out2 = y;
+  p.w1 = w1; p.bias1 = b1; p.sj1 = 32 * 32; p.si1 = 32; p.so1 = 1; p.flip1 = 0;   // B[n=co][k=ci] = W1[j][ci][co]
+  p.w2 = w2; p.bias2 = b2; p.sj2 = 32 * 32; p.si2 = 32; p.so2 = 1; p.flip2 = 0;
+  p.B = d->B; p.L = d->L; p.d1 = d->dilation; p.d2 = 1; p.relu1 = 1; p.relu2 = 1;
+  return d->precision == VQB_PREC_TF32 ? launch_rb<true>(p, st) : launch_rb<false>(p, st);
+}
+
+int resblock_bwd_tc(const vqb_resblock_desc* d, const float* x, const float* h, const float* dy, const float* w1,
+                    const float* w2, float* dh, float* dx, cudaStream_t st) {
+  if (!resblock_tc_supported(d))
+    return set_err(VQB_ERR_UNIMPLEMENTED, "tensor-core residual block backward: unsupported shape / precision");
+  if (d->B == 0 || d->L == 0) return VQB_OK;
+  RbTcParams p{};
+  p.in1 = dy; p.mask1 = h; p.out1 = dh; p.mask2 = x; p.add2 = dy; p.out2 = dx;
+  // stage 1 = conv2^T: dA[t][f] = sum_j sum_c W2[j][f][c] dy[t + (1-j)*1][c]  -> tap n = 2-j, B[n=f][k=c]
+  p.w1 = w2; p.sj1 = 32 * 32; p.si1 = 1; p.so1 = 32; p.flip1 = 1;
+  // stage 2 = conv1^T with the block's dilation
+  p.w2 = w1; p.sj2 = 32 * 32; p.si2 = 1; p.so2 = 32; p.flip2 = 1;
+  p.B = d->B; p.L = d->L; p.d1 = 1; p.d2 = d->dilation; p.relu1 = 0; p.relu2 = 0;
+  return d->precision == VQB_PREC_TF32 ? launch_rb<true>(p, st) : launch_rb<false>(p, st);
+}
+
+}  // namespace vqb

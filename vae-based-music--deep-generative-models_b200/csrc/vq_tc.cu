@@ -6,8 +6,4 @@ int vq_search_tc(const vqb_vq_desc*, const float*, const float*, const float*, c
                  cudaStream_t) {
   return set_err(VQB_ERR_UNIMPLEMENTED, "tensor-core VQ search is not built into this library");
 }
-int resblock_fwd_tc(const vqb_resblock_desc*, const float*, const float*, const float*, const float*, const float*,
-                    float*, float*, cudaStream_t) {
-  return set_err(VQB_ERR_UNIMPLEMENTED, "tensor-core residual block is not built into this library");
-}
 }  // namespace vqb

@@ -107,6 +107,14 @@ def conv1d_transpose_wgrad(x, dy, dw, db, stride=2):
 
 
 # ------------------------------------------------------------------------------------------- resblock
+def resblock_precision(C_, F_, dilation, precision):
+    """The requested precision if libvqvae_b200 has a kernel for this block shape in it, else fp32."""
+    if precision == 0:
+        return 0
+    d = ResblockDesc(1, 1, C_, F_, dilation, precision)
+    return precision if _lib.lib().vqb_resblock_supports(C.byref(d)) else 0
+
+
 def resblock_fwd(x, w1, b1, w2, b2, dilation, precision=0):
     for t, n in ((x, "x"), (w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2")):
         _chk(t, n)

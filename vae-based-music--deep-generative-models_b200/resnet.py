@@ -35,13 +35,14 @@ class ResnetConv1DBlock(layers.Layer):
         if x.shape[-1] != self.input_dim:
             raise ValueError(f"{self.name}: input has {x.shape[-1]} channels, block was built for {self.input_dim}")
         x = x if x.is_contiguous() else x.contiguous()
-        d, prec = self.dilation, self.precision
+        d = self.dilation
+        prec = ops.resblock_precision(self.input_dim, self.filters, d, self.precision)
         # y = x + conv2(relu(conv1(relu(x))))   (resnet.py:11-18,29)
         y, h = ops.resblock_fwd(x, conv1.kernel.value, conv1.bias.value, conv2.kernel.value, conv2.bias.value, d, prec)
 
         def bwd(g, needs):
             dy = g[0].contiguous()
-            dx, dh = ops.resblock_bwd_data(x, h, dy, conv1.kernel.value, conv2.kernel.value, d)
+            dx, dh = ops.resblock_bwd_data(x, h, dy, conv1.kernel.value, conv2.kernel.value, d, prec)
             write_grad(conv2.kernel, lambda buf: ops.conv1d_wgrad(h, dy, buf, grad_buffer(conv2.bias), 1, 1, True))
             conv2.bias._grad_written = True
             write_grad(conv1.kernel, lambda buf: ops.conv1d_wgrad(x, dh, buf, grad_buffer(conv1.bias), 1, d, True))
