@@ -1,0 +1,66 @@
+"""tcgen05 (tensor-core) kernels against the oracle.  Operands are rounded to bf16 / tf32 before the MMA (fp32
+accumulate), so the tolerance is that of the operand format, stated per test: bf16 2^-8 ~ 4e-3 per operand,
+tf32 2^-11 ~ 5e-4 per operand; errors are measured relative to the output's max magnitude."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vqvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = {"bf16": 1.5e-2, "tf32": 2e-3}
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).float().cuda().contiguous()
+
+
+def rel(got, want):
+    got, want = got.detach().cpu().double(), want.detach().cpu().double()
+    return float((got - want).abs().max() / want.abs().max().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("B,L,d", [(2, 1000, 1), (3, 881, 27), (1, 254, 3), (2, 20, 27), (2, 255, 9), (1, 1, 1), (4, 3520, 9)])
+def test_resblock_tc_fwd_bwd(gpu, prec, B, L, d):
+    ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
+    rng = np.random.default_rng(L + d)
+    C = 32
+    x = rng.normal(size=(B, L, C)).astype(np.float32)
+    w1 = (rng.normal(size=(3, C, C)) / np.sqrt(3 * C)).astype(np.float32); b1 = (rng.normal(size=C) * 0.1).astype(np.float32)
+    w2 = (rng.normal(size=(3, C, C)) / np.sqrt(3 * C)).astype(np.float32); b2 = (rng.normal(size=C) * 0.1).astype(np.float32)
+    dy = rng.normal(size=(B, L, C)).astype(np.float32)
+    assert ops.resblock_precision(C, C, d, P) == P
+    ts = [torch.tensor(a, requires_grad=True) for a in (x, w1, b1, w2, b2)]
+    h_ref = O.conv1d(torch.relu(ts[0]), ts[1], ts[2], 1, d)
+    y_ref = ts[0] + O.conv1d(torch.relu(h_ref), ts[3], ts[4], 1, 1)
+    gx, gh = torch.autograd.grad(y_ref, (ts[0], h_ref), torch.tensor(dy))
+    y, h = ops.resblock_fwd(dev(x), dev(w1), dev(b1), dev(w2), dev(b2), d, P)
+    torch.cuda.synchronize()
+    assert rel(h, h_ref) < TOL[prec], ("h", rel(h, h_ref))
+    assert rel(y, y_ref) < TOL[prec], ("y", rel(y, y_ref))
+    # the oracle's h keeps the ReLU masks identical, so the comparison isolates the arithmetic of the backward kernel
+    dx, dh = ops.resblock_bwd_data(dev(x), dev(h_ref.detach().numpy()), dev(dy), dev(w1), dev(w2), d, P)
+    torch.cuda.synchronize()
+    assert rel(dh, gh) < TOL[prec], ("dh", rel(dh, gh))
+    assert rel(dx, gx) < TOL[prec], ("dx", rel(dx, gx))
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_resblock_tc_full_size_matches_fp32_kernel(gpu, prec):
+    """[32, 14080, 32] (the largest stage of SMALL_VQ_VAE at batch 32): tensor-core path vs the exact-fp32 CUDA path."""
+    ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(32, 14080, 32, device="cuda", generator=g)
+    w1 = torch.randn(3, 32, 32, device="cuda", generator=g) / 96 ** 0.5
+    w2 = torch.randn(3, 32, 32, device="cuda", generator=g) / 96 ** 0.5
+    b1 = torch.randn(32, device="cuda", generator=g) * 0.1
+    b2 = torch.randn(32, device="cuda", generator=g) * 0.1
+    dy = torch.randn(32, 14080, 32, device="cuda", generator=g)
+    for d in (1, 27):
+        y0, h0 = ops.resblock_fwd(x, w1, b1, w2, b2, d, 0)
+        y1, h1 = ops.resblock_fwd(x, w1, b1, w2, b2, d, P)
+        assert rel(h1, h0) < TOL[prec] and rel(y1, y0) < TOL[prec]
+        dx0, dh0 = ops.resblock_bwd_data(x, h0, dy, w1, w2, d, 0)
+        dx1, dh1 = ops.resblock_bwd_data(x, h0, dy, w1, w2, d, P)
+        assert rel(dh1, dh0) < TOL[prec] and rel(dx1, dx0) < TOL[prec]
