@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run train_step eagerly (profiling)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -163,6 +164,8 @@ def main():
                 V.dist.broadcast(v.value, 0)
     model.compile(optimizer=V.keras.optimizers.Adam())
     model.use_cuda_graph = not args.no_graph
+    model.set_precision(args.precision)
+    config["precision"] = args.precision
     rng = np.random.Generator(np.random.PCG64(1000 + rank))
     x_host = torch.from_numpy(rng.uniform(0, 1, size=(args.batch, T_WINDOW, 1)).astype(np.float32)).pin_memory()
     x_dev = x_host.cuda(non_blocking=True)
@@ -216,7 +219,7 @@ def main():
     pk = peaks()
     line = {"metric": METRIC, "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": config,
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
@@ -224,7 +227,7 @@ def main():
             "step_tflops": FLOP_PER_SAMPLE_FWD_BWD * samples / (ms * 1e-3) / 1e12,
             "step_frac_of_bf16_sustained": FLOP_PER_SAMPLE_FWD_BWD * samples / (ms * 1e-3) / 1e12 / (pk["tf_sust"] * world)}
     if not args.no_roofline:
-        line.update(roofline_section(V, pk))
+        line.update(roofline_section(V, pk, args.precision))
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(1, 1, args.cpu_batch)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
@@ -234,12 +237,13 @@ def main():
         torch.distributed.destroy_process_group()
 
 
-def roofline_section(V, pk):
+def roofline_section(V, pk, precision="fp32"):
     """The dominant kernel timed ALONE with CUDA events on its launch stream: the residual-block forward at the
     largest stage of the model ([32, 14080, 32], dilation 1) — 80 of level 0's 93 and 128 of level 1's 149 forward
     convolutions are inside such blocks.  Two buffer sets (231 MB) are alternated so that inputs do not sit in L2."""
     import torch
     ops = V.ops
+    P = V._lib.PRECISIONS[precision]
     B, L, C, d = 32, 14080, 32, 1
     g = torch.Generator(device="cuda").manual_seed(0)
     xs = [torch.randn(B, L, C, device="cuda", generator=g) for _ in range(2)]
@@ -247,13 +251,13 @@ def roofline_section(V, pk):
     w2 = torch.randn(3, C, C, device="cuda", generator=g) * 0.1
     b1 = torch.zeros(C, device="cuda"); b2 = torch.zeros(C, device="cuda")
     for i in range(4):
-        ops.resblock_fwd(xs[i % 2], w1, b1, w2, b2, d)
+        ops.resblock_fwd(xs[i % 2], w1, b1, w2, b2, d, P)
     torch.cuda.synchronize()
     n = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n):
-        ops.resblock_fwd(xs[i % 2], w1, b1, w2, b2, d)
+        ops.resblock_fwd(xs[i % 2], w1, b1, w2, b2, d, P)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
@@ -261,7 +265,7 @@ def roofline_section(V, pk):
     bytes_alg = B * L * C * 4 * 3.0                # read x, write h (kept for backward), write y
     tf = flops / (ms * 1e-3) / 1e12
     gbs = bytes_alg / (ms * 1e-3) / 1e9
-    return {"roofline": {"kernel": "vqb_resblock_fwd [32,14080,32] dil 1 (fp32 path: 2 x tgc_kernel)", "bound": "tensor",
+    return {"roofline": {"kernel": "vqb_resblock_fwd [32,14080,32] dil 1 (" + ("fp32 path: 2 x tgc_kernel" if precision == "fp32" else "rb_tc_kernel, tcgen05 " + precision) + ")", "bound": "tensor",
                          "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tf / pk["tf_burst"],
                          "traffic": None, "peak_source": pk["src"] + " bf16 burst", "ms_per_launch": ms,
                          "flop_per_launch": flops},

@@ -12,6 +12,8 @@
  *   - all pointers are DEVICE pointers owned by the caller (fp32 unless stated), alive until `stream` has passed
  *     the call; functions never allocate device memory, never synchronise and only enqueue work on `stream`
  *     (a cudaStream_t passed as void*), so every call is CUDA-graph capturable.
+ *   - activation / gradient tensors must be 16-byte aligned; weights, biases and codebooks only 4-byte aligned
+ *     (they may be slices of one packed parameter buffer).
  *   - activations are channels-last [B, L, C] fp32 (Keras layout); Conv1D kernels are [k, Cin, Cout],
  *     Conv1DTranspose kernels [k, Cout, Cin] (Keras layouts); the codebook is [D, K] column-per-code
  *     (VectorQuantizer.py:38-44); code indices are int64 (tf.argmin default).

@@ -51,7 +51,7 @@ def test_structure_names_and_variable_order(cpu_backend):
     off = 0
     for v in m.trainable_variables:
         assert v.value.data_ptr() == base + 4 * off and v.grad.data_ptr() == m._packed.grads.data_ptr() + 4 * off
-        off += v.value.numel()
+        off += (v.value.numel() + 3) & ~3  # 16-byte aligned slices
     # VQ state: non-trainable [D,K], m_t = E, N_t = ones (VectorQuantizer.py:38-60)
     vq = m.get_quantizer()
     assert vq.embeddings.shape == (64, 512) and not vq.embeddings.trainable

@@ -142,12 +142,9 @@ __global__ void __launch_bounds__(256, 2) rb_tc_kernel(const RbTcParams p) {
   {
     const int g = s0 + i;
     const bool inrange = g >= 0 && g < L;
-    if (p.bias1) {
+    if (p.bias1) {  // weights / biases are only assumed 4-byte aligned (they may be slices of a packed buffer)
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        const float4 bv = *reinterpret_cast<const float4*>(p.bias1 + c);
-        v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
-      }
+      for (int c = 0; c < 32; ++c) v[c] += __ldg(p.bias1 + c);
     }
     if (inrange) {
       const size_t ro = ((size_t)b * L + g) * 32;
@@ -209,8 +206,7 @@ __global__ void __launch_bounds__(256, 2) rb_tc_kernel(const RbTcParams p) {
       for (int c = 0; c < 32; c += 4) {
         float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
         if (p.bias2) {
-          const float4 bv = *reinterpret_cast<const float4*>(p.bias2 + c);
-          o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          o.x += __ldg(p.bias2 + c); o.y += __ldg(p.bias2 + c + 1); o.z += __ldg(p.bias2 + c + 2); o.w += __ldg(p.bias2 + c + 3);
         }
         if (p.mask2) {
           const float4 m = *reinterpret_cast<const float4*>(p.mask2 + ro + c);

@@ -814,9 +814,10 @@ class Packed:
 
     def __init__(self, variables: Sequence[Variable], extra_floats: int = 0):
         self.vars = list(variables)
-        n = sum(v.value.numel() for v in self.vars)
+        al = lambda k: (k + 3) & ~3  # every variable starts on a 16-byte boundary (vector loads in the kernels)
+        n = sum(al(v.value.numel()) for v in self.vars)
         self.n_params = n
-        self.params = ops.empty(n)
+        self.params = ops.zeros(n)
         self.comm = ops.zeros(n + extra_floats)  # [grads | extra (EMA statistics, loss scalars)]
         self.grads = self.comm[:n]
         self.extra = self.comm[n:]
@@ -825,7 +826,7 @@ class Packed:
             k = v.value.numel()
             v._rebind(self.params[off:off + k].view(v.shape), self.grads[off:off + k].view(v.shape))
             v._pack = self
-            off += k
+            off += al(k)
 
 
 class MeanSquaredError:

@@ -99,6 +99,19 @@ class VQVAE(Model):
         for i, m in enumerate(trackers):
             m._bind(self._metric_totals[i:i + 1])
 
+    def set_precision(self, precision="fp32"):
+        """Arithmetic of the contraction kernels: "fp32" (exact CUDA-core FMA), "tf32" or "bf16" (tcgen05 tensor cores,
+        fp32 accumulate).  Layers whose shape has no tensor-core kernel keep fp32 (vqb_resblock_supports)."""
+        from .resnet import ResnetConv1DBlock
+        code = _lib.PRECISIONS[precision]
+        for m in self.vqvaes:
+            for l in m._flatten_layers():
+                if isinstance(l, ResnetConv1DBlock):
+                    l.precision = code
+        self.precision = precision
+        self._graphs = {}
+        return self
+
     def _all_trackers(self):
         return self.metrics + list(chain.from_iterable(vq.metrics for vq in self.vqs))
 
@@ -204,7 +217,8 @@ class VQVAE(Model):
         return torch.cat(vec)
 
     def _graph_train_step(self, raw):
-        key = (tuple(raw.shape), vdist.world_size(), self.train_step_training, self.spectral_weight)
+        key = (tuple(raw.shape), vdist.world_size(), self.train_step_training, self.spectral_weight,
+               getattr(self, "precision", "fp32"))
         st = self._graphs.get(key)
         world = vdist.world_size()
         if st is not None:
