@@ -73,6 +73,9 @@ typedef struct vqb_conv_desc {
   int32_t precision; /* VQB_PREC_* */
 } vqb_conv_desc;
 
+/* 1 if d->precision has a kernel for this shape and op (0 = forward, 1 = data gradient, 2 = weight gradient); fp32: always.
+ * Tensor-core (bf16 / tf32) kernels: weight gradient of k = 3, stride 1, 32 -> 32 convolutions with dilation <= 32. */
+int vqb_conv1d_supports(const vqb_conv_desc* d, int op);
 /* y[B, ceil(L/stride), C_out] = conv(act(x)) + bias (+ residual, same shape as y; may be NULL) */
 int vqb_conv1d_fwd(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
                    const float* residual, float* y, void* stream);

@@ -58,6 +58,9 @@ class FakeBackend:
     def _act(x, d):
         return torch.relu(x) if d.relu_in else x
 
+    def vqb_conv1d_supports(self, dref, op):
+        return 1
+
     def vqb_conv1d_fwd(self, dref, x, w, b, res, y, stream):
         d = _d(dref)
         Lo = -(-d.L // d.stride)

@@ -64,3 +64,28 @@ def test_resblock_tc_full_size_matches_fp32_kernel(gpu, prec):
         dx0, dh0 = ops.resblock_bwd_data(x, h0, dy, w1, w2, d, 0)
         dx1, dh1 = ops.resblock_bwd_data(x, h0, dy, w1, w2, d, P)
         assert rel(dh1, dh0) < TOL[prec] and rel(dx1, dx0) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("B,L,d,relu", [(2, 1000, 1, 1), (3, 881, 27, 1), (1, 256, 3, 0), (2, 20, 27, 1), (5, 3520, 9, 1), (1, 1, 1, 1),
+                                        (32, 14080, 3, 1)])
+def test_conv_wgrad_tc(gpu, prec, B, L, d, relu):
+    """tcgen05 weight gradient (time = MMA K dimension, persistent CTAs) vs autograd of the oracle conv."""
+    ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
+    g = torch.Generator().manual_seed(L + d)
+    x = torch.randn(B, L, 32, generator=g)
+    dy = torch.randn(B, L, 32, generator=g)
+    w = torch.zeros(3, 32, 32, requires_grad=True)
+    bz = torch.zeros(32, requires_grad=True)
+    y = O.conv1d(torch.relu(x) if relu else x, w, bz, 1, d)
+    gw, gb = torch.autograd.grad(y, (w, bz), dy)
+    dw, db = ops.empty(3, 32, 32), ops.empty(32)
+    ops.conv1d_wgrad(x.cuda(), dy.cuda(), dw, db, 1, d, bool(relu), P)
+    torch.cuda.synchronize()
+    # operands are rounded to bf16/tf32 but the sum runs over B*L terms: the error averages down, the tolerance holds
+    assert rel(dw, gw) < TOL[prec], rel(dw, gw)
+    assert rel(db, gb) < TOL[prec], rel(db, gb)
+    # determinism: two runs are bit-identical (fixed-order reduction of per-CTA partials, no atomics)
+    dw2, db2 = ops.empty(3, 32, 32), ops.empty(32)
+    ops.conv1d_wgrad(x.cuda(), dy.cuda(), dw2, db2, 1, d, bool(relu), P)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)

@@ -45,6 +45,14 @@ void count_launch();
     if (a__ != VQB_OK) return a__;        \
   } while (0)
 
+// fixed-order reduction of per-chunk partial sums (conv_fp32.cu)
+void reduce_chunks_strided(const float* partial, int nchunk, long stride, int offset, int n, float* out, cudaStream_t st);
+// tensor-core weight gradient (wgrad_tc.cu)
+bool wgrad_tc_supported(const vqb_conv_desc* d);
+size_t wgrad_tc_workspace_bytes(const vqb_conv_desc* d);
+int conv1d_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, void* ws,
+                    size_t ws_bytes, cudaStream_t st);
+
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float warp_sum(float v) {

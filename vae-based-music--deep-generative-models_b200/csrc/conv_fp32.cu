@@ -354,15 +354,15 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WgParams p) {
   }
 }
 
-// out[e] = sum_{c < nchunk} partial[c][e]; block = 32 elements x 8 chunk lanes, fixed summation tree
-__global__ void __launch_bounds__(256) reduce_chunks_kernel(const float* __restrict__ partial, int nchunk, int n,
-                                                            float* __restrict__ out) {
+// out[e] = sum_{c < nchunk} partial[c*stride + offset + e]; block = 32 elements x 8 chunk lanes, fixed summation tree
+__global__ void __launch_bounds__(256) reduce_chunks_kernel(const float* __restrict__ partial, int nchunk, long stride,
+                                                            int offset, int n, float* __restrict__ out) {
   __shared__ float red[8][33];
   const int ex = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + ex;
   float s = 0.f;
   if (e < n)
-    for (int c = ly; c < nchunk; c += 8) s += partial[(size_t)c * n + e];
+    for (int c = ly; c < nchunk; c += 8) s += partial[(size_t)c * stride + offset + e];
   red[ly][ex] = s;
   __syncthreads();
   if (ly == 0 && e < n) {
@@ -371,6 +371,10 @@ __global__ void __launch_bounds__(256) reduce_chunks_kernel(const float* __restr
     for (int l = 0; l < 8; ++l) t += red[l][ex];
     out[e] = t;
   }
+}
+
+void reduce_chunks_strided(const float* partial, int nchunk, long stride, int offset, int n, float* out, cudaStream_t st) {
+  reduce_chunks_kernel<<<cdiv(n, 32), 256, 0, st>>>(partial, nchunk, stride, offset, n, out);
 }
 
 // column sums of a [rows, C] matrix (Conv1DTranspose bias gradient): partial[block][c]
@@ -470,17 +474,17 @@ static int run_wgrad(WgParams& p, float* dw, bool bias_from_ot, const float* bia
                                                                       : launch_wgrad<3>(q, grid, smem, st);
     if (rc) return rc;
   }
-  reduce_chunks_kernel<<<cdiv(n, 32), 256, 0, st>>>(p.partial, nchunks, n, dw);
+  reduce_chunks_strided(p.partial, nchunks, n, 0, n, dw, st);
   VQB_LAUNCH_CHECK();
   if (dbias) {
     if (bias_from_ot) {
-      reduce_chunks_kernel<<<cdiv(Cb, 32), 256, 0, st>>>(bp, nchunks, Cb, dbias);
+      reduce_chunks_strided(bp, nchunks, Cb, 0, Cb, dbias, st);
       VQB_LAUNCH_CHECK();
     } else {
       const int nb = cdiv(bias_rows, COLSUM_ROWS);
       colsum_kernel<<<nb, 256, 0, st>>>(bias_src, bias_rows, Cb, bp);
       VQB_LAUNCH_CHECK();
-      reduce_chunks_kernel<<<cdiv(Cb, 32), 256, 0, st>>>(bp, nb, Cb, dbias);
+      reduce_chunks_strided(bp, nb, Cb, 0, Cb, dbias, st);
       VQB_LAUNCH_CHECK();
     }
   }
@@ -604,8 +608,15 @@ int vqb_conv1d_dgrad(const vqb_conv_desc* d, const float* dy, const float* w, co
   return conv1d_dgrad_fp32(d, dy, w, x, dx_add, dx, (cudaStream_t)stream);
 }
 
+int vqb_conv1d_supports(const vqb_conv_desc* d, int op) {
+  if (!d || d->k < 1 || d->k > MAX_TAPS) return 0;
+  if (d->precision == VQB_PREC_FP32) return 1;
+  return op == 2 && wgrad_tc_supported(d) ? 1 : 0;
+}
+
 size_t vqb_conv1d_wgrad_workspace_bytes(const vqb_conv_desc* d) {
   if (!d || d->k < 1 || d->k > MAX_TAPS) return 0;
+  if (d->precision != VQB_PREC_FP32 && wgrad_tc_supported(d)) return wgrad_tc_workspace_bytes(d);
   int Lo, padL;
   same_pad(d->L, d->k, d->stride, d->dilation, &Lo, &padL);
   return wgrad_ws_floats(d->B, Lo, d->k, d->C_in, d->C_out, (long)d->B * Lo, d->C_out) * sizeof(float);
@@ -617,6 +628,16 @@ int vqb_conv1d_wgrad(const vqb_conv_desc* d, const float* x, const float* dy, fl
   int rc = check_desc(d, false);
   if (rc) return rc;
   VQB_REQUIRE(x && dy && dw, "vqb_conv1d_wgrad: NULL pointer");
+  if (d->precision != VQB_PREC_FP32) {
+    VQB_REQUIRE(wgrad_tc_supported(d), "vqb_conv1d_wgrad: no tensor-core kernel for this shape (k=%d stride=%d %d->%d dil=%d); use VQB_PREC_FP32",
+                d->k, d->stride, d->C_in, d->C_out, d->dilation);
+    if (d->B == 0 || d->L == 0) {
+      VQB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 3 * 32 * 32, (cudaStream_t)stream));
+      if (dbias) VQB_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * 32, (cudaStream_t)stream));
+      return VQB_OK;
+    }
+    return conv1d_wgrad_tc(d, x, dy, dw, dbias, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
   int Lo, padL;
   same_pad(d->L, d->k, d->stride, d->dilation, &Lo, &padL);
   WgParams p{};

@@ -63,11 +63,13 @@ def conv1d_dgrad(dy, w, x_shape, x=None, stride=1, dilation=1, relu_in=False, dx
     return dx
 
 
-def conv1d_wgrad(x, dy, dw, db, stride=1, dilation=1, relu_in=False):
+def conv1d_wgrad(x, dy, dw, db, stride=1, dilation=1, relu_in=False, precision=0):
     _chk(x, "x"); _chk(dy, "dy"); _chk(dw, "dw"); _chk(db, "db")
     B, L, cin = x.shape
     k, _, cout = dw.shape
-    d = _cdesc(B, L, cin, cout, k, stride, dilation, relu_in)
+    d = _cdesc(B, L, cin, cout, k, stride, dilation, relu_in, precision)
+    if precision and not _lib.lib().vqb_conv1d_supports(C.byref(d), 2):
+        d.precision = 0  # no tensor-core kernel for this shape: exact fp32 path
     n = _lib.lib().vqb_conv1d_wgrad_workspace_bytes(C.byref(d))
     ws = _ws(n)
     call("vqb_conv1d_wgrad", C.byref(d), ptr(x), ptr(dy), ptr(dw), ptr(db), ptr(ws), ws.numel(), _lib.stream())

@@ -43,9 +43,9 @@ class ResnetConv1DBlock(layers.Layer):
         def bwd(g, needs):
             dy = g[0].contiguous()
             dx, dh = ops.resblock_bwd_data(x, h, dy, conv1.kernel.value, conv2.kernel.value, d, prec)
-            write_grad(conv2.kernel, lambda buf: ops.conv1d_wgrad(h, dy, buf, grad_buffer(conv2.bias), 1, 1, True))
+            write_grad(conv2.kernel, lambda buf: ops.conv1d_wgrad(h, dy, buf, grad_buffer(conv2.bias), 1, 1, True, prec))
             conv2.bias._grad_written = True
-            write_grad(conv1.kernel, lambda buf: ops.conv1d_wgrad(x, dh, buf, grad_buffer(conv1.bias), 1, d, True))
+            write_grad(conv1.kernel, lambda buf: ops.conv1d_wgrad(x, dh, buf, grad_buffer(conv1.bias), 1, d, True, prec))
             conv1.bias._grad_written = True
             return [dx if needs[0] else None]
 
