@@ -82,8 +82,53 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int 
       }
 }
 
+// ---- warp-cooperative row I/O --------------------------------------------------------------------------------------
+// In the epilogues thread `lane` of a warp owns tile row i0 + lane (its TMEM lane).  Reading / writing its 64-byte half
+// row straight from global memory would make every warp instruction touch 32 different lines, so rows move through a
+// per-warp 2 KB staging area (32 rows x 64 B, 16-byte chunks XOR-swizzled by (row >> 1) & 3: conflict-free both ways)
+// and the global side is done with lane -> (row = lane / 4, chunk = lane % 4): 64 contiguous bytes per row.
+__device__ __forceinline__ uint32_t stg_off(int row, int q) { return (uint32_t)(row * 64 + ((q ^ ((row >> 1) & 3)) << 4)); }
+
+// v[16] <- src[(g0 + lane) * 32 + half * 16 + 0..15]  (zero where the row is outside [0, L))
+__device__ __forceinline__ void warp_load_rows(const float* __restrict__ src, long batch_off, int g0, int L, int half,
+                                               uint8_t* stg, int lane, float* v) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = k * 32 + lane, row = idx >> 2, q = idx & 3;
+    const int g = g0 + row;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g >= 0 && g < L) t = *reinterpret_cast<const float4*>(src + (batch_off + g) * 32 + half * 16 + q * 4);
+    *reinterpret_cast<float4*>(stg + stg_off(row, q)) = t;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(stg + stg_off(lane, q));
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+  __syncwarp();
+}
+
+// dst[(g0 + row) * 32 + half * 16 + ..] <- v of the thread owning `row`, for tile rows i0 + row in [own_lo, own_hi), g < L
+__device__ __forceinline__ void warp_store_rows(float* __restrict__ dst, long batch_off, int g0, int L, int half, int i0,
+                                                int own_lo, int own_hi, uint8_t* stg, int lane, const float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<float4*>(stg + stg_off(lane, q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = k * 32 + lane, row = idx >> 2, q = idx & 3;
+    const int g = g0 + row, i = i0 + row;
+    if (i >= own_lo && i < own_hi && g >= 0 && g < L)
+      *reinterpret_cast<float4*>(dst + (batch_off + g) * 32 + half * 16 + q * 4) =
+          *reinterpret_cast<const float4*>(stg + stg_off(row, q));
+  }
+  __syncwarp();
+}
+
 template <bool TF32>
-__global__ void __launch_bounds__(256, 2) rb_tc_kernel(const RbTcParams p) {
+__global__ void __launch_bounds__(256, TF32 ? 2 : 3) rb_tc_kernel(const RbTcParams p) {
   using Cfg = RbCfg<TF32>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* A1 = smem;
@@ -100,6 +145,7 @@ __global__ void __launch_bounds__(256, 2) rb_tc_kernel(const RbTcParams p) {
   const int s0 = t0 - p.d2;          // out1 row held by A2 row DMAX (A2 has DMAX guard rows in front)
   const int g1 = s0 - p.d1;          // in1 row held by A1 row 0
   const int rows1 = Cfg::R + 2 * p.d1;
+  const long boff = (long)b * L;
 
   if (warp == 0) tmem_alloc(tslot, 128);
   if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -107,7 +153,7 @@ __global__ void __launch_bounds__(256, 2) rb_tc_kernel(const RbTcParams p) {
   pack_weights<TF32>(W2, p.w2, p.sj2, p.si2, p.so2, p.flip2);
 
   // stage in1 rows [g1, g1 + rows1) as the A operand of stage 1 (zero outside [0, L): SAME padding)
-  const float* inb = p.in1 + (size_t)b * L * 32;
+  const float* inb = p.in1 + (size_t)boff * 32;
   for (int e = tid; e < rows1 * 8; e += 256) {
     const int r = e >> 3, q = e & 7;
     const int g = g1 + r;
@@ -132,52 +178,45 @@ __global__ void __launch_bounds__(256, 2) rb_tc_kernel(const RbTcParams p) {
   }
   __syncwarp();
 
-  // ---- epilogue 1: TMEM -> (+bias, mask) -> out1 (global, owned rows) and act2(out1) -> A2 (shared)
-  const int i = (warp >> 2) * 128 + (warp & 3) * 32 + lane;          // tile row handled by this thread
+  const int i0 = (warp >> 2) * 128 + (warp & 3) * 32;  // first tile row of this warp
+  const int i = i0 + lane;                             // tile row (= TMEM lane) of this thread
+  const int g = s0 + i;                                // global row
+  const bool inrange = g >= 0 && g < L;
   const uint32_t taddr = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 32u;
-  float v[32];
+  uint8_t* stg = A1 + warp * 2048;  // the A1 tile is dead once the stage-1 MMAs have completed: reuse it for row staging
+  float v[16], m[16];
+
+  // ---- epilogue 1: TMEM -> (+bias, mask) -> out1 (global, owned rows) and act2(out1) -> A2 (shared)
   mbar_wait(bar, 0);
   fence_after_sync();
-  tmem_ld32(taddr, v);
-  {
-    const int g = s0 + i;
-    const bool inrange = g >= 0 && g < L;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    tmem_ld16(taddr + half * 16, v);
     if (p.bias1) {  // weights / biases are only assumed 4-byte aligned (they may be slices of a packed buffer)
 #pragma unroll
-      for (int c = 0; c < 32; ++c) v[c] += __ldg(p.bias1 + c);
+      for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias1 + half * 16 + c);
     }
-    if (inrange) {
-      const size_t ro = ((size_t)b * L + g) * 32;
-      if (p.mask1) {
+    if (p.mask1) {
+      warp_load_rows(p.mask1, boff, s0 + i0, L, half, stg, lane, m);
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 m = *reinterpret_cast<const float4*>(p.mask1 + ro + c);
-          v[c] = m.x > 0.f ? v[c] : 0.f; v[c + 1] = m.y > 0.f ? v[c + 1] : 0.f;
-          v[c + 2] = m.z > 0.f ? v[c + 2] : 0.f; v[c + 3] = m.w > 0.f ? v[c + 3] : 0.f;
-        }
-      }
-      if (p.out1 && i >= p.d2 && i < Cfg::R - p.d2) {
+      for (int c = 0; c < 16; ++c) v[c] = m[c] > 0.f ? v[c] : 0.f;
+    }
+    if (p.out1) warp_store_rows(p.out1, boff, s0 + i0, L, half, i0, p.d2, Cfg::R - p.d2, stg, lane, v);
 #pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          *reinterpret_cast<float4*>(p.out1 + ro + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-      }
+    for (int c = 0; c < 16; ++c) {
+      float a = inrange ? v[c] : 0.f;  // rows outside [0, L) are conv2's zero padding
+      v[c] = p.relu2 ? fmaxf(a, 0.f) : a;
     }
     uint8_t* a2row = A2 + (Cfg::DMAX + i) * 16;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      float a = inrange ? v[c] : 0.f;  // rows outside [0, L) are conv2's zero padding
-      if (p.relu2) a = fmaxf(a, 0.f);
-      v[c] = a;
-    }
     if (TF32) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<float4*>(a2row + q * Cfg::PLANE) =
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(a2row + (half * 4 + q) * Cfg::PLANE) =
             make_float4(to_tf32(v[4 * q]), to_tf32(v[4 * q + 1]), to_tf32(v[4 * q + 2]), to_tf32(v[4 * q + 3]));
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(a2row + q * Cfg::PLANE) =
+      for (int q = 0; q < 2; ++q)
+        *reinterpret_cast<uint4*>(a2row + (half * 2 + q) * Cfg::PLANE) =
             make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
                        pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
     }
@@ -194,31 +233,27 @@ __global__ void __launch_bounds__(256, 2) rb_tc_kernel(const RbTcParams p) {
   }
   __syncwarp();
 
-  // ---- epilogue 2: TMEM -> (+bias, mask, + add) -> out2
+  // ---- epilogue 2: TMEM -> (+bias, mask, + add) -> out2 (owned rows)
   mbar_wait(bar, 1);
   fence_after_sync();
-  tmem_ld32(taddr + 64, v);
-  {
-    const int g = s0 + i;
-    if (i >= p.d2 && i < Cfg::R - p.d2 && g < L) {
-      const size_t ro = ((size_t)b * L + g) * 32;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    tmem_ld16(taddr + 64 + half * 16, v);
+    if (p.bias2) {
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-        if (p.bias2) {
-          o.x += __ldg(p.bias2 + c); o.y += __ldg(p.bias2 + c + 1); o.z += __ldg(p.bias2 + c + 2); o.w += __ldg(p.bias2 + c + 3);
-        }
-        if (p.mask2) {
-          const float4 m = *reinterpret_cast<const float4*>(p.mask2 + ro + c);
-          o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
-        }
-        if (p.add2) {
-          const float4 a = *reinterpret_cast<const float4*>(p.add2 + ro + c);
-          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-        }
-        *reinterpret_cast<float4*>(p.out2 + ro + c) = o;
-      }
+      for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias2 + half * 16 + c);
     }
+    if (p.mask2) {
+      warp_load_rows(p.mask2, boff, s0 + i0, L, half, stg, lane, m);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = m[c] > 0.f ? v[c] : 0.f;
+    }
+    if (p.add2) {
+      warp_load_rows(p.add2, boff, s0 + i0, L, half, stg, lane, m);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] += m[c];
+    }
+    warp_store_rows(p.out2, boff, s0 + i0, L, half, i0, p.d2, Cfg::R - p.d2, stg, lane, v);
   }
   fence_before_sync();
   __syncthreads();
