@@ -120,7 +120,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run train_step eagerly (profiling)")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16", "bf16x2", "bf16x3"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -46,7 +46,10 @@ enum {
 enum {
   VQB_PREC_FP32 = 0, /* fp32 FMA on CUDA cores, exact fp32 accumulation */
   VQB_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
-  VQB_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+  VQB_PREC_BF16 = 2, /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+  VQB_PREC_BF16X2 = 3, /* operands split into 2 bf16 pieces (hi + lo), 3 MMAs per product: ~2^-16 */
+  VQB_PREC_BF16X3 = 4  /* operands split into 3 bf16 pieces (all 24 mantissa bits), 6 MMAs per product: fp32-grade
+                          products, fp32 accumulation — the tensor-core path that meets the fp32 parity contract */
 };
 
 int vqb_version(void);

@@ -8,7 +8,7 @@ import torch
 from oracle import vqvae_oracle as O
 
 pytestmark = pytest.mark.gpu
-TOL = {"bf16": 1.5e-2, "tf32": 2e-3}
+TOL = {"bf16": 1.5e-2, "tf32": 2e-3, "bf16x2": 1e-4, "bf16x3": 2e-5}  # bf16x3 carries all 24 mantissa bits: fp32-grade
 
 
 def dev(a):
@@ -20,7 +20,7 @@ def rel(got, want):
     return float((got - want).abs().max() / want.abs().max().clamp_min(1e-12))
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32", "bf16", "bf16x2", "bf16x3"])
 @pytest.mark.parametrize("B,L,d", [(2, 1000, 1), (3, 881, 27), (1, 254, 3), (2, 20, 27), (2, 255, 9), (1, 1, 1), (4, 3520, 9)])
 def test_resblock_tc_fwd_bwd(gpu, prec, B, L, d):
     ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
@@ -46,7 +46,7 @@ def test_resblock_tc_fwd_bwd(gpu, prec, B, L, d):
     assert rel(dx, gx) < TOL[prec], ("dx", rel(dx, gx))
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32", "bf16", "bf16x2", "bf16x3"])
 def test_resblock_tc_full_size_matches_fp32_kernel(gpu, prec):
     """[32, 14080, 32] (the largest stage of SMALL_VQ_VAE at batch 32): tensor-core path vs the exact-fp32 CUDA path."""
     ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
@@ -66,7 +66,7 @@ def test_resblock_tc_full_size_matches_fp32_kernel(gpu, prec):
         assert rel(dh1, dh0) < TOL[prec] and rel(dx1, dx0) < TOL[prec]
 
 
-@pytest.mark.parametrize("prec", ["bf16"])
+@pytest.mark.parametrize("prec", ["bf16", "bf16x2", "bf16x3"])
 @pytest.mark.parametrize("B,L,d,relu", [(2, 1000, 1, 1), (3, 881, 27, 1), (1, 256, 3, 0), (2, 20, 27, 1), (5, 3520, 9, 1), (1, 1, 1, 1),
                                         (32, 14080, 3, 1)])
 def test_conv_wgrad_tc(gpu, prec, B, L, d, relu):

@@ -1,0 +1,48 @@
+"""Runs one hot kernel a few times (for `ncu --set full -k regex:...`).  Usage: python tools/bench_kernel.py resblock_fwd|resblock_bwd|wgrad|vq [precision]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import vqvae_b200 as V  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "resblock_fwd"
+prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+P = V._lib.PRECISIONS[prec]
+ops = V.ops
+g = torch.Generator(device="cuda").manual_seed(0)
+B, L, C = 32, 14080, 32
+xs = [torch.randn(B, L, C, device="cuda", generator=g) for _ in range(2)]
+dy = torch.randn(B, L, C, device="cuda", generator=g)
+w1 = torch.randn(3, C, C, device="cuda", generator=g) * 0.1
+w2 = torch.randn(3, C, C, device="cuda", generator=g) * 0.1
+b1 = torch.zeros(C, device="cuda"); b2 = torch.zeros(C, device="cuda")
+y, h = ops.resblock_fwd(xs[0], w1, b1, w2, b2, 1, P)
+dw, db = ops.empty(3, C, C), ops.empty(C)
+n = int(os.environ.get("N", "6"))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def one(i):
+    if what == "resblock_fwd":
+        ops.resblock_fwd(xs[i % 2], w1, b1, w2, b2, 1, P)
+    elif what == "resblock_bwd":
+        ops.resblock_bwd_data(xs[i % 2], h, dy, w1, w2, int(os.environ.get("DIL", "1")), P)
+    elif what == "wgrad":
+        ops.conv1d_wgrad(xs[i % 2], dy, dw, db, 1, 1, True, P)
+    elif what == "vq":
+        x = xs[0].view(-1, 64)
+        E = torch.randn(64, 512, device="cuda", generator=g)
+        ops.vq_fwd(x, E, 0.25, True, True, ops.empty(64, 512), ops.empty(512), P if prec in ("bf16", "tf32") else 0)
+
+
+for i in range(4):
+    one(i)
+torch.cuda.synchronize()
+e0.record()
+for i in range(n):
+    one(i)
+e1.record()
+torch.cuda.synchronize()
+print(what, prec, "ms per call", e0.elapsed_time(e1) / n)

@@ -28,7 +28,7 @@ def main():
             "recon": float((res[l]["recon"].double() - res64[l]["recon"]).abs().max() / res64[l]["recon"].abs().max()),
             "grad_max_rel_to_largest": max(float((a.double() - b).abs().max()) for a, b in zip(grads[l], grads64[l])) / gm,
             "idx_mismatch": int((res[l]["idx"] != res64[l]["idx"]).sum())}
-    for prec in ("fp32", "tf32", "bf16"):
+    for prec in (sys.argv[1:] or ("fp32", "bf16x3", "bf16x2", "tf32", "bf16")):
         V.keras_compat.reset_name_counters(); V.set_seed(0)
         m = V.VQVAE((28160, 1), **V.SMALL_VQ_VAE)
         m.use_cuda_graph = False
@@ -48,19 +48,24 @@ def main():
             rec, r, c, s = outs[l]
             idx = m.encode(x)[l].reshape(-1).cpu()
             gm = max(float(t.abs().max()) for t in grads[l])
-            gerr, gerr_own = 0.0, 0.0
-            for want in grads[l]:
+            gerr, gerr_own, worst = 0.0, 0.0, []
+            names = [v.name for v in m.vqvaes[l].trainable_variables]
+            for j, want in enumerate(grads[l]):
                 e = float((g[i].cpu() - want).abs().max())
                 gerr = max(gerr, e / gm)
-                gerr_own = max(gerr_own, e / max(float(want.abs().max()), 1e-3 * gm))
+                own = e / max(float(want.abs().max()), 1e-3 * gm)
+                gerr_own = max(gerr_own, own)
+                worst.append((own, j, names[j], list(want.shape), float(want.abs().max()), e))
                 i += 1
+            worst.sort(reverse=True)
             rep[f"level{l}"] = {
                 "recon_rel": float((rec.cpu() - res[l]["recon"]).abs().max() / res[l]["recon"].abs().max()),
                 "recon_loss_rel": abs(float(r) - float(res[l]["recon_loss"])) / float(res[l]["recon_loss"]),
                 "commit_loss_rel": abs(float(c) - float(res[l]["commit_loss"])) / float(res[l]["commit_loss"]),
                 "spec_loss_rel": abs(float(s) - float(res[l]["spec_loss"])) / float(res[l]["spec_loss"]),
                 "grad_err_rel_to_largest_grad": gerr, "grad_err_rel_to_own_max": gerr_own,
-                "idx_mismatch": int((idx != res[l]["idx"]).sum()), "n_idx": int(idx.numel())}
+                "idx_mismatch": int((idx != res[l]["idx"]).sum()), "n_idx": int(idx.numel()),
+                "worst_tensors": [dict(rel=w[0], index=w[1], name=w[2], shape=w[3], own_max=w[4], abs_err=w[5]) for w in worst[:6]]}
         out[prec] = rep
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "precision_report.json"), "w"), indent=1)

@@ -14,8 +14,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libvqvae_b200.so")
 
-PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}
+PREC_FP32, PREC_TF32, PREC_BF16, PREC_BF16X2, PREC_BF16X3 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "bf16x2": PREC_BF16X2, "bf16x3": PREC_BF16X3}
 
 
 class VQBError(RuntimeError):

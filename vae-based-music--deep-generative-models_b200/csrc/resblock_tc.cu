@@ -34,10 +34,15 @@ struct RbTcParams {
   int sj1, si1, so1, flip1;
   int sj2, si2, so2, flip2;
   int B, L, d1, d2, relu1, relu2;
+  int tiles_x, total_tiles;  // time tiles per batch item, B * tiles_x
 };
 
-template <bool TF32>
+// MODE 0: bf16   1: tf32   2: bf16x2 (operands split hi+lo, 3 MMAs per product, ~2^-16)   3: bf16x3 (hi+mid+lo, 6 MMAs,
+// all 24 mantissa bits of both operands: fp32-grade products with fp32 accumulation)
+template <int MODE>
 struct RbCfg {
+  static constexpr bool TF32 = MODE == 1;
+  static constexpr int S = MODE == 2 ? 2 : MODE == 3 ? 3 : 1;  // bf16 pieces per operand
   static constexpr int R = 256;     // stage-1 rows per CTA (2 x M128)
   static constexpr int DMAX = 32;   // largest supported dilation
   static constexpr int C = 32;
@@ -49,37 +54,73 @@ struct RbCfg {
   static constexpr int WPLANE = 32 * 16;
   static constexpr int WTAP = NP * WPLANE;
   static constexpr int WCONV = 3 * WTAP;
-  static constexpr int SMEM = 2 * NP * PLANE + 2 * WCONV + 64;
+  static constexpr int TILE = NP * PLANE;   // one operand tile (one split piece)
+  static constexpr int SMEM = 2 * S * TILE + 2 * S * WCONV + 64 + 256;
+  static constexpr int MINB = MODE == 0 ? 3 : MODE == 3 ? 1 : 2;  // CTAs per SM the shared-memory footprint allows
 };
 
-template <bool TF32>
+template <int MODE>
 __device__ __forceinline__ void pack_weights(uint8_t* dst, const float* __restrict__ w, int sj, int si, int so, int flip) {
-  using Cfg = RbCfg<TF32>;
+  using Cfg = RbCfg<MODE>;
   for (int e = threadIdx.x; e < 3 * 32 * 32; e += blockDim.x) {
     const int n = e & 31, k = (e >> 5) & 31, j = e >> 10;
     const int jj = flip ? 2 - j : j;
     const float v = w[(size_t)jj * sj + (size_t)k * si + (size_t)n * so];
     uint8_t* a = dst + j * Cfg::WTAP + (k / Cfg::T) * Cfg::WPLANE + n * 16 + (k % Cfg::T) * Cfg::ES;
-    if (TF32) *reinterpret_cast<float*>(a) = to_tf32(v);
-    else *reinterpret_cast<__nv_bfloat16*>(a) = __float2bfloat16_rn(v);
+    if (Cfg::TF32) {
+      *reinterpret_cast<float*>(a) = to_tf32(v);
+    } else {
+      float pc[3];
+      split_bf16<Cfg::S>(v, pc);
+#pragma unroll
+      for (int s = 0; s < Cfg::S; ++s) *reinterpret_cast<__nv_bfloat16*>(a + s * Cfg::WCONV) = __float2bfloat16_rn(pc[s]);
+    }
   }
 }
 
-// 3 taps x KSTEPS accumulating MMAs for both M blocks of one stage (issued by a single thread)
-template <bool TF32>
+// 3 taps x KSTEPS accumulating MMAs (x the operand-piece pairs of the split modes) for both M blocks of one stage,
+// issued by a single thread
+template <int MODE>
 __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int row_shift0, int dil, uint32_t w_base) {
-  using Cfg = RbCfg<TF32>;
-  const uint32_t idesc = instr_desc(TF32 ? FMT_TF32 : FMT_BF16, 128, 32, false, false);
+  using Cfg = RbCfg<MODE>;
+  const uint32_t idesc = instr_desc(Cfg::TF32 ? FMT_TF32 : FMT_BF16, 128, 32, false, false);
 #pragma unroll
-  for (int mb = 0; mb < 2; ++mb)
+  for (int mb = 0; mb < 2; ++mb) {
+    uint32_t first = 1;
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
       for (int kk = 0; kk < Cfg::KSTEPS; ++kk) {
         const uint32_t a = a_base + (uint32_t)((mb * 128 + row_shift0 + j * dil) * 16) + kk * 2 * Cfg::PLANE;
         const uint32_t b = w_base + j * Cfg::WTAP + kk * 2 * Cfg::WPLANE;
-        mma<TF32>(tmem + mb * 32, smem_desc(a, Cfg::PLANE, 128), smem_desc(b, Cfg::WPLANE, 128), idesc, (j | kk) != 0);
+        // pieces (sa, sw) with sa + sw < S, smallest contributions first
+#pragma unroll
+        for (int lvl = Cfg::S - 1; lvl >= 0; --lvl)
+#pragma unroll
+          for (int sa = 0; sa <= lvl; ++sa) {
+            const int sw = lvl - sa;
+            mma<Cfg::TF32>(tmem + mb * 32, smem_desc(a + sa * Cfg::TILE, Cfg::PLANE, 128),
+                           smem_desc(b + sw * Cfg::WCONV, Cfg::WPLANE, 128), idesc, first ? 0u : 1u);
+            first = 0;
+          }
       }
+  }
+}
+
+// one float4 (4 channels q*4..q*4+3 of row r) -> operand tile(s)
+template <int MODE>
+__device__ __forceinline__ void stage4(uint8_t* tile, int r, int q, float4 v) {
+  using Cfg = RbCfg<MODE>;
+  if (Cfg::TF32) {
+    *reinterpret_cast<float4*>(tile + q * Cfg::PLANE + r * 16) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+  } else {
+    float a[3], b[3], c[3], d[3];
+    split_bf16<Cfg::S>(v.x, a); split_bf16<Cfg::S>(v.y, b); split_bf16<Cfg::S>(v.z, c); split_bf16<Cfg::S>(v.w, d);
+#pragma unroll
+    for (int s = 0; s < Cfg::S; ++s)
+      *reinterpret_cast<uint2*>(tile + s * Cfg::TILE + (q >> 1) * Cfg::PLANE + r * 16 + (q & 1) * 8) =
+          make_uint2(pack_bf16(a[s], b[s]), pack_bf16(c[s], d[s]));
+  }
 }
 
 // ---- warp-cooperative row I/O --------------------------------------------------------------------------------------
@@ -127,30 +168,42 @@ __device__ __forceinline__ void warp_store_rows(float* __restrict__ dst, long ba
   __syncwarp();
 }
 
-template <bool TF32>
-__global__ void __launch_bounds__(256, TF32 ? 2 : 3) rb_tc_kernel(const RbTcParams p) {
-  using Cfg = RbCfg<TF32>;
+template <int MODE>
+__global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbTcParams p) {
+  using Cfg = RbCfg<MODE>;
+  constexpr bool TF32 = Cfg::TF32;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* A1 = smem;
-  uint8_t* A2 = A1 + Cfg::NP * Cfg::PLANE;
-  uint8_t* W1 = A2 + Cfg::NP * Cfg::PLANE;
-  uint8_t* W2 = W1 + Cfg::WCONV;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(W2 + Cfg::WCONV);
+  uint8_t* A2 = A1 + Cfg::S * Cfg::TILE;
+  uint8_t* W1 = A2 + Cfg::S * Cfg::TILE;
+  uint8_t* W2 = W1 + Cfg::S * Cfg::WCONV;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(W2 + Cfg::S * Cfg::WCONV);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y, L = p.L;
+  const int L = p.L;
   const int Rout = Cfg::R - 2 * p.d2;
-  const int t0 = blockIdx.x * Rout;  // first out2 row of this CTA
-  const int s0 = t0 - p.d2;          // out1 row held by A2 row DMAX (A2 has DMAX guard rows in front)
-  const int g1 = s0 - p.d1;          // in1 row held by A1 row 0
   const int rows1 = Cfg::R + 2 * p.d1;
-  const long boff = (long)b * L;
+  float* bias_s = reinterpret_cast<float*>(tslot + 2);  // [64]: bias1, bias2 (zeros when absent)
 
   if (warp == 0) tmem_alloc(tslot, 128);
   if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
-  pack_weights<TF32>(W1, p.w1, p.sj1, p.si1, p.so1, p.flip1);
-  pack_weights<TF32>(W2, p.w2, p.sj2, p.si2, p.so2, p.flip2);
+  pack_weights<MODE>(W1, p.w1, p.sj1, p.si1, p.so1, p.flip1);
+  pack_weights<MODE>(W2, p.w2, p.sj2, p.si2, p.so2, p.flip2);
+  if (tid < 64) bias_s[tid] = tid < 32 ? (p.bias1 ? p.bias1[tid] : 0.f) : (p.bias2 ? p.bias2[tid - 32] : 0.f);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tslot;
+
+  // persistent CTA: weights, TMEM and barriers are set up once; tiles are taken round-robin
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+  const int b = tile / p.tiles_x;
+  const int t0 = (tile - b * p.tiles_x) * Rout;  // first out2 row of this tile
+  const int s0 = t0 - p.d2;          // out1 row held by A2 row DMAX (A2 has DMAX guard rows in front)
+  const int g1 = s0 - p.d1;          // in1 row held by A1 row 0
+  const long boff = (long)b * L;
 
   // stage in1 rows [g1, g1 + rows1) as the A operand of stage 1 (zero outside [0, L): SAME padding)
   const float* inb = p.in1 + (size_t)boff * 32;
@@ -160,20 +213,15 @@ __global__ void __launch_bounds__(256, TF32 ? 2 : 3) rb_tc_kernel(const RbTcPara
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g >= 0 && g < L) v = *reinterpret_cast<const float4*>(inb + (size_t)g * 32 + q * 4);
     if (p.relu1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    if (TF32) {
-      *reinterpret_cast<float4*>(A1 + q * Cfg::PLANE + r * 16) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-    } else {
-      *reinterpret_cast<uint2*>(A1 + (q >> 1) * Cfg::PLANE + r * 16 + (q & 1) * 8) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-    }
+    stage4<MODE>(A1, r, q, v);
   }
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = *tslot;
 
   if (tid == 32) {
-    issue_stage<TF32>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1));
+    issue_stage<MODE>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1));
     commit(bar);
   }
   __syncwarp();
@@ -192,9 +240,10 @@ __global__ void __launch_bounds__(256, TF32 ? 2 : 3) rb_tc_kernel(const RbTcPara
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     tmem_ld16(taddr + half * 16, v);
-    if (p.bias1) {  // weights / biases are only assumed 4-byte aligned (they may be slices of a packed buffer)
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias1 + half * 16 + c);
+    for (int c = 0; c < 16; c += 4) {
+      const float4 bv = *reinterpret_cast<const float4*>(bias_s + half * 16 + c);
+      v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
     }
     if (p.mask1) {
       warp_load_rows(p.mask1, boff, s0 + i0, L, half, stg, lane, m);
@@ -207,19 +256,9 @@ __global__ void __launch_bounds__(256, TF32 ? 2 : 3) rb_tc_kernel(const RbTcPara
       float a = inrange ? v[c] : 0.f;  // rows outside [0, L) are conv2's zero padding
       v[c] = p.relu2 ? fmaxf(a, 0.f) : a;
     }
-    uint8_t* a2row = A2 + (Cfg::DMAX + i) * 16;
-    if (TF32) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<float4*>(a2row + (half * 4 + q) * Cfg::PLANE) =
-            make_float4(to_tf32(v[4 * q]), to_tf32(v[4 * q + 1]), to_tf32(v[4 * q + 2]), to_tf32(v[4 * q + 3]));
-    } else {
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-        *reinterpret_cast<uint4*>(a2row + (half * 2 + q) * Cfg::PLANE) =
-            make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                       pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-    }
+    for (int q = 0; q < 4; ++q)
+      stage4<MODE>(A2, Cfg::DMAX + i, half * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
   }
   fence_proxy_async();
   fence_before_sync();
@@ -228,7 +267,7 @@ __global__ void __launch_bounds__(256, TF32 ? 2 : 3) rb_tc_kernel(const RbTcPara
 
   if (tid == 32) {
     // out2 tile row i uses A2 rows DMAX + i + (j-1)*d2
-    issue_stage<TF32>(tmem + 64, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2));
+    issue_stage<MODE>(tmem + 64, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2));
     commit(bar);
   }
   __syncwarp();
@@ -239,9 +278,10 @@ __global__ void __launch_bounds__(256, TF32 ? 2 : 3) rb_tc_kernel(const RbTcPara
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     tmem_ld16(taddr + 64 + half * 16, v);
-    if (p.bias2) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias2 + half * 16 + c);
+    for (int c = 0; c < 16; c += 4) {
+      const float4 bv = *reinterpret_cast<const float4*>(bias_s + 32 + half * 16 + c);
+      v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
     }
     if (p.mask2) {
       warp_load_rows(p.mask2, boff, s0 + i0, L, half, stg, lane, m);
@@ -256,28 +296,49 @@ __global__ void __launch_bounds__(256, TF32 ? 2 : 3) rb_tc_kernel(const RbTcPara
     warp_store_rows(p.out2, boff, s0 + i0, L, half, i0, p.d2, Cfg::R - p.d2, stg, lane, v);
   }
   fence_before_sync();
-  __syncthreads();
+  __syncthreads();  // the staging area aliases A1: every warp is done before the next tile is staged
+  fence_after_sync();
+  }  // tile loop
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-template <bool TF32>
+template <int MODE>
 static int launch_rb(const RbTcParams& p, cudaStream_t st) {
-  using Cfg = RbCfg<TF32>;
+  using Cfg = RbCfg<MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    VQB_CUDA(cudaFuncSetAttribute(rb_tc_kernel<TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    VQB_CUDA(cudaFuncSetAttribute(rb_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set = true;
   }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    VQB_CUDA(cudaGetDevice(&dev));
+    VQB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  RbTcParams q = p;
   const int Rout = Cfg::R - 2 * p.d2;
-  dim3 grid(cdiv(p.L, Rout), p.B);
-  rb_tc_kernel<TF32><<<grid, 256, Cfg::SMEM, st>>>(p);
+  q.tiles_x = cdiv(p.L, Rout);
+  q.total_tiles = q.tiles_x * p.B;
+  const int grid = q.total_tiles < num_sms * Cfg::MINB ? q.total_tiles : num_sms * Cfg::MINB;
+  rb_tc_kernel<MODE><<<grid, 256, Cfg::SMEM, st>>>(q);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
 
+static int dispatch_rb(int precision, const RbTcParams& p, cudaStream_t st) {
+  switch (precision) {
+    case VQB_PREC_BF16: return launch_rb<0>(p, st);
+    case VQB_PREC_TF32: return launch_rb<1>(p, st);
+    case VQB_PREC_BF16X2: return launch_rb<2>(p, st);
+    case VQB_PREC_BF16X3: return launch_rb<3>(p, st);
+  }
+  return set_err(VQB_ERR_INVALID, "unknown precision %d", precision);
+}
+
 bool resblock_tc_supported(const vqb_resblock_desc* d) {
   return d->C == 32 && d->F == 32 && d->dilation >= 1 && d->dilation <= 32 &&
-         (d->precision == VQB_PREC_BF16 || d->precision == VQB_PREC_TF32);
+         d->precision >= VQB_PREC_TF32 && d->precision <= VQB_PREC_BF16X3;
 }
 
 int resblock_fwd_tc(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1, const float* w2,
@@ -291,7 +352,7 @@ int resblock_fwd_tc(const vqb_resblock_desc* d, const float* x, const float* w1,
   p.w1 = w1; p.bias1 = b1; p.sj1 = 32 * 32; p.si1 = 32; p.so1 = 1; p.flip1 = 0;   // B[n=co][k=ci] = W1[j][ci][co]
   p.w2 = w2; p.bias2 = b2; p.sj2 = 32 * 32; p.si2 = 32; p.so2 = 1; p.flip2 = 0;
   p.B = d->B; p.L = d->L; p.d1 = d->dilation; p.d2 = 1; p.relu1 = 1; p.relu2 = 1;
-  return d->precision == VQB_PREC_TF32 ? launch_rb<true>(p, st) : launch_rb<false>(p, st);
+  return dispatch_rb(d->precision, p, st);
 }
 
 int resblock_bwd_tc(const vqb_resblock_desc* d, const float* x, const float* h, const float* dy, const float* w1,
@@ -306,7 +367,7 @@ int resblock_bwd_tc(const vqb_resblock_desc* d, const float* x, const float* h, 
   // stage 2 = conv1^T with the block's dilation
   p.w2 = w1; p.sj2 = 32 * 32; p.si2 = 1; p.so2 = 32; p.flip2 = 1;
   p.B = d->B; p.L = d->L; p.d1 = 1; p.d2 = d->dilation; p.relu1 = 0; p.relu2 = 0;
-  return d->precision == VQB_PREC_TF32 ? launch_rb<true>(p, st) : launch_rb<false>(p, st);
+  return dispatch_rb(d->precision, p, st);
 }
 
 }  // namespace vqb

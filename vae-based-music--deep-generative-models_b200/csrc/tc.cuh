@@ -150,5 +150,13 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// x = p0 + p1 + p2 with every piece a bf16 (8 mantissa bits each: together the 24 bits of an fp32)
+template <int S>
+__device__ __forceinline__ void split_bf16(float x, float* pc) {
+  pc[0] = __bfloat162float(__float2bfloat16_rn(x));
+  if (S > 1) { pc[1] = __bfloat162float(__float2bfloat16_rn(x - pc[0])); }
+  if (S > 2) { pc[2] = __bfloat162float(__float2bfloat16_rn(x - pc[0] - pc[1])); }
+}
+
 }  // namespace tc
 }  // namespace vqb
