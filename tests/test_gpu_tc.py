@@ -89,3 +89,29 @@ def test_conv_wgrad_tc(gpu, prec, B, L, d, relu):
     dw2, db2 = ops.empty(3, 32, 32), ops.empty(32)
     ops.conv1d_wgrad(x.cuda(), dy.cuda(), dw2, db2, 1, d, bool(relu), P)
     assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+@pytest.mark.parametrize("N,K,kind", [(28160, 512, "normal"), (3520, 512, "init"), (1 << 16, 2048, "normal"), (4096, 512, "nearties"),
+                                      (440, 512, "normal"), (1000, 256, "normal"), (129, 1024, "normal")])
+def test_vq_search_tc_is_exact(gpu, N, K, kind):
+    """tcgen05 nearest-code search (bf16 MMA scores, exact fp32 re-evaluation of every code within the rounding margin):
+    same indices as the exact-fp32 kernel, and the fp64 index-parity rule holds."""
+    from tests.test_gpu_kernels import check_indices
+    ops = gpu.ops
+    rng = np.random.default_rng(N + K)
+    D = 64
+    x = rng.normal(size=(N, D)).astype(np.float32)
+    if kind == "init":
+        E = rng.uniform(-0.05, 0.05, size=(D, K)).astype(np.float32)
+    elif kind == "nearties":
+        E = (x[rng.integers(0, N, K)] + 1e-3 * rng.normal(size=(K, D))).T.astype(np.float32).copy()
+    else:
+        E = rng.normal(size=(D, K)).astype(np.float32)
+    idx0, _, _, loss0 = ops.vq_fwd(dev(x), dev(E), 0.25, True, True, None, None, 0)
+    m_batch, n_batch = ops.empty(D, K), ops.empty(K)
+    idx1, q_st, q, loss1 = ops.vq_fwd(dev(x), dev(E), 0.25, True, True, m_batch, n_batch, gpu._lib.PREC_BF16)
+    torch.cuda.synchronize()
+    check_indices(idx1, x, E)
+    assert int((idx0 != idx1).sum()) == 0
+    assert float(n_batch.sum()) == N and torch.equal(q.cpu(), torch.tensor(E).t()[idx1.cpu()])
+    assert float(loss0) == float(loss1)

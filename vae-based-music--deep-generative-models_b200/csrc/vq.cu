@@ -14,6 +14,7 @@ namespace vqb {
 int vq_search_tc(const vqb_vq_desc* d, const float* x, const float* E, const float* Et, const float* ee,
                  int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t vq_search_tc_workspace_bytes(const vqb_vq_desc* d);
+bool vq_search_tc_supported(const vqb_vq_desc* d);
 
 __global__ void vq_prep_kernel(const float* __restrict__ E, int D, int K, float* __restrict__ Et,
                                float* __restrict__ ee) {
@@ -320,7 +321,7 @@ size_t vqb_vq_fwd_workspace_bytes(const vqb_vq_desc* d) {
   if (!d || d->N < 0 || d->D <= 0 || d->K <= 0) return 0;
   size_t b = vq_base_ws_floats(d) * sizeof(float);
   b = (b + 1023) & ~(size_t)1023;
-  if (d->precision != VQB_PREC_FP32) b += vq_search_tc_workspace_bytes(d);
+  if (d->precision != VQB_PREC_FP32 && vq_search_tc_supported(d)) b += vq_search_tc_workspace_bytes(d);
   return b;
 }
 
@@ -349,7 +350,7 @@ int vqb_vq_fwd(const vqb_vq_desc* d, const float* x, const float* E, int64_t* id
     if (loss) VQB_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
     return VQB_OK;
   }
-  if (d->precision == VQB_PREC_FP32) {
+  if (d->precision == VQB_PREC_FP32 || !vq_search_tc_supported(d)) {  // shapes without a tensor-core kernel: exact fp32 search
     vq_search_kernel<<<cdiv(N, VQ_RT), 256, 0, st>>>(x, E, ee, N, D, K, idx);
     VQB_LAUNCH_CHECK();
   } else {

@@ -108,6 +108,8 @@ class VQVAE(Model):
             for l in m._flatten_layers():
                 if isinstance(l, ResnetConv1DBlock):
                     l.precision = code
+        for vq in self.vqs:
+            vq.precision = code  # tensor-core search + exact fp32 re-ranking (same indices as the fp32 search)
         self.precision = precision
         self._graphs = {}
         return self
