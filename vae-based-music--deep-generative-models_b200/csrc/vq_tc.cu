@@ -29,6 +29,7 @@ constexpr int VT_PLANE_A = VT_ROWS * 16 + 32;
 constexpr int VT_PLANE_B = VT_CHUNK * 16 + 32;
 constexpr int VT_CHUNK_BYTES = VT_NP * VT_PLANE_B;   // one packed 256-code chunk
 constexpr int VT_MAX_RESIDENT = 2;                   // chunks kept in shared memory (K <= 512)
+constexpr int VT_MAXC = 8;                           // candidate slots per latent
 
 struct VqTcParams {
   const float* x;       // [N, 64]
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(128, 2) vq_tc_kernel(const VqTcParams p) {
     // rigorous bound on |(approx score_a - approx score_b) - (exact ...)|: each score is off by <= 2^-7 |x||e|
     const float margin = 2.f * 0.0078125f * sqrtf(xx * ee_max) * 1.01f + 1e-30f;
     float run_min = INFINITY;     // running minimum of the approximate scores
-    float best = INFINITY;        // exact best distance so far
-    int best_k = 0;
+    int cand[VT_MAXC];            // codes within the margin of the running minimum (a superset of what the final minimum admits)
+    int ncand = 0;
 
 #pragma unroll 1
     for (int ch = 0; ch < p.nchunks; ++ch) {
@@ -161,32 +162,44 @@ __global__ void __launch_bounds__(128, 2) vq_tc_kernel(const VqTcParams p) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) run_min = fminf(run_min, fmaf(-2.f, v[c], eec[c0 + c]));
       }
-      // pass 2: exact evaluation of every code within the margin
+      // pass 2: remember every code within the margin (ascending code order)
       const float thr = run_min + margin;
 #pragma unroll 1
       for (int c0 = 0; c0 < VT_CHUNK; c0 += 32) {
         tmem_ld32(taddr + c0, v);
-        uint32_t cand = 0;
+        uint32_t m = 0;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) cand |= (fmaf(-2.f, v[c], eec[c0 + c]) <= thr ? 1u : 0u) << c;
-        if (!valid) cand = 0;
-        while (cand) {
-          const int c = __ffs(cand) - 1;
-          cand &= cand - 1;
-          const int k = ch * VT_CHUNK + c0 + c;
-          const float* er = p.Et + (size_t)k * VT_D;
-          float acc = 0.f;
-#pragma unroll
-          for (int q = 0; q < VT_D / 4; ++q) {
-            const float4 e = *reinterpret_cast<const float4*>(er + q * 4);
-            acc = fmaf(xr[4 * q], e.x, acc); acc = fmaf(xr[4 * q + 1], e.y, acc);
-            acc = fmaf(xr[4 * q + 2], e.z, acc); acc = fmaf(xr[4 * q + 3], e.w, acc);
-          }
-          const float dist = __fsub_rn(__fadd_rn(xx, eec[c0 + c]), 2.f * acc);  // VectorQuantizer.py:175-182 op order
-          if (dist < best) { best = dist; best_k = k; }                        // codes are visited in ascending order
+        for (int c = 0; c < 32; ++c) m |= (fmaf(-2.f, v[c], eec[c0 + c]) <= thr ? 1u : 0u) << c;
+        while (m) {
+          const int c = __ffs(m) - 1;
+          m &= m - 1;
+          if (ncand < VT_MAXC) cand[ncand] = ch * VT_CHUNK + c0 + c;
+          ++ncand;
         }
       }
       fence_before_sync();
+    }
+    // exact fp32 evaluation (VectorQuantizer.py:175-182 op order, sequential FMAs as in vq_search_kernel).  A single
+    // candidate needs none: the exact argmin is always inside the margin set.
+    int best_k = cand[0];
+    if (valid && ncand > 1) {
+      float best = INFINITY;
+      const bool overflow = ncand > VT_MAXC;        // rare: more candidates than slots -> exact scan of every code
+      const int cnt = overflow ? p.K : ncand;
+#pragma unroll 1
+      for (int ci = 0; ci < cnt; ++ci) {
+        const int k = overflow ? ci : cand[ci];
+        const float* er = p.Et + (size_t)k * VT_D;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < VT_D / 4; ++q) {
+          const float4 e = *reinterpret_cast<const float4*>(er + q * 4);
+          acc = fmaf(xr[4 * q], e.x, acc); acc = fmaf(xr[4 * q + 1], e.y, acc);
+          acc = fmaf(xr[4 * q + 2], e.z, acc); acc = fmaf(xr[4 * q + 3], e.w, acc);
+        }
+        const float dist = __fsub_rn(__fadd_rn(xx, ee_s[k]), 2.f * acc);
+        if (dist < best) { best = dist; best_k = k; }   // candidates are in ascending code order: first minimum wins
+      }
     }
     if (valid) p.idx[n] = best_k;
   }
