@@ -170,6 +170,53 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
   if (threadIdx.x == 0) loss_partial[blockIdx.x] = s;
 }
 
+// Shared-memory privatised variant (K*D + K floats fit one CTA's shared memory, e.g. 512 x 64): persistent CTAs of 1024
+// threads accumulate the per-code sums of their slab of rows with SHARED-memory reductions and write one [K, D] partial
+// each; the partials are reduced in a fixed order.  No global atomics at all.
+constexpr int VQ_FS_THREADS = 1024;
+__global__ void __launch_bounds__(VQ_FS_THREADS, 1) vq_finish_smem_kernel(
+    const float* __restrict__ x, const float* __restrict__ Et, const int64_t* __restrict__ idx, long N, int D, int K,
+    float* __restrict__ q_st, float* __restrict__ q, int stats, float* __restrict__ partial_kd,
+    float* __restrict__ partial_n, float* __restrict__ loss_partial) {
+  extern __shared__ __align__(16) float fsm[];  // [K*D] sums, [K] counts
+  __shared__ float red[32];
+  float* sm_n = fsm + (size_t)K * D;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (stats) {
+    for (int e = tid; e < K * D + K; e += VQ_FS_THREADS) fsm[e] = 0.f;
+    __syncthreads();
+  }
+  const long per = (N + gridDim.x - 1) / gridDim.x;
+  const long r0 = (long)blockIdx.x * per, r1 = min(N, r0 + per);
+  const int hl = lane & 15, hw = lane >> 4;  // half-warp per row: 16 lanes x float4 = 64 channels per pass
+  float ls = 0.f;
+  for (long n = r0 + wid * 2 + hw; n < r1; n += (VQ_FS_THREADS / 32) * 2) {
+    const int k = (int)idx[n];
+    for (int d = hl * 4; d < D; d += 64) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + n * D + d);
+      const float4 qv = *reinterpret_cast<const float4*>(Et + (size_t)k * D + d);
+      const float4 df = make_float4(__fsub_rn(qv.x, xv.x), __fsub_rn(qv.y, xv.y), __fsub_rn(qv.z, xv.z), __fsub_rn(qv.w, xv.w));
+      if (q) *reinterpret_cast<float4*>(q + n * D + d) = qv;
+      if (q_st) *reinterpret_cast<float4*>(q_st + n * D + d) =
+          make_float4(__fadd_rn(xv.x, df.x), __fadd_rn(xv.y, df.y), __fadd_rn(xv.z, df.z), __fadd_rn(xv.w, df.w));
+      ls = fmaf(df.x, df.x, ls); ls = fmaf(df.y, df.y, ls); ls = fmaf(df.z, df.z, ls); ls = fmaf(df.w, df.w, ls);
+      if (stats) {
+        float* a = fsm + (size_t)k * D + d;
+        atomicAdd(a, xv.x); atomicAdd(a + 1, xv.y); atomicAdd(a + 2, xv.z); atomicAdd(a + 3, xv.w);
+      }
+    }
+    if (stats && hl == 0) atomicAdd(&sm_n[k], 1.0f);
+  }
+  const float s = block_sum(ls, red);
+  if (tid == 0) loss_partial[blockIdx.x] = s;
+  if (stats) {
+    __syncthreads();
+    float* pk = partial_kd + (size_t)blockIdx.x * K * D;
+    for (int e = tid; e < K * D; e += VQ_FS_THREADS) pk[e] = fsm[e];
+    for (int e = tid; e < K; e += VQ_FS_THREADS) partial_n[(size_t)blockIdx.x * K + e] = sm_n[e];
+  }
+}
+
 // m_batch[d, k] = m_kd[k, d]
 __global__ void vq_stats_transpose_kernel(const float* __restrict__ m_kd, int D, int K, float* __restrict__ m_batch) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -340,9 +387,15 @@ extern "C" {
 
 size_t vqb_reduce_workspace_bytes(int64_t n) { return (size_t)cdiv(n, 2048) * sizeof(float) + 16; }
 
+constexpr int VQ_FS_GRID = 148;
+static bool vq_finish_smem_ok(const vqb_vq_desc* d) {
+  return (d->D & 3) == 0 && ((size_t)d->K * d->D + d->K) * sizeof(float) <= 200 * 1024 && d->N >= 4096;
+}
 static size_t vq_base_ws_floats(const vqb_vq_desc* d) {
-  const size_t nfin = (size_t)cdiv(d->N, 8 * VQ_FR);
-  return 2 * (size_t)d->K * d->D + d->K + nfin + 64;  // Et, code-major statistics scratch, ee, loss partials
+  const size_t nfin = (size_t)cdiv(d->N, 8 * VQ_FR) + VQ_FS_GRID;
+  size_t n = 2 * (size_t)d->K * d->D + d->K + nfin + 64;  // Et, code-major statistics scratch, ee, loss partials
+  if (vq_finish_smem_ok(d)) n += (size_t)VQ_FS_GRID * ((size_t)d->K * d->D + d->K);  // per-CTA partial sums / counts
+  return n;
 }
 
 size_t vqb_vq_fwd_workspace_bytes(const vqb_vq_desc* d) {
@@ -387,9 +440,29 @@ int vqb_vq_fwd(const vqb_vq_desc* d, const float* x, const float* E, int64_t* id
     int rc = vq_search_tc(d, x, E, Et, ee, idx, (char*)workspace + off, workspace_bytes - off, st);
     if (rc != VQB_OK) return rc;
   }
-  const int nfin = cdiv(N, 8 * VQ_FR);
-  vq_finish_kernel<<<nfin, 256, 0, st>>>(x, Et, idx, N, D, K, q_st, q, m_batch ? m_kd : nullptr, n_batch, part);
-  VQB_LAUNCH_CHECK();
+  int nfin = cdiv(N, 8 * VQ_FR);
+  if (vq_finish_smem_ok(d)) {
+    nfin = VQ_FS_GRID;
+    float* pkd = part + cdiv(N, 8 * VQ_FR) + VQ_FS_GRID;
+    float* pn = pkd + (size_t)VQ_FS_GRID * K * D;
+    const size_t smem = ((size_t)K * D + K) * sizeof(float);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      VQB_CUDA(cudaFuncSetAttribute(vq_finish_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    vq_finish_smem_kernel<<<VQ_FS_GRID, VQ_FS_THREADS, smem, st>>>(x, Et, idx, N, D, K, q_st, q, m_batch ? 1 : 0, pkd, pn, part);
+    VQB_LAUNCH_CHECK();
+    if (m_batch) {
+      reduce_chunks_strided(pkd, VQ_FS_GRID, (long)K * D, 0, K * D, m_kd, st);
+      VQB_LAUNCH_CHECK();
+      reduce_chunks_strided(pn, VQ_FS_GRID, K, 0, K, n_batch, st);
+      VQB_LAUNCH_CHECK();
+    }
+  } else {
+    vq_finish_kernel<<<nfin, 256, 0, st>>>(x, Et, idx, N, D, K, q_st, q, m_batch ? m_kd : nullptr, n_batch, part);
+    VQB_LAUNCH_CHECK();
+  }
   if (m_batch) {
     vq_stats_transpose_kernel<<<cdiv((long)D * K, 256), 256, 0, st>>>(m_kd, D, K, m_batch);
     VQB_LAUNCH_CHECK();

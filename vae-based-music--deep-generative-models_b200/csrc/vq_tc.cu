@@ -29,7 +29,7 @@ constexpr int VT_PLANE_A = VT_ROWS * 16 + 32;
 constexpr int VT_PLANE_B = VT_CHUNK * 16 + 32;
 constexpr int VT_CHUNK_BYTES = VT_NP * VT_PLANE_B;   // one packed 256-code chunk
 constexpr int VT_MAX_RESIDENT = 2;                   // chunks kept in shared memory (K <= 512)
-constexpr int VT_MAXC = 8;                           // candidate slots per latent
+constexpr int VT_MAXC = 12;                          // candidate slots per latent
 
 struct VqTcParams {
   const float* x;       // [N, 64]
@@ -127,7 +127,9 @@ __global__ void __launch_bounds__(128, 2) vq_tc_kernel(const VqTcParams p) {
     const float margin = 2.f * 0.0078125f * sqrtf(xx * ee_max) * 1.01f + 1e-30f;
     float run_min = INFINITY;     // running minimum of the approximate scores
     int cand[VT_MAXC];            // codes within the margin of the running minimum (a superset of what the final minimum admits)
+    float cscore[VT_MAXC];        // their approximate scores (to drop the ones a later, lower minimum rules out)
     int ncand = 0;
+    bool overflow = false;
 
 #pragma unroll 1
     for (int ch = 0; ch < p.nchunks; ++ch) {
@@ -173,19 +175,38 @@ __global__ void __launch_bounds__(128, 2) vq_tc_kernel(const VqTcParams p) {
         while (m) {
           const int c = __ffs(m) - 1;
           m &= m - 1;
-          if (ncand < VT_MAXC) cand[ncand] = ch * VT_CHUNK + c0 + c;
-          ++ncand;
+          if (ncand == VT_MAXC) {  // full: drop the entries the current (lower) minimum has ruled out, keeping code order
+            int w = 0;
+#pragma unroll
+            for (int i = 0; i < VT_MAXC; ++i)
+              if (cscore[i] <= thr) { cand[w] = cand[i]; cscore[w] = cscore[i]; ++w; }
+            ncand = w;
+          }
+          if (ncand < VT_MAXC) {
+            cand[ncand] = ch * VT_CHUNK + c0 + c;
+            cscore[ncand] = fmaf(-2.f, v[c], eec[c0 + c]);
+            ++ncand;
+          } else {
+            overflow = true;
+          }
         }
       }
       fence_before_sync();
     }
+    if (!overflow) {  // final pruning with the final minimum
+      const float thr = run_min + margin;
+      int w = 0;
+#pragma unroll
+      for (int i = 0; i < VT_MAXC; ++i)
+        if (i < ncand && cscore[i] <= thr) { cand[w] = cand[i]; ++w; }
+      ncand = w;
+    }
     // exact fp32 evaluation (VectorQuantizer.py:175-182 op order, sequential FMAs as in vq_search_kernel).  A single
     // candidate needs none: the exact argmin is always inside the margin set.
     int best_k = cand[0];
-    if (valid && ncand > 1) {
+    if (valid && (ncand > 1 || overflow)) {
       float best = INFINITY;
-      const bool overflow = ncand > VT_MAXC;        // rare: more candidates than slots -> exact scan of every code
-      const int cnt = overflow ? p.K : ncand;
+      const int cnt = overflow ? p.K : ncand;       // overflow (rare): more candidates than slots -> exact scan of every code
 #pragma unroll 1
       for (int ci = 0; ci < cnt; ++ci) {
         const int k = overflow ? ci : cand[ci];
