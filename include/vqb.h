@@ -90,6 +90,13 @@ size_t vqb_conv1d_wgrad_workspace_bytes(const vqb_conv_desc* d);
 int vqb_conv1d_wgrad(const vqb_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Optional batching of the weight-gradient reductions: between vqb_reduce_begin() and vqb_reduce_flush(stream) (same host
+ * thread) the *_wgrad calls only enqueue their partial-sum kernels and leave dw / dbias UNWRITTEN; vqb_reduce_flush launches
+ * all pending fixed-order reductions as a few batched kernels.  Workspaces passed to those calls must stay alive until the
+ * flush.  Without begin/flush every *_wgrad call is self-contained. */
+int vqb_reduce_begin(void);
+int vqb_reduce_flush(void* stream);
+
 /* y[B, L*stride, C_out] = convT(x) + bias ; w is [k, C_out, C_in] */
 int vqb_conv1d_transpose_fwd(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
                              float* y, void* stream);

@@ -58,6 +58,12 @@ class FakeBackend:
     def _act(x, d):
         return torch.relu(x) if d.relu_in else x
 
+    def vqb_reduce_begin(self):
+        return 0
+
+    def vqb_reduce_flush(self, stream):
+        return 0
+
     def vqb_conv1d_supports(self, dref, op):
         return 1
 

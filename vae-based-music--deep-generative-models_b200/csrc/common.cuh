@@ -47,6 +47,8 @@ void count_launch();
 
 // fixed-order reduction of per-chunk partial sums (conv_fp32.cu)
 void reduce_chunks_strided(const float* partial, int nchunk, long stride, int offset, int n, float* out, cudaStream_t st);
+void reduce_begin();
+int reduce_flush(cudaStream_t st);
 // tensor-core weight gradient (wgrad_tc.cu)
 bool wgrad_tc_supported(const vqb_conv_desc* d);
 size_t wgrad_tc_workspace_bytes(const vqb_conv_desc* d);

@@ -10,6 +10,8 @@
 //   Conv1DTranspose data grad Conv1D-forward form over dy
 // so one kernel (tgc_kernel) serves all four; tgc_narrow_kernel covers C_out <= 4 (the final 64->1 conv),
 // wgrad_kernel the weight gradients (split over time chunks, reduced in a fixed order => deterministic).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vqb {
@@ -373,9 +375,86 @@ __global__ void __launch_bounds__(256) reduce_chunks_kernel(const float* __restr
   }
 }
 
+// ---- deferred / batched reductions -------------------------------------------------------------------------
+// Between vqb_reduce_begin() and vqb_reduce_flush() the fixed-order reductions requested by the weight-gradient entry
+// points are queued (thread-local) instead of launched, and flushed as a few batched kernels: a training step has
+// ~480 of them (kernel + bias per convolution), each only a few microseconds of work.
+constexpr int RB_ITEMS = 64;
+struct ReduceItem {
+  const float* partial;
+  float* out;
+  int nchunk, stride, offset, n, block0;
+};
+struct ReduceBatch {
+  ReduceItem it[RB_ITEMS];
+  int n_items;
+};
+
+__global__ void __launch_bounds__(256) reduce_batched_kernel(const ReduceBatch b) {
+  __shared__ float red[8][33];
+  int lo = 0, hi = b.n_items - 1;  // last item whose block0 <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (b.it[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const ReduceItem& t = b.it[lo];
+  const int ex = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int e = ((int)blockIdx.x - t.block0) * 32 + ex;
+  float s = 0.f;
+  if (e < t.n)
+    for (int c = ly; c < t.nchunk; c += 8) s += t.partial[(size_t)c * t.stride + t.offset + e];
+  red[ly][ex] = s;
+  __syncthreads();
+  if (ly == 0 && e < t.n) {
+    float v = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) v += red[l][ex];
+    t.out[e] = v;
+  }
+}
+
+struct ReduceQueue {
+  bool active = false;
+  int n = 0, cap = 0;
+  ReduceItem* items = nullptr;
+};
+static thread_local ReduceQueue g_rq;
+
 void reduce_chunks_strided(const float* partial, int nchunk, long stride, int offset, int n, float* out, cudaStream_t st) {
+  if (g_rq.active) {
+    if (g_rq.n == g_rq.cap) {
+      g_rq.cap = g_rq.cap ? 2 * g_rq.cap : 1024;
+      g_rq.items = (ReduceItem*)realloc(g_rq.items, sizeof(ReduceItem) * g_rq.cap);
+    }
+    g_rq.items[g_rq.n++] = ReduceItem{partial, out, nchunk, (int)stride, offset, n, 0};
+    return;
+  }
   reduce_chunks_kernel<<<cdiv(n, 32), 256, 0, st>>>(partial, nchunk, stride, offset, n, out);
 }
+
+int reduce_flush(cudaStream_t st) {
+  int i = 0;
+  while (i < g_rq.n) {
+    ReduceBatch b;
+    int blocks = 0, k = 0;
+    for (; k < RB_ITEMS && i + k < g_rq.n; ++k) {
+      b.it[k] = g_rq.items[i + k];
+      b.it[k].block0 = blocks;
+      blocks += cdiv(b.it[k].n, 32);
+    }
+    b.n_items = k;
+    if (blocks > 0) {
+      reduce_batched_kernel<<<blocks, 256, 0, st>>>(b);
+      VQB_LAUNCH_CHECK();
+    }
+    i += k;
+  }
+  g_rq.n = 0;
+  g_rq.active = false;
+  return VQB_OK;
+}
+
+void reduce_begin() { g_rq.active = true; g_rq.n = 0; }
 
 // column sums of a [rows, C] matrix (Conv1DTranspose bias gradient): partial[block][c]
 constexpr int COLSUM_ROWS = 2048;
@@ -587,6 +666,16 @@ int conv1d_transpose_dgrad_fp32(const vqb_conv_desc* d, const float* dy, const f
 using namespace vqb;
 
 extern "C" {
+
+int vqb_reduce_begin(void) {
+  reduce_begin();
+  return VQB_OK;
+}
+
+int vqb_reduce_flush(void* stream) {
+  VQB_ARCH();
+  return reduce_flush((cudaStream_t)stream);
+}
 
 int vqb_conv1d_fwd(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
                    const float* residual, float* y, void* stream) {

@@ -44,19 +44,23 @@ struct RbCfg {
   static constexpr bool TF32 = MODE == 1;
   static constexpr int S = MODE == 2 ? 2 : MODE == 3 ? 3 : 1;  // bf16 pieces per operand
   static constexpr int R = 256;     // stage-1 rows per CTA (2 x M128)
-  static constexpr int DMAX = 32;   // largest supported dilation
+  static constexpr bool ALIAS = MODE == 3;           // A2 reuses A1's memory (A1 is dead once the stage-1 MMAs completed)
+  static constexpr int DMAX = MODE == 3 ? 28 : 32;   // largest supported dilation (guard rows of the operand tiles)
   static constexpr int C = 32;
   static constexpr int ES = TF32 ? 4 : 2;
   static constexpr int T = 16 / ES;
   static constexpr int NP = C / T;          // planes per operand tile
   static constexpr int KSTEPS = NP / 2;     // one MMA consumes 32 bytes of K = 2 planes
   static constexpr int PLANE = (R + 2 * DMAX) * 16 + (TF32 ? 16 : 32);  // bytes; padding de-aliases the planes' banks
-  static constexpr int WPLANE = 32 * 16;
+  static constexpr int NW = S * 32;         // MMA N: the S bf16 pieces of the weights are stacked along N
+  static constexpr int WPLANE = NW * 16;
   static constexpr int WTAP = NP * WPLANE;
   static constexpr int WCONV = 3 * WTAP;
   static constexpr int TILE = NP * PLANE;   // one operand tile (one split piece)
-  static constexpr int SMEM = 2 * S * TILE + 2 * S * WCONV + 64 + 256;
-  static constexpr int MINB = MODE == 0 ? 3 : MODE == 3 ? 1 : 2;  // CTAs per SM the shared-memory footprint allows
+  static constexpr int STG = ALIAS ? 8 * 2048 : 0;  // dedicated row-staging area when A1 cannot be reused for it
+  static constexpr int SMEM = (ALIAS ? 1 : 2) * S * TILE + 2 * WCONV + STG + 64 + 256;
+  static constexpr int TCOLS = 2 * NW <= 64 ? 64 : 2 * NW <= 128 ? 128 : 256;  // TMEM columns (2 M blocks x NW)
+  static constexpr int MINB = MODE == 0 ? 3 : 2;  // CTAs per SM the shared-memory footprint allows
 };
 
 template <int MODE>
@@ -73,38 +77,34 @@ __device__ __forceinline__ void pack_weights(uint8_t* dst, const float* __restri
       float pc[3];
       split_bf16<Cfg::S>(v, pc);
 #pragma unroll
-      for (int s = 0; s < Cfg::S; ++s) *reinterpret_cast<__nv_bfloat16*>(a + s * Cfg::WCONV) = __float2bfloat16_rn(pc[s]);
+      for (int s = 0; s < Cfg::S; ++s) *reinterpret_cast<__nv_bfloat16*>(a + s * 32 * 16) = __float2bfloat16_rn(pc[s]);  // row s*32 + n
     }
   }
 }
 
-// 3 taps x KSTEPS accumulating MMAs (x the operand-piece pairs of the split modes) for both M blocks of one stage,
-// issued by a single thread
+// 3 taps x KSTEPS x S accumulating MMAs for both M blocks of one stage, issued by a single thread.  In the split modes
+// the S weight pieces are stacked along N (N = 32 S) and every activation piece is multiplied with all of them into the
+// SAME accumulator: column block c then holds a . W_c, and the epilogue adds the S column blocks.  (All S*S piece
+// products are formed — the extra ones beyond the 2^-16 terms are real, smaller terms of the exact product.)
 template <int MODE>
 __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int row_shift0, int dil, uint32_t w_base) {
   using Cfg = RbCfg<MODE>;
-  const uint32_t idesc = instr_desc(Cfg::TF32 ? FMT_TF32 : FMT_BF16, 128, 32, false, false);
+  const uint32_t idesc = instr_desc(Cfg::TF32 ? FMT_TF32 : FMT_BF16, 128, Cfg::NW, false, false);
+  uint32_t acc = 0;
 #pragma unroll
-  for (int mb = 0; mb < 2; ++mb) {
-    uint32_t first = 1;
+  for (int j = 0; j < 3; ++j)
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
+    for (int kk = 0; kk < Cfg::KSTEPS; ++kk)
 #pragma unroll
-      for (int kk = 0; kk < Cfg::KSTEPS; ++kk) {
-        const uint32_t a = a_base + (uint32_t)((mb * 128 + row_shift0 + j * dil) * 16) + kk * 2 * Cfg::PLANE;
-        const uint32_t b = w_base + j * Cfg::WTAP + kk * 2 * Cfg::WPLANE;
-        // pieces (sa, sw) with sa + sw < S, smallest contributions first
+      for (int sa = Cfg::S - 1; sa >= 0; --sa) {
+        const uint64_t bd = smem_desc(w_base + j * Cfg::WTAP + kk * 2 * Cfg::WPLANE, Cfg::WPLANE, 128);
 #pragma unroll
-        for (int lvl = Cfg::S - 1; lvl >= 0; --lvl)
-#pragma unroll
-          for (int sa = 0; sa <= lvl; ++sa) {
-            const int sw = lvl - sa;
-            mma<Cfg::TF32>(tmem + mb * 32, smem_desc(a + sa * Cfg::TILE, Cfg::PLANE, 128),
-                           smem_desc(b + sw * Cfg::WCONV, Cfg::WPLANE, 128), idesc, first ? 0u : 1u);
-            first = 0;
-          }
+        for (int mb = 0; mb < 2; ++mb) {  // the two M blocks alternate: two independent accumulator chains in flight
+          const uint32_t a = a_base + sa * Cfg::TILE + (uint32_t)((mb * 128 + row_shift0 + j * dil) * 16) + kk * 2 * Cfg::PLANE;
+          mma<Cfg::TF32>(tmem + mb * Cfg::NW, smem_desc(a, Cfg::PLANE, 128), bd, idesc, acc);
+        }
+        acc = 1;
       }
-  }
 }
 
 // one float4 (4 channels q*4..q*4+3 of row r) -> operand tile(s)
@@ -174,10 +174,11 @@ __global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbT
   constexpr bool TF32 = Cfg::TF32;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* A1 = smem;
-  uint8_t* A2 = A1 + Cfg::S * Cfg::TILE;
+  uint8_t* A2 = Cfg::ALIAS ? A1 : A1 + Cfg::S * Cfg::TILE;
   uint8_t* W1 = A2 + Cfg::S * Cfg::TILE;
-  uint8_t* W2 = W1 + Cfg::S * Cfg::WCONV;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(W2 + Cfg::S * Cfg::WCONV);
+  uint8_t* W2 = W1 + Cfg::WCONV;
+  uint8_t* stg_base = Cfg::ALIAS ? W2 + Cfg::WCONV : A1;  // row staging: A1 is dead during the epilogues unless it is A2
+  uint64_t* bar = reinterpret_cast<uint64_t*>(W2 + Cfg::WCONV + Cfg::STG);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbT
   const int rows1 = Cfg::R + 2 * p.d1;
   float* bias_s = reinterpret_cast<float*>(tslot + 2);  // [64]: bias1, bias2 (zeros when absent)
 
-  if (warp == 0) tmem_alloc(tslot, 128);
+  if (warp == 0) tmem_alloc(tslot, Cfg::TCOLS);
   if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
   pack_weights<MODE>(W1, p.w1, p.sj1, p.si1, p.so1, p.flip1);
   pack_weights<MODE>(W2, p.w2, p.sj2, p.si2, p.so2, p.flip2);
@@ -230,8 +231,8 @@ __global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbT
   const int i = i0 + lane;                             // tile row (= TMEM lane) of this thread
   const int g = s0 + i;                                // global row
   const bool inrange = g >= 0 && g < L;
-  const uint32_t taddr = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 32u;
-  uint8_t* stg = A1 + warp * 2048;  // the A1 tile is dead once the stage-1 MMAs have completed: reuse it for row staging
+  const uint32_t taddr = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * Cfg::NW;
+  uint8_t* stg = stg_base + warp * 2048;
   float v[16], m[16];
 
   // ---- epilogue 1: TMEM -> (+bias, mask) -> out1 (global, owned rows) and act2(out1) -> A2 (shared)
@@ -240,6 +241,12 @@ __global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbT
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     tmem_ld16(taddr + half * 16, v);
+#pragma unroll
+    for (int sp = 1; sp < Cfg::S; ++sp) {  // split modes: add the column blocks of the other weight pieces
+      tmem_ld16(taddr + sp * 32 + half * 16, m);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] += m[c];
+    }
 #pragma unroll
     for (int c = 0; c < 16; c += 4) {
       const float4 bv = *reinterpret_cast<const float4*>(bias_s + half * 16 + c);
@@ -267,7 +274,7 @@ __global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbT
 
   if (tid == 32) {
     // out2 tile row i uses A2 rows DMAX + i + (j-1)*d2
-    issue_stage<MODE>(tmem + 64, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2));
+    issue_stage<MODE>(tmem, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2));  // same TMEM columns: epilogue 1 has drained them
     commit(bar);
   }
   __syncwarp();
@@ -277,7 +284,13 @@ __global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbT
   fence_after_sync();
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
-    tmem_ld16(taddr + 64 + half * 16, v);
+    tmem_ld16(taddr + half * 16, v);
+#pragma unroll
+    for (int sp = 1; sp < Cfg::S; ++sp) {
+      tmem_ld16(taddr + sp * 32 + half * 16, m);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] += m[c];
+    }
 #pragma unroll
     for (int c = 0; c < 16; c += 4) {
       const float4 bv = *reinterpret_cast<const float4*>(bias_s + 32 + half * 16 + c);
@@ -299,7 +312,7 @@ __global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbT
   __syncthreads();  // the staging area aliases A1: every warp is done before the next tile is staged
   fence_after_sync();
   }  // tile loop
-  if (warp == 0) tmem_dealloc(tmem, 128);
+  if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
 template <int MODE>
@@ -337,7 +350,7 @@ static int dispatch_rb(int precision, const RbTcParams& p, cudaStream_t st) {
 }
 
 bool resblock_tc_supported(const vqb_resblock_desc* d) {
-  return d->C == 32 && d->F == 32 && d->dilation >= 1 && d->dilation <= 32 &&
+  return d->C == 32 && d->F == 32 && d->dilation >= 1 && d->dilation <= (d->precision == VQB_PREC_BF16X3 ? 28 : 32) &&
          d->precision >= VQB_PREC_TF32 && d->precision <= VQB_PREC_BF16X3;
 }
 

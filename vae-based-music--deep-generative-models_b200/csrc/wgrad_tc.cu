@@ -121,21 +121,21 @@ __global__ void __launch_bounds__(256, WgCfg<S>::MINB) wgrad_tc_kernel(const WgT
       fence_after_sync();
       const uint32_t a0 = smem_u32(At), b0 = smem_u32(Bt);
       uint32_t acc = it != 0;
+      // The S pieces of dy are consecutive plane groups of the A tile, i.e. consecutive 32-row blocks of ONE M = 128
+      // operand: a single MMA multiplies all of them with one piece of act(x); accumulator row block r then holds
+      // dy_r^T act(x) summed over the x pieces, and the epilogue adds the S row blocks.
 #pragma unroll 1
       for (int ks = 0; ks < Cfg::TK / Cfg::KMMA; ++ks) {
+        const uint64_t ad = smem_desc(a0 + ks * Cfg::KMMA * 16, 128, Cfg::PLANE_A);
 #pragma unroll
-        for (int lvl = S - 1; lvl >= 0; --lvl)
-#pragma unroll
-          for (int sa = 0; sa <= lvl; ++sa) {
-            const int sb = lvl - sa;
-            const uint64_t ad = smem_desc(a0 + sa * Cfg::TILE_A + ks * Cfg::KMMA * 16, 128, Cfg::PLANE_A);
-            const uint32_t bb = b0 + sb * Cfg::TILE_B + (ks * Cfg::KMMA) * 16;
-            // tap j reads act(x) rows t + (j-1)*dil = B-tile rows ks*KMMA + j*dil
-            mma<false>(tmem + 0, ad, smem_desc(bb, 128, Cfg::PLANE_B), idesc32, acc);
-            mma<false>(tmem + 32, ad, smem_desc(bb + p.dil * 16, 128, Cfg::PLANE_B), idesc48, acc);
-            mma<false>(tmem + 80, ad, smem_desc(bb + 2 * p.dil * 16, 128, Cfg::PLANE_B), idesc32, acc);
-            acc = 1;
-          }
+        for (int sb = S - 1; sb >= 0; --sb) {
+          const uint32_t bb = b0 + sb * Cfg::TILE_B + (ks * Cfg::KMMA) * 16;
+          // tap j reads act(x) rows t + (j-1)*dil = B-tile rows ks*KMMA + j*dil
+          mma<false>(tmem + 0, ad, smem_desc(bb, 128, Cfg::PLANE_B), idesc32, acc);
+          mma<false>(tmem + 32, ad, smem_desc(bb + p.dil * 16, 128, Cfg::PLANE_B), idesc48, acc);
+          mma<false>(tmem + 80, ad, smem_desc(bb + 2 * p.dil * 16, 128, Cfg::PLANE_B), idesc32, acc);
+          acc = 1;
+        }
       }
       commit(&bars[buf]);
     }
@@ -149,20 +149,31 @@ __global__ void __launch_bounds__(256, WgCfg<S>::MINB) wgrad_tc_kernel(const WgT
   } else {
     mbar_wait(&bars[2], 0);
     fence_after_sync();
-    if (warp == 0) {  // accumulator rows 0..31 = output channel co = lane
+    float* red = reinterpret_cast<float*>(smem);  // [S][PART]: the operand tiles are dead now
+    if (warp < S) {  // accumulator rows 32*warp .. +31 = output channel co = lane, for dy piece `warp`
       float v[32];
-      const int co = tid;
-      tmem_ld32(tmem + 0, v);
+      const int co = tid & 31;
+      float* r = red + warp * Cfg::PART;
+      const uint32_t ta = tmem + (((uint32_t)warp * 32u) << 16);
+      tmem_ld32(ta + 0, v);
 #pragma unroll
-      for (int n = 0; n < 32; ++n) out[(0 * 32 + n) * 32 + co] = v[n];
-      tmem_ld32(tmem + 32, v);
+      for (int n = 0; n < 32; ++n) r[(0 * 32 + n) * 32 + co] = v[n];
+      tmem_ld32(ta + 32, v);
 #pragma unroll
-      for (int n = 0; n < 32; ++n) out[(1 * 32 + n) * 32 + co] = v[n];
-      tmem_ld32(tmem + 80, v);
+      for (int n = 0; n < 32; ++n) r[(1 * 32 + n) * 32 + co] = v[n];
+      tmem_ld32(ta + 80, v);
 #pragma unroll
-      for (int n = 0; n < 32; ++n) out[(2 * 32 + n) * 32 + co] = v[n];
-      tmem_ld32(tmem + 64, v);  // column 64 = centre tap's column 32 = bias gradient
-      out[3 * 32 * 32 + co] = v[0];
+      for (int n = 0; n < 32; ++n) r[(2 * 32 + n) * 32 + co] = v[n];
+      tmem_ld32(ta + 64, v);  // column 64 = centre tap's column 32 = bias gradient
+      r[3 * 32 * 32 + co] = v[0];
+    }
+    fence_before_sync();
+    __syncthreads();
+    for (int e = tid; e < Cfg::PART; e += 256) {
+      float t = red[e];
+#pragma unroll
+      for (int w = 1; w < S; ++w) t += red[w * Cfg::PART + e];
+      out[e] = t;
     }
   }
   fence_before_sync();

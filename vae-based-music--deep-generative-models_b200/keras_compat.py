@@ -199,6 +199,14 @@ class GradientTape:
         produced = {id(o) for n in self.nodes for o in n.outputs}
         for v in sources:
             v._grad_written = False
+        ops.reduce_begin()  # the ~480 per-variable partial-sum reductions of one backward pass are flushed together
+        try:
+            self._backprop(grads, produced)
+        finally:
+            ops.reduce_flush()
+        return [v.grad if getattr(v, "_grad_written", False) else None for v in sources]
+
+    def _backprop(self, grads, produced):
         for node in reversed(self.nodes):
             gouts = [grads.pop(id(o), None) for o in node.outputs]
             if all(g is None for g in gouts):
@@ -210,7 +218,6 @@ class GradientTape:
                     continue
                 k = id(inp)
                 grads[k] = g if k not in grads else grads[k] + g
-        return [v.grad if getattr(v, "_grad_written", False) else None for v in sources]
 
 
 def record(inputs, outputs, bwd):
@@ -232,6 +239,9 @@ def write_grad(v: Variable, fn):
     if getattr(v, "_grad_written", False):
         tmp = torch.empty_like(v.value)
         fn(tmp)
+        if ops._deferred is not None:  # queued reductions must land before the sum is formed
+            ops.reduce_flush()
+            ops.reduce_begin()
         v.grad += tmp
     else:
         fn(grad_buffer(v))

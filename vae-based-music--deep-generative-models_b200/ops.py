@@ -20,8 +20,28 @@ def zeros(*shape, dtype=F32):
     return torch.zeros(*shape, dtype=dtype, device=_lib.device())
 
 
+_deferred = None  # list of workspaces kept alive while weight-gradient reductions are queued (reduce_begin/flush)
+
+
 def _ws(nbytes: int):
-    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=_lib.device())
+    t = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=_lib.device())
+    if _deferred is not None:
+        _deferred.append(t)
+    return t
+
+
+def reduce_begin():
+    """Queue the fixed-order reductions of the following *_wgrad calls (vqb_reduce_begin)."""
+    global _deferred
+    _deferred = []
+    call("vqb_reduce_begin")
+
+
+def reduce_flush():
+    """Launch all queued reductions as a few batched kernels (vqb_reduce_flush)."""
+    global _deferred
+    call("vqb_reduce_flush", _lib.stream())
+    _deferred = None
 
 
 def _chk(t, name):
