@@ -211,3 +211,46 @@ def test_small_vqvae_training_trajectory(gpu):
             if step == 0:
                 assert logs[f"[{l}]batch_codebook_usage"] == float(mets[l]["batch_usage"])
                 assert abs(logs[f"[{l}]codebook_entropy"] - float(mets[l]["entropy"])) < 1e-4
+
+
+def test_small_vqvae_fp32_grade_tensor_core_mode(gpu):
+    """precision "bf16x3" — every fp32 operand split into 3 bf16 pieces (all 24 mantissa bits), piece products on tcgen05,
+    fp32 accumulation in TMEM — against the fp32 oracle on SMALL_VQ_VAE (batch 2): identical code indices (up to the 1e-5
+    near-tie allowance), reconstructions and losses within 1e-3, gradient vector within 1e-3 of its largest entry per level
+    (single tensors can deviate more when a ReLU mask flips at |h| ~ 1e-6: the block is discontinuous there)."""
+    V = gpu
+    spec = O.ModelSpec(T=28160, **O.SMALL_VQ_VAE)
+    weights, vq = O.init_model(spec, 0, bias_scale=0.02)
+    rng = np.random.Generator(np.random.PCG64(0))
+    x = rng.uniform(0, 1, size=(2, 28160, 1)).astype(np.float32)
+    m = V.VQVAE((28160, 1), **V.SMALL_VQ_VAE)
+    m.use_cuda_graph = False
+    m.set_precision("bf16x3")
+    load_into(m, weights, vq)
+    res, grads = O.loss_and_grads(spec, weights, vq, torch.tensor(x))
+    with V.GradientTape() as tape:
+        total = V.keras.Scalar()
+        outs = []
+        for l in range(2):
+            rec, r, s, c = m._level_losses(l, V.keras.convert_to_tensor(x), False)
+            outs.append((rec, r, c, s))
+            total += r + c + s
+    g = tape.gradient(total, m.trainable_variables)
+    i = 0
+    for l in range(2):
+        rec, r, c, s = outs[l]
+        assert rel_err(rec, res[l]["recon"]) < REL
+        for got, key in ((r, "recon_loss"), (c, "commit_loss"), (s, "spec_loss")):
+            assert abs(float(got) - float(res[l][key])) < REL * abs(float(res[l][key]))
+        idx = m.encode(x)[l].reshape(-1).cpu()
+        zt, Et = res[l]["z"].reshape(-1, 64).double(), torch.tensor(vq[l]["E"]).double()
+        d64 = O.vq_distances(zt, Et)
+        srt = torch.sort(d64, 1).values
+        scale = (zt ** 2).sum(1) + (Et ** 2).sum(0)[d64.argmin(1)]
+        ok = (srt[:, 1] - srt[:, 0]) > 1e-5 * scale
+        assert int(((idx != res[l]["idx"]) & ok).sum()) == 0
+        gmax = max(float(t.abs().max()) for t in grads[l])
+        for want in grads[l]:
+            err = float((g[i].cpu() - want).abs().max())
+            assert err <= REL * gmax, (l, i, err, gmax)
+            i += 1
