@@ -253,7 +253,7 @@ struct WgParams {
   const float* ot;
   float* partial;       // [B*nchunk][ntaps*Cg*Co]
   float* bias_partial;  // [B*nchunk][Co] or null
-  int B, Lg, Cg, Lo, Co, Lt, g_step, relu_ga, nchunk, sub, rows;
+  int B, Lg, Cg, Lo, Co, Lt, g_step, relu_ga, nchunk, sub, rows, tch;
   TapTable taps;
 };
 
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WgParams p) {
   const int j0 = tg * 4;
   const int cg0 = cgt * 32, co0 = blockIdx.z * 32;
   const int b = blockIdx.x / p.nchunk, ch = blockIdx.x - b * p.nchunk;
-  const int tb = ch * WG_TCH, te = min(tb + WG_TCH, p.Lt);
+  const int tb = ch * p.tch, te = min(tb + p.tch, p.Lt);
   int off[NT], minoff = 1 << 30;
 #pragma unroll
   for (int j = 0; j < NT; ++j) { off[j] = p.taps.off[j0 + j]; minoff = min(minoff, off[j]); }
@@ -483,9 +483,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   }
 }
 
+// time positions per CTA: 1024, halved while the grid would leave most of the 148 SMs idle (short sequences)
+static int pick_tch(int B, int Lt, int ntaps, int Cg, int Co) {
+  int tch = WG_TCH;
+  const long yz = (long)cdiv(ntaps, 4) * cdiv(Cg, 32) * cdiv(Co, 32);
+  while (tch > WG_SUB && (long)B * cdiv(Lt, tch) * yz < 592) tch >>= 1;
+  return tch;
+}
+
 // workspace: [B*nchunk][ntaps*Cg*Co] weight partials, then the bias partials
 static size_t wgrad_ws_floats(int B, int Lt, int ntaps, int Cg, int Co, long bias_rows, int Cb) {
-  const size_t nchunk = (size_t)B * cdiv(Lt, WG_TCH);
+  const size_t nchunk = (size_t)B * cdiv(Lt, pick_tch(B, Lt, ntaps, Cg, Co));
   const size_t nb = (size_t)cdiv(bias_rows, COLSUM_ROWS);
   return nchunk * ntaps * Cg * Co + (nchunk > nb ? nchunk : nb) * Cb + 64;
 }
@@ -506,7 +514,8 @@ static int launch_wgrad(const WgParams& p, dim3 grid, size_t smem, cudaStream_t 
 static int run_wgrad(WgParams& p, float* dw, bool bias_from_ot, const float* bias_src, long bias_rows, int Cb,
                      float* dbias, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int ntaps = p.taps.ntaps;
-  p.nchunk = cdiv(p.Lt, WG_TCH);
+  p.tch = pick_tch(p.B, p.Lt, ntaps, p.Cg, p.Co);
+  p.nchunk = cdiv(p.Lt, p.tch);
   const size_t need = wgrad_ws_floats(p.B, p.Lt, ntaps, p.Cg, p.Co, bias_rows, Cb) * sizeof(float);
   if (ws_bytes < need || !ws) return set_err(VQB_ERR_WORKSPACE, "wgrad workspace: need %zu bytes, got %zu", need, ws_bytes);
   const int nchunks = p.B * p.nchunk;
