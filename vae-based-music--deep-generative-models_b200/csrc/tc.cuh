@@ -126,16 +126,35 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// Waits for the phase with the given parity.  try_wait suspends in hardware for a bounded time; a wait that lasts longer
+// than ~2 s of SM clocks is a pipeline bug, and trapping turns it into a launch error instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(a), "r"(parity)
       : "memory");
+  if (ok) return;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+// one arrival (release semantics: this thread's earlier shared-memory writes are visible to whoever observes the phase)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // ---- element packing -------------------------------------------------------------------------------------
@@ -156,6 +175,27 @@ __device__ __forceinline__ void split_bf16(float x, float* pc) {
   pc[0] = __bfloat162float(__float2bfloat16_rn(x));
   if (S > 1) { pc[1] = __bfloat162float(__float2bfloat16_rn(x - pc[0])); }
   if (S > 2) { pc[2] = __bfloat162float(__float2bfloat16_rn(x - pc[0] - pc[1])); }
+}
+
+
+// 8 consecutive fp32 channels -> S 16-byte chunks of bf16 pieces (piece s of channel c in half-word c of out[s]);
+// x = p0 + p1 + p2 exactly as in split_bf16, but with the packed two-at-a-time conversion (cvt.rn.bf16x2.f32)
+template <int S>
+__device__ __forceinline__ void split8(const float4& a, const float4& b, uint4* out) {
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+      if (s + 1 < S) {  // exact remainders (the piece is the leading 8 bits of the value)
+        v[2 * i] -= __uint_as_float(pk[i] << 16);
+        v[2 * i + 1] -= __uint_as_float(pk[i] & 0xffff0000u);
+      }
+    }
+    out[s] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
 }
 
 }  // namespace tc

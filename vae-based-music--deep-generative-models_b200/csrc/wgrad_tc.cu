@@ -3,16 +3,16 @@
 //                                  dbias[co]     = sum_{b,t} dy[b, t, co].
 // The reduction over time is the MMA K dimension: per tile of TK time rows both operands are staged once in the
 // "plane layout" of tc.cuh and consumed as MN-major operands (rows = time = K):
-//   A (M side)  = dy tile,            M = 128 rows of which the first 32 are the output channels (the MMA costs the
-//                                     same for M = 64 and 128; rows 32..127 read whatever follows in shared memory and
-//                                     their accumulator rows are never read),
-//   B (N side)  = act(x) tile shifted by (j-1)*dil rows for tap j, N = 32 input channels; the centre tap uses N = 48
-//                 with an extra constant plane of ones, so that accumulator column 32 is the bias gradient.
-// Accumulators (3 taps x fp32 [128 x 32/48]) stay in TMEM for ALL tiles a CTA processes (persistent CTAs, two-stage
-// shared-memory pipeline: the MMAs of tile i run while tile i+1 is being staged); one partial result per CTA goes to
-// the workspace and is reduced in a fixed order (deterministic).
+//   A (M side)  = act(x) tile shifted by (j-1)*dil rows for tap j.  Its S bf16 pieces are consecutive plane groups, i.e.
+//                 consecutive 32-row blocks of ONE M = 128 operand (row sx*32 + ci), followed by a constant plane whose
+//                 first channel is 1.0: accumulator row 32*S is then the bias gradient;
+//   B (N side)  = dy tile, its S pieces stacked the same way along N = 32*S (column sy*32 + co).
+// One MMA per tap and K step therefore forms ALL S*S piece products; the epilogue adds the S*S accumulator blocks.
+// Accumulators (3 taps x fp32 [128 x 32 S]) stay in TMEM for ALL tiles a CTA processes (persistent CTAs); one partial
+// result per CTA goes to the workspace and is reduced in a fixed order (deterministic).
 #include "common.cuh"
 #include "tc.cuh"
+#include <stdlib.h>
 
 namespace vqb {
 
@@ -26,58 +26,62 @@ struct WgTcParams {
 };
 
 // S = number of bf16 pieces each operand is split into (1: bf16, 2: bf16x2, 3: bf16x3 = fp32-grade products)
-template <int S_>
+template <int S_, int NT_ = 256>
 struct WgCfg {
   static constexpr int S = S_;
-  static constexpr int T = 8;                     // channels per 16-byte chunk (bf16)
-  static constexpr int NP = 4;                    // data planes per operand
+  static constexpr int NT = NT_;                  // converter threads; one more warp issues the MMAs
   static constexpr int KMMA = 16;                 // K per MMA
-  static constexpr int TK = S == 1 ? 256 : 128;   // time rows per tile
+  static constexpr int TK = 128;                  // time rows per tile
   static constexpr int DMAX = 32;
-  static constexpr int NPB = 6;                   // B planes incl. the ones plane and zero padding up to N = 48
-  static constexpr int PLANE_A = TK * 16 + 32;
-  static constexpr int PLANE_B = (TK + 2 * DMAX) * 16 + 32;
-  static constexpr int TILE_A = NP * PLANE_A;
-  static constexpr int TILE_B = NPB * PLANE_B;
-  static constexpr int BUF = S * (TILE_A + TILE_B);
-  static constexpr int SPAN = 16 * PLANE_A;       // bytes an M = 128 A descriptor may touch from its start
-  static constexpr int NEED = BUF + (S - 1) * TILE_A + SPAN;
-  static constexpr int SMEM = (2 * BUF > NEED ? 2 * BUF : NEED) + 128;
+  static constexpr int NS = 32 * S;               // MMA N; live accumulator rows
+  static constexpr int PLANE_D = TK * 16 + 32;                 // dy planes (8 bf16 channels x TK rows)
+  static constexpr int PLANE_X = (TK + 2 * DMAX) * 16 + 32;    // act(x) planes (with the dilation halo)
+  static constexpr int TILE_X = (4 * S + 1) * PLANE_X;         // S x 4 data planes + the constant ones plane
+  static constexpr int TILE_D = 4 * S * PLANE_D;
+  static constexpr int BUF = TILE_X + TILE_D;
+  static constexpr int SPAN = 16 * PLANE_X;       // bytes an M = 128 A descriptor may touch from its start
+  static constexpr int SMEM = (2 * BUF > BUF + SPAN ? 2 * BUF : BUF + SPAN) + 128;
+  static constexpr int TCOLS = 3 * NS <= 128 ? 128 : 3 * NS <= 256 ? 256 : 512;  // TMEM columns: 3 taps x NS
   static constexpr int PART = 3 * 32 * 32 + 32;
-  static constexpr int MINB = SMEM > 113 * 1024 ? 1 : 2;
+  static constexpr int RPAD = 33;                 // row stride of the epilogue's shared-memory transpose (bank-conflict free)
+  static constexpr int RED = 3 * 32 * RPAD + 32;  // floats per x piece in that buffer
+  static constexpr int NA = TK * 4 / NT;                          // 8-channel units of the dy tile per converter thread
+  static constexpr int NB = ((TK + 2 * DMAX) * 4 + NT - 1) / NT;  // ... of the act(x) tile
+  static constexpr int NSETS = 3;                 // register sets: tiles i+1 and i+2 are in flight while tile i is converted
 };
 
-template <int S>
-__device__ __forceinline__ void stage_split(uint8_t* tile, int tile_bytes, int plane_bytes, int r, int q, float4 v) {
-  float a[3], b[3], c[3], d[3];
-  split_bf16<S>(v.x, a); split_bf16<S>(v.y, b); split_bf16<S>(v.z, c); split_bf16<S>(v.w, d);
-#pragma unroll
-  for (int s = 0; s < S; ++s)
-    *reinterpret_cast<uint2*>(tile + s * tile_bytes + (q >> 1) * plane_bytes + r * 16 + (q & 1) * 8) =
-        make_uint2(pack_bf16(a[s], b[s]), pack_bf16(c[s], d[s]));
-}
+// one tile's worth of global data held by a converter thread: its 8 channels of one dy row and of up to NB act(x) rows
+template <int NA, int NB>
+struct WgRegs {
+  float4 a[NA][2];
+  float4 b[NB][2];
+};
 
-template <int S>
-__global__ void __launch_bounds__(256, WgCfg<S>::MINB) wgrad_tc_kernel(const WgTcParams p) {
-  using Cfg = WgCfg<S>;
+// Pipeline: the 16 converter warps keep NSETS-1 tiles of global loads in flight in registers, split the tile whose data
+// has arrived into bf16 pieces in one of two shared-memory operand buffers and signal full[buf]; the issuing warp waits
+// for full[buf], issues the tile's MMAs and commits them to empty[buf], which the converters wait on before they
+// overwrite that buffer two tiles later.  Nobody waits for a global load it issued less than two tiles ago.
+template <int S, int NT_>
+__global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams p) {
+  using Cfg = WgCfg<S, NT_>;
+  constexpr int NT = Cfg::NT, NA = Cfg::NA, NB = Cfg::NB, NSETS = Cfg::NSETS;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bars[3];
+  __shared__ uint64_t full[2], empty[2], done;
   __shared__ uint32_t tslot;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (warp == 0) tmem_alloc(&tslot, 128);
-  if (tid == 32) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }
-  // constant planes of every B tile: piece 0 has channel 32 = 1 (bias column); everything else in channels 32..47 is 0
-  for (int t = 0; t < 2 * S; ++t) {
-    const int buf = t / S, sp = t - buf * S;
-    uint8_t* Bt = smem + buf * Cfg::BUF + S * Cfg::TILE_A + sp * Cfg::TILE_B;
-    for (int e = tid; e < (Cfg::NPB - Cfg::NP) * (Cfg::PLANE_B / 16); e += 256) {
-      const int pl = e / (Cfg::PLANE_B / 16), r = e - pl * (Cfg::PLANE_B / 16);
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (pl == 0 && sp == 0) v.x = 0x00003F80u;  // element 0 of the chunk = bf16 1.0
-      *reinterpret_cast<uint4*>(Bt + (Cfg::NP + pl) * Cfg::PLANE_B + r * 16) = v;
-    }
+  if (warp == 0) tmem_alloc(&tslot, Cfg::TCOLS);
+  if (tid == 32) {
+    mbar_init(&full[0], NT / 32); mbar_init(&full[1], NT / 32);
+    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1); mbar_init(&done, 1);
+    fence_mbar_init();
   }
+  // constant plane of both act(x) tiles: channel 32*S = 1.0 in every row (bias row of the accumulator), the other 7 are 0
+  for (int e = tid; e < 2 * (Cfg::PLANE_X / 16); e += NT + 32) {
+    const int buf = e / (Cfg::PLANE_X / 16), r = e - buf * (Cfg::PLANE_X / 16);
+    *reinterpret_cast<uint4*>(smem + buf * Cfg::BUF + 4 * S * Cfg::PLANE_X + r * 16) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+  }
+  fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -85,100 +89,164 @@ __global__ void __launch_bounds__(256, WgCfg<S>::MINB) wgrad_tc_kernel(const WgT
 
   const long first = (long)blockIdx.x * p.total_tiles / gridDim.x;
   const long last = (long)(blockIdx.x + 1) * p.total_tiles / gridDim.x;
+  const int ntiles = (int)(last - first);
   const int rowsB = Cfg::TK + 2 * p.dil;
-  const uint32_t idesc32 = instr_desc(FMT_BF16, 128, 32, true, true);
-  const uint32_t idesc48 = instr_desc(FMT_BF16, 128, 48, true, true);
 
-  int it = 0;
-  for (long tile = first; tile < last; ++tile, ++it) {
-    const int buf = it & 1;
-    const int b = (int)(tile / p.tiles_per_b);
-    const int t0 = (int)(tile - (long)b * p.tiles_per_b) * Cfg::TK;
-    uint8_t* At = smem + buf * Cfg::BUF;
-    uint8_t* Bt = At + S * Cfg::TILE_A;
-    if (it >= 2) mbar_wait(&bars[buf], ((it >> 1) - 1) & 1);  // the MMAs that read this buffer have completed
-    const float* otb = p.ot + (size_t)b * p.L * 32;
-    const float* gab = p.ga + (size_t)b * p.L * 32;
-    for (int e = tid; e < Cfg::TK * 8; e += 256) {
-      const int r = e >> 3, q = e & 7;
-      const int g = t0 + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (g < p.L) v = *reinterpret_cast<const float4*>(otb + (size_t)g * 32 + q * 4);
-      stage_split<S>(At, Cfg::TILE_A, Cfg::PLANE_A, r, q, v);
-    }
-    for (int e = tid; e < rowsB * 8; e += 256) {
-      const int r = e >> 3, q = e & 7;
-      const int g = t0 - p.dil + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (g >= 0 && g < p.L) v = *reinterpret_cast<const float4*>(gab + (size_t)g * 32 + q * 4);
-      if (p.relu_ga) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      stage_split<S>(Bt, Cfg::TILE_B, Cfg::PLANE_B, r, q, v);
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      const uint32_t a0 = smem_u32(At), b0 = smem_u32(Bt);
-      uint32_t acc = it != 0;
-      // The S pieces of dy are consecutive plane groups of the A tile, i.e. consecutive 32-row blocks of ONE M = 128
-      // operand: a single MMA multiplies all of them with one piece of act(x); accumulator row block r then holds
-      // dy_r^T act(x) summed over the x pieces, and the epilogue adds the S row blocks.
-#pragma unroll 1
-      for (int ks = 0; ks < Cfg::TK / Cfg::KMMA; ++ks) {
-        const uint64_t ad = smem_desc(a0 + ks * Cfg::KMMA * 16, 128, Cfg::PLANE_A);
+  if (warp == NT / 32) {
+    // ---------------------------------------------------------------------------------- MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(FMT_BF16, 128, Cfg::NS, true, true);
+      const uint64_t dil = (uint64_t)p.dil;  // a row is 16 bytes = one unit of the descriptor's start-address field
+      for (int it = 0; it < ntiles; ++it) {
+        const int buf = it & 1;
+        mbar_wait(&full[buf], (it >> 1) & 1);
+        fence_after_sync();
+        const uint64_t ad0 = smem_desc(smem_u32(smem + buf * Cfg::BUF), 128, Cfg::PLANE_X);
+        const uint64_t bd0 = smem_desc(smem_u32(smem + buf * Cfg::BUF + Cfg::TILE_X), 128, Cfg::PLANE_D);
+        uint32_t acc = it != 0;
 #pragma unroll
-        for (int sb = S - 1; sb >= 0; --sb) {
-          const uint32_t bb = b0 + sb * Cfg::TILE_B + (ks * Cfg::KMMA) * 16;
-          // tap j reads act(x) rows t + (j-1)*dil = B-tile rows ks*KMMA + j*dil
-          mma<false>(tmem + 0, ad, smem_desc(bb, 128, Cfg::PLANE_B), idesc32, acc);
-          mma<false>(tmem + 32, ad, smem_desc(bb + p.dil * 16, 128, Cfg::PLANE_B), idesc48, acc);
-          mma<false>(tmem + 80, ad, smem_desc(bb + 2 * p.dil * 16, 128, Cfg::PLANE_B), idesc32, acc);
+        for (int ks = 0; ks < Cfg::TK / Cfg::KMMA; ++ks) {
+          // tap j reads act(x) rows t + (j-1)*dil = x-tile rows ks*KMMA + j*dil
+          const uint64_t ad = ad0 + (uint64_t)(ks * Cfg::KMMA), bd = bd0 + (uint64_t)(ks * Cfg::KMMA);
+          mma<false>(tmem + 0 * Cfg::NS, ad, bd, idesc, acc);
+          mma<false>(tmem + 1 * Cfg::NS, ad + dil, bd, idesc, acc);
+          mma<false>(tmem + 2 * Cfg::NS, ad + 2 * dil, bd, idesc, acc);
           acc = 1;
         }
+        commit(&empty[buf]);
       }
-      commit(&bars[buf]);
+      commit(&done);  // everything issued so far
     }
     __syncwarp();
-  }
-  if (tid == 0) commit(&bars[2]);  // everything issued so far
-  __syncwarp();
-  float* out = p.partial + (size_t)blockIdx.x * Cfg::PART;
-  if (it == 0) {  // no tiles: zero partial
-    for (int e = tid; e < Cfg::PART; e += 256) out[e] = 0.f;
   } else {
-    mbar_wait(&bars[2], 0);
+    // ---------------------------------------------------------------------------------- loaders / converters
+    const int o = tid & 3;  // 8-channel unit of this thread (the same for all its rows: idx = tid + k*NT, NT % 4 == 0)
+    auto load = [&](int it, WgRegs<NA, NB>& R) {
+      const long tile = first + it;
+      const int b = (int)(tile / p.tiles_per_b);
+      const int t0 = (int)(tile - (long)b * p.tiles_per_b) * Cfg::TK;
+      const float* otb = p.ot + (size_t)b * p.L * 32 + o * 8;
+      const float* gab = p.ga + (size_t)b * p.L * 32 + o * 8;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < NA; ++k) {
+        const int g = t0 + ((tid + k * NT) >> 2);
+        const bool ok = g < p.L;
+        R.a[k][0] = ok ? *reinterpret_cast<const float4*>(otb + (size_t)g * 32) : z;
+        R.a[k][1] = ok ? *reinterpret_cast<const float4*>(otb + (size_t)g * 32 + 4) : z;
+      }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const int r = (tid + k * NT) >> 2;
+        const int g = t0 - p.dil + r;
+        const bool ok = r < rowsB && g >= 0 && g < p.L;
+        R.b[k][0] = ok ? *reinterpret_cast<const float4*>(gab + (long)g * 32) : z;
+        R.b[k][1] = ok ? *reinterpret_cast<const float4*>(gab + (long)g * 32 + 4) : z;
+      }
+    };
+    auto convert = [&](int it, WgRegs<NA, NB>& R) {
+      const int buf = it & 1;
+      uint8_t* Xt = smem + buf * Cfg::BUF;
+      uint8_t* Dt = Xt + Cfg::TILE_X;
+      if (it >= 2) mbar_wait(&empty[buf], ((it >> 1) - 1) & 1);  // the MMAs that read this buffer have completed
+      uint4 pc[S];
+#pragma unroll
+      for (int k = 0; k < NA; ++k) {
+        split8<S>(R.a[k][0], R.a[k][1], pc);
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          *reinterpret_cast<uint4*>(Dt + (s * 4 + o) * Cfg::PLANE_D + ((tid + k * NT) >> 2) * 16) = pc[s];
+      }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const int r = (tid + k * NT) >> 2;
+        if (r < rowsB) {
+          float4 u = R.b[k][0], w = R.b[k][1];
+          if (p.relu_ga) {
+            u.x = fmaxf(u.x, 0.f); u.y = fmaxf(u.y, 0.f); u.z = fmaxf(u.z, 0.f); u.w = fmaxf(u.w, 0.f);
+            w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f);
+          }
+          split8<S>(u, w, pc);
+#pragma unroll
+          for (int s = 0; s < S; ++s) *reinterpret_cast<uint4*>(Xt + (s * 4 + o) * Cfg::PLANE_X + r * 16) = pc[s];
+        }
+      }
+      fence_proxy_async();  // these generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[buf]);
+    };
+    WgRegs<NA, NB> R[NSETS];
+#pragma unroll
+    for (int u = 0; u < NSETS - 1; ++u)
+      if (u < ntiles) load(u, R[u]);
+#pragma unroll 1
+    for (int base = 0; base < ntiles; base += NSETS) {
+#pragma unroll
+      for (int u = 0; u < NSETS; ++u) {
+        const int it = base + u;
+        if (it < ntiles) {
+          if (it + NSETS - 1 < ntiles) load(it + NSETS - 1, R[(u + NSETS - 1) % NSETS]);
+          convert(it, R[u]);
+        }
+      }
+    }
+  }
+
+  float* out = p.partial + (size_t)blockIdx.x * Cfg::PART;
+  if (ntiles == 0) {  // no tiles: zero partial
+    for (int e = tid; e < Cfg::PART; e += NT + 32) out[e] = 0.f;
+  } else {
+    mbar_wait(&done, 0);
     fence_after_sync();
-    float* red = reinterpret_cast<float*>(smem);  // [S][PART]: the operand tiles are dead now
-    if (warp < S) {  // accumulator rows 32*warp .. +31 = output channel co = lane, for dy piece `warp`
-      float v[32];
-      const int co = tid & 31;
-      float* r = red + warp * Cfg::PART;
+    float* red = reinterpret_cast<float*>(smem);  // [S][RED]: the operand tiles are dead now
+    if (warp < S) {  // accumulator rows 32*warp .. +31: x piece `warp`, input channel ci = lane
+      float* r = red + warp * Cfg::RED;
       const uint32_t ta = tmem + (((uint32_t)warp * 32u) << 16);
-      tmem_ld32(ta + 0, v);
 #pragma unroll
-      for (int n = 0; n < 32; ++n) r[(0 * 32 + n) * 32 + co] = v[n];
-      tmem_ld32(ta + 32, v);
+      for (int j = 0; j < 3; ++j) {
+        float v[32], m[32];
+        tmem_ld32(ta + j * Cfg::NS, v);
 #pragma unroll
-      for (int n = 0; n < 32; ++n) r[(1 * 32 + n) * 32 + co] = v[n];
-      tmem_ld32(ta + 80, v);
+        for (int sy = 1; sy < S; ++sy) {  // add the column blocks of the other dy pieces
+          tmem_ld32(ta + j * Cfg::NS + sy * 32, m);
 #pragma unroll
-      for (int n = 0; n < 32; ++n) r[(2 * 32 + n) * 32 + co] = v[n];
-      tmem_ld32(ta + 64, v);  // column 64 = centre tap's column 32 = bias gradient
-      r[3 * 32 * 32 + co] = v[0];
+          for (int c = 0; c < 32; ++c) v[c] += m[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) r[(j * 32 + lane) * Cfg::RPAD + c] = v[c];
+      }
+    }
+    if (warp == S) {  // accumulator row 32*S (lane 0 of this warp's quadrant; S < 4): the ones row = bias gradient
+      float v[32], m[32];
+      const uint32_t ta = tmem + (((uint32_t)S * 32u) << 16);
+      tmem_ld32(ta + 1 * Cfg::NS, v);
+#pragma unroll
+      for (int sy = 1; sy < S; ++sy) {
+        tmem_ld32(ta + 1 * Cfg::NS + sy * 32, m);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] += m[c];
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) red[3 * 32 * Cfg::RPAD + c] = v[c];
+      }
     }
     fence_before_sync();
     __syncthreads();
-    for (int e = tid; e < Cfg::PART; e += 256) {
-      float t = red[e];
+    for (int e = tid; e < Cfg::PART; e += NT + 32) {
+      const int row = e >> 5, c = e & 31;  // row = j*32 + ci for the weights, 96 for the bias
+      const int a = row * Cfg::RPAD + c;
+      float t = red[a];
+      if (row < 96) {
 #pragma unroll
-      for (int w = 1; w < S; ++w) t += red[w * Cfg::PART + e];
+        for (int w = 1; w < S; ++w) t += red[w * Cfg::RED + a];
+      }
       out[e] = t;
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 128);
+  if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
 static int wg_split(int precision) { return precision == VQB_PREC_BF16X3 ? 3 : precision == VQB_PREC_BF16X2 ? 2 : 1; }
@@ -190,10 +258,14 @@ bool wgrad_tc_supported(const vqb_conv_desc* d) {
 }
 
 static int wgrad_tc_grid(const vqb_conv_desc* d, int* tiles_per_b) {
-  const int TK = wg_split(d->precision) == 1 ? WgCfg<1>::TK : WgCfg<2>::TK;
-  *tiles_per_b = cdiv(d->L, TK);
+  *tiles_per_b = cdiv(d->L, WgCfg<1>::TK);
   const long total = (long)d->B * *tiles_per_b;
-  return (int)(total < 296 ? (total > 0 ? total : 1) : 296);
+  static int num_sms = 0;  // one persistent CTA per SM (the operand buffers take most of its shared memory)
+  if (!num_sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) num_sms = 148;
+  }
+  return (int)(total < num_sms ? (total > 0 ? total : 1) : num_sms);
 }
 
 size_t wgrad_tc_workspace_bytes(const vqb_conv_desc* d) {
@@ -201,15 +273,15 @@ size_t wgrad_tc_workspace_bytes(const vqb_conv_desc* d) {
   return (size_t)wgrad_tc_grid(d, &tpb) * WgCfg<1>::PART * sizeof(float) + 64;
 }
 
-template <int S>
+template <int S, int NT = 256>
 static int launch_wg(const WgTcParams& p, int grid, cudaStream_t st) {
-  using Cfg = WgCfg<S>;
+  using Cfg = WgCfg<S, NT>;
   static bool attr_set = false;
   if (!attr_set) {
-    VQB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    VQB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<S, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set = true;
   }
-  wgrad_tc_kernel<S><<<grid, 256, Cfg::SMEM, st>>>(p);
+  wgrad_tc_kernel<S, NT><<<grid, Cfg::NT + 32, Cfg::SMEM, st>>>(p);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
@@ -224,7 +296,9 @@ int conv1d_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* dy, flo
   const int grid = wgrad_tc_grid(d, &p.tiles_per_b);
   p.total_tiles = d->B * p.tiles_per_b;
   const int S = wg_split(d->precision);
-  int rc = S == 3 ? launch_wg<3>(p, grid, st) : S == 2 ? launch_wg<2>(p, grid, st) : launch_wg<1>(p, grid, st);
+  static const int nt = getenv("VQB_WGRAD_NT") ? atoi(getenv("VQB_WGRAD_NT")) : 256;  // tuning knob (converter threads)
+  int rc = nt == 512 ? (S == 3 ? launch_wg<3, 512>(p, grid, st) : S == 2 ? launch_wg<2, 512>(p, grid, st) : launch_wg<1, 512>(p, grid, st))
+                     : (S == 3 ? launch_wg<3>(p, grid, st) : S == 2 ? launch_wg<2>(p, grid, st) : launch_wg<1>(p, grid, st));
   if (rc) return rc;
   constexpr int PART = WgCfg<1>::PART;
   // dw and dbias are separate buffers: two fixed-order reductions over the per-CTA partials
