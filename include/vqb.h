@@ -127,6 +127,28 @@ int vqb_resblock_bwd_data(const vqb_resblock_desc* d, const float* x, const floa
                           const float* w1, const float* w2, float* dh, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Decoder tail: the last Conv1DTranspose(C_mid, k=4, s=2) (encdec.py:67-68) and the final Conv1D(1, 3) (encdec.py:148)
+ * as ONE composed linear operator (no activation separates them), forward and backward, exact fp32.  The
+ * [B, 2L, C_mid] intermediate — the largest tensor of the model — is never formed.
+ *   x [B, L, C_in]; wt [4, C_mid, C_in], bt [C_mid] (may be NULL); wf [3, C_mid, 1], bf [1] (may be NULL)
+ *   recon [B, 2L, 1];  gbuf [VQB_TAIL_GBUF floats]: composed taps written by the forward call, read by the backward call.
+ * Requires C_in a multiple of 4 in [4, 32] (vqb_dec_tail_supports); other shapes run the two layers separately.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define VQB_TAIL_GBUF 272
+typedef struct vqb_tail_desc {
+  int32_t B, L, C_in, C_mid;
+} vqb_tail_desc;
+int vqb_dec_tail_supports(const vqb_tail_desc* d);
+int vqb_dec_tail_fwd(const vqb_tail_desc* d, const float* x, const float* wt, const float* bt, const float* wf,
+                     const float* bf, float* gbuf, float* recon, void* stream);
+size_t vqb_dec_tail_bwd_workspace_bytes(const vqb_tail_desc* d);
+/* given drecon [B, 2L, 1]: dx [B, L, C_in] (may be NULL) and the gradients of both layers' parameters
+ * (dwt [4, C_mid, C_in], dbt [C_mid] or NULL, dwf [3, C_mid, 1], dbf [1] or NULL), all OVERWRITTEN. */
+int vqb_dec_tail_bwd(const vqb_tail_desc* d, const float* x, const float* drecon, const float* wt, const float* bt,
+                     const float* wf, const float* gbuf, float* dx, float* dwt, float* dbt, float* dwf, float* dbf,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * VectorQuantizer  (replaces VectorQuantizer.call / get_code_indices, VectorQuantizer.py:75-186)
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct vqb_vq_desc {

@@ -131,6 +131,39 @@ class FakeBackend:
             _t(db, (d.C_out,)).copy_(DY.sum((0, 1)))
         return 0
 
+    # ---- decoder tail (the two layers evaluated one after the other with the oracle)
+    def vqb_dec_tail_supports(self, dref):
+        d = _d(dref)
+        return int(4 <= d.C_in <= 32 and d.C_in % 4 == 0)
+
+    def vqb_dec_tail_fwd(self, dref, x, wt, bt, wf, bf, gbuf, recon, stream):
+        d = _d(dref)
+        X = _t(x, (d.B, d.L, d.C_in)); Wt = _t(wt, (4, d.C_mid, d.C_in)); Wf = _t(wf, (3, d.C_mid, 1))
+        y = O.conv1d_transpose(X, Wt, _t(bt, (d.C_mid,)), 2)
+        _t(recon, (d.B, 2 * d.L, 1)).copy_(O.conv1d(y, Wf, _t(bf, (1,)), 1, 1))
+        return 0
+
+    def vqb_dec_tail_bwd_workspace_bytes(self, dref):
+        return 64
+
+    def vqb_dec_tail_bwd(self, dref, x, dr, wt, bt, wf, gbuf, dx, dwt, dbt, dwf, dbf, ws, wsn, stream):
+        d = _d(dref)
+        X = _t(x, (d.B, d.L, d.C_in)).clone().requires_grad_(True)
+        Wt = _t(wt, (4, d.C_mid, d.C_in)).clone().requires_grad_(True)
+        Wf = _t(wf, (3, d.C_mid, 1)).clone().requires_grad_(True)
+        Bt = (_t(bt, (d.C_mid,)).clone() if bt is not None else torch.zeros(d.C_mid)).requires_grad_(True)
+        Bf = torch.zeros(1, requires_grad=True)  # the bias value does not enter any gradient
+        r = O.conv1d(O.conv1d_transpose(X, Wt, Bt, 2), Wf, Bf, 1, 1)
+        gx, gwt, gwf, gbt, gbf = torch.autograd.grad(r, (X, Wt, Wf, Bt, Bf), _t(dr, (d.B, 2 * d.L, 1)))
+        if dx is not None:
+            _t(dx, (d.B, d.L, d.C_in)).copy_(gx)
+        _t(dwt, (4, d.C_mid, d.C_in)).copy_(gwt); _t(dwf, (3, d.C_mid, 1)).copy_(gwf)
+        if dbt is not None:
+            _t(dbt, (d.C_mid,)).copy_(gbt)
+        if dbf is not None:
+            _t(dbf, (1,)).copy_(gbf)
+        return 0
+
     # ---- resblock
     def vqb_resblock_supports(self, dref):
         return 1

@@ -268,3 +268,46 @@ def test_errors_are_reported_not_swallowed(gpu):
         ops.conv1d_fwd(dev(np.zeros((1, 8, 4))), dev(np.zeros((17, 4, 4))), None)
     with pytest.raises(gpu._lib.VQBError, match="not built|precision|UNIMPLEMENTED|available"):
         ops.conv1d_fwd(dev(np.zeros((1, 8, 4))), dev(np.zeros((3, 4, 4))), None, precision=7)
+
+
+TAIL_CASES = [  # B, L, cin, cmid, bias
+    (3, 37, 8, 16, True), (2, 300, 32, 64, True), (2, 513, 32, 64, False), (1, 1, 32, 64, True), (4, 2, 4, 8, True),
+    (2, 28160 // 8, 32, 64, True),
+]
+
+
+@pytest.mark.parametrize("B,L,cin,cmid,bias", TAIL_CASES)
+def test_decoder_tail_matches_two_layer_oracle(gpu, B, L, cin, cmid, bias):
+    """vqb_dec_tail_*: Conv1DTranspose(cmid, 4, 2) followed by Conv1D(1, 3) (encdec.py:67-68,148) run as ONE composed
+    operator equals the two layers evaluated one after the other — forward, input gradient and all four parameter
+    gradients (fp32; only the association of the sums differs)."""
+    ops = gpu.ops
+    rng = np.random.default_rng(B * 100 + L + cin)
+    x = rng.normal(size=(B, L, cin)).astype(np.float32)
+    wt = (rng.normal(size=(4, cmid, cin)) / np.sqrt(2 * cin)).astype(np.float32)
+    wf = (rng.normal(size=(3, cmid, 1)) / np.sqrt(3 * cmid)).astype(np.float32)
+    bt = rng.normal(size=cmid).astype(np.float32) if bias else None
+    bf = rng.normal(size=1).astype(np.float32) if bias else None
+    dr = rng.normal(size=(B, 2 * L, 1)).astype(np.float32)
+    T = lambda a: None if a is None else torch.tensor(a, dtype=torch.float64, requires_grad=True)
+    xt, wtt, wft, btt, bft = T(x), T(wt), T(wf), T(bt), T(bf)
+    r_ref = O.conv1d(O.conv1d_transpose(xt, wtt, btt, 2), wft, bft, 1, 1)
+    leaves = [t for t in (xt, wtt, wft, btt, bft) if t is not None]
+    g = torch.autograd.grad(r_ref, leaves, torch.tensor(dr, dtype=torch.float64))
+    gx, gwt, gwf = g[0], g[1], g[2]
+    D = lambda a: None if a is None else dev(a)
+    recon, gbuf = ops.dec_tail_fwd(dev(x), dev(wt), D(bt), dev(wf), D(bf))
+    close(recon, r_ref.detach(), tol=2e-5, what="recon")
+    dwt, dwf = ops.empty(4, cmid, cin), ops.empty(3, cmid, 1)
+    dbt, dbf = (ops.empty(cmid), ops.empty(1)) if bias else (None, None)
+    dx = ops.dec_tail_bwd(dev(x), dev(dr), dev(wt), D(bt), dev(wf), gbuf, dwt, dbt, dwf, dbf)
+    close(dx, gx, tol=2e-5, what="dx")
+    close(dwt, gwt, tol=5e-5, what="dwt")
+    close(dwf, gwf, tol=5e-5, what="dwf")
+    if bias:
+        close(dbt, g[3], tol=5e-5, what="dbt")
+        close(dbf, g[4], tol=5e-5, what="dbf")
+    # and against the library's own two-layer path
+    y = ops.conv1d_transpose_fwd(dev(x), dev(wt), D(bt) if bias else ops.zeros(cmid), 2)
+    r2 = ops.conv1d_fwd(y, dev(wf), D(bf) if bias else ops.zeros(1), 1, 1, False, None)
+    close(recon, r2, tol=2e-5, what="recon vs two kernels")

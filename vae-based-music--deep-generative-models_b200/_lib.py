@@ -36,8 +36,14 @@ class VQDesc(C.Structure):
                 ("precision", C.c_int32)]
 
 
+class TailDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "L", "C_in", "C_mid")]
+
+
+TAIL_GBUF = 272  # VQB_TAIL_GBUF
+
 _P = C.c_void_p
-_CD, _RD, _VD = C.POINTER(ConvDesc), C.POINTER(ResblockDesc), C.POINTER(VQDesc)
+_CD, _RD, _VD, _TD = C.POINTER(ConvDesc), C.POINTER(ResblockDesc), C.POINTER(VQDesc), C.POINTER(TailDesc)
 
 # name -> (restype, argtypes); mirrors include/vqb.h one to one
 SIGNATURES = {
@@ -59,6 +65,10 @@ SIGNATURES = {
     "vqb_resblock_supports": (C.c_int, [_RD]),
     "vqb_resblock_fwd": (C.c_int, [_RD, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vqb_resblock_bwd_data": (C.c_int, [_RD, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vqb_dec_tail_supports": (C.c_int, [_TD]),
+    "vqb_dec_tail_fwd": (C.c_int, [_TD, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vqb_dec_tail_bwd_workspace_bytes": (C.c_size_t, [_TD]),
+    "vqb_dec_tail_bwd": (C.c_int, [_TD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_vq_fwd_workspace_bytes": (C.c_size_t, [_VD]),
     "vqb_vq_fwd": (C.c_int, [_VD, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_vq_bwd": (C.c_int, [_VD, _P, _P, _P, C.c_float, _P, _P]),

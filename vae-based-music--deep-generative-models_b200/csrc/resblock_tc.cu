@@ -123,6 +123,31 @@ __device__ __forceinline__ void stage4(uint8_t* tile, int r, int q, float4 v) {
   }
 }
 
+// 8 channels o*8..o*8+7 of row r (two float4) -> operand tile(s): one 16-byte chunk per bf16 piece, two for tf32
+template <int MODE>
+__device__ __forceinline__ void stage8(uint8_t* tile, int r, int o, const float4& a, const float4& b) {
+  using Cfg = RbCfg<MODE>;
+  if (Cfg::TF32) {
+    *reinterpret_cast<float4*>(tile + (2 * o) * Cfg::PLANE + r * 16) = make_float4(to_tf32(a.x), to_tf32(a.y), to_tf32(a.z), to_tf32(a.w));
+    *reinterpret_cast<float4*>(tile + (2 * o + 1) * Cfg::PLANE + r * 16) = make_float4(to_tf32(b.x), to_tf32(b.y), to_tf32(b.z), to_tf32(b.w));
+  } else {
+    uint4 pc[Cfg::S];
+    split8<Cfg::S>(a, b, pc);
+#pragma unroll
+    for (int s = 0; s < Cfg::S; ++s) *reinterpret_cast<uint4*>(tile + s * Cfg::TILE + o * Cfg::PLANE + r * 16) = pc[s];
+  }
+}
+
+// asks the memory system to bring [p, p + bytes) into L2 (no destination: a hint that hides the DRAM latency of the next tile)
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// rows [r0, r1) clipped to [0, L) of batch item b of a [B, L, 32] fp32 tensor
+__device__ __forceinline__ void prefetch_rows(const float* base, long b, int L, int r0, int r1) {
+  r0 = max(r0, 0); r1 = min(r1, L);
+  if (base && r1 > r0) prefetch_l2(base + ((size_t)b * L + r0) * 32, (uint32_t)(r1 - r0) * 128u);
+}
+
 // ---- warp-cooperative row I/O --------------------------------------------------------------------------------------
 // In the epilogues thread `lane` of a warp owns tile row i0 + lane (its TMEM lane).  Reading / writing its 64-byte half
 // row straight from global memory would make every warp instruction touch 32 different lines, so rows move through a
@@ -206,15 +231,44 @@ __global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbT
   const int g1 = s0 - p.d1;          // in1 row held by A1 row 0
   const long boff = (long)b * L;
 
-  // stage in1 rows [g1, g1 + rows1) as the A operand of stage 1 (zero outside [0, L): SAME padding)
-  const float* inb = p.in1 + (size_t)boff * 32;
-  for (int e = tid; e < rows1 * 8; e += 256) {
-    const int r = e >> 3, q = e & 7;
-    const int g = g1 + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g >= 0 && g < L) v = *reinterpret_cast<const float4*>(inb + (size_t)g * 32 + q * 4);
-    if (p.relu1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    stage4<MODE>(A1, r, q, v);
+  // hint the next tile's rows into L2 while this one is processed
+  if (tid == 0) {
+    const int nt = tile + gridDim.x;
+    if (nt < p.total_tiles) {
+      const int nb = nt / p.tiles_x;
+      const int ns0 = (nt - nb * p.tiles_x) * Rout - p.d2;
+      prefetch_rows(p.in1, nb, L, ns0 - p.d1, ns0 - p.d1 + rows1);
+      prefetch_rows(p.mask1, nb, L, ns0, ns0 + Cfg::R);
+      prefetch_rows(p.mask2, nb, L, ns0 + p.d2, ns0 + Cfg::R - p.d2);
+      if (p.add2 != p.in1) prefetch_rows(p.add2, nb, L, ns0 + p.d2, ns0 + Cfg::R - p.d2);
+    }
+  }
+  // stage in1 rows [g1, g1 + rows1) as the A operand of stage 1 (zero outside [0, L): SAME padding).  All loads of a
+  // thread are issued before the first conversion, so one memory latency is exposed per tile rather than one per row.
+  {
+    constexpr int NU = ((Cfg::R + 2 * Cfg::DMAX) * 4 + 255) / 256;  // 8-channel units per thread
+    const float* inb = p.in1 + (size_t)boff * 32 + (tid & 3) * 8;
+    float4 ra[NU], rb[NU];
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      const int r = (tid + k * 256) >> 2;
+      const int g = g1 + r;
+      const bool ok = r < rows1 && g >= 0 && g < L;
+      ra[k] = ok ? *reinterpret_cast<const float4*>(inb + (long)g * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[k] = ok ? *reinterpret_cast<const float4*>(inb + (long)g * 32 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      const int r = (tid + k * 256) >> 2;
+      if (r < rows1) {
+        float4 a = ra[k], b = rb[k];
+        if (p.relu1) {
+          a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+          b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+        }
+        stage8<MODE>(A1, r, tid & 3, a, b);
+      }
+    }
   }
   fence_proxy_async();
   fence_before_sync();
@@ -264,8 +318,9 @@ __global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbT
       v[c] = p.relu2 ? fmaxf(a, 0.f) : a;
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      stage4<MODE>(A2, Cfg::DMAX + i, half * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    for (int q = 0; q < 2; ++q)
+      stage8<MODE>(A2, Cfg::DMAX + i, half * 2 + q, make_float4(v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]),
+                   make_float4(v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]));
   }
   fence_proxy_async();
   fence_before_sync();

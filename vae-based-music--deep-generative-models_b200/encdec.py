@@ -3,7 +3,7 @@
 same layer creation (= variable) order."""
 from __future__ import annotations
 
-from .keras_compat import Sequential, layers
+from .keras_compat import Sequential, _is_symbolic, decoder_tail_fusable, decoder_tail_op, layers
 from .resnet import DilatedResnet1D
 
 
@@ -90,5 +90,17 @@ class Decoder(layers.Layer):
                                             down_depth=up_sampling_depth))
         self.model.add(layers.Conv1D(output_dim, 3, strides=1, padding="same"))  # encdec.py:148
 
+    fuse_tail = True  # run the last Conv1DTranspose + the final Conv1D as one composed operator when the shapes allow
+
     def call(self, inputs, **kwargs):
+        seq = self.model.layers
+        if self.fuse_tail and not _is_symbolic(inputs) and len(seq) >= 2 and isinstance(seq[-2], DecoderConvBlock):
+            last_block = seq[-2].model.layers
+            if decoder_tail_fusable(last_block[-1], seq[-1]):
+                x = inputs
+                for l in seq[:-2]:
+                    x = l(x)
+                for l in last_block[:-1]:
+                    x = l(x)
+                return decoder_tail_op(x, last_block[-1], seq[-1])
         return self.model(inputs)

@@ -576,6 +576,48 @@ class Conv1DTranspose(Layer):
         return y
 
 
+def decoder_tail_fusable(up: "Conv1DTranspose", out: "Conv1D") -> bool:
+    """The decoder's last Conv1DTranspose(k=4, s=2) followed by Conv1D(1, 3) (encdec.py:67-68,148) in a shape
+    libvqvae_b200 runs as one composed linear operator."""
+    return (isinstance(up, Conv1DTranspose) and isinstance(out, Conv1D) and up.built and out.built
+            and up.kernel_size == 4 and up.strides == 2 and out.kernel_size == 3 and out.strides == 1
+            and out.dilation_rate == 1 and out.filters == 1
+            and ops.dec_tail_supported(up.kernel.shape[2], up.filters))
+
+
+def decoder_tail_op(x, up: "Conv1DTranspose", out: "Conv1D"):
+    """out(up(x)) without materialising up(x); the backward writes the gradients of both layers' variables."""
+    wt, bt, wf, bf = up.kernel, up.bias, out.kernel, out.bias
+    val = lambda v: None if v is None else v.value
+    recon, gbuf = ops.dec_tail_fwd(x, wt.value, val(bt), wf.value, val(bf))
+
+    def bwd(g, needs):
+        dr = g[0].contiguous()
+        if any(getattr(v, "_grad_written", False) for v in (wt, wf)):
+            # a layer applied twice in one pass: write temporaries and accumulate (what write_grad does per variable)
+            tmp = [torch.empty_like(v.value) if v is not None else None for v in (wt, bt, wf, bf)]
+            dx = ops.dec_tail_bwd(x, dr, wt.value, val(bt), wf.value, gbuf, tmp[0], tmp[1], tmp[2], tmp[3], needs[0])
+            for v, t in zip((wt, bt, wf, bf), tmp):
+                if v is None:
+                    continue
+                if getattr(v, "_grad_written", False):
+                    v.grad += t
+                else:
+                    grad_buffer(v).copy_(t)
+                    v._grad_written = True
+            return [dx]
+        dx = ops.dec_tail_bwd(x, dr, wt.value, val(bt), wf.value, gbuf, grad_buffer(wt),
+                              None if bt is None else grad_buffer(bt), grad_buffer(wf),
+                              None if bf is None else grad_buffer(bf), needs[0])
+        for v in (wt, bt, wf, bf):
+            if v is not None:
+                v._grad_written = True
+        return [dx]
+
+    record([x], [recon], bwd)
+    return recon
+
+
 # ------------------------------------------------------------------------------------------------ Model
 class History:
     def __init__(self):

@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, ResblockDesc, VQDesc, call, ptr
+from ._lib import ConvDesc, ResblockDesc, TailDesc, VQDesc, call, ptr
 
 F32 = torch.float32
 
@@ -126,6 +126,36 @@ def conv1d_transpose_wgrad(x, dy, dw, db, stride=2):
     ws = _ws(n)
     call("vqb_conv1d_transpose_wgrad", C.byref(d), ptr(x), ptr(dy), ptr(dw), ptr(db), ptr(ws), ws.numel(),
          _lib.stream())
+
+
+# --------------------------------------------------------------------------------------- decoder tail
+def dec_tail_supported(cin, cmid):
+    """1 if libvqvae_b200 fuses Conv1DTranspose(cmid, 4, strides=2) -> Conv1D(1, 3) for this input width."""
+    return bool(_lib.lib().vqb_dec_tail_supports(C.byref(TailDesc(1, 1, int(cin), int(cmid)))))
+
+
+def dec_tail_fwd(x, wt, bt, wf, bf):
+    """recon [B, 2L, 1] = Conv1D(1,3)(Conv1DTranspose(k=4,s=2)(x)) as one composed operator; returns (recon, gbuf)."""
+    _chk(x, "x"); _chk(wt, "wt"); _chk(bt, "bt"); _chk(wf, "wf"); _chk(bf, "bf")
+    B, L, cin = x.shape
+    k, cmid, wcin = wt.shape
+    if k != 4 or wcin != cin or tuple(wf.shape) != (3, cmid, 1):
+        raise ValueError(f"decoder tail: kernels {tuple(wt.shape)} / {tuple(wf.shape)} do not match input {tuple(x.shape)}")
+    recon, gbuf = empty(B, 2 * L, 1), empty(_lib.TAIL_GBUF)
+    d = TailDesc(B, L, cin, cmid)
+    call("vqb_dec_tail_fwd", C.byref(d), ptr(x), ptr(wt), ptr(bt), ptr(wf), ptr(bf), ptr(gbuf), ptr(recon), _lib.stream())
+    return recon, gbuf
+
+
+def dec_tail_bwd(x, dr, wt, bt, wf, gbuf, dwt, dbt, dwf, dbf, want_dx=True):
+    _chk(x, "x"); _chk(dr, "dr"); _chk(dwt, "dwt"); _chk(dbt, "dbt"); _chk(dwf, "dwf"); _chk(dbf, "dbf")
+    B, L, cin = x.shape
+    d = TailDesc(B, L, cin, wt.shape[1])
+    dx = empty(B, L, cin) if want_dx else None
+    ws = _ws(_lib.lib().vqb_dec_tail_bwd_workspace_bytes(C.byref(d)))
+    call("vqb_dec_tail_bwd", C.byref(d), ptr(x), ptr(dr), ptr(wt), ptr(bt), ptr(wf), ptr(gbuf), ptr(dx), ptr(dwt),
+         ptr(dbt), ptr(dwf), ptr(dbf), ptr(ws), ws.numel(), _lib.stream())
+    return dx
 
 
 # ------------------------------------------------------------------------------------------- resblock
