@@ -44,8 +44,8 @@ struct RbCfg {
   static constexpr bool TF32 = MODE == 1;
   static constexpr int S = MODE == 2 ? 2 : MODE == 3 ? 3 : 1;  // bf16 pieces per operand
   static constexpr int R = 256;     // stage-1 rows per CTA (2 x M128)
-  static constexpr bool ALIAS = MODE == 3;           // A2 reuses A1's memory (A1 is dead once the stage-1 MMAs completed)
-  static constexpr int DMAX = MODE == 3 ? 28 : 32;   // largest supported dilation (guard rows of the operand tiles)
+  static constexpr int NT = 512;    // threads: two per tile row (one per 16-channel half)
+  static constexpr int DMAX = 32;   // largest supported dilation (guard rows of the operand tiles)
   static constexpr int C = 32;
   static constexpr int ES = TF32 ? 4 : 2;
   static constexpr int T = 16 / ES;
@@ -57,10 +57,10 @@ struct RbCfg {
   static constexpr int WTAP = NP * WPLANE;
   static constexpr int WCONV = 3 * WTAP;
   static constexpr int TILE = NP * PLANE;   // one operand tile (one split piece)
-  static constexpr int STG = ALIAS ? 8 * 2048 : 0;  // dedicated row-staging area when A1 cannot be reused for it
-  static constexpr int SMEM = (ALIAS ? 1 : 2) * S * TILE + 2 * WCONV + STG + 64 + 256;
-  static constexpr int TCOLS = 2 * NW <= 64 ? 64 : 2 * NW <= 128 ? 128 : 256;  // TMEM columns (2 M blocks x NW)
-  static constexpr int MINB = MODE == 0 ? 3 : 2;  // CTAs per SM the shared-memory footprint allows
+  static constexpr int STG = (NT / 32) * 2048;  // per-warp row staging (32 rows x 64 B)
+  static constexpr int SMEM = 2 * S * TILE + 2 * WCONV + STG + 64 + 256;
+  static constexpr int TCOLS = 4 * NW <= 128 ? 128 : 4 * NW <= 256 ? 256 : 512;  // TMEM columns: 2 stages x 2 M blocks x NW
+  static constexpr int NU = ((R + 2 * DMAX) * 4 + NT - 1) / NT;  // 8-channel units of the stage-1 input tile per thread
 };
 
 template <int MODE>
@@ -83,44 +83,32 @@ __device__ __forceinline__ void pack_weights(uint8_t* dst, const float* __restri
 }
 
 // 3 taps x KSTEPS x S accumulating MMAs for both M blocks of one stage, issued by a single thread.  In the split modes
-// the S weight pieces are stacked along N (N = 32 S) and every activation piece is multiplied with all of them into the
-// SAME accumulator: column block c then holds a . W_c, and the epilogue adds the S column blocks.  (All S*S piece
-// products are formed — the extra ones beyond the 2^-16 terms are real, smaller terms of the exact product.)
+// the S weight pieces are stacked along N and activation piece `sa` is multiplied with the first S - sa of them into the
+// SAME accumulator (hi x {hi, mid, lo}, mid x {hi, mid}, lo x {hi}: every product down to 2^-16 of the leading one plus
+// mid x mid; the three omitted ones are below 2^-23): column block c then holds the sum over the activation pieces of
+// a . W_c, and the epilogue adds the S column blocks.
 template <int MODE>
 __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int row_shift0, int dil, uint32_t w_base) {
   using Cfg = RbCfg<MODE>;
-  const uint32_t idesc = instr_desc(Cfg::TF32 ? FMT_TF32 : FMT_BF16, 128, Cfg::NW, false, false);
+  // descriptors differ only in their start-address field (units of 16 bytes = one tile row): add offsets to two bases
+  const uint64_t ad0 = smem_desc(a_base + (uint32_t)row_shift0 * 16u, Cfg::PLANE, 128);
+  const uint64_t bd0 = smem_desc(w_base, Cfg::WPLANE, 128);
   uint32_t acc = 0;
 #pragma unroll
   for (int j = 0; j < 3; ++j)
 #pragma unroll
     for (int kk = 0; kk < Cfg::KSTEPS; ++kk)
 #pragma unroll
-      for (int sa = Cfg::S - 1; sa >= 0; --sa) {
-        const uint64_t bd = smem_desc(w_base + j * Cfg::WTAP + kk * 2 * Cfg::WPLANE, Cfg::WPLANE, 128);
+      for (int sa = 0; sa < Cfg::S; ++sa) {  // the widest MMA first: it initialises every column block
+        const uint32_t idesc = instr_desc(Cfg::TF32 ? FMT_TF32 : FMT_BF16, 128, 32 * (Cfg::S - sa), false, false);
+        const uint64_t bd = bd0 + (uint64_t)((j * Cfg::WTAP + kk * 2 * Cfg::WPLANE) >> 4);
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {  // the two M blocks alternate: two independent accumulator chains in flight
-          const uint32_t a = a_base + sa * Cfg::TILE + (uint32_t)((mb * 128 + row_shift0 + j * dil) * 16) + kk * 2 * Cfg::PLANE;
-          mma<Cfg::TF32>(tmem + mb * Cfg::NW, smem_desc(a, Cfg::PLANE, 128), bd, idesc, acc);
+          const uint64_t ad = ad0 + (uint64_t)((sa * Cfg::TILE + kk * 2 * Cfg::PLANE + mb * 128 * 16) >> 4) + (uint64_t)(j * dil);
+          mma<Cfg::TF32>(tmem + mb * Cfg::NW, ad, bd, idesc, acc);
         }
         acc = 1;
       }
-}
-
-// one float4 (4 channels q*4..q*4+3 of row r) -> operand tile(s)
-template <int MODE>
-__device__ __forceinline__ void stage4(uint8_t* tile, int r, int q, float4 v) {
-  using Cfg = RbCfg<MODE>;
-  if (Cfg::TF32) {
-    *reinterpret_cast<float4*>(tile + q * Cfg::PLANE + r * 16) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-  } else {
-    float a[3], b[3], c[3], d[3];
-    split_bf16<Cfg::S>(v.x, a); split_bf16<Cfg::S>(v.y, b); split_bf16<Cfg::S>(v.z, c); split_bf16<Cfg::S>(v.w, d);
-#pragma unroll
-    for (int s = 0; s < Cfg::S; ++s)
-      *reinterpret_cast<uint2*>(tile + s * Cfg::TILE + (q >> 1) * Cfg::PLANE + r * 16 + (q & 1) * 8) =
-          make_uint2(pack_bf16(a[s], b[s]), pack_bf16(c[s], d[s]));
-  }
 }
 
 // 8 channels o*8..o*8+7 of row r (two float4) -> operand tile(s): one 16-byte chunk per bf16 piece, two for tf32
@@ -155,16 +143,24 @@ __device__ __forceinline__ void prefetch_rows(const float* base, long b, int L, 
 // and the global side is done with lane -> (row = lane / 4, chunk = lane % 4): 64 contiguous bytes per row.
 __device__ __forceinline__ uint32_t stg_off(int row, int q) { return (uint32_t)(row * 64 + ((q ^ ((row >> 1) & 3)) << 4)); }
 
-// v[16] <- src[(g0 + lane) * 32 + half * 16 + 0..15]  (zero where the row is outside [0, L))
-__device__ __forceinline__ void warp_load_rows(const float* __restrict__ src, long batch_off, int g0, int L, int half,
-                                               uint8_t* stg, int lane, float* v) {
+// f <- the warp's 32 rows x 64 B (rows g0.., channels half*16..+15), coalesced: lane -> (row = idx / 4, chunk = idx % 4);
+// zero where the row is outside [0, L).  Split from warp_unpack_rows so that the loads can be issued long before use.
+__device__ __forceinline__ void warp_fetch_rows(const float* __restrict__ src, long batch_off, int g0, int L, int half,
+                                                int lane, float4 (&f)[4]) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int idx = k * 32 + lane, row = idx >> 2, q = idx & 3;
     const int g = g0 + row;
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g >= 0 && g < L) t = *reinterpret_cast<const float4*>(src + (batch_off + g) * 32 + half * 16 + q * 4);
-    *reinterpret_cast<float4*>(stg + stg_off(row, q)) = t;
+    f[k] = (g >= 0 && g < L) ? *reinterpret_cast<const float4*>(src + (batch_off + g) * 32 + half * 16 + q * 4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+// v[16] <- the 16 channels of the row this thread owns (row = lane), through the warp's staging area
+__device__ __forceinline__ void warp_unpack_rows(const float4 (&f)[4], uint8_t* stg, int lane, float* v) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = k * 32 + lane, row = idx >> 2, q = idx & 3;
+    *reinterpret_cast<float4*>(stg + stg_off(row, q)) = f[k];
   }
   __syncwarp();
 #pragma unroll
@@ -193,111 +189,133 @@ __device__ __forceinline__ void warp_store_rows(float* __restrict__ dst, long ba
   __syncwarp();
 }
 
+// Software pipeline over the tiles of a persistent CTA (one CTA per SM, 512 threads, all threads take part in every phase):
+//     load(i+1) -> registers | wait MMA1(i) | epilogue 1(i): TMEM -> out1, -> A2 | issue MMA2(i) |
+//     convert(i+1): registers -> A1 | issue MMA1(i+1) | wait MMA2(i) | epilogue 2(i): TMEM -> out2
+// so the global loads of the next tile fly during epilogue 1, the stage-2 MMAs run under the conversion of the next tile
+// and the next tile's stage-1 MMAs under epilogue 2.  A1 / A2 and the two stages' TMEM accumulators are separate buffers.
+// (A variant with a dedicated MMA-issuing warp and mbarrier-only hand-offs measured slower: 17 warps cap the register
+// file at 96 per thread; so did epilogues that access their rows in global memory directly instead of through the
+// per-warp staging transposes: 32 lines per access instruction saturate the L1 pipeline.)
 template <int MODE>
-__global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbTcParams p) {
+__global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcParams p) {
   using Cfg = RbCfg<MODE>;
-  constexpr bool TF32 = Cfg::TF32;
+  constexpr int NT = Cfg::NT, NU = Cfg::NU;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* A1 = smem;
-  uint8_t* A2 = Cfg::ALIAS ? A1 : A1 + Cfg::S * Cfg::TILE;
+  uint8_t* A2 = A1 + Cfg::S * Cfg::TILE;
   uint8_t* W1 = A2 + Cfg::S * Cfg::TILE;
   uint8_t* W2 = W1 + Cfg::WCONV;
-  uint8_t* stg_base = Cfg::ALIAS ? W2 + Cfg::WCONV : A1;  // row staging: A1 is dead during the epilogues unless it is A2
-  uint64_t* bar = reinterpret_cast<uint64_t*>(W2 + Cfg::WCONV + Cfg::STG);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint8_t* stg_base = W2 + Cfg::WCONV;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stg_base + Cfg::STG);  // bar[0]: stage-1 MMAs done, bar[1]: stage-2 MMAs done
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 2);
+  float* bias_s = reinterpret_cast<float*>(bar + 4);  // [64]: bias1, bias2 (zeros when absent); 16-byte aligned
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.L;
   const int Rout = Cfg::R - 2 * p.d2;
   const int rows1 = Cfg::R + 2 * p.d1;
-  float* bias_s = reinterpret_cast<float*>(tslot + 2);  // [64]: bias1, bias2 (zeros when absent)
 
   if (warp == 0) tmem_alloc(tslot, Cfg::TCOLS);
-  if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (tid == 32) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
   pack_weights<MODE>(W1, p.w1, p.sj1, p.si1, p.so1, p.flip1);
   pack_weights<MODE>(W2, p.w2, p.sj2, p.si2, p.so2, p.flip2);
   if (tid < 64) bias_s[tid] = tid < 32 ? (p.bias1 ? p.bias1[tid] : 0.f) : (p.bias2 ? p.bias2[tid - 32] : 0.f);
+  fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tslot;
 
-  // persistent CTA: weights, TMEM and barriers are set up once; tiles are taken round-robin
-#pragma unroll 1
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-  const int b = tile / p.tiles_x;
-  const int t0 = (tile - b * p.tiles_x) * Rout;  // first out2 row of this tile
-  const int s0 = t0 - p.d2;          // out1 row held by A2 row DMAX (A2 has DMAX guard rows in front)
-  const int g1 = s0 - p.d1;          // in1 row held by A1 row 0
-  const long boff = (long)b * L;
+  // epilogue role of this thread: TMEM lane quadrant (warp % 4), M block, 16-channel half
+  const int qd = warp & 3, mb = (warp >> 2) & 1, half = warp >> 3;
+  const int i0 = mb * 128 + qd * 32;   // first tile row of this warp
+  const int i = i0 + lane;             // tile row (= TMEM lane) of this thread
+  const uint32_t taddr = tmem + (((uint32_t)qd * 32u) << 16) + (uint32_t)(mb * Cfg::NW + half * 16);
+  uint8_t* stg = stg_base + warp * 2048;
+  const int oct = tid & 3;  // 8-channel unit of this thread in the staging loops (NT % 4 == 0)
 
-  // hint the next tile's rows into L2 while this one is processed
-  if (tid == 0) {
-    const int nt = tile + gridDim.x;
-    if (nt < p.total_tiles) {
-      const int nb = nt / p.tiles_x;
-      const int ns0 = (nt - nb * p.tiles_x) * Rout - p.d2;
-      prefetch_rows(p.in1, nb, L, ns0 - p.d1, ns0 - p.d1 + rows1);
-      prefetch_rows(p.mask1, nb, L, ns0, ns0 + Cfg::R);
-      prefetch_rows(p.mask2, nb, L, ns0 + p.d2, ns0 + Cfg::R - p.d2);
-      if (p.add2 != p.in1) prefetch_rows(p.add2, nb, L, ns0 + p.d2, ns0 + Cfg::R - p.d2);
-    }
-  }
-  // stage in1 rows [g1, g1 + rows1) as the A operand of stage 1 (zero outside [0, L): SAME padding).  All loads of a
-  // thread are issued before the first conversion, so one memory latency is exposed per tile rather than one per row.
-  {
-    constexpr int NU = ((Cfg::R + 2 * Cfg::DMAX) * 4 + 255) / 256;  // 8-channel units per thread
-    const float* inb = p.in1 + (size_t)boff * 32 + (tid & 3) * 8;
-    float4 ra[NU], rb[NU];
+  float4 ra[NU], rb[NU];
+  // global rows of tile `tile`: A1 row r holds in1 row g1 + r
+  auto load = [&](int tile) {
+    const int b = tile / p.tiles_x;
+    const int g1 = (tile - b * p.tiles_x) * Rout - p.d2 - p.d1;
+    const float* inb = p.in1 + (size_t)b * L * 32 + oct * 8;
 #pragma unroll
     for (int k = 0; k < NU; ++k) {
-      const int r = (tid + k * 256) >> 2;
+      const int r = (tid + k * NT) >> 2;
       const int g = g1 + r;
       const bool ok = r < rows1 && g >= 0 && g < L;
       ra[k] = ok ? *reinterpret_cast<const float4*>(inb + (long)g * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
       rb[k] = ok ? *reinterpret_cast<const float4*>(inb + (long)g * 32 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  auto convert = [&]() {
 #pragma unroll
     for (int k = 0; k < NU; ++k) {
-      const int r = (tid + k * 256) >> 2;
+      const int r = (tid + k * NT) >> 2;
       if (r < rows1) {
         float4 a = ra[k], b = rb[k];
         if (p.relu1) {
           a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
           b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
         }
-        stage8<MODE>(A1, r, tid & 3, a, b);
+        stage8<MODE>(A1, r, oct, a, b);
       }
     }
+    fence_proxy_async();
+  };
+
+  int tile = blockIdx.x;
+  if (tile < p.total_tiles) {
+    load(tile);
+    convert();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (tid == 32) {
+      issue_stage<MODE>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1));
+      commit(&bar[0]);
+    }
+    __syncwarp();
   }
-  fence_proxy_async();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-
-  if (tid == 32) {
-    issue_stage<MODE>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1));
-    commit(bar);
-  }
-  __syncwarp();
-
-  const int i0 = (warp >> 2) * 128 + (warp & 3) * 32;  // first tile row of this warp
-  const int i = i0 + lane;                             // tile row (= TMEM lane) of this thread
-  const int g = s0 + i;                                // global row
-  const bool inrange = g >= 0 && g < L;
-  const uint32_t taddr = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * Cfg::NW;
-  uint8_t* stg = stg_base + warp * 2048;
-  float v[16], m[16];
-
-  // ---- epilogue 1: TMEM -> (+bias, mask) -> out1 (global, owned rows) and act2(out1) -> A2 (shared)
-  mbar_wait(bar, 0);
-  fence_after_sync();
+  uint32_t phase = 0;
 #pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    tmem_ld16(taddr + half * 16, v);
+  for (; tile < p.total_tiles; tile += gridDim.x, phase ^= 1) {
+    const int b = tile / p.tiles_x;
+    const int t0 = (tile - b * p.tiles_x) * Rout;  // first out2 row of this tile
+    const int s0 = t0 - p.d2;          // out1 row held by A2 row DMAX (A2 has DMAX guard rows in front)
+    const long boff = (long)b * L;
+    const int g = s0 + i;              // global row of this thread
+    const bool inrange = g >= 0 && g < L;
+    const int next = tile + gridDim.x;
+    const bool has_next = next < p.total_tiles;
+
+    if (tid == 0 && has_next) {  // L2 hints: the epilogue operands of the next tile and the stage-1 input of the one after it
+      const int nb = next / p.tiles_x;
+      const int ns0 = (next - nb * p.tiles_x) * Rout - p.d2;
+      prefetch_rows(p.mask1, nb, L, ns0, ns0 + Cfg::R);
+      prefetch_rows(p.mask2, nb, L, ns0 + p.d2, ns0 + Cfg::R - p.d2);
+      if (p.add2 != p.in1) prefetch_rows(p.add2, nb, L, ns0 + p.d2, ns0 + Cfg::R - p.d2);
+      const int nn = next + gridDim.x;
+      if (nn < p.total_tiles) {
+        const int nnb = nn / p.tiles_x;
+        const int ng1 = (nn - nnb * p.tiles_x) * Rout - p.d2 - p.d1;
+        prefetch_rows(p.in1, nnb, L, ng1, ng1 + rows1);
+      }
+    }
+    if (has_next) load(next);
+
+    float v[16], m[16];
+    float4 f[4];
+    // ---- epilogue 1: TMEM -> (+bias, mask) -> out1 (global, owned rows) and act2(out1) -> A2 (shared)
+    if (p.mask1) warp_fetch_rows(p.mask1, boff, s0 + i0, L, half, lane, f);
+    mbar_wait(&bar[0], phase);
+    fence_after_sync();
+    tmem_ld16(taddr, v);
 #pragma unroll
     for (int sp = 1; sp < Cfg::S; ++sp) {  // split modes: add the column blocks of the other weight pieces
-      tmem_ld16(taddr + sp * 32 + half * 16, m);
+      tmem_ld16(taddr + sp * 32, m);
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] += m[c];
     }
@@ -307,42 +325,52 @@ __global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbT
       v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
     }
     if (p.mask1) {
-      warp_load_rows(p.mask1, boff, s0 + i0, L, half, stg, lane, m);
+      warp_unpack_rows(f, stg, lane, m);
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] = m[c] > 0.f ? v[c] : 0.f;
     }
     if (p.out1) warp_store_rows(p.out1, boff, s0 + i0, L, half, i0, p.d2, Cfg::R - p.d2, stg, lane, v);
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
-      float a = inrange ? v[c] : 0.f;  // rows outside [0, L) are conv2's zero padding
+      const float a = inrange ? v[c] : 0.f;  // rows outside [0, L) are conv2's zero padding
       v[c] = p.relu2 ? fmaxf(a, 0.f) : a;
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q)
       stage8<MODE>(A2, Cfg::DMAX + i, half * 2 + q, make_float4(v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]),
                    make_float4(v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]));
-  }
-  fence_proxy_async();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();  // A2 complete; every warp has drained the stage-1 accumulators
+    fence_after_sync();
+    if (tid == 32) {
+      // out2 tile row i uses A2 rows DMAX + i + (j-1)*d2
+      issue_stage<MODE>(tmem + 2 * Cfg::NW, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2));
+      commit(&bar[1]);
+    }
+    __syncwarp();
+    if (has_next) {  // A1 is free (its MMAs completed before epilogue 1): stage the next tile under the stage-2 MMAs
+      convert();
+      fence_before_sync();
+      __syncthreads();
+      fence_after_sync();
+      if (tid == 32) {
+        issue_stage<MODE>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1));
+        commit(&bar[0]);
+      }
+      __syncwarp();
+    }
 
-  if (tid == 32) {
-    // out2 tile row i uses A2 rows DMAX + i + (j-1)*d2
-    issue_stage<MODE>(tmem, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2));  // same TMEM columns: epilogue 1 has drained them
-    commit(bar);
-  }
-  __syncwarp();
-
-  // ---- epilogue 2: TMEM -> (+bias, mask, + add) -> out2 (owned rows)
-  mbar_wait(bar, 1);
-  fence_after_sync();
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    tmem_ld16(taddr + half * 16, v);
+    // ---- epilogue 2: TMEM -> (+bias, mask, + add) -> out2 (owned rows)
+    float4 f2[4];
+    if (p.mask2) warp_fetch_rows(p.mask2, boff, s0 + i0, L, half, lane, f);
+    if (p.add2) warp_fetch_rows(p.add2, boff, s0 + i0, L, half, lane, f2);
+    mbar_wait(&bar[1], phase);
+    fence_after_sync();
+    tmem_ld16(taddr + 2 * Cfg::NW, v);
 #pragma unroll
     for (int sp = 1; sp < Cfg::S; ++sp) {
-      tmem_ld16(taddr + sp * 32 + half * 16, m);
+      tmem_ld16(taddr + 2 * Cfg::NW + sp * 32, m);
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] += m[c];
     }
@@ -352,21 +380,19 @@ __global__ void __launch_bounds__(256, RbCfg<MODE>::MINB) rb_tc_kernel(const RbT
       v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
     }
     if (p.mask2) {
-      warp_load_rows(p.mask2, boff, s0 + i0, L, half, stg, lane, m);
+      warp_unpack_rows(f, stg, lane, m);
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] = m[c] > 0.f ? v[c] : 0.f;
     }
     if (p.add2) {
-      warp_load_rows(p.add2, boff, s0 + i0, L, half, stg, lane, m);
+      warp_unpack_rows(f2, stg, lane, m);
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] += m[c];
     }
     warp_store_rows(p.out2, boff, s0 + i0, L, half, i0, p.d2, Cfg::R - p.d2, stg, lane, v);
-  }
-  fence_before_sync();
-  __syncthreads();  // the staging area aliases A1: every warp is done before the next tile is staged
-  fence_after_sync();
+    fence_before_sync();  // orders this tile's TMEM reads before the barriers of the next iteration
   }  // tile loop
+  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
@@ -388,8 +414,8 @@ static int launch_rb(const RbTcParams& p, cudaStream_t st) {
   const int Rout = Cfg::R - 2 * p.d2;
   q.tiles_x = cdiv(p.L, Rout);
   q.total_tiles = q.tiles_x * p.B;
-  const int grid = q.total_tiles < num_sms * Cfg::MINB ? q.total_tiles : num_sms * Cfg::MINB;
-  rb_tc_kernel<MODE><<<grid, 256, Cfg::SMEM, st>>>(q);
+  const int grid = q.total_tiles < num_sms ? q.total_tiles : num_sms;
+  rb_tc_kernel<MODE><<<grid, Cfg::NT, Cfg::SMEM, st>>>(q);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
@@ -405,7 +431,7 @@ static int dispatch_rb(int precision, const RbTcParams& p, cudaStream_t st) {
 }
 
 bool resblock_tc_supported(const vqb_resblock_desc* d) {
-  return d->C == 32 && d->F == 32 && d->dilation >= 1 && d->dilation <= (d->precision == VQB_PREC_BF16X3 ? 28 : 32) &&
+  return d->C == 32 && d->F == 32 && d->dilation >= 1 && d->dilation <= 32 &&
          d->precision >= VQB_PREC_TF32 && d->precision <= VQB_PREC_BF16X3;
 }
 
