@@ -240,6 +240,8 @@ def main():
             "step_frac_of_bf16_sustained": FLOP_PER_SAMPLE_FWD_BWD * samples / (ms * 1e-3) / 1e12 / (pk["tf_sust"] * world)}
     if not args.no_roofline:
         line.update(roofline_section(V, pk, args.precision))
+        if world == 1:
+            line.update(vq_section(V, pk))
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(1, 1, args.cpu_batch)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
@@ -249,10 +251,21 @@ def main():
         torch.distributed.destroy_process_group()
 
 
+def ncu_traffic(name):
+    """DRAM bytes (read + write) of one launch from the committed `ncu --set full` capture (profiles/r1_ncu.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_ncu.json")))[name]["traffic_bytes"]
+    except Exception:
+        return None
+
+
 def roofline_section(V, pk, precision="fp32"):
-    """The dominant kernel timed ALONE with CUDA events on its launch stream: the residual-block forward at the
-    largest stage of the model ([32, 14080, 32], dilation 1) — 80 of level 0's 93 and 128 of level 1's 149 forward
-    convolutions are inside such blocks.  Two buffer sets (231 MB) are alternated so that inputs do not sit in L2."""
+    """The dominant kernel timed ALONE with CUDA events on its launch stream: the fused residual-block forward at the
+    largest stage of the model ([32, 14080, 32], dilation 1) — 208 of the model's 242 forward convolutions are inside
+    such blocks, and the block kernels (forward + data gradient) are the largest share of the step (profiles/).
+    After fusion the block is HBM-bound: 384 algorithmic bytes per time position (read x, write h for the backward pass,
+    write y) against 12 288 FLOP, i.e. 26 us of HBM time vs 3.4 us of bf16 tensor time at this shape (20 us with the 6
+    piece products of bf16x3).  Two input buffers are alternated; inputs + outputs per launch (173 MB) exceed the L2."""
     import torch
     ops = V.ops
     P = V._lib.PRECISIONS[precision]
@@ -277,12 +290,45 @@ def roofline_section(V, pk, precision="fp32"):
     bytes_alg = B * L * C * 4 * 3.0                # read x, write h (kept for backward), write y
     tf = flops / (ms * 1e-3) / 1e12
     gbs = bytes_alg / (ms * 1e-3) / 1e9
-    return {"roofline": {"kernel": "vqb_resblock_fwd [32,14080,32] dil 1 (" + ("fp32 path: 2 x tgc_kernel" if precision == "fp32" else "rb_tc_kernel, tcgen05 " + precision) + ")", "bound": "tensor",
-                         "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tf / pk["tf_burst"],
-                         "traffic": None, "peak_source": pk["src"] + " bf16 burst", "ms_per_launch": ms,
-                         "flop_per_launch": flops},
-            "roofline_hbm": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
-                             "algorithmic_bytes_per_launch": bytes_alg}}
+    kname = "vqb_resblock_fwd [32,14080,32] dil 1 (" + ("fp32 path: 2 x tgc_kernel" if precision == "fp32" else "rb_tc_kernel, tcgen05 " + precision) + ")"
+    return {"roofline": {"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": gbs / pk["hbm"], "traffic": ncu_traffic("rb_fwd_" + precision),
+                         "peak_source": pk["src"] + " HBM copy bandwidth", "ms_per_launch": ms,
+                         "algorithmic_bytes_per_launch": bytes_alg,
+                         "algorithmic_bytes_per_unit": "384 B per time position (SURVEY 8d / DESIGN 4)"},
+            "roofline_tensor": {"bound": "tensor", "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                                "frac": tf / pk["tf_burst"], "flop_per_launch": flops,
+                                "note": "algorithmic FLOP of the two convolutions; the tensor pipe is not the limiter of this block"}}
+
+
+def vq_section(V, pk):
+    """BASELINE.json's second metric: VectorQuantizer latents/s (configs[3]: 2^20 latents x 512 codes x 64 dims, forward =
+    indices + gather + straight-through output + commitment loss + batch statistics), against its HBM roofline
+    (520 algorithmic bytes per latent: x 256 + q_st 256 + idx 8)."""
+    import torch
+    ops = V.ops
+    N, D, K = 1 << 20, 64, 512
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xs = [torch.randn(N, D, device="cuda", generator=g) for _ in range(2)]  # 2 x 268 MB alternate: not L2 resident
+    E = torch.randn(D, K, device="cuda", generator=g)
+    mb, nb = ops.empty(D, K), ops.empty(K)
+    P = V._lib.PRECISIONS["bf16"]  # tensor-core search with exact fp32 re-ranking: same indices as the fp32 search
+    for i in range(3):
+        ops.vq_fwd(xs[i % 2], E, 0.25, True, False, mb, nb, P)
+    torch.cuda.synchronize()
+    n = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        ops.vq_fwd(xs[i % 2], E, 0.25, True, False, mb, nb, P)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    t_hbm = N * 520 / (pk["hbm"] * 1e9)
+    return {"vq": {"metric": "VQ latents/sec", "workload": "VectorQuantizer forward, 2^20 latents x 512 codes x 64 dims, fp32 I/O, exact fp32 indices",
+                   "value": N / (ms * 1e-3), "unit": "latents/s", "ms": ms,
+                   "roofline": {"bound": "hbm", "achieved": N * 520 / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                "frac": t_hbm * 1e3 / ms, "algorithmic_bytes_per_unit": 520}}}
 
 
 if __name__ == "__main__":
