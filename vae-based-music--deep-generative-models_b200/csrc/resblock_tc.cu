@@ -252,6 +252,8 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
   };
   auto convert = [&]() {
 #pragma unroll
+    for (int k = 0; k < NU; ++k) { reg_fence(ra[k]); reg_fence(rb[k]); }  // keep the conversion below the waits it follows
+#pragma unroll
     for (int k = 0; k < NU; ++k) {
       const int r = (tid + k * NT) >> 2;
       if (r < rows1) {

@@ -198,5 +198,11 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4* 
   }
 }
 
+
+// Compiler-level fence on a register value: arithmetic on `a` cannot be scheduled above this point.  Used after an
+// mbarrier wait so that work on prefetched global data is not hoisted to right behind its loads (which would expose the
+// DRAM latency the prefetch is meant to hide); volatile asm statements keep their order relative to one another.
+__device__ __forceinline__ void reg_fence(float4& a) { asm volatile("" : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w)); }
+
 }  // namespace tc
 }  // namespace vqb
