@@ -77,8 +77,11 @@ typedef struct vqb_conv_desc {
 } vqb_conv_desc;
 
 /* 1 if d->precision has a kernel for this shape and op (0 = forward, 1 = data gradient, 2 = weight gradient); fp32: always.
- * Tensor-core (bf16 / tf32) kernels: weight gradient of k = 3, stride 1, 32 -> 32 convolutions with dilation <= 32. */
+ * Tensor-core (bf16 family) kernels: forward / data gradient of k = 4, stride 2, 32 -> 32 convolutions (no fused ReLU,
+ * residual or dx_add); weight gradient of k = 3, stride 1, 32 -> 32 convolutions with dilation <= 32. */
 int vqb_conv1d_supports(const vqb_conv_desc* d, int op);
+/* the same question for Conv1DTranspose (tensor-core kernels: forward / data gradient of k = 4, stride 2, 32 -> 32) */
+int vqb_conv1d_transpose_supports(const vqb_conv_desc* d, int op);
 /* y[B, ceil(L/stride), C_out] = conv(act(x)) + bias (+ residual, same shape as y; may be NULL) */
 int vqb_conv1d_fwd(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
                    const float* residual, float* y, void* stream);

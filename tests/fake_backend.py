@@ -67,6 +67,9 @@ class FakeBackend:
     def vqb_conv1d_supports(self, dref, op):
         return 1
 
+    def vqb_conv1d_transpose_supports(self, dref, op):
+        return 1
+
     def vqb_conv1d_fwd(self, dref, x, w, b, res, y, stream):
         d = _d(dref)
         Lo = -(-d.L // d.stride)

@@ -115,3 +115,48 @@ def test_vq_search_tc_is_exact(gpu, N, K, kind):
     assert int((idx0 != idx1).sum()) == 0
     assert float(n_batch.sum()) == N and torch.equal(q.cpu(), torch.tensor(E).t()[idx1.cpu()])
     assert float(loss0) == float(loss1)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "bf16x2", "bf16x3"])
+@pytest.mark.parametrize("B,L", [(2, 512), (3, 1000), (2, 333), (1, 2), (2, 14080)])
+def test_strided_conv_tc(gpu, prec, B, L):
+    """Tensor-core Conv1D(32, 4, strides=2) / Conv1DTranspose(32, 4, strides=2) forward and data gradient (conv_tc.cu)
+    against the exact fp32 kernels of the same library on the same inputs; tolerance = that of the operand format."""
+    ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
+    g = torch.Generator(device="cuda").manual_seed(L + B)
+    x = torch.randn(B, L, 32, device="cuda", generator=g)
+    w = torch.randn(4, 32, 32, device="cuda", generator=g) * 0.1
+    b = torch.randn(32, device="cuda", generator=g)
+    Lo = (L + 1) // 2
+    dy = torch.randn(B, Lo, 32, device="cuda", generator=g)
+    tol = TOL[prec]
+    for got, want, what in (
+            (ops.conv1d_fwd(x, w, b, 2, 1, False, None, P), ops.conv1d_fwd(x, w, b, 2, 1, False, None, 0), "conv fwd"),
+            (ops.conv1d_dgrad(dy, w, x.shape, None, 2, 1, False, None, P), ops.conv1d_dgrad(dy, w, x.shape, None, 2, 1, False, None, 0), "conv dgrad"),
+            (ops.conv1d_transpose_fwd(x, w, b, 2, P), ops.conv1d_transpose_fwd(x, w, b, 2, 0), "convT fwd"),
+            (ops.conv1d_transpose_dgrad(torch.randn(B, 2 * L, 32, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7)), w, x.shape, 2, P),
+             ops.conv1d_transpose_dgrad(torch.randn(B, 2 * L, 32, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7)), w, x.shape, 2, 0), "convT dgrad")):
+        assert got.shape == want.shape, what
+        err = float((got - want).abs().max() / want.abs().max())
+        assert err < tol, (what, err)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "bf16x2", "bf16x3"])
+@pytest.mark.parametrize("B,L", [(2, 512), (3, 1000), (2, 333), (1, 2), (4, 7040)])
+def test_strided_conv_wgrad_tc(gpu, prec, B, L):
+    """Tensor-core weight / bias gradients of Conv1D(32, 4, strides=2) and Conv1DTranspose(32, 4, strides=2) (wgrad4_tc.cu)
+    against the exact fp32 kernels of the same library."""
+    ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
+    g = torch.Generator(device="cuda").manual_seed(3 * L + B)
+    x = torch.randn(B, L, 32, device="cuda", generator=g)
+    dy = torch.randn(B, (L + 1) // 2, 32, device="cuda", generator=g)
+    dyT = torch.randn(B, 2 * L, 32, device="cuda", generator=g)
+    tol = TOL[prec] * (4 if prec == "bf16" else 1)
+    for fn, a, b_ in ((ops.conv1d_wgrad, x, dy), (ops.conv1d_transpose_wgrad, x, dyT)):
+        got_w, got_b, want_w, want_b = ops.empty(4, 32, 32), ops.empty(32), ops.empty(4, 32, 32), ops.empty(32)
+        if fn is ops.conv1d_wgrad:
+            fn(a, b_, got_w, got_b, 2, 1, False, P); fn(a, b_, want_w, want_b, 2, 1, False, 0)
+        else:
+            fn(a, b_, got_w, got_b, 2, P); fn(a, b_, want_w, want_b, 2, 0)
+        assert float((got_w - want_w).abs().max() / want_w.abs().max()) < tol, fn.__name__
+        assert float((got_b - want_b).abs().max() / want_b.abs().max().clamp_min(1e-6)) < tol, fn.__name__ + " bias"

@@ -52,6 +52,7 @@ SIGNATURES = {
     "vqb_kernel_launch_count": (C.c_int64, []),
     "vqb_device_check": (C.c_int, [C.c_int]),
     "vqb_conv1d_supports": (C.c_int, [_CD, C.c_int]),
+    "vqb_conv1d_transpose_supports": (C.c_int, [_CD, C.c_int]),
     "vqb_reduce_begin": (C.c_int, []),
     "vqb_reduce_flush": (C.c_int, [_P]),
     "vqb_conv1d_fwd": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P]),

@@ -55,6 +55,18 @@ size_t wgrad_tc_workspace_bytes(const vqb_conv_desc* d);
 int conv1d_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, void* ws,
                     size_t ws_bytes, cudaStream_t st);
 
+// tensor-core stride-2 convolutions (conv_tc.cu)
+bool conv_tc_supported(const vqb_conv_desc* d);
+int conv1d_fwd_tc(const vqb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+int conv1d_dgrad_tc(const vqb_conv_desc* d, const float* dy, const float* w, float* dx, cudaStream_t st);
+int conv1d_transpose_fwd_tc(const vqb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+int conv1d_transpose_dgrad_tc(const vqb_conv_desc* d, const float* dy, const float* w, float* dx, cudaStream_t st);
+
+// tensor-core weight gradient of the k = 4, stride-2, 32 <-> 32 convolutions (wgrad4_tc.cu)
+size_t wgrad4_tc_workspace_bytes(int B, int Lo);
+int wgrad4_tc(int precision, const float* ga, int Lg, const float* ot, int Lo, int B, float* dw, float* dbias, bool bias_from_ga,
+              void* ws, size_t ws_bytes, cudaStream_t st);
+
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float warp_sum(float v) {

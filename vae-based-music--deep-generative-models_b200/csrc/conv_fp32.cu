@@ -692,7 +692,11 @@ int vqb_conv1d_fwd(const vqb_conv_desc* d, const float* x, const float* w, const
   int rc = check_desc(d, false);
   if (rc) return rc;
   VQB_REQUIRE(x && w && y, "vqb_conv1d_fwd: NULL pointer");
-  VQB_REQUIRE(d->precision == VQB_PREC_FP32, "vqb_conv1d_fwd: precision %d not available for this op", d->precision);
+  if (d->precision != VQB_PREC_FP32) {
+    VQB_REQUIRE(conv_tc_supported(d) && !residual, "vqb_conv1d_fwd: no tensor-core kernel for this shape (k=%d stride=%d %d->%d); use VQB_PREC_FP32",
+                d->k, d->stride, d->C_in, d->C_out);
+    return conv1d_fwd_tc(d, x, w, bias, y, (cudaStream_t)stream);
+  }
   return conv1d_fwd_fp32(d, x, w, bias, residual, y, (cudaStream_t)stream);
 }
 
@@ -703,18 +707,31 @@ int vqb_conv1d_dgrad(const vqb_conv_desc* d, const float* dy, const float* w, co
   if (rc) return rc;
   VQB_REQUIRE(dy && w && dx, "vqb_conv1d_dgrad: NULL pointer");
   VQB_REQUIRE(!d->relu_in || x, "vqb_conv1d_dgrad: relu_in needs x for the ReLU mask");
+  if (d->precision != VQB_PREC_FP32) {
+    VQB_REQUIRE(conv_tc_supported(d) && !dx_add, "vqb_conv1d_dgrad: no tensor-core kernel for this shape (k=%d stride=%d %d->%d); use VQB_PREC_FP32",
+                d->k, d->stride, d->C_in, d->C_out);
+    return conv1d_dgrad_tc(d, dy, w, dx, (cudaStream_t)stream);
+  }
   return conv1d_dgrad_fp32(d, dy, w, x, dx_add, dx, (cudaStream_t)stream);
 }
 
 int vqb_conv1d_supports(const vqb_conv_desc* d, int op) {
   if (!d || d->k < 1 || d->k > MAX_TAPS) return 0;
   if (d->precision == VQB_PREC_FP32) return 1;
-  return op == 2 && wgrad_tc_supported(d) ? 1 : 0;
+  if (op == 2) return wgrad_tc_supported(d) || conv_tc_supported(d) ? 1 : 0;
+  return conv_tc_supported(d) ? 1 : 0;
+}
+
+int vqb_conv1d_transpose_supports(const vqb_conv_desc* d, int op) {
+  if (!d || d->k < 1 || d->k > MAX_TAPS) return 0;
+  if (d->precision == VQB_PREC_FP32) return 1;
+  return conv_tc_supported(d) ? 1 : 0;
 }
 
 size_t vqb_conv1d_wgrad_workspace_bytes(const vqb_conv_desc* d) {
   if (!d || d->k < 1 || d->k > MAX_TAPS) return 0;
   if (d->precision != VQB_PREC_FP32 && wgrad_tc_supported(d)) return wgrad_tc_workspace_bytes(d);
+  if (d->precision != VQB_PREC_FP32 && conv_tc_supported(d)) return wgrad4_tc_workspace_bytes(d->B, (d->L + 1) / 2);
   int Lo, padL;
   same_pad(d->L, d->k, d->stride, d->dilation, &Lo, &padL);
   return wgrad_ws_floats(d->B, Lo, d->k, d->C_in, d->C_out, (long)d->B * Lo, d->C_out) * sizeof(float);
@@ -727,13 +744,17 @@ int vqb_conv1d_wgrad(const vqb_conv_desc* d, const float* x, const float* dy, fl
   if (rc) return rc;
   VQB_REQUIRE(x && dy && dw, "vqb_conv1d_wgrad: NULL pointer");
   if (d->precision != VQB_PREC_FP32) {
-    VQB_REQUIRE(wgrad_tc_supported(d), "vqb_conv1d_wgrad: no tensor-core kernel for this shape (k=%d stride=%d %d->%d dil=%d); use VQB_PREC_FP32",
+    VQB_REQUIRE(wgrad_tc_supported(d) || conv_tc_supported(d),
+                "vqb_conv1d_wgrad: no tensor-core kernel for this shape (k=%d stride=%d %d->%d dil=%d); use VQB_PREC_FP32",
                 d->k, d->stride, d->C_in, d->C_out, d->dilation);
     if (d->B == 0 || d->L == 0) {
-      VQB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 3 * 32 * 32, (cudaStream_t)stream));
+      VQB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * d->k * 32 * 32, (cudaStream_t)stream));
       if (dbias) VQB_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * 32, (cudaStream_t)stream));
       return VQB_OK;
     }
+    if (conv_tc_supported(d))
+      return wgrad4_tc(d->precision, x, d->L, dy, (d->L + 1) / 2, d->B, dw, dbias, false, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
     return conv1d_wgrad_tc(d, x, dy, dw, dbias, workspace, workspace_bytes, (cudaStream_t)stream);
   }
   int Lo, padL;
@@ -753,6 +774,10 @@ int vqb_conv1d_transpose_fwd(const vqb_conv_desc* d, const float* x, const float
   int rc = check_desc(d, true);
   if (rc) return rc;
   VQB_REQUIRE(x && w && y, "vqb_conv1d_transpose_fwd: NULL pointer");
+  if (d->precision != VQB_PREC_FP32) {
+    VQB_REQUIRE(conv_tc_supported(d), "vqb_conv1d_transpose_fwd: no tensor-core kernel for this shape; use VQB_PREC_FP32");
+    return conv1d_transpose_fwd_tc(d, x, w, bias, y, (cudaStream_t)stream);
+  }
   return conv1d_transpose_fwd_fp32(d, x, w, bias, y, (cudaStream_t)stream);
 }
 
@@ -761,11 +786,16 @@ int vqb_conv1d_transpose_dgrad(const vqb_conv_desc* d, const float* dy, const fl
   int rc = check_desc(d, true);
   if (rc) return rc;
   VQB_REQUIRE(dy && w && dx, "vqb_conv1d_transpose_dgrad: NULL pointer");
+  if (d->precision != VQB_PREC_FP32) {
+    VQB_REQUIRE(conv_tc_supported(d), "vqb_conv1d_transpose_dgrad: no tensor-core kernel for this shape; use VQB_PREC_FP32");
+    return conv1d_transpose_dgrad_tc(d, dy, w, dx, (cudaStream_t)stream);
+  }
   return conv1d_transpose_dgrad_fp32(d, dy, w, dx, (cudaStream_t)stream);
 }
 
 size_t vqb_conv1d_transpose_wgrad_workspace_bytes(const vqb_conv_desc* d) {
   if (!d || d->k < 1 || d->k > MAX_TAPS) return 0;
+  if (d->precision != VQB_PREC_FP32 && conv_tc_supported(d)) return wgrad4_tc_workspace_bytes(d->B, d->L);
   return wgrad_ws_floats(d->B, d->L, d->k, d->C_out, d->C_in, (long)d->B * d->L * d->stride, d->C_out) * sizeof(float);
 }
 
@@ -775,6 +805,15 @@ int vqb_conv1d_transpose_wgrad(const vqb_conv_desc* d, const float* x, const flo
   int rc = check_desc(d, true);
   if (rc) return rc;
   VQB_REQUIRE(x && dy && dw, "vqb_conv1d_transpose_wgrad: NULL pointer");
+  if (d->precision != VQB_PREC_FP32) {
+    VQB_REQUIRE(conv_tc_supported(d), "vqb_conv1d_transpose_wgrad: no tensor-core kernel for this shape; use VQB_PREC_FP32");
+    if (d->B == 0 || d->L == 0) {
+      VQB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * d->k * 32 * 32, (cudaStream_t)stream));
+      if (dbias) VQB_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * 32, (cudaStream_t)stream));
+      return VQB_OK;
+    }
+    return wgrad4_tc(d->precision, dy, 2 * d->L, x, d->L, d->B, dw, dbias, true, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
   const int padL = (d->k > d->stride ? d->k - d->stride : 0) / 2;
   WgParams p{};
   p.ga = dy; p.ot = x;  // dW[j][co][ci] = sum dy[m*s + j - padL][co] * x[m][ci]

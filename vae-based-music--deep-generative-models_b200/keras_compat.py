@@ -530,11 +530,11 @@ def conv1d_op(x, kernel: Variable, bias: Optional[Variable], stride, dilation, r
     def bwd(g, needs):
         dy = g[0].contiguous()
         write_grad(kernel, lambda buf: ops.conv1d_wgrad(
-            x, dy, buf, None if bias is None else grad_buffer(bias), stride, dilation, relu_in))
+            x, dy, buf, None if bias is None else grad_buffer(bias), stride, dilation, relu_in, precision))
         if bias is not None:
             bias._grad_written = True
-        dx = ops.conv1d_dgrad(dy, kernel.value, x.shape, x if relu_in else None, stride, dilation, relu_in) \
-            if needs[0] else None
+        dx = ops.conv1d_dgrad(dy, kernel.value, x.shape, x if relu_in else None, stride, dilation, relu_in, None,
+                              precision) if needs[0] else None
         return [dx]
 
     record([x], [y], bwd)
@@ -550,6 +550,7 @@ class Conv1DTranspose(Layer):
         _same_only(padding, "Conv1DTranspose")
         self.filters, self.kernel_size, self.strides, self.use_bias = int(filters), int(kernel_size), int(strides), use_bias
         self.kernel = self.bias = None
+        self.precision = _lib.PREC_FP32
 
     def build(self, input_shape):
         cin = int(input_shape[-1])
@@ -561,16 +562,16 @@ class Conv1DTranspose(Layer):
         if _is_symbolic(x):
             L = x.shape[1]
             return KerasTensor((x.shape[0], None if L is None else L * self.strides, self.filters))
-        kernel, bias, s = self.kernel, self.bias, self.strides
-        y = ops.conv1d_transpose_fwd(x, kernel.value, None if bias is None else bias.value, s)
+        kernel, bias, s, prec = self.kernel, self.bias, self.strides, self.precision
+        y = ops.conv1d_transpose_fwd(x, kernel.value, None if bias is None else bias.value, s, prec)
 
         def bwd(g, needs):
             dy = g[0].contiguous()
             write_grad(kernel, lambda buf: ops.conv1d_transpose_wgrad(
-                x, dy, buf, None if bias is None else grad_buffer(bias), s))
+                x, dy, buf, None if bias is None else grad_buffer(bias), s, prec))
             if bias is not None:
                 bias._grad_written = True
-            return [ops.conv1d_transpose_dgrad(dy, kernel.value, x.shape, s) if needs[0] else None]
+            return [ops.conv1d_transpose_dgrad(dy, kernel.value, x.shape, s, prec) if needs[0] else None]
 
         record([x], [y], bwd)
         return y

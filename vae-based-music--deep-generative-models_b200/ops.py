@@ -61,6 +61,18 @@ def _cdesc(B, L, cin, cout, k, stride, dilation, relu_in, precision=0):
     return ConvDesc(B, L, cin, cout, k, stride, dilation, int(bool(relu_in)), precision)
 
 
+def _pick(d, op, transpose=False, plain=True):
+    """Keeps d.precision if libvqvae_b200 has a kernel for this (shape, op) in it and the call needs no fused extras
+    the tensor-core kernels lack (`plain`), else falls back to the exact fp32 path."""
+    if d.precision not in _lib.PRECISIONS.values():
+        raise _lib.VQBError(f"precision code {d.precision} is not available (include/vqb.h: VQB_PREC_*)")
+    if d.precision:
+        fn = _lib.lib().vqb_conv1d_transpose_supports if transpose else _lib.lib().vqb_conv1d_supports
+        if not plain or not fn(C.byref(d), op):
+            d.precision = 0
+    return d
+
+
 def conv1d_fwd(x, w, b, stride=1, dilation=1, relu_in=False, residual=None, precision=0):
     _chk(x, "x"); _chk(w, "w"); _chk(b, "b"); _chk(residual, "residual")
     B, L, cin = x.shape
@@ -68,17 +80,17 @@ def conv1d_fwd(x, w, b, stride=1, dilation=1, relu_in=False, residual=None, prec
     if wcin != cin:
         raise ValueError(f"Conv1D: input has {cin} channels, kernel expects {wcin}")
     y = empty(B, out_len(L, stride), cout)
-    d = _cdesc(B, L, cin, cout, k, stride, dilation, relu_in, precision)
+    d = _pick(_cdesc(B, L, cin, cout, k, stride, dilation, relu_in, precision), 0, plain=residual is None)
     call("vqb_conv1d_fwd", C.byref(d), ptr(x), ptr(w), ptr(b), ptr(residual), ptr(y), _lib.stream())
     return y
 
 
-def conv1d_dgrad(dy, w, x_shape, x=None, stride=1, dilation=1, relu_in=False, dx_add=None):
+def conv1d_dgrad(dy, w, x_shape, x=None, stride=1, dilation=1, relu_in=False, dx_add=None, precision=0):
     _chk(dy, "dy"); _chk(w, "w"); _chk(x, "x"); _chk(dx_add, "dx_add")
     B, L, cin = x_shape
     k, _, cout = w.shape
     dx = empty(B, L, cin)
-    d = _cdesc(B, L, cin, cout, k, stride, dilation, relu_in)
+    d = _pick(_cdesc(B, L, cin, cout, k, stride, dilation, relu_in, precision), 1, plain=dx_add is None)
     call("vqb_conv1d_dgrad", C.byref(d), ptr(dy), ptr(w), ptr(x), ptr(dx_add), ptr(dx), _lib.stream())
     return dx
 
@@ -87,41 +99,39 @@ def conv1d_wgrad(x, dy, dw, db, stride=1, dilation=1, relu_in=False, precision=0
     _chk(x, "x"); _chk(dy, "dy"); _chk(dw, "dw"); _chk(db, "db")
     B, L, cin = x.shape
     k, _, cout = dw.shape
-    d = _cdesc(B, L, cin, cout, k, stride, dilation, relu_in, precision)
-    if precision and not _lib.lib().vqb_conv1d_supports(C.byref(d), 2):
-        d.precision = 0  # no tensor-core kernel for this shape: exact fp32 path
+    d = _pick(_cdesc(B, L, cin, cout, k, stride, dilation, relu_in, precision), 2)  # no tensor-core kernel: exact fp32
     n = _lib.lib().vqb_conv1d_wgrad_workspace_bytes(C.byref(d))
     ws = _ws(n)
     call("vqb_conv1d_wgrad", C.byref(d), ptr(x), ptr(dy), ptr(dw), ptr(db), ptr(ws), ws.numel(), _lib.stream())
 
 
-def conv1d_transpose_fwd(x, w, b, stride=2):
+def conv1d_transpose_fwd(x, w, b, stride=2, precision=0):
     _chk(x, "x"); _chk(w, "w"); _chk(b, "b")
     B, L, cin = x.shape
     k, cout, wcin = w.shape
     if wcin != cin:
         raise ValueError(f"Conv1DTranspose: input has {cin} channels, kernel expects {wcin}")
     y = empty(B, L * stride, cout)
-    d = _cdesc(B, L, cin, cout, k, stride, 1, 0)
+    d = _pick(_cdesc(B, L, cin, cout, k, stride, 1, 0, precision), 0, transpose=True)
     call("vqb_conv1d_transpose_fwd", C.byref(d), ptr(x), ptr(w), ptr(b), ptr(y), _lib.stream())
     return y
 
 
-def conv1d_transpose_dgrad(dy, w, x_shape, stride=2):
+def conv1d_transpose_dgrad(dy, w, x_shape, stride=2, precision=0):
     _chk(dy, "dy"); _chk(w, "w")
     B, L, cin = x_shape
     k, cout, _ = w.shape
     dx = empty(B, L, cin)
-    d = _cdesc(B, L, cin, cout, k, stride, 1, 0)
+    d = _pick(_cdesc(B, L, cin, cout, k, stride, 1, 0, precision), 1, transpose=True)
     call("vqb_conv1d_transpose_dgrad", C.byref(d), ptr(dy), ptr(w), ptr(dx), _lib.stream())
     return dx
 
 
-def conv1d_transpose_wgrad(x, dy, dw, db, stride=2):
+def conv1d_transpose_wgrad(x, dy, dw, db, stride=2, precision=0):
     _chk(x, "x"); _chk(dy, "dy"); _chk(dw, "dw"); _chk(db, "db")
     B, L, cin = x.shape
     k, cout, _ = dw.shape
-    d = _cdesc(B, L, cin, cout, k, stride, 1, 0)
+    d = _pick(_cdesc(B, L, cin, cout, k, stride, 1, 0, precision), 2, transpose=True)
     n = _lib.lib().vqb_conv1d_transpose_wgrad_workspace_bytes(C.byref(d))
     ws = _ws(n)
     call("vqb_conv1d_transpose_wgrad", C.byref(d), ptr(x), ptr(dy), ptr(dw), ptr(db), ptr(ws), ws.numel(),

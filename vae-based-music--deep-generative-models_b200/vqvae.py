@@ -102,12 +102,13 @@ class VQVAE(Model):
     def set_precision(self, precision="fp32"):
         """Arithmetic of the contraction kernels: "fp32" (exact CUDA-core FMA), "tf32" or "bf16" (tcgen05 tensor cores,
         fp32 accumulate).  Layers whose shape has no tensor-core kernel keep fp32 (vqb_resblock_supports)."""
+        from .keras_compat import Conv1D, Conv1DTranspose
         from .resnet import ResnetConv1DBlock
         code = _lib.PRECISIONS[precision]
         for m in self.vqvaes:
             for l in m._flatten_layers():
-                if isinstance(l, ResnetConv1DBlock):
-                    l.precision = code
+                if isinstance(l, (ResnetConv1DBlock, Conv1D, Conv1DTranspose)):
+                    l.precision = code  # shapes without a tensor-core kernel fall back to fp32 per call (ops._pick)
         for vq in self.vqs:
             vq.precision = code  # tensor-core search + exact fp32 re-ranking (same indices as the fp32 search)
         self.precision = precision
