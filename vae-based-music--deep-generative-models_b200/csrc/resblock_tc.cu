@@ -83,13 +83,14 @@ __device__ __forceinline__ void pack_weights(uint8_t* dst, const float* __restri
   }
 }
 
-// 3 taps x KSTEPS x S accumulating MMAs for both M blocks of one stage, issued by a single thread.  In the split modes
+// 3 taps x KSTEPS x S accumulating MMAs for ONE of the two M blocks of a stage (two threads of different warps issue the
+// two blocks concurrently: the issue loop is on every warp's critical path between two block barriers).  In the split modes
 // the S weight pieces are stacked along N and activation piece `sa` is multiplied with the first S - sa of them into the
 // SAME accumulator (hi x {hi, mid, lo}, mid x {hi, mid}, lo x {hi}: every product down to 2^-16 of the leading one plus
 // mid x mid; the three omitted ones are below 2^-23): column block c then holds the sum over the activation pieces of
 // a . W_c, and the epilogue adds the S column blocks.
 template <int MODE>
-__device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int row_shift0, int dil, uint32_t w_base) {
+__device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int row_shift0, int dil, uint32_t w_base, int mb) {
   using Cfg = RbCfg<MODE>;
   // descriptors differ only in their start-address field (units of 16 bytes = one tile row): add offsets to two bases
   const uint64_t ad0 = smem_desc(a_base + (uint32_t)row_shift0 * 16u, Cfg::PLANE, 128);
@@ -103,11 +104,8 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int 
       for (int sa = 0; sa < Cfg::S; ++sa) {  // the widest MMA first: it initialises every column block
         const uint32_t idesc = instr_desc(Cfg::TF32 ? FMT_TF32 : FMT_BF16, 128, 32 * (Cfg::S - sa), false, false);
         const uint64_t bd = bd0 + (uint64_t)((j * Cfg::WTAP + kk * 2 * Cfg::WPLANE) >> 4);
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {  // the two M blocks alternate: two independent accumulator chains in flight
-          const uint64_t ad = ad0 + (uint64_t)((sa * Cfg::TILE + kk * 2 * Cfg::PLANE + mb * 128 * 16) >> 4) + (uint64_t)(j * dil);
-          mma<Cfg::TF32>(tmem + mb * Cfg::NW, ad, bd, idesc, acc);
-        }
+        const uint64_t ad = ad0 + (uint64_t)((sa * Cfg::TILE + kk * 2 * Cfg::PLANE) >> 4) + (uint64_t)(mb * 128 + j * dil);
+        mma<Cfg::TF32>(tmem + mb * Cfg::NW, ad, bd, idesc, acc);
         acc = 1;
       }
 }
@@ -155,7 +153,7 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
   const int rows1 = Cfg::R + 2 * p.d1;
 
   if (warp == 0) tmem_alloc(tslot, Cfg::TCOLS);
-  if (tid == 32) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+  if (tid == 32) { mbar_init(&bar[0], 2); mbar_init(&bar[1], 2); fence_mbar_init(); }  // one arrival per issuing thread
   pack_weights<MODE>(W1, p.w1, p.sj1, p.si1, p.so1, p.flip1);
   pack_weights<MODE>(W2, p.w2, p.sj2, p.si2, p.so2, p.flip2);
   if (tid < 64) bias_s[tid] = tid < 32 ? (p.bias1 ? p.bias1[tid] : 0.f) : (p.bias2 ? p.bias2[tid - 32] : 0.f);
@@ -213,8 +211,8 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (tid == 32) {
-      issue_stage<MODE>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1));
+    if (tid == 32 || tid == 160) {
+      issue_stage<MODE>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1), tid >> 7);
       commit(&bar[0]);
     }
     __syncwarp();
@@ -283,9 +281,9 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
     fence_before_sync();
     __syncthreads();  // A2 complete; every warp has drained the stage-1 accumulators
     fence_after_sync();
-    if (tid == 32) {
+    if (tid == 32 || tid == 160) {
       // out2 tile row i uses A2 rows DMAX + i + (j-1)*d2
-      issue_stage<MODE>(tmem + 2 * Cfg::NW, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2));
+      issue_stage<MODE>(tmem + 2 * Cfg::NW, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2), tid >> 7);
       commit(&bar[1]);
     }
     __syncwarp();
@@ -294,8 +292,8 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
       fence_before_sync();
       __syncthreads();
       fence_after_sync();
-      if (tid == 32) {
-        issue_stage<MODE>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1));
+      if (tid == 32 || tid == 160) {
+        issue_stage<MODE>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1), tid >> 7);
         commit(&bar[0]);
       }
       __syncwarp();
