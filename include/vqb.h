@@ -201,6 +201,33 @@ int vqb_gather_codes(const float* E, int32_t D, int32_t K, const int64_t* idx, i
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Multi-scale spectral convergence loss (vqvae.py:309-326, data_utils.py:25-40): the element-wise halves around the
+ * FFT (cuFFT, called by the host layer).  tf.signal.stft semantics: F = 1 + (T - win) / hop frames of `win` samples,
+ * periodic Hann window, zero padding at the END up to n_fft.  Spectra are complex64 (interleaved re, im),
+ * [B, per_example = F * bins] with bins = n_fft / 2 + 1.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* frames [B, F, n_fft] = windowed, zero-padded frames of x [B, T] */
+int vqb_stft_frames(const float* x, int64_t B, int32_t T, int32_t n_fft, int32_t hop, int32_t win, float* frames,
+                    void* stream);
+size_t vqb_spec_workspace_bytes(int64_t B, int64_t per_example);
+/* mag = |S|, sums[b] = sum |S[b]|^2   (target side; cached by the caller) */
+int vqb_spec_mag(const float* S, int64_t B, int64_t per_example, float* mag, float* sums, void* workspace,
+                 size_t workspace_bytes, void* stream);
+/* sums[b] = sum (mag_t[b] - |S[b]|)^2 */
+int vqb_spec_diff(const float* S, const float* mag_t, int64_t B, int64_t per_example, float* sums, void* workspace,
+                  size_t workspace_bytes, void* stream);
+/* dsum, tsum [nscales, B] -> loss[0] = mean_b mean_s sqrt(dsum) / sqrt(tsum); coef [nscales, B] (may be NULL) =
+ * d loss / d(sum-of-squares root) factors consumed by vqb_spec_grad */
+int vqb_spec_loss(const float* dsum, const float* tsum, int32_t nscales, int32_t B, float* loss, float* coef,
+                  void* stream);
+/* G [B, F, bins] complex64: irfft(G, n = n_fft) is d(upstream[0] * loss) / d frames (coef = this scale's row) */
+int vqb_spec_grad(const float* S, const float* mag_t, const float* coef, const float* upstream, int64_t B,
+                  int64_t per_example, int32_t bins, int32_t n_fft, float* G, void* stream);
+/* dx [B, T] (+)= overlap-add of dframes [B, F, n_fft] * window (accumulate != 0: add to dx) */
+int vqb_stft_frames_bwd(const float* dframes, int64_t B, int32_t T, int32_t n_fft, int32_t hop, int32_t win,
+                        int32_t accumulate, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * loss head + optimiser pieces of VQVAE.train_step (vqvae.py:125,143-144)
  * ---------------------------------------------------------------------------------------------------------- */
 size_t vqb_reduce_workspace_bytes(int64_t n);

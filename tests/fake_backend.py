@@ -167,6 +167,62 @@ class FakeBackend:
             _t(dbf, (1,)).copy_(gbf)
         return 0
 
+    # ---- spectral loss pieces (torch restatement of csrc/spectral.cu)
+    @staticmethod
+    def _hann(win):
+        i = torch.arange(win, dtype=torch.float64)
+        return (0.5 - 0.5 * torch.cos(2.0 * np.pi * i / win)).float()
+
+    def vqb_stft_frames(self, x, B, T, n_fft, hop, win, frames, stream):
+        F = 1 + (T - win) // hop
+        fr = _t(x, (B, T)).unfold(-1, win, hop) * self._hann(win)
+        out = _t(frames, (B, F, n_fft))
+        out.zero_()
+        out[..., :win] = fr
+        return 0
+
+    def vqb_spec_workspace_bytes(self, B, per):
+        return 64
+
+    def vqb_spec_mag(self, S, B, per, mag, sums, ws, wsn, stream):
+        s = _t(S, (B, per, 2))
+        m = torch.sqrt(s[..., 0] ** 2 + s[..., 1] ** 2)
+        _t(mag, (B, per)).copy_(m); _t(sums, (B,)).copy_((m * m).sum(1))
+        return 0
+
+    def vqb_spec_diff(self, S, mag_t, B, per, sums, ws, wsn, stream):
+        s = _t(S, (B, per, 2))
+        d = _t(mag_t, (B, per)) - torch.sqrt(s[..., 0] ** 2 + s[..., 1] ** 2)
+        _t(sums, (B,)).copy_((d * d).sum(1))
+        return 0
+
+    def vqb_spec_loss(self, dsum, tsum, nscales, B, loss, coef, stream):
+        nd, nt = torch.sqrt(_t(dsum, (nscales, B))), torch.sqrt(_t(tsum, (nscales, B)))
+        _t(loss, (1,)).copy_((nd / nt).mean().reshape(1))
+        if coef is not None:
+            _t(coef, (nscales, B)).copy_(torch.where(nd > 0, 1.0 / (nscales * B * nt * nd), torch.zeros_like(nd)))
+        return 0
+
+    def vqb_spec_grad(self, S, mag_t, coef, upstream, B, per, bins, n_fft, G, stream):
+        s = _t(S, (B, per, 2)); mt = _t(mag_t, (B, per))
+        m = torch.sqrt(s[..., 0] ** 2 + s[..., 1] ** 2)
+        k = torch.arange(per) % bins
+        w = torch.where((k == 0) | (k == bins - 1), float(n_fft), 0.5 * n_fft)
+        c = _t(upstream, (1,))[0] * _t(coef, (B,))[:, None] * (m - mt) / torch.where(m > 0, m, torch.ones_like(m)) * w
+        c = torch.where(m > 0, c, torch.zeros_like(c))
+        _t(G, (B, per, 2)).copy_(c[..., None] * s)
+        return 0
+
+    def vqb_stft_frames_bwd(self, dframes, B, T, n_fft, hop, win, accumulate, dx, stream):
+        F = 1 + (T - win) // hop
+        d = _t(dframes, (B, F, n_fft))[..., :win] * self._hann(win)
+        out = torch.zeros(B, T)
+        for f in range(F):
+            out[:, f * hop:f * hop + win] += d[:, f]
+        tgt = _t(dx, (B, T))
+        tgt.copy_(tgt + out if accumulate else out)
+        return 0
+
     # ---- resblock
     def vqb_resblock_supports(self, dref):
         return 1

@@ -311,3 +311,28 @@ def test_decoder_tail_matches_two_layer_oracle(gpu, B, L, cin, cmid, bias):
     y = ops.conv1d_transpose_fwd(dev(x), dev(wt), D(bt) if bias else ops.zeros(cmid), 2)
     r2 = ops.conv1d_fwd(y, dev(wf), D(bf) if bias else ops.zeros(1), 1, 1, False, None)
     close(recon, r2, tol=2e-5, what="recon vs two kernels")
+
+
+@pytest.mark.parametrize("B,T", [(3, 2048), (2, 28160), (1, 4096)])
+def test_multispectral_loss_kernels_match_oracle(gpu, B, T):
+    """csrc/spectral.cu around cuFFT (framing + periodic Hann + end padding, magnitudes, Frobenius sums, loss, gradient w.r.t.
+    the spectrum, overlap-add) against the oracle's tf.signal.stft restatement and its autograd gradient
+    (vqvae.py:309-326, data_utils.py:25-40)."""
+    V = gpu
+    rng = np.random.default_rng(T + B)
+    x = rng.uniform(0, 1, size=(B, T, 1)).astype(np.float32)
+    r = (x + 0.1 * rng.normal(size=(B, T, 1))).astype(np.float32)
+    rt = torch.tensor(r, requires_grad=True)
+    want = O.multispectral_loss(torch.tensor(x).squeeze(-1), rt.squeeze(-1)).mean()
+    (gwant,) = torch.autograd.grad(want, rt)
+    V.data_utils.clear_cache()
+    rd = dev(r)
+    with V.GradientTape() as tape:
+        loss = V.data_utils.MultiSpectralLoss(dev(x), rd)._reduce_mean()
+    node = tape.nodes[-1]
+    (dr,) = node.bwd([1.0], [True])
+    assert abs(float(loss) - float(want)) <= 2e-5 * abs(float(want))
+    close(dr, gwant, tol=2e-4, what="d loss / d recon")
+    # the public helpers keep the reference's semantics (data_utils.py:25-40)
+    s = V.data_utils.spectral(dev(x).squeeze(-1), 512, 50, 240)
+    close(s, O.spectral(torch.tensor(x).squeeze(-1), 512, 50, 240), tol=2e-5, what="spectral")

@@ -77,6 +77,13 @@ SIGNATURES = {
     "vqb_gather_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     "vqb_restart_ids": (C.c_int, [C.c_int64, C.c_int32, C.c_uint64, _P, _P, _P]),
     "vqb_gather_codes": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P]),
+    "vqb_stft_frames": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "vqb_spec_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "vqb_spec_mag": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
+    "vqb_spec_diff": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, C.c_size_t, _P]),
+    "vqb_spec_loss": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "vqb_spec_grad": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    "vqb_stft_frames_bwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "vqb_reduce_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "vqb_mse": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,

@@ -1,10 +1,11 @@
 """data_utils — the loss-head part of the reference's `data_utils.py` (:19-40): `STFT_ARGS`, `spectral`, `norm`,
 plus the multi-scale spectral loss of `vqvae.py:309-326`.
 
-ROUND-1 STATUS (a "next" row): the STFT is evaluated with torch.fft (cuFFT) on the device and
-differentiated by torch autograd; it is not yet a libvqvae_b200 kernel.  Semantics follow tf.signal.stft: frames of
-`window_length` samples every `hop_length`, periodic Hann window, zero padding at the END up to `n_fft`,
-pad_end=False (torch.stft centres/pads differently and is NOT used)."""
+SURVEY.md section 8f-1: the FFT itself is cuFFT (torch.fft.rfft / irfft on the device); everything around it — framing +
+periodic Hann window + zero padding, magnitudes, Frobenius sums, the loss, its gradient with respect to the spectrum and
+the overlap-add back onto the waveform — is libvqvae_b200 (csrc/spectral.cu), forward AND backward, with no autograd.
+Semantics follow tf.signal.stft: frames of `window_length` samples every `hop_length`, periodic Hann window, zero padding
+at the END up to `n_fft`, pad_end=False (torch.stft centres/pads differently and is NOT used)."""
 from __future__ import annotations
 
 import contextlib
@@ -12,27 +13,19 @@ import math
 
 import torch
 
+from . import ops
 from .keras_compat import GradientTape, Scalar, convert_to_tensor, record
 
 STFT_ARGS = [(2048, 1024, 512),  # n_fft
              (240, 120, 50),     # hop_length
              (1200, 600, 240)]   # window_size
 
-_windows = {}
-
-
-def _hann(n, device):
-    key = (n, str(device))
-    if key not in _windows:
-        i = torch.arange(n, dtype=torch.float64)
-        _windows[key] = (0.5 - 0.5 * torch.cos(2.0 * math.pi * i / n)).to(torch.float32).to(device)
-    return _windows[key]
-
-
 def spectral(x, n_fft, hop_length, window_length):
     """|STFT|: x [..., T] -> [..., frames, n_fft//2 + 1]   (data_utils.py:25-30)"""
-    frames = x.unfold(-1, window_length, hop_length) * _hann(window_length, x.device)
-    return torch.fft.rfft(frames, n=n_fft, dim=-1).abs()
+    x = convert_to_tensor(x)
+    lead, T = x.shape[:-1], x.shape[-1]
+    S = _rfft_frames(x.reshape(-1, T).contiguous(), n_fft, hop_length, window_length)
+    return S.abs().reshape(*lead, S.shape[-2], S.shape[-1])
 
 
 def norm(x):
@@ -43,15 +36,21 @@ def norm(x):
 _target_cache = {"key": None, "val": None}
 
 
+def _rfft_frames(x2d, n_fft, hop, win):
+    """complex64 [B, F, n_fft // 2 + 1]: cuFFT over the windowed frames produced by vqb_stft_frames."""
+    return torch.fft.rfft(ops.stft_frames(x2d, n_fft, hop, win), dim=-1)
+
+
 def _target_specs(t):
+    """per scale: (|S(target)| [B, F, bins]); and tsum [nscales, B] = their squared Frobenius norms.  Cached per batch: both
+    levels of the model compare against the same target (vqvae.py:119-127)."""
     key = (t.data_ptr(), t._version, tuple(t.shape))
     if _target_cache["key"] != key:
-        with torch.no_grad():
-            specs = []
-            for n_fft, hop, win in zip(*STFT_ARGS):
-                s = spectral(t, n_fft, hop, win)
-                specs.append((s, norm(s)))
-        _target_cache["key"], _target_cache["val"] = key, specs
+        mags, sums = [], []
+        for n_fft, hop, win in zip(*STFT_ARGS):
+            m, s_ = ops.spec_mag(_rfft_frames(t, n_fft, hop, win))
+            mags.append(m); sums.append(s_)
+        _target_cache["key"], _target_cache["val"] = key, (mags, torch.stack(sums))
     return _target_cache["val"]
 
 
@@ -60,29 +59,35 @@ def clear_cache():
 
 
 class MultiSpectralLoss:
-    """Lazy per-example multi-scale spectral convergence loss (vqvae.py:309-326); `reduce_mean` evaluates it."""
+    """Lazy per-example multi-scale spectral convergence loss (vqvae.py:309-326); `reduce_mean` evaluates it:
+    mean over the batch of the mean over the three scales of ||S(x) - S(x_hat)||_F / ||S(x)||_F."""
 
     def __init__(self, target, recon):
         self.target, self.recon = convert_to_tensor(target), recon
 
-    def _per_example(self, t, r):
-        losses = []
-        for (st, nt), (n_fft, hop, win) in zip(_target_specs(t), zip(*STFT_ARGS)):
-            losses.append(norm(st - spectral(r, n_fft, hop, win)) / nt)
-        return torch.stack(losses, dim=-1).mean(dim=-1)
-
     def _reduce_mean(self):
         r = self.recon
-        t = self.target.squeeze(-1)
+        B, T = r.shape[0], r.shape[1]
+        t2, r2 = self.target.reshape(B, T).contiguous(), r.reshape(B, T).contiguous()
+        mags, tsum = _target_specs(t2)
+        scales = list(zip(*STFT_ARGS))
         taped = GradientTape.current() is not None
-        with (torch.enable_grad() if taped else contextlib.nullcontext()):
-            rl = r.detach().requires_grad_(taped)
-            val = self._per_example(t, rl.squeeze(-1)).mean()
-        loss = val.detach().reshape(1)
+        dsum = ops.empty(len(scales), B)
+        specs = []
+        for s, (n_fft, hop, win) in enumerate(scales):
+            S = _rfft_frames(r2, n_fft, hop, win)
+            ops.spec_diff(S, mags[s], dsum[s])
+            specs.append(S if taped else None)
+        loss, coef = ops.spec_loss(dsum, tsum, taped)
 
         def bwd(g, needs):
-            (dr,) = torch.autograd.grad(val, rl, grad_outputs=torch.full_like(val, float(g[0])))
-            return [dr]
+            up = torch.full((1,), float(g[0]), dtype=torch.float32, device=r.device)
+            dr = ops.empty(B, T)
+            for s, (n_fft, hop, win) in enumerate(scales):
+                G = ops.spec_grad(specs[s], mags[s], coef[s], up, n_fft)
+                dfr = torch.fft.irfft(G, n=n_fft, dim=-1).contiguous()
+                ops.stft_frames_bwd(dfr, T, hop, win, dr, s > 0)
+            return [dr.reshape(r.shape)]
 
         record([r], [loss], bwd)
         return Scalar.leaf(loss)

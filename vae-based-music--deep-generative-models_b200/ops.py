@@ -278,3 +278,56 @@ def adam_step(p, g, m, v, lr, b1, b2, eps, grad_scale, step_counter):
 
 def increment(counter):
     call("vqb_increment", ptr(counter), _lib.stream())
+
+
+# ------------------------------------------------------------------------------------- spectral loss pieces
+def stft_frames(x2d, n_fft, hop, win):
+    """x [B, T] -> windowed, zero-padded frames [B, F, n_fft] (tf.signal.stft framing, data_utils.py:25-30)."""
+    _chk(x2d, "x")
+    B, T = x2d.shape
+    F = 1 + (T - win) // hop
+    fr = empty(B, F, n_fft)
+    call("vqb_stft_frames", ptr(x2d), B, T, n_fft, hop, win, ptr(fr), _lib.stream())
+    return fr
+
+
+def _spec_ws(B, per):
+    return _ws(_lib.lib().vqb_spec_workspace_bytes(B, per))
+
+
+def spec_mag(S):
+    """S complex64 [B, F, bins] -> (|S| [B, F, bins], sum |S|^2 per example [B])."""
+    Sr = torch.view_as_real(S)
+    B, per = S.shape[0], S.shape[1] * S.shape[2]
+    mag, sums, ws = empty(*S.shape), empty(B), _spec_ws(B, per)
+    call("vqb_spec_mag", ptr(Sr), B, per, ptr(mag), ptr(sums), ptr(ws), ws.numel(), _lib.stream())
+    return mag, sums
+
+
+def spec_diff(S, mag_t, sums):
+    """sums[b] = sum (mag_t - |S|)^2 over example b (the squared norm of data_utils.norm(S_t - S_r))."""
+    Sr = torch.view_as_real(S)
+    B, per = S.shape[0], S.shape[1] * S.shape[2]
+    ws = _spec_ws(B, per)
+    call("vqb_spec_diff", ptr(Sr), ptr(mag_t), B, per, ptr(sums), ptr(ws), ws.numel(), _lib.stream())
+
+
+def spec_loss(dsum, tsum, want_coef):
+    nscales, B = dsum.shape
+    loss, coef = empty(1), (empty(nscales, B) if want_coef else None)
+    call("vqb_spec_loss", ptr(dsum), ptr(tsum), nscales, B, ptr(loss), ptr(coef), _lib.stream())
+    return loss, coef
+
+
+def spec_grad(S, mag_t, coef_row, upstream, n_fft):
+    Sr = torch.view_as_real(S)
+    B, F, bins = S.shape
+    G = torch.empty_like(S)
+    call("vqb_spec_grad", ptr(Sr), ptr(mag_t), ptr(coef_row), ptr(upstream), B, F * bins, bins, n_fft,
+         ptr(torch.view_as_real(G)), _lib.stream())
+    return G
+
+
+def stft_frames_bwd(dframes, T, hop, win, dx, accumulate):
+    B, F, n_fft = dframes.shape
+    call("vqb_stft_frames_bwd", ptr(dframes), B, T, n_fft, hop, win, int(bool(accumulate)), ptr(dx), _lib.stream())
