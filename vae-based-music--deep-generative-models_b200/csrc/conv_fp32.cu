@@ -621,10 +621,100 @@ static int run_phases(TgcParams base, int k, int s, int dil, int padL, int L_ful
   return VQB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// C_in = 1 (the first encoder convolution, encdec.py:33 on the raw waveform): a k-tap FIR into C_out <= 32 channels.
+// Pure bandwidth: the forward pass writes y once; the weight/bias gradient reads dy once (lane = output channel, the
+// k waveform samples of a row are fetched by k lanes and broadcast), per-CTA partials, fixed-order reduction.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int IN1_MAXK = 8;
+__global__ void __launch_bounds__(256) conv_in1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ y, int L, int Lo,
+                                                           int Co, int k, int stride, int padL, long total) {
+  __shared__ float ws[IN1_MAXK * 32 + 32];
+  for (int e = threadIdx.x; e < k * Co; e += 256) ws[e] = w[e];
+  for (int e = threadIdx.x; e < Co; e += 256) ws[IN1_MAXK * 32 + e] = bias ? bias[e] : 0.f;
+  __syncthreads();
+  const long e = (long)blockIdx.x * 256 + threadIdx.x;  // one thread per (row, 4 channels)
+  if (e >= total) return;
+  const int c4n = Co >> 2;
+  const int c = (int)(e % c4n) * 4;
+  const long row = e / c4n;
+  const long b = row / Lo;
+  const int t = (int)(row - b * Lo);
+  const float* xb = x + b * L;
+  float4 acc = *reinterpret_cast<const float4*>(ws + IN1_MAXK * 32 + c);
+  for (int j = 0; j < k; ++j) {
+    const int g = t * stride + j - padL;
+    if (g >= 0 && g < L) {
+      const float xv = xb[g];
+      const float4 wv = *reinterpret_cast<const float4*>(ws + j * Co + c);
+      acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+    }
+  }
+  *reinterpret_cast<float4*>(y + row * Co + c) = acc;
+}
+
+constexpr int IN1_PART = (IN1_MAXK + 1) * 32;  // per-CTA partial: k tap rows + the bias row, 32 channels each
+__global__ void __launch_bounds__(256) conv_in1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                             float* __restrict__ partial, long rows, int L, int Lo, int Co, int k,
+                                                             int stride, int padL, long rpw) {
+  __shared__ float red[8][IN1_PART];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float acc[IN1_MAXK + 1];
+#pragma unroll
+  for (int j = 0; j <= IN1_MAXK; ++j) acc[j] = 0.f;
+  const long r0 = ((long)blockIdx.x * 8 + warp) * rpw;
+  const long r1 = r0 + rpw < rows ? r0 + rpw : rows;
+#pragma unroll 4
+  for (long row = r0; row < r1; ++row) {
+    const long b = row / Lo;
+    const int t = (int)(row - b * Lo);
+    const int g = t * stride + lane - padL;
+    const float xv = (lane < k && g >= 0 && g < L) ? x[b * L + g] : 0.f;
+    const float d = lane < Co ? dy[row * Co + lane] : 0.f;
+#pragma unroll
+    for (int j = 0; j < IN1_MAXK; ++j) acc[j] = fmaf(__shfl_sync(0xffffffffu, xv, j), d, acc[j]);
+    acc[IN1_MAXK] += d;
+  }
+#pragma unroll
+  for (int j = 0; j <= IN1_MAXK; ++j) red[warp][j * 32 + lane] = acc[j];
+  __syncthreads();
+  for (int e = tid; e < IN1_PART; e += 256) {
+    float s_ = red[0][e];
+#pragma unroll
+    for (int w_ = 1; w_ < 8; ++w_) s_ += red[w_][e];
+    partial[(size_t)blockIdx.x * IN1_PART + e] = s_;
+  }
+}
+
+static bool conv_in1_ok(const vqb_conv_desc* d) {
+  return d->C_in == 1 && d->C_out <= 32 && (d->C_out & 3) == 0 && d->k <= IN1_MAXK && d->dilation == 1 && !d->relu_in;
+}
+static int conv_in1_grid(long rows, long* rpw) {
+  long warps = cdiv(rows, 64);
+  if (warps > 592 * 8) warps = 592 * 8;
+  if (warps < 1) warps = 1;
+  const int grid = cdiv(warps, 8);
+  *rpw = cdiv(rows, (long)grid * 8);
+  if (*rpw < 1) *rpw = 1;
+  return grid;
+}
+static size_t conv_in1_ws_floats(const vqb_conv_desc* d) {
+  long rpw;
+  return (size_t)conv_in1_grid((long)d->B * ((d->L + d->stride - 1) / d->stride), &rpw) * IN1_PART + 64;
+}
+
 int conv1d_fwd_fp32(const vqb_conv_desc* d, const float* x, const float* w, const float* bias,
                     const float* residual, float* y, cudaStream_t st) {
   int Lo, padL;
   same_pad(d->L, d->k, d->stride, d->dilation, &Lo, &padL);
+  if (conv_in1_ok(d) && !residual) {
+    const long total = (long)d->B * Lo * (d->C_out >> 2);
+    if (total == 0) return VQB_OK;
+    conv_in1_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, w, bias, y, d->L, Lo, d->C_out, d->k, d->stride, padL, total);
+    VQB_LAUNCH_CHECK();
+    return VQB_OK;
+  }
   TgcParams p{};
   p.in = x; p.w = w; p.bias = bias; p.res = residual; p.out = y;
   p.B = d->B; p.L_in = d->L; p.CIN = d->C_in; p.COUT = d->C_out; p.L_out = Lo;
@@ -734,7 +824,9 @@ size_t vqb_conv1d_wgrad_workspace_bytes(const vqb_conv_desc* d) {
   if (d->precision != VQB_PREC_FP32 && conv_tc_supported(d)) return wgrad4_tc_workspace_bytes(d->B, (d->L + 1) / 2);
   int Lo, padL;
   same_pad(d->L, d->k, d->stride, d->dilation, &Lo, &padL);
-  return wgrad_ws_floats(d->B, Lo, d->k, d->C_in, d->C_out, (long)d->B * Lo, d->C_out) * sizeof(float);
+  size_t n = wgrad_ws_floats(d->B, Lo, d->k, d->C_in, d->C_out, (long)d->B * Lo, d->C_out);
+  if (conv_in1_ok(d) && conv_in1_ws_floats(d) > n) n = conv_in1_ws_floats(d);
+  return n * sizeof(float);
 }
 
 int vqb_conv1d_wgrad(const vqb_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
@@ -759,6 +851,25 @@ int vqb_conv1d_wgrad(const vqb_conv_desc* d, const float* x, const float* dy, fl
   }
   int Lo, padL;
   same_pad(d->L, d->k, d->stride, d->dilation, &Lo, &padL);
+  if (conv_in1_ok(d) && (long)d->B * Lo > 0) {
+    const size_t need = conv_in1_ws_floats(d) * sizeof(float);
+    if (!workspace || workspace_bytes < need) return set_err(VQB_ERR_WORKSPACE, "wgrad workspace: need %zu bytes, got %zu", need, workspace_bytes);
+    long rpw;
+    const long rows = (long)d->B * Lo;
+    const int grid = conv_in1_grid(rows, &rpw);
+    float* partial = (float*)workspace;
+    conv_in1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, dy, partial, rows, d->L, Lo, d->C_out, d->k, d->stride, padL, rpw);
+    VQB_LAUNCH_CHECK();
+    for (int j = 0; j < d->k; ++j) {  // dw [k, 1, C_out]: one fixed-order reduction per tap row (32-float rows in the partials)
+      reduce_chunks_strided(partial, grid, IN1_PART, j * 32, d->C_out, dw + (size_t)j * d->C_out, (cudaStream_t)stream);
+      VQB_LAUNCH_CHECK();
+    }
+    if (dbias) {
+      reduce_chunks_strided(partial, grid, IN1_PART, IN1_MAXK * 32, d->C_out, dbias, (cudaStream_t)stream);
+      VQB_LAUNCH_CHECK();
+    }
+    return VQB_OK;
+  }
   WgParams p{};
   p.ga = x; p.ot = dy;
   p.B = d->B; p.Lg = d->L; p.Cg = d->C_in; p.Lo = Lo; p.Co = d->C_out; p.Lt = Lo;

@@ -61,7 +61,8 @@ struct RbCfg {
   static constexpr int STG = (NT / 32) * 2048;  // per-warp row staging (32 rows x 64 B)
   static constexpr int SMEM = 2 * S * TILE + 2 * WCONV + STG + 64 + 256;
   static constexpr int TCOLS = 4 * NW <= 128 ? 128 : 4 * NW <= 256 ? 256 : 512;  // TMEM columns: 2 stages x 2 M blocks x NW
-  static constexpr int NU = ((R + 2 * DMAX) * 4 + NT - 1) / NT;  // 8-channel units of the stage-1 input tile per thread
+  static constexpr int NCV = NT - 64;   // threads that load / convert the stage-1 input (all but the two MMA-issuing warps)
+  static constexpr int NU = ((R + 2 * DMAX) * 4 + NCV - 1) / NCV;  // 8-channel units of the stage-1 input tile per converter thread
 };
 
 template <int MODE>
@@ -169,17 +170,23 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
   const int i = i0 + lane;             // tile row (= TMEM lane) of this thread
   const uint32_t taddr = tmem + (((uint32_t)qd * 32u) << 16) + (uint32_t)(mb * Cfg::NW + half * 16);
   uint8_t* stg = stg_base + warp * 2048;
-  const int oct = tid & 3;  // 8-channel unit of this thread in the staging loops (NT % 4 == 0)
+  // warps 1 and 5 issue the MMAs (one M block each) while the other 14 warps stage the next tile: they take no part in load /
+  // convert, so that both groups reach the barrier behind the conversion at about the same time
+  const bool issuer = warp == 1 || warp == 5;
+  const int ctid = (warp - (warp > 1) - (warp > 5)) * 32 + lane;  // index among the converter threads
+  const int oct = ctid & 3;  // 8-channel unit of this thread in the staging loops (NCV % 4 == 0)
+  constexpr int NCV = Cfg::NCV;
 
   float4 ra[NU], rb[NU];
   // global rows of tile `tile`: A1 row r holds in1 row g1 + r
   auto load = [&](int tile) {
+    if (issuer) return;
     const int b = tile / p.tiles_x;
     const int g1 = (tile - b * p.tiles_x) * Rout - p.d2 - p.d1;
     const float* inb = p.in1 + (size_t)b * L * 32 + oct * 8;
 #pragma unroll
     for (int k = 0; k < NU; ++k) {
-      const int r = (tid + k * NT) >> 2;
+      const int r = (ctid + k * NCV) >> 2;
       const int g = g1 + r;
       const bool ok = r < rows1 && g >= 0 && g < L;
       ra[k] = ok ? *reinterpret_cast<const float4*>(inb + (long)g * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -187,11 +194,12 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
     }
   };
   auto convert = [&]() {
+    if (issuer) return;
 #pragma unroll
     for (int k = 0; k < NU; ++k) { reg_fence(ra[k]); reg_fence(rb[k]); }  // keep the conversion below the waits it follows
 #pragma unroll
     for (int k = 0; k < NU; ++k) {
-      const int r = (tid + k * NT) >> 2;
+      const int r = (ctid + k * NCV) >> 2;
       if (r < rows1) {
         float4 a = ra[k], b = rb[k];
         if (p.relu1) {

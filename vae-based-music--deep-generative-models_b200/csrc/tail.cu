@@ -32,23 +32,30 @@ __device__ __forceinline__ int tail_group(int j, int k) {
   return tab[j * 4 + k];
 }
 
-__global__ void __launch_bounds__(128) tail_prep_kernel(const float* __restrict__ wt, const float* __restrict__ bt,
+__global__ void __launch_bounds__(256) tail_prep_kernel(const float* __restrict__ wt, const float* __restrict__ bt,
                                                         const float* __restrict__ wf, const float* __restrict__ bf, int C,
                                                         int Cm, float* __restrict__ gbuf) {
+  extern __shared__ __align__(16) float psm[];  // wt [4*Cm*C], wf [3*Cm], bt [Cm] staged once (coalesced), then V from shared memory
+  float* wts = psm;
+  float* wfs = wts + 4 * Cm * C;
+  float* bts = wfs + 3 * Cm;
   __shared__ float V[12][32];
   __shared__ float cj[3];
   const int tid = threadIdx.x;
+  for (int e = tid; e < 4 * Cm * C; e += blockDim.x) wts[e] = wt[e];
+  for (int e = tid; e < 3 * Cm; e += blockDim.x) wfs[e] = wf[e];
+  for (int e = tid; e < Cm; e += blockDim.x) bts[e] = bt ? bt[e] : 0.f;
+  __syncthreads();
   for (int e = tid; e < 12 * 32; e += blockDim.x) {
     const int ci = e & 31, k = (e >> 5) & 3, j = e >> 7;
     float a = 0.f;
     if (ci < C)
-      for (int c = 0; c < Cm; ++c) a = fmaf(wf[j * Cm + c], wt[((size_t)k * Cm + c) * C + ci], a);
+      for (int c = 0; c < Cm; ++c) a = fmaf(wfs[j * Cm + c], wts[(k * Cm + c) * C + ci], a);
     V[j * 4 + k][ci] = a;
   }
   if (tid < 3) {
     float a = 0.f;
-    if (bt)
-      for (int c = 0; c < Cm; ++c) a = fmaf(wf[tid * Cm + c], bt[c], a);
+    for (int c = 0; c < Cm; ++c) a = fmaf(wfs[tid * Cm + c], bts[c], a);
     cj[tid] = a;
   }
   __syncthreads();
@@ -131,10 +138,11 @@ __global__ void __launch_bounds__(256) tail_bwd_kernel(const float* __restrict__
   const long r0 = ((long)blockIdx.x * 8 + warp) * rpw;
   const long r1 = r0 + rpw < rows ? r0 + rpw : rows;
   const int L2 = 2 * L;
+  long b = r0 / L;
+  int m = (int)(r0 - b * L) - 1;
 #pragma unroll 4
   for (long row = r0; row < r1; ++row) {
-    const long b = row / L;
-    const int m = (int)(row - b * L);
+    if (++m == L) { m = 0; ++b; }
     const int t = 2 * m - 2 + lane;  // lanes 0..5 fetch dr[2m-2 .. 2m+3]
     const float val = (lane < 6 && t >= 0 && t < L2) ? dr[b * L2 + t] : 0.f;
     const float xv = act ? x[row * C + lane] : 0.f;
@@ -173,10 +181,23 @@ __global__ void __launch_bounds__(256) tail_finish_kernel(const float* __restric
   __shared__ float dV[12][32];
   __shared__ float b0[32], b1[32], sc[8];  // sc: sdr, e0, e1, dc_0..2
   const int tid = threadIdx.x;
-  if (tid < TAIL_PART) {
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * TAIL_PART + tid];
-    dG[tid] = s;
+  // weights staged once (coalesced): the gradient formulas below re-read them Cin * 4 times per output
+  extern __shared__ __align__(16) float fsm[];
+  float* wts = fsm;                 // [4*Cm*C]
+  float* wfs = wts + 4 * Cm * C;    // [3*Cm]
+  float* bts = wfs + 3 * Cm;        // [Cm]
+  for (int e = tid; e < 4 * Cm * C; e += blockDim.x) wts[e] = wt[e];
+  for (int e = tid; e < 3 * Cm; e += blockDim.x) wfs[e] = wf[e];
+  for (int e = tid; e < Cm; e += blockDim.x) bts[e] = bt ? bt[e] : 0.f;
+  if (tid < TAIL_PART) {  // fixed-order sum over the CTA partials: 8 independent chains, coalesced across threads
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int p = 0;
+    for (; p + 8 <= nparts; p += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += partial[(size_t)(p + u) * TAIL_PART + tid];
+    }
+    for (; p < nparts; ++p) a[0] += partial[(size_t)p * TAIL_PART + tid];
+    dG[tid] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
   // boundary rows: the terms the zero padding of y removes at t = 0 and t = 2L-1
   if (tid < 32) {
@@ -210,21 +231,21 @@ __global__ void __launch_bounds__(256) tail_finish_kernel(const float* __restric
   __syncthreads();
   for (int e = tid; e < 4 * Cm * C; e += blockDim.x) {  // dWt[k][c][ci]
     const int ci = e % C, c = (e / C) % Cm, k = e / (C * Cm);
-    float s = dV[0 * 4 + k][ci] * wf[0 * Cm + c];
-    s = fmaf(dV[1 * 4 + k][ci], wf[1 * Cm + c], s);
-    s = fmaf(dV[2 * 4 + k][ci], wf[2 * Cm + c], s);
+    float s = dV[0 * 4 + k][ci] * wfs[0 * Cm + c];
+    s = fmaf(dV[1 * 4 + k][ci], wfs[1 * Cm + c], s);
+    s = fmaf(dV[2 * 4 + k][ci], wfs[2 * Cm + c], s);
     dwt[e] = s;
   }
   for (int e = tid; e < 3 * Cm; e += blockDim.x) {  // dWf[j][c]
     const int c = e % Cm, j = e / Cm;
-    float s = bt ? sc[3 + j] * bt[c] : 0.f;
+    float s = sc[3 + j] * bts[c];
     for (int k = 0; k < 4; ++k)
-      for (int ci = 0; ci < C; ++ci) s = fmaf(dV[j * 4 + k][ci], wt[((size_t)k * Cm + c) * C + ci], s);
+      for (int ci = 0; ci < C; ++ci) s = fmaf(dV[j * 4 + k][ci], wts[(k * Cm + c) * C + ci], s);
     dwf[e] = s;
   }
   if (dbt)
     for (int c = tid; c < Cm; c += blockDim.x)
-      dbt[c] = fmaf(sc[5], wf[2 * Cm + c], fmaf(sc[4], wf[1 * Cm + c], sc[3] * wf[0 * Cm + c]));
+      dbt[c] = fmaf(sc[5], wfs[2 * Cm + c], fmaf(sc[4], wfs[1 * Cm + c], sc[3] * wfs[0 * Cm + c]));
   if (dbf && tid == 0) dbf[0] = sc[0];
 }
 
@@ -263,7 +284,9 @@ int vqb_dec_tail_fwd(const vqb_tail_desc* d, const float* x, const float* wt, co
   if (int rc = tail_check(d)) return rc;
   VQB_REQUIRE(wt && wf && gbuf, "decoder tail: null weight / gbuf pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  tail_prep_kernel<<<1, 128, 0, st>>>(wt, bt, wf, bf, d->C_in, d->C_mid, gbuf);
+  const size_t psm = ((size_t)4 * d->C_mid * d->C_in + 4 * d->C_mid) * sizeof(float);
+  VQB_REQUIRE(psm <= 48 * 1024, "decoder tail: C_mid = %d too wide for the weight staging buffer", d->C_mid);
+  tail_prep_kernel<<<1, 256, psm, st>>>(wt, bt, wf, bf, d->C_in, d->C_mid, gbuf);
   VQB_LAUNCH_CHECK();
   if (d->B == 0 || d->L == 0) return VQB_OK;
   VQB_REQUIRE(x && recon, "decoder tail: null activation pointer");
@@ -296,7 +319,9 @@ int vqb_dec_tail_bwd(const vqb_tail_desc* d, const float* x, const float* drecon
   if (rows > 0) VQB_REQUIRE(x && drecon, "decoder tail backward: null activation pointer");
   tail_bwd_kernel<<<grid, 256, 0, st>>>(x, drecon, gbuf, dx, partial, rows, d->L > 0 ? d->L : 1, d->C_in, rpw);
   VQB_LAUNCH_CHECK();
-  tail_finish_kernel<<<1, 256, 0, st>>>(partial, grid, x, drecon, wt, bt, wf, d->L > 0 ? d->B : 0, d->L, d->C_in, d->C_mid,
+  const size_t fsm = ((size_t)4 * d->C_mid * d->C_in + 4 * d->C_mid) * sizeof(float);
+  VQB_REQUIRE(fsm <= 48 * 1024, "decoder tail: C_mid = %d too wide for the weight staging buffer", d->C_mid);
+  tail_finish_kernel<<<1, 256, fsm, st>>>(partial, grid, x, drecon, wt, bt, wf, d->L > 0 ? d->B : 0, d->L, d->C_in, d->C_mid,
                                         dwt, dbt, dwf, dbf);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
