@@ -16,6 +16,8 @@ int set_err(int code, const char* fmt, ...);
 int require_arch();
 // bumps the process-wide kernel-launch counter (vqb_kernel_launch_count)
 void count_launch();
+// cancels the count_launch() of a caller whose kernel was queued for a batched launch instead of launched (reduce_begin)
+void uncount_launch();
 
 #define VQB_REQUIRE(cond, ...)                                   \
   do {                                                           \

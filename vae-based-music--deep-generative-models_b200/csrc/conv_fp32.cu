@@ -427,6 +427,7 @@ void reduce_chunks_strided(const float* partial, int nchunk, long stride, int of
       g_rq.items = (ReduceItem*)realloc(g_rq.items, sizeof(ReduceItem) * g_rq.cap);
     }
     g_rq.items[g_rq.n++] = ReduceItem{partial, out, nchunk, (int)stride, offset, n, 0};
+    uncount_launch();  // the caller's VQB_LAUNCH_CHECK counts a launch that happens, batched, in reduce_flush
     return;
   }
   reduce_chunks_kernel<<<cdiv(n, 32), 256, 0, st>>>(partial, nchunk, stride, offset, n, out);

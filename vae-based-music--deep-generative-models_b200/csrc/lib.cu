@@ -6,6 +6,7 @@ namespace vqb {
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void uncount_launch() { g_launches.fetch_sub(1, std::memory_order_relaxed); }
 
 char* err_buf() {
   static thread_local char buf[512] = {0};
