@@ -254,3 +254,27 @@ def test_small_vqvae_fp32_grade_tensor_core_mode(gpu):
             err = float((g[i].cpu() - want).abs().max())
             assert err <= REL * gmax, (l, i, err, gmax)
             i += 1
+
+
+def test_long_window_inference_is_time_tiling_consistent(gpu):
+    """BASELINE.json configs[4]: encode -> quantize -> decode of a 2^20-sample window.  Size-independent property: the codes
+    of a prefix of the window, encoded on its own, equal the codes of the full window away from the cut (the stack is fully
+    convolutional: receptive field < 3k samples at level 0, < 24k at level 1), and decoding them reproduces the same audio
+    there."""
+    V = gpu
+    T = 1 << 20
+    m = V.VQVAE((T, 1), **V.SMALL_VQ_VAE)
+    m.set_precision("bf16x3")
+    rng = np.random.Generator(np.random.PCG64(11))
+    x = rng.uniform(0, 1, size=(1, T, 1)).astype(np.float32)
+    full = m.encode(x)
+    half = m.encode(x[:, :T // 2])
+    assert [tuple(c.shape) for c in full] == [(1, T // 32), (1, T // 256)] and full[0].dtype == torch.int64
+    for l, hop, halo in ((0, 32, 4096), (1, 256, 32768)):
+        n = (T // 2 - halo) // hop
+        assert torch.equal(full[l][:, :n], half[l][:, :n]), f"level {l}: codes differ away from the cut"
+        rec_full = m.decode(full[l], level=l)
+        rec_half = m.decode(half[l], level=l)
+        assert rec_full.shape == (1, T, 1) and bool(torch.isfinite(rec_full).all())
+        k = T // 2 - 2 * halo
+        assert torch.equal(rec_full[:, :k], rec_half[:, :k]), f"level {l}: reconstructions differ away from the cut"
