@@ -25,12 +25,16 @@ sys.path.insert(0, ROOT)
 T_WINDOW = 28160
 FLOP_PER_SAMPLE_FWD_BWD = 691680.0  # SURVEY.md section 8d (both levels; conv + VQ distance, bwd = 2x fwd)
 METRIC = "VQ-VAE fwd+bwd audio samples/sec"
-DTYPE = {"fp32": "fp32", "bf16x3": "fp32", "bf16x2": "bf16x2", "bf16": "bf16", "tf32": "tf32"}
+DTYPE = {"fp32": "fp32", "bf16x3": "fp32", "fp16x2": "fp32", "bf16x2": "bf16x2", "bf16": "bf16", "tf32": "tf32"}
 PRECISION_NOTE = {
     "fp32": "exact fp32 FMA on CUDA cores for every contraction",
     "bf16x3": "fp32-grade on tensor cores: each fp32 operand of the residual-block convolutions (208 of 242 convs) is split "
               "into 3 bf16 pieces (8+8+8 = 24 mantissa bits), all piece products on tcgen05 with fp32 TMEM accumulation; the "
               "remaining convolutions and the VQ re-ranking are exact fp32",
+    "fp16x2": "fp32-grade on tensor cores: in the residual-block convolutions (208 of 242 convs) every fp32 operand is scaled by "
+              "a power of two (per tile for activations, per convolution for weights) and split into 2 fp16 pieces (11+11 "
+              "mantissa bits), 3 piece products on tcgen05 with fp32 TMEM accumulation; the strided convolutions and weight "
+              "gradients use 3 bf16 pieces (24 bits); the remaining convolutions and the VQ re-ranking are exact fp32",
     "bf16x2": "2 bf16 pieces per operand (~2^-16 products)", "bf16": "bf16 operands, fp32 accumulate",
     "tf32": "tf32 operands, fp32 accumulate"}
 
@@ -128,7 +132,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run train_step eagerly (profiling)")
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "tf32", "bf16", "bf16x2", "bf16x3"],
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "tf32", "bf16", "bf16x2", "bf16x3", "fp16x2"],
                     help="bf16x3 (default): fp32 operands split into 3 bf16 pieces = all 24 mantissa bits, piece products on "
                          "tcgen05, fp32 accumulation (meets the fp32 parity contract, tests/test_gpu_model.py); fp32: exact "
                          "CUDA-core FMA path; bf16 / tf32 / bf16x2: reduced-precision tensor-core modes")

@@ -48,8 +48,12 @@ enum {
   VQB_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
   VQB_PREC_BF16 = 2, /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
   VQB_PREC_BF16X2 = 3, /* operands split into 2 bf16 pieces (hi + lo), 3 MMAs per product: ~2^-16 */
-  VQB_PREC_BF16X3 = 4  /* operands split into 3 bf16 pieces (all 24 mantissa bits), 6 MMAs per product: fp32-grade
+  VQB_PREC_BF16X3 = 4, /* operands split into 3 bf16 pieces (all 24 mantissa bits), 6 MMAs per product: fp32-grade
                           products, fp32 accumulation — the tensor-core path that meets the fp32 parity contract */
+  VQB_PREC_FP16X2 = 5  /* fp32-grade at the cost of bf16x2: operands scaled by a power of two (per tile for activations,
+                          per convolution for weights) and split into 2 fp16 pieces (11 + 11 mantissa bits), 3 piece
+                          products, fp32 accumulation.  Implemented by the residual-block kernels; every other
+                          tensor-core kernel runs its bf16x3 variant under this setting */
 };
 
 int vqb_version(void);

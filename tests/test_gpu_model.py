@@ -213,8 +213,9 @@ def test_small_vqvae_training_trajectory(gpu):
                 assert abs(logs[f"[{l}]codebook_entropy"] - float(mets[l]["entropy"])) < 1e-4
 
 
-def test_small_vqvae_fp32_grade_tensor_core_mode(gpu):
-    """precision "bf16x3" — every fp32 operand split into 3 bf16 pieces (all 24 mantissa bits), piece products on tcgen05,
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x2"])
+def test_small_vqvae_fp32_grade_tensor_core_mode(gpu, prec):
+    """precision "fp16x2": see tc.cuh (two scaled fp16 pieces in the residual blocks, bf16x3 elsewhere).  precision "bf16x3" — every fp32 operand split into 3 bf16 pieces (all 24 mantissa bits), piece products on tcgen05,
     fp32 accumulation in TMEM — against the fp32 oracle on SMALL_VQ_VAE (batch 2): identical code indices (up to the 1e-5
     near-tie allowance), reconstructions and losses within 1e-3, gradient vector within 1e-3 of its largest entry per level
     (single tensors can deviate more when a ReLU mask flips at |h| ~ 1e-6: the block is discontinuous there)."""
@@ -225,7 +226,7 @@ def test_small_vqvae_fp32_grade_tensor_core_mode(gpu):
     x = rng.uniform(0, 1, size=(2, 28160, 1)).astype(np.float32)
     m = V.VQVAE((28160, 1), **V.SMALL_VQ_VAE)
     m.use_cuda_graph = False
-    m.set_precision("bf16x3")
+    m.set_precision(prec)
     load_into(m, weights, vq)
     res, grads = O.loss_and_grads(spec, weights, vq, torch.tensor(x))
     with V.GradientTape() as tape:

@@ -8,7 +8,7 @@ import torch
 from oracle import vqvae_oracle as O
 
 pytestmark = pytest.mark.gpu
-TOL = {"bf16": 1.5e-2, "tf32": 2e-3, "bf16x2": 1e-4, "bf16x3": 2e-5}  # bf16x3 carries all 24 mantissa bits: fp32-grade
+TOL = {"bf16": 1.5e-2, "tf32": 2e-3, "bf16x2": 1e-4, "bf16x3": 2e-5, "fp16x2": 2e-5}  # bf16x3 (24 mantissa bits) and fp16x2 (22) are fp32-grade
 
 
 def dev(a):
@@ -20,7 +20,7 @@ def rel(got, want):
     return float((got - want).abs().max() / want.abs().max().clamp_min(1e-12))
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16", "bf16x2", "bf16x3"])
+@pytest.mark.parametrize("prec", ["tf32", "bf16", "bf16x2", "bf16x3", "fp16x2"])
 @pytest.mark.parametrize("B,L,d", [(2, 1000, 1), (3, 881, 27), (1, 254, 3), (2, 20, 27), (2, 255, 9), (1, 1, 1), (4, 3520, 9)])
 def test_resblock_tc_fwd_bwd(gpu, prec, B, L, d):
     ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
@@ -46,7 +46,7 @@ def test_resblock_tc_fwd_bwd(gpu, prec, B, L, d):
     assert rel(dx, gx) < TOL[prec], ("dx", rel(dx, gx))
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16", "bf16x2", "bf16x3"])
+@pytest.mark.parametrize("prec", ["tf32", "bf16", "bf16x2", "bf16x3", "fp16x2"])
 def test_resblock_tc_full_size_matches_fp32_kernel(gpu, prec):
     """[32, 14080, 32] (the largest stage of SMALL_VQ_VAE at batch 32): tensor-core path vs the exact-fp32 CUDA path."""
     ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
@@ -64,6 +64,38 @@ def test_resblock_tc_full_size_matches_fp32_kernel(gpu, prec):
         dx0, dh0 = ops.resblock_bwd_data(x, h0, dy, w1, w2, d, 0)
         dx1, dh1 = ops.resblock_bwd_data(x, h0, dy, w1, w2, d, P)
         assert rel(dh1, dh0) < TOL[prec] and rel(dx1, dx0) < TOL[prec]
+
+
+@pytest.mark.parametrize("xs,ws,bs", [(1e-6, 1.0, 0.0), (3e4, 1.0, 0.1), (1.0, 1e-5, 1e-7), (1e-3, 50.0, 10.0), (1e-12, 1e-12, 0.0),
+                                      (1e12, 1e3, 1.0), (0.0, 1.0, 0.3)])
+def test_resblock_fp16x2_is_scale_free(gpu, xs, ws, bs):
+    """fp16x2 multiplies every operand tile / weight tensor by a power of two that fits it into fp16's range before the
+    split (tc.cuh) and undoes it in the epilogue: the result must stay fp32-grade for magnitudes far outside fp16's range,
+    for tiles of very different magnitude inside one launch, and for an all-zero input (scale 1)."""
+    ops, P = gpu.ops, gpu._lib.PRECISIONS["fp16x2"]
+    rng = np.random.default_rng(5)
+    B, L, C, d = 3, 2100, 32, 3
+    x = (rng.normal(size=(B, L, C)) * xs).astype(np.float32)
+    x[1, 700:1400] *= 1e-4   # whole tiles far below their neighbours
+    x[2, 10] *= 300.0        # one dominant row inside a tile
+    w1 = (rng.normal(size=(3, C, C)) / np.sqrt(3 * C) * ws).astype(np.float32); b1 = (rng.normal(size=C) * bs).astype(np.float32)
+    w2 = (rng.normal(size=(3, C, C)) / np.sqrt(3 * C) * ws).astype(np.float32); b2 = (rng.normal(size=C) * bs).astype(np.float32)
+    dy = (rng.normal(size=(B, L, C)) * xs).astype(np.float32)
+    ts = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, w1, b1, w2, b2)]
+    h_ref = O.conv1d(torch.relu(ts[0]), ts[1], ts[2], 1, d)
+    y_ref = ts[0] + O.conv1d(torch.relu(h_ref), ts[3], ts[4], 1, 1)
+    gx, gh = torch.autograd.grad(y_ref, (ts[0], h_ref), torch.tensor(dy, dtype=torch.float64))
+    y, h = ops.resblock_fwd(dev(x), dev(w1), dev(b1), dev(w2), dev(b2), d, P)
+    dx, dh = ops.resblock_bwd_data(dev(x), dev(h_ref.detach().float().numpy()), dev(dy), dev(w1), dev(w2), d, P)
+    torch.cuda.synchronize()
+    for name, got, want in (("h", h, h_ref), ("y", y, y_ref), ("dh", dh, gh), ("dx", dx, gx)):
+        assert bool(torch.isfinite(got).all()), name
+        if float(want.abs().max()) > 1e-30:  # below that the fp32 result itself underflows
+            assert rel(got, want) < TOL["fp16x2"], (name, rel(got, want))
+    # a quiet stretch next to a loud one keeps its own relative accuracy (per-tile scales)
+    quiet = slice(800, 1300)
+    if xs > 0:
+        assert rel(h[1, quiet], h_ref[1, quiet]) < 1e-4
 
 
 @pytest.mark.parametrize("prec", ["bf16", "bf16x2", "bf16x3"])

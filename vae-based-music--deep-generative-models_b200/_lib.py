@@ -14,8 +14,9 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libvqvae_b200.so")
 
-PREC_FP32, PREC_TF32, PREC_BF16, PREC_BF16X2, PREC_BF16X3 = 0, 1, 2, 3, 4
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "bf16x2": PREC_BF16X2, "bf16x3": PREC_BF16X3}
+PREC_FP32, PREC_TF32, PREC_BF16, PREC_BF16X2, PREC_BF16X3, PREC_FP16X2 = 0, 1, 2, 3, 4, 5
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "bf16x2": PREC_BF16X2, "bf16x3": PREC_BF16X3,
+              "fp16x2": PREC_FP16X2}
 
 
 class VQBError(RuntimeError):

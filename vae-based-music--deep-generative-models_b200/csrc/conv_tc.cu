@@ -271,7 +271,8 @@ static int dispatch_ct(int precision, const ConvTcParams& p, cudaStream_t st) {
   switch (precision) {
     case VQB_PREC_BF16: return launch_ct<1, UP>(p, st);
     case VQB_PREC_BF16X2: return launch_ct<2, UP>(p, st);
-    case VQB_PREC_BF16X3: return launch_ct<3, UP>(p, st);
+    case VQB_PREC_BF16X3:
+    case VQB_PREC_FP16X2: return launch_ct<3, UP>(p, st);  // fp16x2 is a residual-block mode: bf16x3 here
   }
   return set_err(VQB_ERR_INVALID, "tensor-core strided convolution: precision %d has no kernel", precision);
 }
@@ -279,7 +280,8 @@ static int dispatch_ct(int precision, const ConvTcParams& p, cudaStream_t st) {
 // k = 4, stride 2, 32 -> 32 channels, no fused ReLU, bf16-family precision
 bool conv_tc_supported(const vqb_conv_desc* d) {
   return d->k == 4 && d->stride == 2 && d->dilation == 1 && d->C_in == 32 && d->C_out == 32 && !d->relu_in &&
-         (d->precision == VQB_PREC_BF16 || d->precision == VQB_PREC_BF16X2 || d->precision == VQB_PREC_BF16X3);
+         (d->precision == VQB_PREC_BF16 || d->precision == VQB_PREC_BF16X2 || d->precision == VQB_PREC_BF16X3 ||
+          d->precision == VQB_PREC_FP16X2);
 }
 
 // Conv1D forward: y [B, ceil(L/2), 32]

@@ -13,6 +13,8 @@
 // residual add and the conversion of the intermediate to the next A operand happen in the TMEM->register epilogue.
 // Activations are converted on the fly while being staged (fp32 global -> act -> bf16/tf32 shared), which is why the
 // A tile is written by threads rather than by TMA.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 #include "tc_rows.cuh"
@@ -39,13 +41,16 @@ struct RbTcParams {
 };
 
 // MODE 0: bf16   1: tf32   2: bf16x2 (operands split hi+lo, 3 MMAs per product, ~2^-16)   3: bf16x3 (hi+mid+lo, 6 MMAs,
-// all 24 mantissa bits of both operands: fp32-grade products with fp32 accumulation)
-template <int MODE>
-struct RbCfg {
+// all 24 mantissa bits of both operands: fp32-grade products with fp32 accumulation)   4: fp16x2 (operands scaled by a
+// power of two — per tile for the activations, per convolution for the weights — and split into two fp16 pieces, 11 + 11
+// mantissa bits: fp32-grade products for the MMA count of bf16x2; see tc.cuh)
+template <int MODE, int MB = 2>  // MB = 128-row M blocks per CTA: 2 -> 256-row tiles, 512 threads, one CTA per SM;
+struct RbCfg {                   //      1 -> 128-row tiles, 256 threads, two CTAs per SM (modes with <= 2 pieces)
   static constexpr bool TF32 = MODE == 1;
-  static constexpr int S = MODE == 2 ? 2 : MODE == 3 ? 3 : 1;  // bf16 pieces per operand
-  static constexpr int R = 256;     // stage-1 rows per CTA (2 x M128)
-  static constexpr int NT = 512;    // threads: two per tile row (one per 16-channel half)
+  static constexpr bool F16 = MODE == 4;
+  static constexpr int S = (MODE == 2 || MODE == 4) ? 2 : MODE == 3 ? 3 : 1;  // 16-bit pieces per operand
+  static constexpr int R = 128 * MB;  // stage-1 rows per CTA
+  static constexpr int NT = 256 * MB;  // threads: two per tile row (one per 16-channel half)
   static constexpr int DMAX = 32;   // largest supported dilation (guard rows of the operand tiles)
   static constexpr int C = 32;
   static constexpr int ES = TF32 ? 4 : 2;
@@ -60,14 +65,15 @@ struct RbCfg {
   static constexpr int TILE = NP * PLANE;   // one operand tile (one split piece)
   static constexpr int STG = (NT / 32) * 2048;  // per-warp row staging (32 rows x 64 B)
   static constexpr int SMEM = 2 * S * TILE + 2 * WCONV + STG + 64 + 256;
-  static constexpr int TCOLS = 4 * NW <= 128 ? 128 : 4 * NW <= 256 ? 256 : 512;  // TMEM columns: 2 stages x 2 M blocks x NW
-  static constexpr int NCV = NT - 64;   // threads that load / convert the stage-1 input (all but the two MMA-issuing warps)
+  static constexpr int TCOLS = 2 * MB * NW <= 64 ? 64 : 2 * MB * NW <= 128 ? 128 : 2 * MB * NW <= 256 ? 256 : 512;  // TMEM columns: 2 stages x MB M blocks x NW
+  static constexpr int NCV = NT - 32 * MB;   // threads that load / convert the stage-1 input (all but the MMA-issuing warps)
   static constexpr int NU = ((R + 2 * DMAX) * 4 + NCV - 1) / NCV;  // 8-channel units of the stage-1 input tile per converter thread
 };
 
-template <int MODE>
-__device__ __forceinline__ void pack_weights(uint8_t* dst, const float* __restrict__ w, int sj, int si, int so, int flip) {
-  using Cfg = RbCfg<MODE>;
+template <int MODE, int MB>
+__device__ __forceinline__ void pack_weights(uint8_t* dst, const float* __restrict__ w, int sj, int si, int so, int flip,
+                                             float scale) {
+  using Cfg = RbCfg<MODE, MB>;
   for (int e = threadIdx.x; e < 3 * 32 * 32; e += blockDim.x) {
     const int n = e & 31, k = (e >> 5) & 31, j = e >> 10;
     const int jj = flip ? 2 - j : j;
@@ -75,6 +81,11 @@ __device__ __forceinline__ void pack_weights(uint8_t* dst, const float* __restri
     uint8_t* a = dst + j * Cfg::WTAP + (k / Cfg::T) * Cfg::WPLANE + n * 16 + (k % Cfg::T) * Cfg::ES;
     if (Cfg::TF32) {
       *reinterpret_cast<float*>(a) = to_tf32(v);
+    } else if (Cfg::F16) {
+      const __half hi = __float2half_rn(v * scale);
+      const __half lo = __float2half_rn(v * scale - __half2float(hi));
+      *reinterpret_cast<__half*>(a) = hi;                // row n
+      *reinterpret_cast<__half*>(a + 32 * 16) = lo;      // row 32 + n
     } else {
       float pc[3];
       split_bf16<Cfg::S>(v, pc);
@@ -90,9 +101,9 @@ __device__ __forceinline__ void pack_weights(uint8_t* dst, const float* __restri
 // SAME accumulator (hi x {hi, mid, lo}, mid x {hi, mid}, lo x {hi}: every product down to 2^-16 of the leading one plus
 // mid x mid; the three omitted ones are below 2^-23): column block c then holds the sum over the activation pieces of
 // a . W_c, and the epilogue adds the S column blocks.
-template <int MODE>
+template <int MODE, int MB>
 __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int row_shift0, int dil, uint32_t w_base, int mb) {
-  using Cfg = RbCfg<MODE>;
+  using Cfg = RbCfg<MODE, MB>;
   // descriptors differ only in their start-address field (units of 16 bytes = one tile row): add offsets to two bases
   const uint64_t ad0 = smem_desc(a_base + (uint32_t)row_shift0 * 16u, Cfg::PLANE, 128);
   const uint64_t bd0 = smem_desc(w_base, Cfg::WPLANE, 128);
@@ -103,7 +114,7 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int 
     for (int kk = 0; kk < Cfg::KSTEPS; ++kk)
 #pragma unroll
       for (int sa = 0; sa < Cfg::S; ++sa) {  // the widest MMA first: it initialises every column block
-        const uint32_t idesc = instr_desc(Cfg::TF32 ? FMT_TF32 : FMT_BF16, 128, 32 * (Cfg::S - sa), false, false);
+        const uint32_t idesc = instr_desc(Cfg::TF32 ? FMT_TF32 : Cfg::F16 ? FMT_F16 : FMT_BF16, 128, 32 * (Cfg::S - sa), false, false);
         const uint64_t bd = bd0 + (uint64_t)((j * Cfg::WTAP + kk * 2 * Cfg::WPLANE) >> 4);
         const uint64_t ad = ad0 + (uint64_t)((sa * Cfg::TILE + kk * 2 * Cfg::PLANE) >> 4) + (uint64_t)(mb * 128 + j * dil);
         mma<Cfg::TF32>(tmem + mb * Cfg::NW, ad, bd, idesc, acc);
@@ -112,10 +123,15 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int 
 }
 
 // 8 channels o*8..o*8+7 of row r (two float4) -> operand tile(s): one 16-byte chunk per bf16 piece, two for tf32
-template <int MODE>
-__device__ __forceinline__ void stage8(uint8_t* tile, int r, int o, const float4& a, const float4& b) {
-  using Cfg = RbCfg<MODE>;
-  if (Cfg::TF32) {
+template <int MODE, int MB>
+__device__ __forceinline__ void stage8(uint8_t* tile, int r, int o, const float4& a, const float4& b, float scale) {
+  using Cfg = RbCfg<MODE, MB>;
+  if (Cfg::F16) {
+    uint4 pc[2];
+    split8_f16(a, b, scale, pc);
+    *reinterpret_cast<uint4*>(tile + o * Cfg::PLANE + r * 16) = pc[0];
+    *reinterpret_cast<uint4*>(tile + Cfg::TILE + o * Cfg::PLANE + r * 16) = pc[1];
+  } else if (Cfg::TF32) {
     *reinterpret_cast<float4*>(tile + (2 * o) * Cfg::PLANE + r * 16) = make_float4(to_tf32(a.x), to_tf32(a.y), to_tf32(a.z), to_tf32(a.w));
     *reinterpret_cast<float4*>(tile + (2 * o + 1) * Cfg::PLANE + r * 16) = make_float4(to_tf32(b.x), to_tf32(b.y), to_tf32(b.z), to_tf32(b.w));
   } else {
@@ -134,9 +150,9 @@ __device__ __forceinline__ void stage8(uint8_t* tile, int r, int o, const float4
 // (A variant with a dedicated MMA-issuing warp and mbarrier-only hand-offs measured slower: 17 warps cap the register
 // file at 96 per thread; so did epilogues that access their rows in global memory directly instead of through the
 // per-warp staging transposes: 32 lines per access instruction saturate the L1 pipeline.)
-template <int MODE>
-__global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcParams p) {
-  using Cfg = RbCfg<MODE>;
+template <int MODE, int MB>
+__global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(const RbTcParams p) {
+  using Cfg = RbCfg<MODE, MB>;
   constexpr int NT = Cfg::NT, NU = Cfg::NU;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* A1 = smem;
@@ -147,6 +163,8 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
   uint64_t* bar = reinterpret_cast<uint64_t*>(stg_base + Cfg::STG);  // bar[0]: stage-1 MMAs done, bar[1]: stage-2 MMAs done
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 2);
   float* bias_s = reinterpret_cast<float*>(bar + 4);  // [64]: bias1, bias2 (zeros when absent); 16-byte aligned
+  // fp16x2: [0], [1] largest |stage-1 input| of the tile in flight (alternating slots), [2] max|w1|, [3] max|w2|, [4] max|bias1|
+  uint32_t* tmx = reinterpret_cast<uint32_t*>(bias_s + 64);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.L;
@@ -154,26 +172,47 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
   const int rows1 = Cfg::R + 2 * p.d1;
 
   if (warp == 0) tmem_alloc(tslot, Cfg::TCOLS);
-  if (tid == 32) { mbar_init(&bar[0], 2); mbar_init(&bar[1], 2); fence_mbar_init(); }  // one arrival per issuing thread
-  pack_weights<MODE>(W1, p.w1, p.sj1, p.si1, p.so1, p.flip1);
-  pack_weights<MODE>(W2, p.w2, p.sj2, p.si2, p.so2, p.flip2);
+  if (tid == 32) { mbar_init(&bar[0], MB); mbar_init(&bar[1], MB); fence_mbar_init(); }  // one arrival per issuing thread
+  float sw1 = 1.f, sw2 = 1.f;  // fp16x2: power-of-two scales of the two weight tensors
+  if (Cfg::F16) {
+    if (tid < 8) tmx[tid] = 0u;
+    __syncthreads();
+    uint32_t m1 = 0u, m2 = 0u, mb1 = 0u;
+    for (int e = tid; e < 3 * 32 * 32; e += blockDim.x) { m1 = max(m1, absbits(p.w1[e])); m2 = max(m2, absbits(p.w2[e])); }
+    if (tid < 32 && p.bias1) mb1 = absbits(p.bias1[tid]);
+    m1 = __reduce_max_sync(0xffffffffu, m1);
+    m2 = __reduce_max_sync(0xffffffffu, m2);
+    mb1 = __reduce_max_sync(0xffffffffu, mb1);
+    if (lane == 0) { atomicMax(&tmx[2], m1); atomicMax(&tmx[3], m2); if (warp == 0) tmx[4] = mb1; }
+    __syncthreads();
+    sw1 = pow2_scale(__uint_as_float(tmx[2]));
+    sw2 = pow2_scale(__uint_as_float(tmx[3]));
+  }
+  pack_weights<MODE, MB>(W1, p.w1, p.sj1, p.si1, p.so1, p.flip1, sw1);
+  pack_weights<MODE, MB>(W2, p.w2, p.sj2, p.si2, p.so2, p.flip2, sw2);
   if (tid < 64) bias_s[tid] = tid < 32 ? (p.bias1 ? p.bias1[tid] : 0.f) : (p.bias2 ? p.bias2[tid - 32] : 0.f);
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tslot;
+  // fp16x2 bound on |out1| used to scale the stage-2 operand without a block-wide reduction:
+  // |out1| <= 96 max|w1| max|in1 of the tile| + max|bias1|   (masks and ReLU only shrink it)
+  const float w1bound = Cfg::F16 ? 96.f * __uint_as_float(tmx[2]) : 0.f;
+  const float b1bound = Cfg::F16 ? __uint_as_float(tmx[4]) : 0.f;
+  const float isw1 = pow2_inv(sw1), isw2 = pow2_inv(sw2);
 
   // epilogue role of this thread: TMEM lane quadrant (warp % 4), M block, 16-channel half
-  const int qd = warp & 3, mb = (warp >> 2) & 1, half = warp >> 3;
+  const int qd = warp & 3, mb = (warp >> 2) & (MB - 1), half = warp / (4 * MB);
   const int i0 = mb * 128 + qd * 32;   // first tile row of this warp
   const int i = i0 + lane;             // tile row (= TMEM lane) of this thread
   const uint32_t taddr = tmem + (((uint32_t)qd * 32u) << 16) + (uint32_t)(mb * Cfg::NW + half * 16);
   uint8_t* stg = stg_base + warp * 2048;
   // warps 1 and 5 issue the MMAs (one M block each) while the other 14 warps stage the next tile: they take no part in load /
   // convert, so that both groups reach the barrier behind the conversion at about the same time
-  const bool issuer = warp == 1 || warp == 5;
-  const int ctid = (warp - (warp > 1) - (warp > 5)) * 32 + lane;  // index among the converter threads
+  const bool issuer = warp == 1 || (MB == 2 && warp == 5);
+  const bool issue_thread = issuer && lane == 0;
+  const int ctid = (warp - (warp > 1) - (MB == 2 && warp > 5)) * 32 + lane;  // index among the converter threads
   const int oct = ctid & 3;  // 8-channel unit of this thread in the staging loops (NCV % 4 == 0)
   constexpr int NCV = Cfg::NCV;
 
@@ -193,7 +232,19 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
       rb[k] = ok ? *reinterpret_cast<const float4*>(inb + (long)g * 32 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  auto convert = [&]() {
+  // fp16x2: largest magnitude of the loaded tile -> tmx[slot] (order-independent, hence deterministic)
+  auto publish_max = [&](int slot) {
+    if (!Cfg::F16 || issuer) return;
+    uint32_t m = 0u;
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      m = max(max(max(m, absbits(ra[k].x)), max(absbits(ra[k].y), absbits(ra[k].z))), absbits(ra[k].w));
+      m = max(max(max(m, absbits(rb[k].x)), max(absbits(rb[k].y), absbits(rb[k].z))), absbits(rb[k].w));
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0) atomicMax(&tmx[slot], m);
+  };
+  auto convert = [&](float scale) {
     if (issuer) return;
 #pragma unroll
     for (int k = 0; k < NU; ++k) { reg_fence(ra[k]); reg_fence(rb[k]); }  // keep the conversion below the waits it follows
@@ -206,23 +257,33 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
           a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
           b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
         }
-        stage8<MODE>(A1, r, oct, a, b);
+        stage8<MODE, MB>(A1, r, oct, a, b, scale);
       }
     }
     fence_proxy_async();
   };
 
   int tile = blockIdx.x;
+  float amax = 0.f, sa1 = 1.f;  // fp16x2: largest |stage-1 input| of the current tile and its operand scale
+  int slot = 0;                 // tmx slot of the NEXT tile
   if (tile < p.total_tiles) {
     load(tile);
-    convert();
+    if (Cfg::F16) {
+      publish_max(0);
+      __syncthreads();
+      amax = __uint_as_float(tmx[0]);
+      sa1 = pow2_scale(amax);
+      slot = 1;
+    }
+    convert(sa1);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (tid == 32 || tid == 160) {
-      issue_stage<MODE>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1), tid >> 7);
+    if (issue_thread) {
+      issue_stage<MODE, MB>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1), warp >> 2);
       commit(&bar[0]);
     }
+    if (Cfg::F16 && tid == 0) tmx[0] = 0u;  // read by every thread before the barrier above
     __syncwarp();
   }
   uint32_t phase = 0;
@@ -265,10 +326,16 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] += m[c];
     }
+    const float inv1 = Cfg::F16 ? pow2_inv(sa1) * isw1 : 1.f;  // undoes the operand scales (exact: a power of two)
 #pragma unroll
     for (int c = 0; c < 16; c += 4) {
       const float4 bv = *reinterpret_cast<const float4*>(bias_s + half * 16 + c);
-      v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
+      if (Cfg::F16) {
+        v[c] = fmaf(v[c], inv1, bv.x); v[c + 1] = fmaf(v[c + 1], inv1, bv.y);
+        v[c + 2] = fmaf(v[c + 2], inv1, bv.z); v[c + 3] = fmaf(v[c + 3], inv1, bv.w);
+      } else {
+        v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
+      }
     }
     if (p.mask1) {
       warp_unpack_rows(f, stg, lane, m);
@@ -281,27 +348,35 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
       const float a = inrange ? v[c] : 0.f;  // rows outside [0, L) are conv2's zero padding
       v[c] = p.relu2 ? fmaxf(a, 0.f) : a;
     }
+    const float sa2 = Cfg::F16 ? pow2_scale(fmaf(w1bound, amax, b1bound)) : 1.f;
 #pragma unroll
     for (int q = 0; q < 2; ++q)
-      stage8<MODE>(A2, Cfg::DMAX + i, half * 2 + q, make_float4(v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]),
-                   make_float4(v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]));
+      stage8<MODE, MB>(A2, Cfg::DMAX + i, half * 2 + q, make_float4(v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]),
+                   make_float4(v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]), sa2);
+    if (has_next) publish_max(slot);
     fence_proxy_async();
     fence_before_sync();
-    __syncthreads();  // A2 complete; every warp has drained the stage-1 accumulators
+    __syncthreads();  // A2 complete; every warp has drained the stage-1 accumulators; the next tile's maximum is published
     fence_after_sync();
-    if (tid == 32 || tid == 160) {
+    if (Cfg::F16 && has_next) {
+      amax = __uint_as_float(tmx[slot]);
+      sa1 = pow2_scale(amax);
+    }
+    if (issue_thread) {
       // out2 tile row i uses A2 rows DMAX + i + (j-1)*d2
-      issue_stage<MODE>(tmem + 2 * Cfg::NW, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2), tid >> 7);
+      issue_stage<MODE, MB>(tmem + MB * Cfg::NW, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2), warp >> 2);
       commit(&bar[1]);
     }
     __syncwarp();
     if (has_next) {  // A1 is free (its MMAs completed before epilogue 1): stage the next tile under the stage-2 MMAs
-      convert();
+      convert(sa1);
       fence_before_sync();
       __syncthreads();
       fence_after_sync();
-      if (tid == 32 || tid == 160) {
-        issue_stage<MODE>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1), tid >> 7);
+      if (Cfg::F16 && tid == 0) tmx[slot] = 0u;  // every thread has read it; written again two tiles from now
+      slot ^= 1;
+      if (issue_thread) {
+        issue_stage<MODE, MB>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1), warp >> 2);
         commit(&bar[0]);
       }
       __syncwarp();
@@ -313,17 +388,23 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
     if (p.add2) warp_fetch_rows(p.add2, boff, s0 + i0, L, half, lane, f2);
     mbar_wait(&bar[1], phase);
     fence_after_sync();
-    tmem_ld16(taddr + 2 * Cfg::NW, v);
+    tmem_ld16(taddr + MB * Cfg::NW, v);
 #pragma unroll
     for (int sp = 1; sp < Cfg::S; ++sp) {
-      tmem_ld16(taddr + 2 * Cfg::NW + sp * 32, m);
+      tmem_ld16(taddr + MB * Cfg::NW + sp * 32, m);
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] += m[c];
     }
+    const float inv2 = Cfg::F16 ? pow2_inv(sa2) * isw2 : 1.f;
 #pragma unroll
     for (int c = 0; c < 16; c += 4) {
       const float4 bv = *reinterpret_cast<const float4*>(bias_s + 32 + half * 16 + c);
-      v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
+      if (Cfg::F16) {
+        v[c] = fmaf(v[c], inv2, bv.x); v[c + 1] = fmaf(v[c + 1], inv2, bv.y);
+        v[c + 2] = fmaf(v[c + 2], inv2, bv.z); v[c + 3] = fmaf(v[c + 3], inv2, bv.w);
+      } else {
+        v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
+      }
     }
     if (p.mask2) {
       warp_unpack_rows(f, stg, lane, m);
@@ -342,12 +423,12 @@ __global__ void __launch_bounds__(RbCfg<MODE>::NT, 1) rb_tc_kernel(const RbTcPar
   if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
-template <int MODE>
+template <int MODE, int MB>
 static int launch_rb(const RbTcParams& p, cudaStream_t st) {
-  using Cfg = RbCfg<MODE>;
+  using Cfg = RbCfg<MODE, MB>;
   static bool attr_set = false;
   if (!attr_set) {
-    VQB_CUDA(cudaFuncSetAttribute(rb_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    VQB_CUDA(cudaFuncSetAttribute(rb_tc_kernel<MODE, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -360,25 +441,32 @@ static int launch_rb(const RbTcParams& p, cudaStream_t st) {
   const int Rout = Cfg::R - 2 * p.d2;
   q.tiles_x = cdiv(p.L, Rout);
   q.total_tiles = q.tiles_x * p.B;
-  const int grid = q.total_tiles < num_sms ? q.total_tiles : num_sms;
-  rb_tc_kernel<MODE><<<grid, Cfg::NT, Cfg::SMEM, st>>>(q);
+  const int slots = num_sms * (3 - MB);
+  const int grid = q.total_tiles < slots ? q.total_tiles : slots;
+  rb_tc_kernel<MODE, MB><<<grid, Cfg::NT, Cfg::SMEM, st>>>(q);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
 
 static int dispatch_rb(int precision, const RbTcParams& p, cudaStream_t st) {
+  // Tile height (modes with <= 2 pieces fit two CTAs of 128-row tiles per SM): the halo a tile recomputes is 2 * d2 rows,
+  // so 128-row tiles pay off while d2 is small (every forward block: d2 = 1; backward blocks of dilation <= 3).
+  // VQB_RB_MB=1|2 forces one of them (tuning).
+  static const int mb_env = getenv("VQB_RB_MB") ? atoi(getenv("VQB_RB_MB")) : 0;
+  const bool half_tiles = mb_env ? mb_env == 1 : p.d2 <= 3;
   switch (precision) {
-    case VQB_PREC_BF16: return launch_rb<0>(p, st);
-    case VQB_PREC_TF32: return launch_rb<1>(p, st);
-    case VQB_PREC_BF16X2: return launch_rb<2>(p, st);
-    case VQB_PREC_BF16X3: return launch_rb<3>(p, st);
+    case VQB_PREC_BF16: return launch_rb<0, 2>(p, st);
+    case VQB_PREC_TF32: return launch_rb<1, 2>(p, st);
+    case VQB_PREC_BF16X2: return half_tiles ? launch_rb<2, 1>(p, st) : launch_rb<2, 2>(p, st);
+    case VQB_PREC_BF16X3: return launch_rb<3, 2>(p, st);
+    case VQB_PREC_FP16X2: return half_tiles ? launch_rb<4, 1>(p, st) : launch_rb<4, 2>(p, st);
   }
   return set_err(VQB_ERR_INVALID, "unknown precision %d", precision);
 }
 
 bool resblock_tc_supported(const vqb_resblock_desc* d) {
   return d->C == 32 && d->F == 32 && d->dilation >= 1 && d->dilation <= 32 &&
-         d->precision >= VQB_PREC_TF32 && d->precision <= VQB_PREC_BF16X3;
+         d->precision >= VQB_PREC_TF32 && d->precision <= VQB_PREC_FP16X2;
 }
 
 int resblock_fwd_tc(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1, const float* w2,

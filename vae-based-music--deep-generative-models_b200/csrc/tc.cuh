@@ -14,6 +14,7 @@
 // start address + 16*r — which is how the dilated taps of a Conv1D are addressed without copying.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace vqb {
@@ -198,6 +199,38 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4* 
   }
 }
 
+
+// ---- fp16x2: scaled two-piece fp16 split -------------------------------------------------------------------
+// fp16 carries 11 significant bits but only a 5-bit exponent, so operands are first multiplied by a power of two that
+// brings the largest magnitude of the tile / weight tensor into [2^14, 2^15) (exact; undone in the epilogue).  Then
+// hi = rn_f16(x), lo = rn_f16(x - hi) reproduce x to 2^-22 relative for every element within 2^-11 of the largest
+// one and to 2^-25 * 2^-15 of the largest one below that (lo becomes subnormal: absolute step 2^-25).
+// pow2_scale: power of two s with maxabs * s in [2^14, 2^15); 1 for zero / subnormal / non-finite maxabs.
+__device__ __forceinline__ float pow2_scale(float maxabs) {
+  const int e = (int)((__float_as_uint(maxabs) >> 23) & 0xffu);
+  if (e == 0 || e == 255) return 1.f;
+  const int se = min(max(268 - e, 4), 250);  // biased exponent of 2^(14 - (e - 127)), kept invertible
+  return __uint_as_float((uint32_t)se << 23);
+}
+// exact reciprocal of a pow2_scale() value
+__device__ __forceinline__ float pow2_inv(float s) { return __uint_as_float((254u << 23) - __float_as_uint(s)); }
+__device__ __forceinline__ uint32_t absbits(float x) { return __float_as_uint(x) & 0x7fffffffu; }
+
+// 8 consecutive fp32 channels * scale -> two 16-byte chunks of fp16 pieces (hi, lo)
+__device__ __forceinline__ void split8_f16(const float4& a, const float4& b, float scale, uint4* out) {
+  const float v[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);  // exact remainders
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  out[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  out[1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
 
 // Compiler-level fence on a register value: arithmetic on `a` cannot be scheduled above this point.  Used after an
 // mbarrier wait so that work on prefetched global data is not hoisted to right behind its loads (which would expose the

@@ -552,7 +552,7 @@ static size_t vq2_smem_bytes(int nchunks) {
 static bool vq_tc_ok(const vqb_vq_desc* d) {
   return d->D == VT_D && d->K >= VT_CHUNK && d->K % VT_CHUNK == 0 && d->K <= 8192 &&
          (d->precision == VQB_PREC_BF16 || d->precision == VQB_PREC_TF32 || d->precision == VQB_PREC_BF16X2 ||
-          d->precision == VQB_PREC_BF16X3);
+          d->precision == VQB_PREC_BF16X3 || d->precision == VQB_PREC_FP16X2);
 }
 
 bool vq_search_tc_supported(const vqb_vq_desc* d) { return vq_tc_ok(d); }

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(Wg4Cfg<S>::NT + 32, 1) wgrad4_tc_kernel(const 
   if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
-static int wg4_split(int precision) { return precision == VQB_PREC_BF16X3 ? 3 : precision == VQB_PREC_BF16X2 ? 2 : 1; }
+static int wg4_split(int precision) { return (precision == VQB_PREC_BF16X3 || precision == VQB_PREC_FP16X2) ? 3 : precision == VQB_PREC_BF16X2 ? 2 : 1; }
 
 static int wgrad4_grid(int B, int Lo, int* tiles_per_b) {
   *tiles_per_b = cdiv(Lo, Wg4Cfg<1>::TK);

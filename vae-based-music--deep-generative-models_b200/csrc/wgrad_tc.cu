@@ -249,12 +249,13 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
   if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
-static int wg_split(int precision) { return precision == VQB_PREC_BF16X3 ? 3 : precision == VQB_PREC_BF16X2 ? 2 : 1; }
+static int wg_split(int precision) { return (precision == VQB_PREC_BF16X3 || precision == VQB_PREC_FP16X2) ? 3 : precision == VQB_PREC_BF16X2 ? 2 : 1; }
 
 bool wgrad_tc_supported(const vqb_conv_desc* d) {
   // kind::tf32 with MN-major (time-as-K) operands returned zeros on B200, so VQB_PREC_TF32 has no weight-gradient kernel
   return d->k == 3 && d->stride == 1 && d->C_in == 32 && d->C_out == 32 && d->dilation >= 1 && d->dilation <= 32 &&
-         (d->precision == VQB_PREC_BF16 || d->precision == VQB_PREC_BF16X2 || d->precision == VQB_PREC_BF16X3);
+         (d->precision == VQB_PREC_BF16 || d->precision == VQB_PREC_BF16X2 || d->precision == VQB_PREC_BF16X3 ||
+          d->precision == VQB_PREC_FP16X2);
 }
 
 static int wgrad_tc_grid(const vqb_conv_desc* d, int* tiles_per_b) {
