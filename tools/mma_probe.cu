@@ -1,0 +1,100 @@
+// mma_probe.cu — issue-throughput probe for tcgen05.mma (kind::f16, M = 128, K = 16) with both operands in shared memory
+// in the no-swizzle "plane layout" of csrc/tc.cuh: how many SM clocks does one MMA cost as a function of N, of the operand
+// majors (K-major as in resblock_tc.cu / conv_tc.cu, MN-major as in wgrad_tc.cu) and of the plane pitch?  The numbers
+// feed the kernel cost models in DESIGN.md.  Build + run: tools/run_mma_probe.sh (nvcc here, gpurun for the run).
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#include "../vae-based-music--deep-generative-models_b200/csrc/tc.cuh"
+
+using namespace vqb::tc;
+
+struct Probe {
+  int a_mn, b_mn, N, plane_a, plane_b, nacc, reps, shift;
+};
+
+__global__ void __launch_bounds__(128, 1) probe_kernel(Probe p, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 200 * 1024 / 16; e += blockDim.x) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 32) tmem_alloc(&tslot, 512);
+  if (tid == 32) { mbar_init(&bar, 1); fence_mbar_init(); }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tslot;
+  if (tid == 0) {
+    uint8_t* A = smem;
+    uint8_t* B = smem + 100 * 1024;
+    // K-major: LBO = plane pitch (next 16 bytes of K), SBO = 128 (next 8 rows);  MN-major: LBO = 128, SBO = plane pitch
+    const uint64_t ad0 = p.a_mn ? smem_desc(smem_u32(A), 128, p.plane_a) : smem_desc(smem_u32(A), p.plane_a, 128);
+    const uint64_t bd0 = p.b_mn ? smem_desc(smem_u32(B), 128, p.plane_b) : smem_desc(smem_u32(B), p.plane_b, 128);
+    const uint32_t idesc = instr_desc(FMT_BF16, 128, p.N, p.a_mn != 0, p.b_mn != 0);
+    // warm-up
+    for (int i = 0; i < 16; ++i) mma<false>(tmem, ad0, bd0, idesc, 1);
+    commit(&bar);
+    mbar_wait(&bar, 0);
+    // descriptors and accumulator addresses are precomputed: the timed loop is nothing but tcgen05.mma instructions
+    uint64_t ad[6];
+    uint32_t dst[6];
+    for (int i = 0; i < 6; ++i) { ad[i] = ad0 + (uint64_t)((i % 3) * p.shift); dst[i] = tmem + (i % p.nacc) * p.N; }
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < p.reps; i += 6) {
+      mma<false>(dst[0], ad[0], bd0, idesc, 1);
+      mma<false>(dst[1], ad[1], bd0, idesc, 1);
+      mma<false>(dst[2], ad[2], bd0, idesc, 1);
+      mma<false>(dst[3], ad[3], bd0, idesc, 1);
+      mma<false>(dst[4], ad[4], bd0, idesc, 1);
+      mma<false>(dst[5], ad[5], bd0, idesc, 1);
+    }
+    commit(&bar);
+    mbar_wait(&bar, 1);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
+int main() {
+  long long* d;
+  cudaMalloc(&d, 8);
+  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int reps = 600;
+  struct Case { const char* name; Probe p; };
+  const int PK = (256 + 64) * 16 + 32;   // resblock_tc plane pitch (K-major A tile)
+  const int PW = 96 * 16;                // its weight planes
+  const int PX = (128 + 64) * 16 + 32;   // wgrad_tc act(x) plane pitch (MN-major)
+  const int PD = 128 * 16 + 32;          // wgrad_tc dy plane pitch
+  Case cases[] = {
+      {"K-major A / K-major B  N=32  (rb bf16)", {0, 0, 32, PK, PW, 1, reps, 1}},
+      {"K-major A / K-major B  N=64", {0, 0, 64, PK, PW, 1, reps, 1}},
+      {"K-major A / K-major B  N=96  (rb bf16x3 sa=0)", {0, 0, 96, PK, PW, 1, reps, 1}},
+      {"K-major A / K-major B  N=96, 2 accumulators", {0, 0, 96, PK, PW, 2, reps, 1}},
+      {"K-major A / K-major B  N=128", {0, 0, 128, PK, 128 * 16, 1, reps, 1}},
+      {"K-major A / K-major B  N=256", {0, 0, 256, PK, 256 * 16, 1, reps, 1}},
+      {"K-major A / K-major B  N=256, 2 accumulators", {0, 0, 256, PK, 256 * 16, 2, reps, 1}},
+      {"MN-major A / MN-major B N=32  (wgrad bf16)", {1, 1, 32, PX, PD, 3, reps, 3}},
+      {"MN-major A / MN-major B N=64  (wgrad bf16x2)", {1, 1, 64, PX, PD, 3, reps, 3}},
+      {"MN-major A / MN-major B N=96  (wgrad bf16x3)", {1, 1, 96, PX, PD, 3, reps, 3}},
+      {"MN-major A / MN-major B N=96, pitch 2048+16", {1, 1, 96, 2048 + 16, 2048 + 16, 3, reps, 3}},
+      {"MN-major A / MN-major B N=96, pitch 2048+128", {1, 1, 96, 2048 + 128, 2048 + 128, 3, reps, 3}},
+      {"MN-major A / MN-major B N=96, pitch 4096", {1, 1, 96, 4096, 4096, 3, reps, 3}},
+      {"MN-major A / K-major B  N=96", {1, 0, 96, PX, PW, 3, reps, 3}},
+      {"K-major A / MN-major B  N=96", {0, 1, 96, PK, PD, 3, reps, 1}},
+      {"MN-major A / MN-major B N=256", {1, 1, 256, PX, PD, 1, reps, 3}},
+  };
+  for (auto& c : cases) {
+    probe_kernel<<<4, 128, 200 * 1024>>>(c.p, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long cyc = 0;
+    cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+    printf("%-52s %8.1f clk / MMA   (%s)\n", c.name, (double)cyc / reps, cudaGetErrorString(e));
+  }
+  return 0;
+}

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(CtCfg<S, UP>::NT, 1) conv_tc_kernel(const Conv
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (tid == 32) {
+    if (warp == 1 && elect_one()) {
       ct_issue<S, UP>(tmem, smem_u32(A), smem_u32(W));
       commit(&bar[0]);
     }
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(CtCfg<S, UP>::NT, 1) conv_tc_kernel(const Conv
       fence_before_sync();
       __syncthreads();      // also: every warp finished reading the other TMEM buffer (epilogue of tile it-1)
       fence_after_sync();
-      if (tid == 32) {
+      if (warp == 1 && elect_one()) {
         ct_issue<S, UP>(tmem + (buf ^ 1) * Cfg::ACC, smem_u32(A), smem_u32(W));
         commit(&bar[buf ^ 1]);
       }

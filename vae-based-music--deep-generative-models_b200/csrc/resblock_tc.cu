@@ -211,7 +211,6 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(cons
   // warps 1 and 5 issue the MMAs (one M block each) while the other 14 warps stage the next tile: they take no part in load /
   // convert, so that both groups reach the barrier behind the conversion at about the same time
   const bool issuer = warp == 1 || (MB == 2 && warp == 5);
-  const bool issue_thread = issuer && lane == 0;
   const int ctid = (warp - (warp > 1) - (MB == 2 && warp > 5)) * 32 + lane;  // index among the converter threads
   const int oct = ctid & 3;  // 8-channel unit of this thread in the staging loops (NCV % 4 == 0)
   constexpr int NCV = Cfg::NCV;
@@ -279,7 +278,7 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(cons
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (issue_thread) {
+    if (issuer && elect_one()) {
       issue_stage<MODE, MB>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1), warp >> 2);
       commit(&bar[0]);
     }
@@ -362,7 +361,7 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(cons
       amax = __uint_as_float(tmx[slot]);
       sa1 = pow2_scale(amax);
     }
-    if (issue_thread) {
+    if (issuer && elect_one()) {
       // out2 tile row i uses A2 rows DMAX + i + (j-1)*d2
       issue_stage<MODE, MB>(tmem + MB * Cfg::NW, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2), warp >> 2);
       commit(&bar[1]);
@@ -375,7 +374,7 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(cons
       fence_after_sync();
       if (Cfg::F16 && tid == 0) tmx[slot] = 0u;  // every thread has read it; written again two tiles from now
       slot ^= 1;
-      if (issue_thread) {
+      if (issuer && elect_one()) {
         issue_stage<MODE, MB>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1), warp >> 2);
         commit(&bar[0]);
       }

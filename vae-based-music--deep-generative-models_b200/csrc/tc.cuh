@@ -46,6 +46,20 @@ __host__ __device__ constexpr uint32_t instr_desc(int fmt, int M, int N, bool a_
          | ((uint32_t)(M >> 4) << 24);      // M >> 4             [24,29)
 }
 
+// One lane of a CONVERGED warp (elect.sync).  Single-thread tcgen05 work should be guarded by this rather than by a
+// lane-id comparison: under `if (lane == 0)` the compiler cannot prove the descriptor operands warp-uniform and wraps every
+// tcgen05.mma in a waterfall loop (ELECT + 4 x R2UR.BROADCAST + branch, ~15 instructions per MMA); with elect.sync the
+// descriptors stay in uniform registers and an MMA costs 2-3 issue slots.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- MMA issue (one thread) ------------------------------------------------------------------------------
 template <bool TF32>
 __device__ __forceinline__ void mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(128, 2) vq_tc_kernel(const VqTcParams p) {
       fence_proxy_async();
       fence_before_sync();
       __syncthreads();   // A tile (and streamed chunk) visible; every thread has finished reading the previous accumulator
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         fence_after_sync();
         const uint32_t a0 = smem_u32(As), b0 = smem_u32(Bc);
 #pragma unroll
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
 
   if (warp == V2_NSCAN / 32) {
     // ------------------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = instr_desc(FMT_BF16, 128, VT_CHUNK, false, false);
       const uint64_t a_hi = smem_desc(smem_u32(As), V2_PLANE_A, 128), a_lo = a_hi + (uint64_t)(V2_TILE_A >> 4);
       const uint64_t a_c = smem_desc(smem_u32(Ac), V2_PLANE_A, 128);

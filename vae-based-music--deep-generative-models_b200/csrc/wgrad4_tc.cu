@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(Wg4Cfg<S>::NT + 32, 1) wgrad4_tc_kernel(const 
 
   if (warp == NT / 32) {
     // ---------------------------------------------------------------------------------- MMA issuer (one thread)
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = instr_desc(FMT_BF16, 128, Cfg::NCOL, true, true);
       for (int it = 0; it < ntiles; ++it) {
         const int buf = it & 1;

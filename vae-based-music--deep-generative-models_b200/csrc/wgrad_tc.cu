@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
 
   if (warp == NT / 32) {
     // ---------------------------------------------------------------------------------- MMA issuer (one thread)
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = instr_desc(FMT_BF16, 128, Cfg::NS, true, true);
       const uint64_t dil = (uint64_t)p.dil;  // a row is 16 bytes = one unit of the descriptor's start-address field
       for (int it = 0; it < ntiles; ++it) {
