@@ -132,8 +132,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run train_step eagerly (profiling)")
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "tf32", "bf16", "bf16x2", "bf16x3", "fp16x2"],
-                    help="bf16x3 (default): fp32 operands split into 3 bf16 pieces = all 24 mantissa bits, piece products on "
+    ap.add_argument("--precision", default="fp16x2", choices=["fp32", "tf32", "bf16", "bf16x2", "bf16x3", "fp16x2"],
+                    help="fp16x2 (default): fp32-grade two-piece fp16 split in the residual blocks (see PRECISION_NOTE); bf16x3: fp32 operands split into 3 bf16 pieces = all 24 mantissa bits, piece products on "
                          "tcgen05, fp32 accumulation (meets the fp32 parity contract, tests/test_gpu_model.py); fp32: exact "
                          "CUDA-core FMA path; bf16 / tf32 / bf16x2: reduced-precision tensor-core modes")
     args = ap.parse_args()

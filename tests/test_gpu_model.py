@@ -279,3 +279,42 @@ def test_long_window_inference_is_time_tiling_consistent(gpu):
         assert rec_full.shape == (1, T, 1) and bool(torch.isfinite(rec_full).all())
         k = T // 2 - 2 * halo
         assert torch.equal(rec_full[:, :k], rec_half[:, :k]), f"level {l}: reconstructions differ away from the cut"
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("fp16x2", 1e-3)])  # the contract tolerance: 25 blocks deep
+def test_conditioner_decoder_conv_block(gpu, prec, tol):
+    """the DecoderConvBlock the reference's ConditionerNet builds (src/conditioner/conditioners.py:42-46 with the
+    arguments of its own smoke block, :99: embed_width 64, residual_width 32, residual_depth 8, down_depth 3, stride 2,
+    dilation_factor 3, dilation_cycle 4) — another width / depth / dilation schedule (1,3,9,27 repeated twice, reversed)
+    through the same layer class and the same kernels.  Forward and all 110 parameter gradients against the oracle."""
+    V = gpu
+    B, L = 4, 128
+    ops_ = O.decoder_block_ops(64, 64, 32, 8, 3, 2, 3, reverse_dilation=True, dilation_cycle=4)
+    rng = np.random.Generator(np.random.PCG64(3))
+    params = O.init_params(ops_, rng, bias_scale=0.05)
+    x = rng.normal(size=(B, L, 64)).astype(np.float32)
+    dy = rng.normal(size=(B, L * 8, 64)).astype(np.float32)
+    blk = V.DecoderConvBlock(64, 32, 8, dilation_factor=3, reverse_dilation=True, dilation_cycle=4, stride=2, down_depth=3)
+    xin = V.keras.convert_to_tensor(x)
+    blk(xin)  # builds the variables
+    assert len(blk.trainable_variables) == len(params) == 2 + 3 * (8 * 4 + 2)
+    dils = [l.dilation for st in blk.model.layers if hasattr(st, "model") for l in st.model.layers if hasattr(l, "dilation")]
+    assert dils == [27, 9, 3, 1, 27, 9, 3, 1] * 3
+    for v, w in zip(blk.trainable_variables, params):
+        v.assign(w)
+    code = V._lib.PRECISIONS[prec]
+    for l in blk._flatten_layers():
+        if hasattr(l, "precision"):
+            l.precision = code
+    tp = [torch.tensor(p, requires_grad=True) for p in params]
+    want = O.run_ops(ops_, tp, torch.tensor(x))
+    gwant = torch.autograd.grad(((torch.tensor(dy) - want) ** 2).mean(), tp)
+    with V.GradientTape() as tape:
+        y = blk(xin)
+        loss = V.keras.reduce_mean(V.keras.losses.MeanSquaredError(reduction="none")(dy, y))
+    g = tape.gradient(loss, blk.trainable_variables)
+    assert tuple(y.shape) == (B, L * 8, 64)
+    assert rel_err(y, want) < tol
+    gmax = max(float(t.abs().max()) for t in gwant)
+    for got, w in zip(g, gwant):
+        assert float((got.cpu() - w).abs().max()) <= tol * gmax

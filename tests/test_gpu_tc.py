@@ -46,6 +46,32 @@ def test_resblock_tc_fwd_bwd(gpu, prec, B, L, d):
     assert rel(dx, gx) < TOL[prec], ("dx", rel(dx, gx))
 
 
+@pytest.mark.parametrize("env", [{"VQB_RB_MB": "1"}, {"VQB_RB_MB": "2"}, {"VQB_RB_TMA": "1"}])
+@pytest.mark.parametrize("B,L,d", [(2, 1000, 1), (3, 881, 27), (1, 254, 3), (2, 20, 27), (1, 1, 1), (4, 3520, 9)])
+def test_resblock_fp16x2_kernel_variants(gpu, monkeypatch, env, B, L, d):
+    """The fp16x2 residual block has three kernel variants picked per call (resblock_tc.cu: dispatch_rb): 128-row tiles with
+    two CTAs per SM, 256-row tiles, and 256-row tiles whose outputs leave through TMA bulk-tensor stores (tma.cuh: swizzled
+    shared-memory images, rows beyond L clipped by the hardware).  Each must meet the same fp32-grade tolerance."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ops, P = gpu.ops, gpu._lib.PRECISIONS["fp16x2"]
+    rng = np.random.default_rng(L + d)
+    C = 32
+    x = rng.normal(size=(B, L, C)).astype(np.float32)
+    w1 = (rng.normal(size=(3, C, C)) / np.sqrt(3 * C)).astype(np.float32); b1 = (rng.normal(size=C) * 0.1).astype(np.float32)
+    w2 = (rng.normal(size=(3, C, C)) / np.sqrt(3 * C)).astype(np.float32); b2 = (rng.normal(size=C) * 0.1).astype(np.float32)
+    dy = rng.normal(size=(B, L, C)).astype(np.float32)
+    ts = [torch.tensor(a, requires_grad=True) for a in (x, w1, b1, w2, b2)]
+    h_ref = O.conv1d(torch.relu(ts[0]), ts[1], ts[2], 1, d)
+    y_ref = ts[0] + O.conv1d(torch.relu(h_ref), ts[3], ts[4], 1, 1)
+    gx, gh = torch.autograd.grad(y_ref, (ts[0], h_ref), torch.tensor(dy))
+    y, h = ops.resblock_fwd(dev(x), dev(w1), dev(b1), dev(w2), dev(b2), d, P)
+    dx, dh = ops.resblock_bwd_data(dev(x), dev(h_ref.detach().numpy()), dev(dy), dev(w1), dev(w2), d, P)
+    torch.cuda.synchronize()
+    for name, got, want in (("h", h, h_ref), ("y", y, y_ref), ("dh", dh, gh), ("dx", dx, gx)):
+        assert rel(got, want) < TOL["fp16x2"], (env, name, rel(got, want))
+
+
 @pytest.mark.parametrize("prec", ["tf32", "bf16", "bf16x2", "bf16x3", "fp16x2"])
 def test_resblock_tc_full_size_matches_fp32_kernel(gpu, prec):
     """[32, 14080, 32] (the largest stage of SMALL_VQ_VAE at batch 32): tensor-core path vs the exact-fp32 CUDA path."""

@@ -226,3 +226,10 @@ def test_data_parallel_two_ranks_equal_unsharded(cpu_backend, tmp_path):
         np.testing.assert_allclose(r0[f"E{l}"], m.vqs[l].embeddings.numpy(), rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(r0[f"N{l}"], m.vqs[l].N_t.numpy(), rtol=1e-6)
     assert abs(float(r0["loss"]) - float(logs["loss"])) < 1e-4
+
+
+def test_conditioner_decoder_conv_block_host_logic(cpu_backend):
+    """The ConditionerNet-shaped DecoderConvBlock (depth 8, cyclic dilation 4) through the layer classes on the
+    CPU test double: variable count and order, dilation schedule, output shape, tape gradients (same body as the GPU test)."""
+    from tests.test_gpu_model import test_conditioner_decoder_conv_block as body
+    body(cpu_backend, "fp32", 1e-3)

@@ -12,7 +12,7 @@ prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
 P = V._lib.PRECISIONS[prec]
 ops = V.ops
 g = torch.Generator(device="cuda").manual_seed(0)
-B, L, C = 32, 14080, 32
+B, L, C = int(os.environ.get("B", "32")), int(os.environ.get("L", "14080")), 32
 xs = [torch.randn(B, L, C, device="cuda", generator=g) for _ in range(2)]
 dy = torch.randn(B, L, C, device="cuda", generator=g)
 w1 = torch.randn(3, C, C, device="cuda", generator=g) * 0.1
@@ -45,4 +45,4 @@ for i in range(n):
     one(i)
 e1.record()
 torch.cuda.synchronize()
-print(what, prec, "ms per call", e0.elapsed_time(e1) / n)
+print(what, prec, f"B={B} L={L}", "ms per call", e0.elapsed_time(e1) / n)

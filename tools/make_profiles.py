@@ -26,7 +26,11 @@ def raw(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, r = rows[0], rows[1], rows[2]
-    val = lambda k: float(r[hdr.index(k)].replace(",", "")) * UNIT.get(units[hdr.index(k)], 1.0)
+    def val(k):
+        try:
+            return float(r[hdr.index(k)].replace(",", "")) * UNIT.get(units[hdr.index(k)], 1.0)
+        except ValueError:  # "no data" / "n/a": the counter was not collected for this kernel
+            return None
     d = {"kernel": r[hdr.index("Kernel Name")], "duration_us": val("gpu__time_duration.sum"),
          "dram_read_bytes": val("dram__bytes_read.sum"), "dram_write_bytes": val("dram__bytes_write.sum"),
          "dram_pct_of_peak": val("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
@@ -35,8 +39,13 @@ def raw(rep):
          "block": val("launch__block_size")}
     for k in hdr:
         if k.endswith("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"):
-            d["tensor_pipe_active_pct"] = val(k)
-    d["traffic_bytes"] = d["dram_read_bytes"] + d["dram_write_bytes"]
+            d["tensor_pipe_active_realtime_pct"] = val(k)
+    for k, name in (("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor_pipe_active_pct"),
+                    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lsu_data_pipe_pct"),
+                    ("sm__cycles_elapsed.max", "sm_cycles")):
+        if k in hdr:
+            d[name] = val(k)
+    d["traffic_bytes"] = (d["dram_read_bytes"] or 0.0) + (d["dram_write_bytes"] or 0.0)
     return d
 
 

@@ -13,7 +13,11 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__inst_executed.sum',
         'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
-        'lts__throughput.avg.pct_of_peak_sustained_elapsed']
+        'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',  # tcgen05 pipe busy (matches MMA count x tools/mma_probe cost)
+        'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum']
 
 
 def main(rep):

@@ -14,10 +14,12 @@
 // Activations are converted on the fly while being staged (fp32 global -> act -> bf16/tf32 shared), which is why the
 // A tile is written by threads rather than by TMA.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc.cuh"
 #include "tc_rows.cuh"
+#include "tma.cuh"
 
 namespace vqb {
 
@@ -44,7 +46,7 @@ struct RbTcParams {
 // all 24 mantissa bits of both operands: fp32-grade products with fp32 accumulation)   4: fp16x2 (operands scaled by a
 // power of two — per tile for the activations, per convolution for the weights — and split into two fp16 pieces, 11 + 11
 // mantissa bits: fp32-grade products for the MMA count of bf16x2; see tc.cuh)
-template <int MODE, int MB = 2>  // MB = 128-row M blocks per CTA: 2 -> 256-row tiles, 512 threads, one CTA per SM;
+template <int MODE, int MB = 2, bool TMA_ = false>  // MB = 128-row M blocks per CTA: 2 -> 256-row tiles, 512 threads, one CTA per SM;
 struct RbCfg {                   //      1 -> 128-row tiles, 256 threads, two CTAs per SM (modes with <= 2 pieces)
   static constexpr bool TF32 = MODE == 1;
   static constexpr bool F16 = MODE == 4;
@@ -64,16 +66,21 @@ struct RbCfg {                   //      1 -> 128-row tiles, 256 threads, two CT
   static constexpr int WCONV = 3 * WTAP;
   static constexpr int TILE = NP * PLANE;   // one operand tile (one split piece)
   static constexpr int STG = (NT / 32) * 2048;  // per-warp row staging (32 rows x 64 B)
-  static constexpr int SMEM = 2 * S * TILE + 2 * WCONV + STG + 64 + 256;
+  // TMA: out1 / out2 leave through dense 128-byte-swizzled row images in shared memory and one bulk-tensor store per
+  // tile (tma.cuh) instead of per-warp staging transposes + st.global; needs 2 x R rows of shared memory, which fits for
+  // the two-piece modes with 256-row tiles
+  static constexpr bool TMA = TMA_ && S == 2 && MB == 2;
+  static constexpr int OUTB = TMA ? R * 128 : 0;   // bytes of one output image
+  static constexpr int SMEM = 2 * S * TILE + 2 * WCONV + STG + 64 + 256 + (TMA ? 2 * OUTB + 1024 : 0);
   static constexpr int TCOLS = 2 * MB * NW <= 64 ? 64 : 2 * MB * NW <= 128 ? 128 : 2 * MB * NW <= 256 ? 256 : 512;  // TMEM columns: 2 stages x MB M blocks x NW
   static constexpr int NCV = NT - 32 * MB;   // threads that load / convert the stage-1 input (all but the MMA-issuing warps)
   static constexpr int NU = ((R + 2 * DMAX) * 4 + NCV - 1) / NCV;  // 8-channel units of the stage-1 input tile per converter thread
 };
 
-template <int MODE, int MB>
+template <int MODE, int MB, bool TMA_>
 __device__ __forceinline__ void pack_weights(uint8_t* dst, const float* __restrict__ w, int sj, int si, int so, int flip,
                                              float scale) {
-  using Cfg = RbCfg<MODE, MB>;
+  using Cfg = RbCfg<MODE, MB, TMA_>;
   for (int e = threadIdx.x; e < 3 * 32 * 32; e += blockDim.x) {
     const int n = e & 31, k = (e >> 5) & 31, j = e >> 10;
     const int jj = flip ? 2 - j : j;
@@ -101,9 +108,9 @@ __device__ __forceinline__ void pack_weights(uint8_t* dst, const float* __restri
 // SAME accumulator (hi x {hi, mid, lo}, mid x {hi, mid}, lo x {hi}: every product down to 2^-16 of the leading one plus
 // mid x mid; the three omitted ones are below 2^-23): column block c then holds the sum over the activation pieces of
 // a . W_c, and the epilogue adds the S column blocks.
-template <int MODE, int MB>
+template <int MODE, int MB, bool TMA_>
 __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int row_shift0, int dil, uint32_t w_base, int mb) {
-  using Cfg = RbCfg<MODE, MB>;
+  using Cfg = RbCfg<MODE, MB, TMA_>;
   // descriptors differ only in their start-address field (units of 16 bytes = one tile row): add offsets to two bases
   const uint64_t ad0 = smem_desc(a_base + (uint32_t)row_shift0 * 16u, Cfg::PLANE, 128);
   const uint64_t bd0 = smem_desc(w_base, Cfg::WPLANE, 128);
@@ -123,9 +130,9 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem, uint32_t a_base, int 
 }
 
 // 8 channels o*8..o*8+7 of row r (two float4) -> operand tile(s): one 16-byte chunk per bf16 piece, two for tf32
-template <int MODE, int MB>
+template <int MODE, int MB, bool TMA_>
 __device__ __forceinline__ void stage8(uint8_t* tile, int r, int o, const float4& a, const float4& b, float scale) {
-  using Cfg = RbCfg<MODE, MB>;
+  using Cfg = RbCfg<MODE, MB, TMA_>;
   if (Cfg::F16) {
     uint4 pc[2];
     split8_f16(a, b, scale, pc);
@@ -150,12 +157,17 @@ __device__ __forceinline__ void stage8(uint8_t* tile, int r, int o, const float4
 // (A variant with a dedicated MMA-issuing warp and mbarrier-only hand-offs measured slower: 17 warps cap the register
 // file at 96 per thread; so did epilogues that access their rows in global memory directly instead of through the
 // per-warp staging transposes: 32 lines per access instruction saturate the L1 pipeline.)
-template <int MODE, int MB>
-__global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(const RbTcParams p) {
-  using Cfg = RbCfg<MODE, MB>;
+template <int MODE, int MB, bool TMA_>
+__global__ void __launch_bounds__(RbCfg<MODE, MB, TMA_>::NT, 3 - MB)
+    rb_tc_kernel(const RbTcParams p, const __grid_constant__ CUtensorMap tm_out1, const __grid_constant__ CUtensorMap tm_out2) {
+  using Cfg = RbCfg<MODE, MB, TMA_>;
   constexpr int NT = Cfg::NT, NU = Cfg::NU;
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* A1 = smem;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  // the swizzled output images must start on a 1024-byte boundary
+  uint8_t* smem = Cfg::TMA ? smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
+  uint8_t* OUT1 = smem;
+  uint8_t* OUT2 = smem + Cfg::OUTB;
+  uint8_t* A1 = smem + 2 * Cfg::OUTB;
   uint8_t* A2 = A1 + Cfg::S * Cfg::TILE;
   uint8_t* W1 = A2 + Cfg::S * Cfg::TILE;
   uint8_t* W2 = W1 + Cfg::WCONV;
@@ -188,8 +200,8 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(cons
     sw1 = pow2_scale(__uint_as_float(tmx[2]));
     sw2 = pow2_scale(__uint_as_float(tmx[3]));
   }
-  pack_weights<MODE, MB>(W1, p.w1, p.sj1, p.si1, p.so1, p.flip1, sw1);
-  pack_weights<MODE, MB>(W2, p.w2, p.sj2, p.si2, p.so2, p.flip2, sw2);
+  pack_weights<MODE, MB, TMA_>(W1, p.w1, p.sj1, p.si1, p.so1, p.flip1, sw1);
+  pack_weights<MODE, MB, TMA_>(W2, p.w2, p.sj2, p.si2, p.so2, p.flip2, sw2);
   if (tid < 64) bias_s[tid] = tid < 32 ? (p.bias1 ? p.bias1[tid] : 0.f) : (p.bias2 ? p.bias2[tid - 32] : 0.f);
   fence_proxy_async();
   fence_before_sync();
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(cons
           a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
           b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
         }
-        stage8<MODE, MB>(A1, r, oct, a, b, scale);
+        stage8<MODE, MB, TMA_>(A1, r, oct, a, b, scale);
       }
     }
     fence_proxy_async();
@@ -279,13 +291,14 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(cons
     __syncthreads();
     fence_after_sync();
     if (issuer && elect_one()) {
-      issue_stage<MODE, MB>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1), warp >> 2);
+      issue_stage<MODE, MB, TMA_>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1), warp >> 2);
       commit(&bar[0]);
     }
     if (Cfg::F16 && tid == 0) tmx[0] = 0u;  // read by every thread before the barrier above
     __syncwarp();
   }
   uint32_t phase = 0;
+  int pend_t0 = 0, pend_b = -1;  // TMA: tile whose out2 image waits in OUT2 for its bulk store
 #pragma unroll 1
   for (; tile < p.total_tiles; tile += gridDim.x, phase ^= 1) {
     const int b = tile / p.tiles_x;
@@ -341,7 +354,16 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(cons
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] = m[c] > 0.f ? v[c] : 0.f;
     }
-    if (p.out1) warp_store_rows(p.out1, boff, s0 + i0, L, half, i0, p.d2, Cfg::R - p.d2, stg, lane, v);
+    if (Cfg::TMA) {
+      const int j = i - p.d2;  // row of the stored box: global row t0 + j
+      if (p.out1 && j >= 0 && j < Rout) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(OUT1 + tma::swz(j, half * 4 + q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    } else if (p.out1) {
+      warp_store_rows(p.out1, boff, s0 + i0, L, half, i0, p.d2, Cfg::R - p.d2, stg, lane, v);
+    }
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       const float a = inrange ? v[c] : 0.f;  // rows outside [0, L) are conv2's zero padding
@@ -350,7 +372,7 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(cons
     const float sa2 = Cfg::F16 ? pow2_scale(fmaf(w1bound, amax, b1bound)) : 1.f;
 #pragma unroll
     for (int q = 0; q < 2; ++q)
-      stage8<MODE, MB>(A2, Cfg::DMAX + i, half * 2 + q, make_float4(v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]),
+      stage8<MODE, MB, TMA_>(A2, Cfg::DMAX + i, half * 2 + q, make_float4(v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]),
                    make_float4(v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]), sa2);
     if (has_next) publish_max(slot);
     fence_proxy_async();
@@ -363,22 +385,32 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(cons
     }
     if (issuer && elect_one()) {
       // out2 tile row i uses A2 rows DMAX + i + (j-1)*d2
-      issue_stage<MODE, MB>(tmem + MB * Cfg::NW, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2), warp >> 2);
+      issue_stage<MODE, MB, TMA_>(tmem + MB * Cfg::NW, smem_u32(A2), Cfg::DMAX - p.d2, p.d2, smem_u32(W2), warp >> 2);
       commit(&bar[1]);
+      if (Cfg::TMA && warp == 1) {  // this tile's out1 image and the previous tile's out2 image are complete
+        if (pend_b >= 0) tma::store_rows(&tm_out2, OUT2, pend_t0, pend_b);
+        if (p.out1) tma::store_rows(&tm_out1, OUT1, t0, b);
+        tma::commit_group();
+      }
     }
     __syncwarp();
+    pend_t0 = t0; pend_b = b;
     if (has_next) {  // A1 is free (its MMAs completed before epilogue 1): stage the next tile under the stage-2 MMAs
       convert(sa1);
+      if (Cfg::TMA && warp == 1 && elect_one()) tma::wait_read();  // both images may be overwritten after the barrier
       fence_before_sync();
       __syncthreads();
       fence_after_sync();
       if (Cfg::F16 && tid == 0) tmx[slot] = 0u;  // every thread has read it; written again two tiles from now
       slot ^= 1;
       if (issuer && elect_one()) {
-        issue_stage<MODE, MB>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1), warp >> 2);
+        issue_stage<MODE, MB, TMA_>(tmem, smem_u32(A1), 0, p.d1, smem_u32(W1), warp >> 2);
         commit(&bar[0]);
       }
       __syncwarp();
+    } else if (Cfg::TMA) {
+      if (warp == 1 && elect_one()) tma::wait_read();
+      __syncthreads();
     }
 
     // ---- epilogue 2: TMEM -> (+bias, mask, + add) -> out2 (owned rows)
@@ -415,19 +447,37 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB>::NT, 3 - MB) rb_tc_kernel(cons
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] += m[c];
     }
-    warp_store_rows(p.out2, boff, s0 + i0, L, half, i0, p.d2, Cfg::R - p.d2, stg, lane, v);
+    if (Cfg::TMA) {
+      const int j = i - p.d2;
+      if (j >= 0 && j < Rout) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(OUT2 + tma::swz(j, half * 4 + q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    } else {
+      warp_store_rows(p.out2, boff, s0 + i0, L, half, i0, p.d2, Cfg::R - p.d2, stg, lane, v);
+    }
     fence_before_sync();  // orders this tile's TMEM reads before the barriers of the next iteration
   }  // tile loop
+  if (Cfg::TMA) {  // the last tile's out2 image
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 1 && elect_one()) {
+      if (pend_b >= 0) tma::store_rows(&tm_out2, OUT2, pend_t0, pend_b);
+      tma::commit_group();
+      tma::wait_all();
+    }
+  }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
-template <int MODE, int MB>
+template <int MODE, int MB, bool TMA_>
 static int launch_rb(const RbTcParams& p, cudaStream_t st) {
-  using Cfg = RbCfg<MODE, MB>;
+  using Cfg = RbCfg<MODE, MB, TMA_>;
   static bool attr_set = false;
   if (!attr_set) {
-    VQB_CUDA(cudaFuncSetAttribute(rb_tc_kernel<MODE, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    VQB_CUDA(cudaFuncSetAttribute(rb_tc_kernel<MODE, MB, TMA_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -442,7 +492,14 @@ static int launch_rb(const RbTcParams& p, cudaStream_t st) {
   q.total_tiles = q.tiles_x * p.B;
   const int slots = num_sms * (3 - MB);
   const int grid = q.total_tiles < slots ? q.total_tiles : slots;
-  rb_tc_kernel<MODE, MB><<<grid, Cfg::NT, Cfg::SMEM, st>>>(q);
+  CUtensorMap tm1, tm2;
+  memset(&tm1, 0, sizeof(tm1));
+  memset(&tm2, 0, sizeof(tm2));
+  if (Cfg::TMA) {
+    if ((p.out1 && !tma::make_rows_map(&tm1, p.out1, p.B, p.L, Rout)) || !tma::make_rows_map(&tm2, p.out2, p.B, p.L, Rout))
+      return set_err(VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed for a [%d, %d, 32] fp32 tensor (box rows %d)", p.B, p.L, Rout);
+  }
+  rb_tc_kernel<MODE, MB, TMA_><<<grid, Cfg::NT, Cfg::SMEM, st>>>(q, tm1, tm2);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
@@ -451,14 +508,22 @@ static int dispatch_rb(int precision, const RbTcParams& p, cudaStream_t st) {
   // Tile height (modes with <= 2 pieces fit two CTAs of 128-row tiles per SM): the halo a tile recomputes is 2 * d2 rows,
   // so 128-row tiles pay off while d2 is small (every forward block: d2 = 1; backward blocks of dilation <= 3).
   // VQB_RB_MB=1|2 forces one of them (tuning).
-  static const int mb_env = getenv("VQB_RB_MB") ? atoi(getenv("VQB_RB_MB")) : 0;
-  const bool half_tiles = mb_env ? mb_env == 1 : p.d2 <= 3;
+  // VQB_RB_TMA=1 (fp16x2, 256-row tiles) sends out1 / out2 through bulk-tensor stores (tma.cuh).  Measured on B200 it is
+  // correct but 2-9 % SLOWER than the per-warp staged st.global path (fwd 71.4 vs 69.8 us, bwd 100 vs 91 us at
+  // [32, 14080, 32]): the kernel is bound by how little of its DRAM traffic overlaps its compute phases, not by LSU work,
+  // and the bulk stores bunch the writes of a tile right behind one barrier.  Kept as the groundwork for TMA-fed INPUTS.
+  const char* e_mb = getenv("VQB_RB_MB");
+  const char* e_tma = getenv("VQB_RB_TMA");
+  const int mb_env = e_mb ? atoi(e_mb) : 0;
+  const bool use_tma = e_tma && atoi(e_tma) == 1;
+  const bool half_tiles = !use_tma && (mb_env ? mb_env == 1 : p.d2 <= 3);
   switch (precision) {
-    case VQB_PREC_BF16: return launch_rb<0, 2>(p, st);
-    case VQB_PREC_TF32: return launch_rb<1, 2>(p, st);
-    case VQB_PREC_BF16X2: return half_tiles ? launch_rb<2, 1>(p, st) : launch_rb<2, 2>(p, st);
-    case VQB_PREC_BF16X3: return launch_rb<3, 2>(p, st);
-    case VQB_PREC_FP16X2: return half_tiles ? launch_rb<4, 1>(p, st) : launch_rb<4, 2>(p, st);
+    case VQB_PREC_BF16: return launch_rb<0, 2, false>(p, st);
+    case VQB_PREC_TF32: return launch_rb<1, 2, false>(p, st);
+    case VQB_PREC_BF16X2: return half_tiles ? launch_rb<2, 1, false>(p, st) : launch_rb<2, 2, false>(p, st);
+    case VQB_PREC_BF16X3: return launch_rb<3, 2, false>(p, st);
+    case VQB_PREC_FP16X2:
+      return use_tma ? launch_rb<4, 2, true>(p, st) : half_tiles ? launch_rb<4, 1, false>(p, st) : launch_rb<4, 2, false>(p, st);
   }
   return set_err(VQB_ERR_INVALID, "unknown precision %d", precision);
 }

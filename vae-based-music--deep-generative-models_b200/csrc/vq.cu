@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(VQ_FS_THREADS, 1) vq_finish_smem_kernel(
   // VQ_FU rows per half-warp and iteration, every load issued before the first use: the kernel is a gather with a dependent
   // index load per row, so its bandwidth is set by how many rows are in flight per SM (Little: ~35 KB at 6.5 TB/s)
   constexpr int VQ_FU = 4;
+  const bool perm = (D & 63) == 0;  // bank-permuted per-code rows (see the reductions below)
   constexpr int RS = (VQ_FS_THREADS / 32) * 2;  // rows per CTA pass
   for (long n0 = r0 + wid * 2 + hw; n0 < r1; n0 += RS * VQ_FU) {
     int k[VQ_FU];
@@ -217,8 +218,19 @@ __global__ void __launch_bounds__(VQ_FS_THREADS, 1) vq_finish_smem_kernel(
             make_float4(__fadd_rn(xv[u].x, df.x), __fadd_rn(xv[u].y, df.y), __fadd_rn(xv[u].z, df.z), __fadd_rn(xv[u].w, df.w));
         ls = fmaf(df.x, df.x, ls); ls = fmaf(df.y, df.y, ls); ls = fmaf(df.z, df.z, ls); ls = fmaf(df.w, df.w, ls);
         if (stats) {
-          float* a = fsm + (size_t)k[u] * D + d;
-          atomicAdd(a, xv[u].x); atomicAdd(a + 1, xv[u].y); atomicAdd(a + 2, xv[u].z); atomicAdd(a + 3, xv[u].w);
+          // channel d + c lives at word (d & ~63) + 16 * c + (d % 64) / 4 of the code's row: the 16 lanes of a half-warp hit
+          // 16 consecutive banks per instruction, and the two half-warps take c in opposite pairs (0,1,2,3 / 1,0,3,2), i.e.
+          // the other 16 banks: no conflicts (a [d, d+3] float4 per lane straight into the row would be 4-way conflicted)
+          if (perm) {
+            float* a = fsm + (size_t)k[u] * D + (d & ~63) + hl;
+            const float e0 = hw ? xv[u].y : xv[u].x, e1 = hw ? xv[u].x : xv[u].y;
+            const float e2 = hw ? xv[u].w : xv[u].z, e3 = hw ? xv[u].z : xv[u].w;
+            atomicAdd(a + 16 * hw, e0); atomicAdd(a + 16 * (1 - hw), e1);
+            atomicAdd(a + 32 + 16 * hw, e2); atomicAdd(a + 32 + 16 * (1 - hw), e3);
+          } else {  // D not a multiple of 64: rows in natural order
+            float* a = fsm + (size_t)k[u] * D + d;
+            atomicAdd(a, xv[u].x); atomicAdd(a + 1, xv[u].y); atomicAdd(a + 2, xv[u].z); atomicAdd(a + 3, xv[u].w);
+          }
         }
       }
     }
@@ -233,7 +245,10 @@ __global__ void __launch_bounds__(VQ_FS_THREADS, 1) vq_finish_smem_kernel(
   if (stats) {
     __syncthreads();
     float* pk = partial_kd + (size_t)blockIdx.x * K * D;
-    for (int e = tid; e < K * D; e += VQ_FS_THREADS) pk[e] = fsm[e];
+    for (int e = tid; e < K * D; e += VQ_FS_THREADS) {  // undo the bank permutation of the rows
+      const int dd = e % D, c = dd & 3, q4 = (dd & 63) >> 2;
+      pk[e] = perm ? fsm[e - dd + (dd & ~63) + 16 * c + q4] : fsm[e];
+    }
     for (int e = tid; e < K; e += VQ_FS_THREADS) partial_n[(size_t)blockIdx.x * K + e] = sm_n[e];
   }
 }
