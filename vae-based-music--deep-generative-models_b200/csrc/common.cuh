@@ -71,6 +71,35 @@ int wgrad4_tc(int precision, const float* ga, int Lg, const float* ot, int Lo, i
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------
+// The ~600 kernels of a training step form one dependency chain, and the persistent tensor-core kernels have a prologue that
+// does not depend on the previous kernel (TMEM allocation, mbarrier init, packing the layer's weights into shared-memory
+// operand images).  Launched with the programmatic-stream-serialization attribute, a kernel may become resident while its
+// predecessor is still draining; it calls pdl_wait() before its first access to anything the predecessor wrote (and before its
+// first global write), and pdl_launch_dependents() once its own prologue is done so that ITS successor can do the same.
+// Rules kept by every kernel launched through launch_pdl: (1) every CTA executes pdl_wait() before exiting (completion is
+// transitive only then); (2) nothing read before pdl_wait() is written by a kernel of the same graph launch (weights are
+// written by Adam in the second graph of a step; layer inputs never are).  VQB_PDL=0 turns the attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// tier 1: the persistent tensor-core kernels (prologue worth overlapping); tier 2: plain kernels that wait first thing.
+// VQB_PDL = highest tier that gets the attribute (0 = none).
+bool pdl_enabled(int tier);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_tier(int tier, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                          Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled(tier) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#define launch_pdl(...) launch_pdl_tier(1, __VA_ARGS__)
+#define launch_pdl2(...) launch_pdl_tier(2, __VA_ARGS__)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -43,6 +43,8 @@ constexpr int TGC_TT = 128;
 
 // 256 threads; tile = 128 time positions x 32 output channels; thread = 4 positions x 4 channels.
 __global__ void __launch_bounds__(256) tgc_kernel(const TgcParams p) {
+  pdl_launch_dependents();
+  pdl_wait();  // launched through launch_pdl (common.cuh): nothing is read or written above this line
   extern __shared__ __align__(16) float smem[];
   float* in_s = smem;                            // [rows][ci_ch]
   float* w_s = smem + (size_t)p.rows * p.ci_ch;  // [ntaps][ci_ch][32]
@@ -158,6 +160,8 @@ __global__ void __launch_bounds__(256) tgc_kernel(const TgcParams p) {
 
 // C_out <= 4 (e.g. the final Conv1D(1, 3), encdec.py:148): one thread per output position, weights in smem.
 __global__ void __launch_bounds__(256) tgc_narrow_kernel(const TgcParams p) {
+  pdl_launch_dependents();
+  pdl_wait();  // launched through launch_pdl (common.cuh): nothing is read or written above this line
   extern __shared__ __align__(16) float w_s[];  // [ntaps][CIN][COUT]
   const int ntaps = p.taps.ntaps;
   for (int e = threadIdx.x; e < ntaps * p.CIN * p.COUT; e += blockDim.x) {
@@ -215,7 +219,7 @@ static int launch_tgc(TgcParams& p, cudaStream_t st) {
     const size_t smem = (size_t)p.taps.ntaps * p.CIN * p.COUT * sizeof(float);
     VQB_REQUIRE(smem <= 48 * 1024, "narrow conv: weights (%zu B) exceed 48 KB of shared memory", smem);
     const long n = (long)p.B * p.Lt;
-    tgc_narrow_kernel<<<cdiv(n, 256), 256, smem, st>>>(p);
+    VQB_CUDA(launch_pdl2(tgc_narrow_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)smem, st, p));
     VQB_LAUNCH_CHECK();
     return VQB_OK;
   }
@@ -234,7 +238,7 @@ static int launch_tgc(TgcParams& p, cudaStream_t st) {
     smem_set = 200 * 1024;
   }
   dim3 grid(cdiv(p.Lt, TGC_TT), p.B, cdiv(p.COUT, 32));
-  tgc_kernel<<<grid, 256, smem, st>>>(p);
+  VQB_CUDA(launch_pdl2(tgc_kernel, dim3(grid), dim3(256), (size_t)smem, st, p));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
@@ -262,6 +266,8 @@ constexpr int WG_SUB = 128;
 
 template <int NT>
 __global__ void __launch_bounds__(128) wgrad_kernel(const WgParams p) {
+  pdl_launch_dependents();
+  pdl_wait();  // launched through launch_pdl (common.cuh): nothing is read or written above this line
   extern __shared__ __align__(16) float smem[];
   float* g_s = smem;                            // [rows][32]  gather-side tile
   float* o_s = smem + (size_t)p.rows * 32;      // [sub][32]   other-side tile
@@ -391,6 +397,8 @@ struct ReduceBatch {
 };
 
 __global__ void __launch_bounds__(256) reduce_batched_kernel(const ReduceBatch b) {
+  pdl_launch_dependents();
+  pdl_wait();  // launched through launch_pdl (common.cuh): nothing is read or written above this line
   __shared__ float red[8][33];
   int lo = 0, hi = b.n_items - 1;  // last item whose block0 <= blockIdx.x
   while (lo < hi) {
@@ -445,7 +453,7 @@ int reduce_flush(cudaStream_t st) {
     }
     b.n_items = k;
     if (blocks > 0) {
-      reduce_batched_kernel<<<blocks, 256, 0, st>>>(b);
+      VQB_CUDA(launch_pdl2(reduce_batched_kernel, dim3(blocks), dim3(256), (size_t)0, st, b));
       VQB_LAUNCH_CHECK();
     }
     i += k;
@@ -505,7 +513,7 @@ static int launch_wgrad(const WgParams& p, dim3 grid, size_t smem, cudaStream_t 
     static bool set = false;
     if (!set) { VQB_CUDA(cudaFuncSetAttribute(wgrad_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set = true; }
   }
-  wgrad_kernel<NT><<<grid, 128, smem, st>>>(p);
+  VQB_CUDA(launch_pdl2(wgrad_kernel<NT>, dim3(grid), dim3(128), (size_t)smem, st, p));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

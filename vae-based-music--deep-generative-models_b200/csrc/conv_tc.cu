@@ -140,6 +140,8 @@ __global__ void __launch_bounds__(CtCfg<S, UP>::NT, 1) conv_tc_kernel(const Conv
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tslot;
+  pdl_launch_dependents();  // the prologue read only this layer's weights (common.cuh)
+  pdl_wait();
   const int ntiles = (int)blockIdx.x < p.total_tiles ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   // epilogue role: TMEM lane quadrant, accumulator group (DOWN: M block, UP: output phase), 16-channel half
@@ -261,7 +263,7 @@ static int launch_ct(const ConvTcParams& p, cudaStream_t st) {
   q.total_tiles = q.tiles_x * p.B;
   if (q.total_tiles == 0) return VQB_OK;
   const int grid = q.total_tiles < num_sms ? q.total_tiles : num_sms;
-  conv_tc_kernel<S, UP><<<grid, Cfg::NT, Cfg::SMEM, st>>>(q);
+  VQB_CUDA(launch_pdl(conv_tc_kernel<S, UP>, dim3(grid), dim3(Cfg::NT), (size_t)Cfg::SMEM, st, q));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

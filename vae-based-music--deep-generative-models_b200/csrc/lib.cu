@@ -1,6 +1,12 @@
 // lib.cu — version, error text and the architecture gate of libvqvae_b200.so.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include <atomic>
+
+#ifndef VQB_PDL_DEFAULT
+#define VQB_PDL_DEFAULT 1
+#endif
 
 namespace vqb {
 
@@ -34,6 +40,12 @@ int require_arch() {
   cached_rc = major == 10 ? VQB_OK
                           : set_err(VQB_ERR_ARCH, "device %d has compute capability %d.x; libvqvae_b200 is sm_100a only", dev, major);
   return cached_rc;
+}
+
+bool pdl_enabled(int tier) {  // read per call: tests and A/B measurements flip it with the environment
+  const char* e = getenv("VQB_PDL");
+  const int level = e ? atoi(e) : VQB_PDL_DEFAULT;
+  return tier <= level;
 }
 
 }  // namespace vqb

@@ -274,6 +274,9 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB, TMA_>::NT, 3 - MB)
     fence_proxy_async();
   };
 
+  // everything above read only this layer's weights: the previous kernel of the stream may still be running (common.cuh)
+  pdl_launch_dependents();
+  pdl_wait();
   int tile = blockIdx.x;
   float amax = 0.f, sa1 = 1.f;  // fp16x2: largest |stage-1 input| of the current tile and its operand scale
   int slot = 0;                 // tmx slot of the NEXT tile
@@ -499,7 +502,7 @@ static int launch_rb(const RbTcParams& p, cudaStream_t st) {
     if ((p.out1 && !tma::make_rows_map(&tm1, p.out1, p.B, p.L, Rout)) || !tma::make_rows_map(&tm2, p.out2, p.B, p.L, Rout))
       return set_err(VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed for a [%d, %d, 32] fp32 tensor (box rows %d)", p.B, p.L, Rout);
   }
-  rb_tc_kernel<MODE, MB, TMA_><<<grid, Cfg::NT, Cfg::SMEM, st>>>(q, tm1, tm2);
+  VQB_CUDA(launch_pdl(rb_tc_kernel<MODE, MB, TMA_>, dim3(grid), dim3(Cfg::NT), (size_t)Cfg::SMEM, st, q, tm1, tm2));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

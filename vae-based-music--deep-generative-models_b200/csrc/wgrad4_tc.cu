@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(Wg4Cfg<S>::NT + 32, 1) wgrad4_tc_kernel(const 
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tslot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const long first = (long)blockIdx.x * p.total_tiles / gridDim.x;
   const long last = (long)(blockIdx.x + 1) * p.total_tiles / gridDim.x;
@@ -290,7 +292,7 @@ static int launch_wg4(const Wg4Params& p, int grid, cudaStream_t st) {
     VQB_CUDA(cudaFuncSetAttribute(wgrad4_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set = true;
   }
-  wgrad4_tc_kernel<S><<<grid, Cfg::NT + 32, Cfg::SMEM, st>>>(p);
+  VQB_CUDA(launch_pdl(wgrad4_tc_kernel<S>, dim3(grid), dim3(Cfg::NT + 32), (size_t)Cfg::SMEM, st, p));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tslot;
+  pdl_launch_dependents();  // prologue done (common.cuh): the next kernel may become resident ...
+  pdl_wait();               // ... and this one must not touch the previous kernel's outputs before it has completed
 
   const long first = (long)blockIdx.x * p.total_tiles / gridDim.x;
   const long last = (long)(blockIdx.x + 1) * p.total_tiles / gridDim.x;
@@ -282,7 +284,7 @@ static int launch_wg(const WgTcParams& p, int grid, cudaStream_t st) {
     VQB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<S, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set = true;
   }
-  wgrad_tc_kernel<S, NT><<<grid, Cfg::NT + 32, Cfg::SMEM, st>>>(p);
+  VQB_CUDA(launch_pdl(wgrad_tc_kernel<S, NT>, dim3(grid), dim3(Cfg::NT + 32), (size_t)Cfg::SMEM, st, p));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
