@@ -132,6 +132,14 @@ int vqb_resblock_fwd(const vqb_resblock_desc* d, const float* x, const float* w1
  * (h>0)*conv2^T(dy), the gradient at conv1's output, for the weight gradients. */
 int vqb_resblock_bwd_data(const vqb_resblock_desc* d, const float* x, const float* h, const float* dy,
                           const float* w1, const float* w2, float* dh, float* dx, void* stream);
+/* Both weight gradients of the block in one call (tensor-core precisions: one launch):
+ *   dw1[3, C, F] = sum ReLU(x)[t + (j-1) dilation] dh[t],  db1[F] = sum dh   (dilated conv, resnet.py:13-15)
+ *   dw2[3, F, C] = sum ReLU(h)[t + (j-1)] dy[t],           db2[C] = sum dy   (second conv, resnet.py:17)
+ * Takes part in vqb_reduce_begin / vqb_reduce_flush batching like the *_wgrad calls. */
+size_t vqb_resblock_wgrad_workspace_bytes(const vqb_resblock_desc* d);
+int vqb_resblock_wgrad(const vqb_resblock_desc* d, const float* x, const float* h, const float* dy, const float* dh,
+                       float* dw1, float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Decoder tail: the last Conv1DTranspose(C_mid, k=4, s=2) (encdec.py:67-68) and the final Conv1D(1, 3) (encdec.py:148)

@@ -235,6 +235,24 @@ class FakeBackend:
         _t(y, (d.B, d.L, d.C)).copy_(X + O.conv1d(torch.relu(H), _t(w2, (3, d.F, d.C)), _t(b2, (d.C,)), 1, 1))
         return 0
 
+    def vqb_resblock_wgrad_workspace_bytes(self, dref):
+        return 16
+
+    def vqb_resblock_wgrad(self, dref, x, h, dy, dh, dw1, db1, dw2, db2, ws, wsn, stream):
+        d = _d(dref)
+        X = torch.relu(_t(x, (d.B, d.L, d.C))); H = torch.relu(_t(h, (d.B, d.L, d.F)))
+        DY = _t(dy, (d.B, d.L, d.C)); DH = _t(dh, (d.B, d.L, d.F))
+        w1 = torch.zeros(3, d.C, d.F, requires_grad=True)
+        (g1,) = torch.autograd.grad(O.conv1d(X, w1, None, 1, d.dilation), w1, DH)
+        w2 = torch.zeros(3, d.F, d.C, requires_grad=True)
+        (g2,) = torch.autograd.grad(O.conv1d(H, w2, None, 1, 1), w2, DY)
+        _t(dw1, (3, d.C, d.F)).copy_(g1); _t(dw2, (3, d.F, d.C)).copy_(g2)
+        if db1 is not None:
+            _t(db1, (d.F,)).copy_(DH.sum((0, 1)))
+        if db2 is not None:
+            _t(db2, (d.C,)).copy_(DY.sum((0, 1)))
+        return 0
+
     def vqb_resblock_bwd_data(self, dref, x, h, dy, w1, w2, dh, dx, stream):
         d = _d(dref)
         X = _t(x, (d.B, d.L, d.C)); H = _t(h, (d.B, d.L, d.F)); DY = _t(dy, (d.B, d.L, d.C))

@@ -149,6 +149,31 @@ def test_conv_wgrad_tc(gpu, prec, B, L, d, relu):
     assert torch.equal(dw, dw2) and torch.equal(db, db2)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3", "fp16x2"])
+@pytest.mark.parametrize("B,L,d", [(2, 1000, 1), (3, 881, 27), (1, 128, 3), (2, 20, 9), (1, 1, 1), (32, 440, 9), (4, 3520, 3)])
+def test_resblock_wgrad_matches_two_conv_wgrads(gpu, prec, B, L, d):
+    """vqb_resblock_wgrad (one launch for both convolutions of a block on the tensor-core paths: the two problems share the
+    grid) gives exactly what two vqb_conv1d_wgrad calls give — same kernel, same tile order per problem only when the CTA
+    split is the same, so the comparison is to the oracle's autograd within the mode's tolerance and to a second run bit for
+    bit (deterministic fixed-order reduction)."""
+    ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
+    g = torch.Generator().manual_seed(7 * L + d)
+    x, h = torch.randn(B, L, 32, generator=g), torch.randn(B, L, 32, generator=g)
+    dy, dh = torch.randn(B, L, 32, generator=g), torch.randn(B, L, 32, generator=g)
+    w1 = torch.zeros(3, 32, 32, requires_grad=True); b1 = torch.zeros(32, requires_grad=True)
+    w2 = torch.zeros(3, 32, 32, requires_grad=True); b2 = torch.zeros(32, requires_grad=True)
+    g1 = torch.autograd.grad(O.conv1d(torch.relu(x), w1, b1, 1, d), (w1, b1), dh)
+    g2 = torch.autograd.grad(O.conv1d(torch.relu(h), w2, b2, 1, 1), (w2, b2), dy)
+    outs = [[ops.empty(3, 32, 32), ops.empty(32), ops.empty(3, 32, 32), ops.empty(32)] for _ in range(2)]
+    for o in outs:
+        ops.resblock_wgrad(x.cuda(), h.cuda(), dy.cuda(), dh.cuda(), o[0], o[1], o[2], o[3], d, P)
+    torch.cuda.synchronize()
+    tol = 2e-5 if prec == "fp32" else TOL["bf16x3" if prec == "fp16x2" else prec]
+    for got, want in zip(outs[0], (*g1, *g2)):
+        assert rel(got, want) < tol, (prec, rel(got, want))
+    assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
+
+
 @pytest.mark.parametrize("N,K,kind", [(28160, 512, "normal"), (3520, 512, "init"), (1 << 16, 2048, "normal"), (4096, 512, "nearties"),
                                       (440, 512, "normal"), (1000, 256, "normal"), (129, 1024, "normal")])
 def test_vq_search_tc_is_exact(gpu, N, K, kind):

@@ -63,4 +63,35 @@ int vqb_resblock_bwd_data(const vqb_resblock_desc* d, const float* x, const floa
   return conv1d_dgrad_fp32(&c1, dh, w1, x, dy, dx, st);     // dx = (x>0) * conv1^T(dh) + dy
 }
 
+/* both weight gradients of the block: dw1 / db1 from (ReLU(x), dh, dilation), dw2 / db2 from (ReLU(h), dy, 1).  The tensor-core
+   precisions run them as ONE launch (wgrad_tc.cu: two problems share the grid), fp32 as two vqb_conv1d_wgrad calls. */
+size_t vqb_resblock_wgrad_workspace_bytes(const vqb_resblock_desc* d) {
+  if (!d) return 0;
+  vqb_conv_desc c1{d->B, d->L, d->C, d->F, 3, 1, d->dilation, 1, d->precision};
+  vqb_conv_desc c2{d->B, d->L, d->F, d->C, 3, 1, 1, 1, d->precision};
+  if (d->precision != VQB_PREC_FP32 && d->C == d->F && wgrad_tc_supported(&c1)) return resblock_wgrad_tc_workspace_bytes(&c1);
+  const size_t a = (vqb_conv1d_wgrad_workspace_bytes(&c1) + 255) & ~(size_t)255;
+  return a + vqb_conv1d_wgrad_workspace_bytes(&c2);
+}
+
+int vqb_resblock_wgrad(const vqb_resblock_desc* d, const float* x, const float* h, const float* dy, const float* dh,
+                       float* dw1, float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  VQB_ARCH();
+  int rc = check_rb(d);
+  if (rc) return rc;
+  VQB_REQUIRE(x && h && dy && dh && dw1 && dw2, "vqb_resblock_wgrad: NULL pointer");
+  vqb_conv_desc c1{d->B, d->L, d->C, d->F, 3, 1, d->dilation, 1, d->precision};
+  vqb_conv_desc c2{d->B, d->L, d->F, d->C, 3, 1, 1, 1, d->precision};
+  if (d->precision != VQB_PREC_FP32 && d->C == d->F && wgrad_tc_supported(&c1) && d->B > 0 && d->L > 0)
+    return resblock_wgrad_tc(&c1, x, h, dy, dh, dw1, db1, dw2, db2, workspace, workspace_bytes, (cudaStream_t)stream);
+  const size_t a = (vqb_conv1d_wgrad_workspace_bytes(&c1) + 255) & ~(size_t)255;
+  const size_t need = a + vqb_conv1d_wgrad_workspace_bytes(&c2);
+  if (!workspace || workspace_bytes < need)
+    return set_err(VQB_ERR_WORKSPACE, "vqb_resblock_wgrad workspace: need %zu bytes, got %zu", need, workspace_bytes);
+  rc = vqb_conv1d_wgrad(&c1, x, dh, dw1, db1, workspace, a, stream);
+  if (rc) return rc;
+  return vqb_conv1d_wgrad(&c2, h, dy, dw2, db2, (char*)workspace + a, workspace_bytes - a, stream);
+}
+
 }  // extern "C"

@@ -21,8 +21,14 @@ using namespace tc;
 struct WgTcParams {
   const float* ga;  // gather side  [B, L, 32]  (x)
   const float* ot;  // other side   [B, L, 32]  (dy)
-  float* partial;   // [gridDim.x][3*32*32 + 32]
+  float* partial;   // [CTAs of this problem][3*32*32 + 32]
   int B, L, dil, relu_ga, tiles_per_b, total_tiles;
+  // Second problem of the same [B, L] (the other convolution of a residual block: vqb_resblock_wgrad): the upper half of
+  // the grid works on it, so that one launch (one prologue, one drain) yields both weight gradients.  nprob = 1 or 2.
+  const float* ga2;
+  const float* ot2;
+  float* partial2;
+  int dil2, relu_ga2, nprob;
 };
 
 // S = number of bf16 pieces each operand is split into (1: bf16, 2: bf16x2, 3: bf16x3 = fp32-grade products)
@@ -62,8 +68,14 @@ struct WgRegs {
 // for full[buf], issues the tile's MMAs and commits them to empty[buf], which the converters wait on before they
 // overwrite that buffer two tiles later.  Nobody waits for a global load it issued less than two tiles ago.
 template <int S, int NT_>
-__global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams p) {
+__global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams pp) {
   using Cfg = WgCfg<S, NT_>;
+  // CTA-local view: which problem, which slice of its tiles
+  const int half = pp.nprob == 2 ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const bool second = (int)blockIdx.x >= half;
+  const int nblk = second ? (int)gridDim.x - half : half, bidx = second ? (int)blockIdx.x - half : (int)blockIdx.x;
+  WgTcParams p = pp;
+  if (second) { p.ga = pp.ga2; p.ot = pp.ot2; p.partial = pp.partial2; p.dil = pp.dil2; p.relu_ga = pp.relu_ga2; }
   constexpr int NT = Cfg::NT, NA = Cfg::NA, NB = Cfg::NB, NSETS = Cfg::NSETS;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[2], empty[2], done;
@@ -89,8 +101,8 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
   pdl_launch_dependents();  // prologue done (common.cuh): the next kernel may become resident ...
   pdl_wait();               // ... and this one must not touch the previous kernel's outputs before it has completed
 
-  const long first = (long)blockIdx.x * p.total_tiles / gridDim.x;
-  const long last = (long)(blockIdx.x + 1) * p.total_tiles / gridDim.x;
+  const long first = (long)bidx * p.total_tiles / nblk;
+  const long last = (long)(bidx + 1) * p.total_tiles / nblk;
   const int ntiles = (int)(last - first);
   const int rowsB = Cfg::TK + 2 * p.dil;
 
@@ -194,7 +206,7 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
     }
   }
 
-  float* out = p.partial + (size_t)blockIdx.x * Cfg::PART;
+  float* out = p.partial + (size_t)bidx * Cfg::PART;
   if (ntiles == 0) {  // no tiles: zero partial
     for (int e = tid; e < Cfg::PART; e += NT + 32) out[e] = 0.f;
   } else {
@@ -289,6 +301,44 @@ static int launch_wg(const WgTcParams& p, int grid, cudaStream_t st) {
   return VQB_OK;
 }
 
+static int launch_wg_any(int S, const WgTcParams& p, int grid, cudaStream_t st) {
+  const char* e = getenv("VQB_WGRAD_NT");  // tuning knob (converter threads)
+  const int nt = e ? atoi(e) : 256;
+  return nt == 512 ? (S == 3 ? launch_wg<3, 512>(p, grid, st) : S == 2 ? launch_wg<2, 512>(p, grid, st) : launch_wg<1, 512>(p, grid, st))
+                   : (S == 3 ? launch_wg<3>(p, grid, st) : S == 2 ? launch_wg<2>(p, grid, st) : launch_wg<1>(p, grid, st));
+}
+
+// Both weight gradients of a residual block (resnet.py:13-17) in ONE launch: problem 0 = conv1 (act(x), dh, dilation d),
+// problem 1 = conv2 (act(h), dy, dilation 1).  d describes conv1 (k 3, 32 -> 32, dilation, relu_in).
+size_t resblock_wgrad_tc_workspace_bytes(const vqb_conv_desc* d) { return 2 * wgrad_tc_workspace_bytes(d); }
+
+int resblock_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* h, const float* dy, const float* dh, float* dw1,
+                      float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const size_t need = resblock_wgrad_tc_workspace_bytes(d);
+  if (!ws || ws_bytes < need) return set_err(VQB_ERR_WORKSPACE, "residual-block wgrad workspace: need %zu bytes, got %zu", need, ws_bytes);
+  constexpr int PART = WgCfg<1>::PART;
+  WgTcParams p{};
+  int g = wgrad_tc_grid(d, &p.tiles_per_b);  // CTAs a single problem would get
+  g = g > 1 ? (g + 1) / 2 : 1;               // ... per problem here: 2 g <= number of SMs (+1)
+  p.B = d->B; p.L = d->L; p.total_tiles = d->B * p.tiles_per_b; p.nprob = 2;
+  if (g > p.total_tiles) g = p.total_tiles;
+  p.ga = x; p.ot = dh; p.dil = d->dilation; p.relu_ga = 1; p.partial = (float*)ws;
+  p.ga2 = h; p.ot2 = dy; p.dil2 = 1; p.relu_ga2 = 1; p.partial2 = (float*)ws + (size_t)g * PART;
+  int rc = launch_wg_any(wg_split(d->precision), p, 2 * g, st);
+  if (rc) return rc;
+  float* outs[2][2] = {{dw1, db1}, {dw2, db2}};
+  for (int q = 0; q < 2; ++q) {
+    float* part = q ? p.partial2 : p.partial;
+    reduce_chunks_strided(part, g, PART, 0, 3 * 32 * 32, outs[q][0], st);
+    VQB_LAUNCH_CHECK();
+    if (outs[q][1]) {
+      reduce_chunks_strided(part, g, PART, 3 * 32 * 32, 32, outs[q][1], st);
+      VQB_LAUNCH_CHECK();
+    }
+  }
+  return VQB_OK;
+}
+
 int conv1d_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, void* ws,
                     size_t ws_bytes, cudaStream_t st) {
   const size_t need = wgrad_tc_workspace_bytes(d);
@@ -299,9 +349,8 @@ int conv1d_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* dy, flo
   const int grid = wgrad_tc_grid(d, &p.tiles_per_b);
   p.total_tiles = d->B * p.tiles_per_b;
   const int S = wg_split(d->precision);
-  static const int nt = getenv("VQB_WGRAD_NT") ? atoi(getenv("VQB_WGRAD_NT")) : 256;  // tuning knob (converter threads)
-  int rc = nt == 512 ? (S == 3 ? launch_wg<3, 512>(p, grid, st) : S == 2 ? launch_wg<2, 512>(p, grid, st) : launch_wg<1, 512>(p, grid, st))
-                     : (S == 3 ? launch_wg<3>(p, grid, st) : S == 2 ? launch_wg<2>(p, grid, st) : launch_wg<1>(p, grid, st));
+  p.nprob = 1;
+  int rc = launch_wg_any(S, p, grid, st);
   if (rc) return rc;
   constexpr int PART = WgCfg<1>::PART;
   // dw and dbias are separate buffers: two fixed-order reductions over the per-CTA partials

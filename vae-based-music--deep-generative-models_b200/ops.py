@@ -202,6 +202,18 @@ def resblock_bwd_data(x, h, dy, w1, w2, dilation, precision=0):
 
 
 # ------------------------------------------------------------------------------------------------- VQ
+def resblock_wgrad(x, h, dy, dh, dw1, db1, dw2, db2, dilation, precision=0):
+    """Both weight (+ bias) gradients of a residual block in one call (vqb_resblock_wgrad): conv1 from (ReLU(x), dh, dilation),
+    conv2 from (ReLU(h), dy, 1).  One kernel launch in the tensor-core precisions."""
+    for t, n in ((x, "x"), (h, "h"), (dy, "dy"), (dh, "dh"), (dw1, "dw1"), (db1, "db1"), (dw2, "dw2"), (db2, "db2")):
+        _chk(t, n)
+    B, L, Cc = x.shape
+    d = ResblockDesc(B, L, Cc, h.shape[2], dilation, precision)
+    ws = _ws(_lib.lib().vqb_resblock_wgrad_workspace_bytes(C.byref(d)))
+    call("vqb_resblock_wgrad", C.byref(d), ptr(x), ptr(h), ptr(dy), ptr(dh), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(ws),
+         ws.numel(), _lib.stream())
+
+
 def vq_fwd(flat, E, beta, want_q_st=True, want_q=True, m_batch=None, n_batch=None, precision=0):
     """flat [N,D], E [D,K] -> idx int64 [N], q_st, q, loss[1]"""
     _chk(flat, "x"); _chk(E, "embeddings")

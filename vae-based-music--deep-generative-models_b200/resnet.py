@@ -2,7 +2,7 @@
 
 `ResnetConv1DBlock.model` is still the `Sequential([ReLU, Conv1D(dil), ReLU, Conv1D])` the reference builds (callers
 walk it: encdec.py:7-14, src/conditioner/conditioners.py:108-118), but `call` runs the whole pre-activation block
-as ONE fused operation (`vqb_resblock_fwd`), and its backward as `vqb_resblock_bwd_data` + two weight-gradient calls.
+as ONE fused operation (`vqb_resblock_fwd`), and its backward as `vqb_resblock_bwd_data` + `vqb_resblock_wgrad`.
 """
 from __future__ import annotations
 
@@ -43,10 +43,11 @@ class ResnetConv1DBlock(layers.Layer):
         def bwd(g, needs):
             dy = g[0].contiguous()
             dx, dh = ops.resblock_bwd_data(x, h, dy, conv1.kernel.value, conv2.kernel.value, d, prec)
-            write_grad(conv2.kernel, lambda buf: ops.conv1d_wgrad(h, dy, buf, grad_buffer(conv2.bias), 1, 1, True, prec))
-            conv2.bias._grad_written = True
-            write_grad(conv1.kernel, lambda buf: ops.conv1d_wgrad(x, dh, buf, grad_buffer(conv1.bias), 1, d, True, prec))
+            # both weight gradients in one call (one launch on the tensor-core paths): tape.gradient wrt the four variables
+            write_grad(conv1.kernel, lambda buf1: write_grad(conv2.kernel, lambda buf2: ops.resblock_wgrad(
+                x, h, dy, dh, buf1, grad_buffer(conv1.bias), buf2, grad_buffer(conv2.bias), d, prec)))
             conv1.bias._grad_written = True
+            conv2.bias._grad_written = True
             return [dx if needs[0] else None]
 
         record([input_tensor], [y], bwd)
