@@ -125,14 +125,23 @@ __global__ void __launch_bounds__(CtCfg<S, UP>::NT, 1) conv_tc_kernel(const Conv
 
   if (warp == 0) tmem_alloc(tslot, Cfg::TCOLS);
   if (tid == 32) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
-  for (int e = tid; e < 4 * 32 * 32; e += NT) {
-    const int n = e & 31, k = (e >> 5) & 31, j = e >> 10;
-    const float v = p.w[(size_t)j * p.sj + (size_t)k * p.si + (size_t)n * p.so];
-    uint8_t* a = W + j * Cfg::WTAP + (k >> 3) * Cfg::WPLANE + n * 16 + (k & 7) * 2;
-    float pc[3];
-    split_bf16<S>(v, pc);
+  {  // all weight loads of this thread first (independent, in flight together), then the packing from registers
+    constexpr int PER = 4 * 32 * 32 / NT;
+    float wv[PER];
 #pragma unroll
-    for (int s = 0; s < S; ++s) *reinterpret_cast<__nv_bfloat16*>(a + s * 32 * 16) = __float2bfloat16_rn(pc[s]);  // row s*32 + n
+    for (int q = 0; q < PER; ++q) {
+      const int e = tid + q * NT, n = e & 31, k = (e >> 5) & 31, j = e >> 10;
+      wv[q] = p.w[(size_t)j * p.sj + (size_t)k * p.si + (size_t)n * p.so];
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int e = tid + q * NT, n = e & 31, k = (e >> 5) & 31, j = e >> 10;
+      uint8_t* a = W + j * Cfg::WTAP + (k >> 3) * Cfg::WPLANE + n * 16 + (k & 7) * 2;
+      float pc[3];
+      split_bf16<S>(wv[q], pc);
+#pragma unroll
+      for (int s = 0; s < S; ++s) *reinterpret_cast<__nv_bfloat16*>(a + s * 32 * 16) = __float2bfloat16_rn(pc[s]);  // row s*32 + n
+    }
   }
   if (tid < 32) bias_s[tid] = p.bias ? p.bias[tid] : 0.f;
   fence_proxy_async();

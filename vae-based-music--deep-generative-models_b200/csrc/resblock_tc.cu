@@ -77,28 +77,28 @@ struct RbCfg {                   //      1 -> 128-row tiles, 256 threads, two CT
   static constexpr int NU = ((R + 2 * DMAX) * 4 + NCV - 1) / NCV;  // 8-channel units of the stage-1 input tile per converter thread
 };
 
+// element e = (tap j, in-channel k, out-channel n) of a convolution: its global offset and its place in the operand image
+__device__ __forceinline__ size_t weight_offset(int e, int sj, int si, int so, int flip) {
+  const int n = e & 31, k = (e >> 5) & 31, j = e >> 10;
+  return (size_t)(flip ? 2 - j : j) * sj + (size_t)k * si + (size_t)n * so;
+}
 template <int MODE, int MB, bool TMA_>
-__device__ __forceinline__ void pack_weights(uint8_t* dst, const float* __restrict__ w, int sj, int si, int so, int flip,
-                                             float scale) {
+__device__ __forceinline__ void pack_weight(uint8_t* dst, int e, float v, float scale) {
   using Cfg = RbCfg<MODE, MB, TMA_>;
-  for (int e = threadIdx.x; e < 3 * 32 * 32; e += blockDim.x) {
-    const int n = e & 31, k = (e >> 5) & 31, j = e >> 10;
-    const int jj = flip ? 2 - j : j;
-    const float v = w[(size_t)jj * sj + (size_t)k * si + (size_t)n * so];
-    uint8_t* a = dst + j * Cfg::WTAP + (k / Cfg::T) * Cfg::WPLANE + n * 16 + (k % Cfg::T) * Cfg::ES;
-    if (Cfg::TF32) {
-      *reinterpret_cast<float*>(a) = to_tf32(v);
-    } else if (Cfg::F16) {
-      const __half hi = __float2half_rn(v * scale);
-      const __half lo = __float2half_rn(v * scale - __half2float(hi));
-      *reinterpret_cast<__half*>(a) = hi;                // row n
-      *reinterpret_cast<__half*>(a + 32 * 16) = lo;      // row 32 + n
-    } else {
-      float pc[3];
-      split_bf16<Cfg::S>(v, pc);
+  const int n = e & 31, k = (e >> 5) & 31, j = e >> 10;
+  uint8_t* a = dst + j * Cfg::WTAP + (k / Cfg::T) * Cfg::WPLANE + n * 16 + (k % Cfg::T) * Cfg::ES;
+  if (Cfg::TF32) {
+    *reinterpret_cast<float*>(a) = to_tf32(v);
+  } else if (Cfg::F16) {
+    const __half hi = __float2half_rn(v * scale);
+    const __half lo = __float2half_rn(v * scale - __half2float(hi));
+    *reinterpret_cast<__half*>(a) = hi;                // row n
+    *reinterpret_cast<__half*>(a + 32 * 16) = lo;      // row 32 + n
+  } else {
+    float pc[3];
+    split_bf16<Cfg::S>(v, pc);
 #pragma unroll
-      for (int s = 0; s < Cfg::S; ++s) *reinterpret_cast<__nv_bfloat16*>(a + s * 32 * 16) = __float2bfloat16_rn(pc[s]);  // row s*32 + n
-    }
+    for (int s = 0; s < Cfg::S; ++s) *reinterpret_cast<__nv_bfloat16*>(a + s * 32 * 16) = __float2bfloat16_rn(pc[s]);  // row s*32 + n
   }
 }
 
@@ -185,12 +185,22 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB, TMA_>::NT, 3 - MB)
 
   if (warp == 0) tmem_alloc(tslot, Cfg::TCOLS);
   if (tid == 32) { mbar_init(&bar[0], MB); mbar_init(&bar[1], MB); fence_mbar_init(); }  // one arrival per issuing thread
+  // Weights: every thread first loads ALL its elements of both convolutions (2 x 3072 / NT independent loads in flight: the
+  // prologue costs one L2 round trip instead of one per element), then packs them from registers.
+  constexpr int PER = 3 * 32 * 32 / Cfg::NT;
+  float wv1[PER], wv2[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    wv1[q] = p.w1[weight_offset(tid + q * Cfg::NT, p.sj1, p.si1, p.so1, p.flip1)];
+    wv2[q] = p.w2[weight_offset(tid + q * Cfg::NT, p.sj2, p.si2, p.so2, p.flip2)];
+  }
   float sw1 = 1.f, sw2 = 1.f;  // fp16x2: power-of-two scales of the two weight tensors
   if (Cfg::F16) {
     if (tid < 8) tmx[tid] = 0u;
     __syncthreads();
     uint32_t m1 = 0u, m2 = 0u, mb1 = 0u;
-    for (int e = tid; e < 3 * 32 * 32; e += blockDim.x) { m1 = max(m1, absbits(p.w1[e])); m2 = max(m2, absbits(p.w2[e])); }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { m1 = max(m1, absbits(wv1[q])); m2 = max(m2, absbits(wv2[q])); }
     if (tid < 32 && p.bias1) mb1 = absbits(p.bias1[tid]);
     m1 = __reduce_max_sync(0xffffffffu, m1);
     m2 = __reduce_max_sync(0xffffffffu, m2);
@@ -200,8 +210,11 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB, TMA_>::NT, 3 - MB)
     sw1 = pow2_scale(__uint_as_float(tmx[2]));
     sw2 = pow2_scale(__uint_as_float(tmx[3]));
   }
-  pack_weights<MODE, MB, TMA_>(W1, p.w1, p.sj1, p.si1, p.so1, p.flip1, sw1);
-  pack_weights<MODE, MB, TMA_>(W2, p.w2, p.sj2, p.si2, p.so2, p.flip2, sw2);
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    pack_weight<MODE, MB, TMA_>(W1, tid + q * Cfg::NT, wv1[q], sw1);
+    pack_weight<MODE, MB, TMA_>(W2, tid + q * Cfg::NT, wv2[q], sw2);
+  }
   if (tid < 64) bias_s[tid] = tid < 32 ? (p.bias1 ? p.bias1[tid] : 0.f) : (p.bias2 ? p.bias2[tid - 32] : 0.f);
   fence_proxy_async();
   fence_before_sync();
