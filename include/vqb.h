@@ -132,6 +132,14 @@ int vqb_resblock_fwd(const vqb_resblock_desc* d, const float* x, const float* w1
  * (h>0)*conv2^T(dy), the gradient at conv1's output, for the weight gradients. */
 int vqb_resblock_bwd_data(const vqb_resblock_desc* d, const float* x, const float* h, const float* dy,
                           const float* w1, const float* w2, float* dh, float* dx, void* stream);
+/* Sign-mask variants (tensor-core precisions / shapes only, see vqb_resblock_supports): the forward additionally writes
+ * xbits[B, L] and hbits[B, L] — bit c of word t is set iff channel c of x (resp. h) at position t is > 0 — and the data
+ * gradient reads those 8 bytes per position instead of the fp32 tensors x and h (640 -> 392 bytes per position). */
+int vqb_resblock_fwd_masks(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1, const float* w2,
+                           const float* b2, float* h, float* y, uint32_t* xbits, uint32_t* hbits, void* stream);
+int vqb_resblock_bwd_data_masks(const vqb_resblock_desc* d, const uint32_t* xbits, const uint32_t* hbits, const float* dy,
+                                const float* w1, const float* w2, float* dh, float* dx, void* stream);
+
 /* Both weight gradients of the block in one call (tensor-core precisions: one launch):
  *   dw1[3, C, F] = sum ReLU(x)[t + (j-1) dilation] dh[t],  db1[F] = sum dh   (dilated conv, resnet.py:13-15)
  *   dw2[3, F, C] = sum ReLU(h)[t + (j-1)] dy[t],           db2[C] = sum dy   (second conv, resnet.py:17)

@@ -18,7 +18,7 @@ def _t(ptr, shape, dtype=np.float32):
     if ptr is None:
         return None
     n = int(np.prod(shape)) if len(shape) else 1
-    ct = {np.float32: C.c_float, np.int64: C.c_int64, np.uint8: C.c_uint8}[dtype]
+    ct = {np.float32: C.c_float, np.int64: C.c_int64, np.uint8: C.c_uint8, np.int32: C.c_int32}[dtype]
     a = np.frombuffer((ct * max(n, 1)).from_address(int(ptr)), dtype=dtype)[:n].reshape(shape)
     return torch.from_numpy(a)
 
@@ -233,6 +233,31 @@ class FakeBackend:
         H = O.conv1d(torch.relu(X), _t(w1, (3, d.C, d.F)), _t(b1, (d.F,)), 1, d.dilation)
         _t(h, (d.B, d.L, d.F)).copy_(H)
         _t(y, (d.B, d.L, d.C)).copy_(X + O.conv1d(torch.relu(H), _t(w2, (3, d.F, d.C)), _t(b2, (d.C,)), 1, 1))
+        return 0
+
+    def vqb_resblock_fwd_masks(self, dref, x, w1, b1, w2, b2, h, y, xbits, hbits, stream):
+        d = _d(dref)
+        self.vqb_resblock_fwd(dref, x, w1, b1, w2, b2, h, y, stream)
+        w = (1 << torch.arange(32, dtype=torch.int64))
+        for src, C_, dst in ((x, d.C, xbits), (h, d.F, hbits)):
+            bits = ((_t(src, (d.B, d.L, C_)) > 0).to(torch.int64) * w[:C_]).sum(-1)
+            bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+            _t(dst, (d.B, d.L), np.int32).copy_(bits)
+        return 0
+
+    def vqb_resblock_bwd_data_masks(self, dref, xbits, hbits, dy, w1, w2, dh, dx, stream):
+        d = _d(dref)
+        sh = torch.arange(32, dtype=torch.int64)
+        XM = ((_t(xbits, (d.B, d.L), np.int32).to(torch.int64).unsqueeze(-1) >> sh[:d.C]) & 1).bool()
+        HM = ((_t(hbits, (d.B, d.L), np.int32).to(torch.int64).unsqueeze(-1) >> sh[:d.F]) & 1).bool()
+        DY = _t(dy, (d.B, d.L, d.C)); W1 = _t(w1, (3, d.C, d.F)); W2 = _t(w2, (3, d.F, d.C))
+        hr = torch.zeros(d.B, d.L, d.F, requires_grad=True)
+        (g2,) = torch.autograd.grad(O.conv1d(hr, W2, None, 1, 1), hr, DY)
+        DH = g2 * HM
+        xr = torch.zeros(d.B, d.L, d.C, requires_grad=True)
+        (g1,) = torch.autograd.grad(O.conv1d(xr, W1, None, 1, d.dilation), xr, DH)
+        _t(dh, (d.B, d.L, d.F)).copy_(DH)
+        _t(dx, (d.B, d.L, d.C)).copy_(g1 * XM + DY)
         return 0
 
     def vqb_resblock_wgrad_workspace_bytes(self, dref):

@@ -149,6 +149,34 @@ def test_conv_wgrad_tc(gpu, prec, B, L, d, relu):
     assert torch.equal(dw, dw2) and torch.equal(db, db2)
 
 
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3", "fp16x2"])
+@pytest.mark.parametrize("B,L,d", [(2, 1000, 1), (3, 881, 27), (1, 254, 3), (2, 20, 27), (2, 255, 9), (1, 1, 1), (4, 3520, 9), (5, 126, 1),
+                                   (3, 127, 3)])
+def test_resblock_sign_mask_variants(gpu, prec, B, L, d):
+    """vqb_resblock_fwd_masks writes, next to h and y, one uint32 per position for x and for h (bit c = channel c > 0: one half-word per row and 16-channel half from the two
+    epilogues, every in-range row exactly once across overlapping tiles);
+    vqb_resblock_bwd_data_masks must give bit for bit what vqb_resblock_bwd_data gives from the fp32 tensors."""
+    ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
+    rng = np.random.default_rng(3 * L + d)
+    C = 32
+    x = dev(rng.normal(size=(B, L, C)).astype(np.float32))
+    w1 = dev((rng.normal(size=(3, C, C)) / np.sqrt(3 * C)).astype(np.float32)); b1 = dev((rng.normal(size=C) * 0.1).astype(np.float32))
+    w2 = dev((rng.normal(size=(3, C, C)) / np.sqrt(3 * C)).astype(np.float32)); b2 = dev((rng.normal(size=C) * 0.1).astype(np.float32))
+    dy = dev(rng.normal(size=(B, L, C)).astype(np.float32))
+    y0, h0 = ops.resblock_fwd(x, w1, b1, w2, b2, d, P)
+    xb = hb = None
+    y1, h1, xb, hb = ops.resblock_fwd_masks(x, w1, b1, w2, b2, d, P)
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1) and torch.equal(h0, h1)
+    sh = torch.arange(32, device="cuda")
+    assert torch.equal(((xb.long().unsqueeze(-1) >> sh) & 1).bool(), x > 0)
+    assert torch.equal(((hb.long().unsqueeze(-1) >> sh) & 1).bool(), h1 > 0)
+    dx0, dh0 = ops.resblock_bwd_data(x, h1, dy, w1, w2, d, P)
+    dx1, dh1 = ops.resblock_bwd_data_masks(xb, hb, dy, w1, w2, d, P)
+    torch.cuda.synchronize()
+    assert torch.equal(dx0, dx1) and torch.equal(dh0, dh1)
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3", "fp16x2"])
 @pytest.mark.parametrize("B,L,d", [(2, 1000, 1), (3, 881, 27), (1, 128, 3), (2, 20, 9), (1, 1, 1), (32, 440, 9), (4, 3520, 3)])
 def test_resblock_wgrad_matches_two_conv_wgrads(gpu, prec, B, L, d):

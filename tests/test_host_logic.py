@@ -233,3 +233,23 @@ def test_conditioner_decoder_conv_block_host_logic(cpu_backend):
     CPU test double: variable count and order, dilation schedule, output shape, tape gradients (same body as the GPU test)."""
     from tests.test_gpu_model import test_conditioner_decoder_conv_block as body
     body(cpu_backend, "fp32", 1e-3)
+
+
+def test_resblock_sign_mask_variants_on_the_test_double(cpu_backend):
+    """vqb_resblock_fwd_masks / vqb_resblock_bwd_data_masks (include/vqb.h): bit c of xbits / hbits[b, t] is set iff channel c of
+    x / h is > 0, and the masked data gradient equals the one computed from the fp32 tensors (ABI semantics, CPU double)."""
+    V = cpu_backend
+    ops = V.ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 37, 32, generator=g); dy = torch.randn(2, 37, 32, generator=g)
+    w1 = torch.randn(3, 32, 32, generator=g) * 0.1; w2 = torch.randn(3, 32, 32, generator=g) * 0.1
+    b1 = torch.randn(32, generator=g) * 0.1; b2 = torch.randn(32, generator=g) * 0.1
+    y0, h0 = ops.resblock_fwd(x, w1, b1, w2, b2, 3, 0)
+    y1, h1, xb, hb = ops.resblock_fwd_masks(x, w1, b1, w2, b2, 3, 0)
+    assert torch.equal(y0, y1) and torch.equal(h0, h1) and xb.dtype == torch.int32 and tuple(xb.shape) == (2, 37)
+    sh = torch.arange(32)
+    assert torch.equal(((xb.long().unsqueeze(-1) >> sh) & 1).bool(), x > 0)
+    assert torch.equal(((hb.long().unsqueeze(-1) >> sh) & 1).bool(), h0 > 0)
+    dx0, dh0 = ops.resblock_bwd_data(x, h0, dy, w1, w2, 3, 0)
+    dx1, dh1 = ops.resblock_bwd_data_masks(xb, hb, dy, w1, w2, 3, 0)
+    assert torch.equal(dx0, dx1) and torch.equal(dh0, dh1)

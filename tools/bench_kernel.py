@@ -20,6 +20,8 @@ w2 = torch.randn(3, C, C, device="cuda", generator=g) * 0.1
 b1 = torch.zeros(C, device="cuda"); b2 = torch.zeros(C, device="cuda")
 y, h = ops.resblock_fwd(xs[0], w1, b1, w2, b2, 1, P)
 dw, db = ops.empty(3, C, C), ops.empty(C)
+if what.endswith("_masks"):
+    _, _, xb, hb = ops.resblock_fwd_masks(xs[0], w1, b1, w2, b2, 1, P)
 n = int(os.environ.get("N", "6"))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -27,6 +29,10 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 def one(i):
     if what == "resblock_fwd":
         ops.resblock_fwd(xs[i % 2], w1, b1, w2, b2, 1, P)
+    elif what == "resblock_fwd_masks":
+        ops.resblock_fwd_masks(xs[i % 2], w1, b1, w2, b2, 1, P)
+    elif what == "resblock_bwd_masks":
+        ops.resblock_bwd_data_masks(xb, hb, dy, w1, w2, int(os.environ.get("DIL", "1")), P)
     elif what == "resblock_bwd":
         ops.resblock_bwd_data(xs[i % 2], h, dy, w1, w2, int(os.environ.get("DIL", "1")), P)
     elif what == "wgrad":

@@ -67,6 +67,8 @@ SIGNATURES = {
     "vqb_resblock_supports": (C.c_int, [_RD]),
     "vqb_resblock_fwd": (C.c_int, [_RD, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vqb_resblock_bwd_data": (C.c_int, [_RD, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vqb_resblock_fwd_masks": (C.c_int, [_RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vqb_resblock_bwd_data_masks": (C.c_int, [_RD, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vqb_resblock_wgrad_workspace_bytes": (C.c_size_t, [_RD]),
     "vqb_resblock_wgrad": (C.c_int, [_RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_dec_tail_supports": (C.c_int, [_TD]),

@@ -10,9 +10,9 @@ int conv1d_fwd_fp32(const vqb_conv_desc* d, const float* x, const float* w, cons
 int conv1d_dgrad_fp32(const vqb_conv_desc* d, const float* dy, const float* w, const float* x,
                       const float* dx_add, float* dx, cudaStream_t st);
 int resblock_fwd_tc(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1,
-                    const float* w2, const float* b2, float* h, float* y, cudaStream_t st);
+                    const float* w2, const float* b2, float* h, float* y, uint32_t* xbits, uint32_t* hbits, cudaStream_t st);
 int resblock_bwd_tc(const vqb_resblock_desc* d, const float* x, const float* h, const float* dy, const float* w1,
-                    const float* w2, float* dh, float* dx, cudaStream_t st);
+                    const float* w2, float* dh, float* dx, const uint32_t* xbits, const uint32_t* hbits, cudaStream_t st);
 bool resblock_tc_supported(const vqb_resblock_desc* d);
 }  // namespace vqb
 
@@ -40,7 +40,7 @@ int vqb_resblock_fwd(const vqb_resblock_desc* d, const float* x, const float* w1
   if (rc) return rc;
   VQB_REQUIRE(x && w1 && w2 && h && y, "vqb_resblock_fwd: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->precision != VQB_PREC_FP32) return resblock_fwd_tc(d, x, w1, b1, w2, b2, h, y, st);
+  if (d->precision != VQB_PREC_FP32) return resblock_fwd_tc(d, x, w1, b1, w2, b2, h, y, nullptr, nullptr, st);
   vqb_conv_desc c1{d->B, d->L, d->C, d->F, 3, 1, d->dilation, 1, VQB_PREC_FP32};
   rc = conv1d_fwd_fp32(&c1, x, w1, b1, nullptr, h, st);
   if (rc) return rc;
@@ -55,12 +55,37 @@ int vqb_resblock_bwd_data(const vqb_resblock_desc* d, const float* x, const floa
   if (rc) return rc;
   VQB_REQUIRE(x && h && dy && w1 && w2 && dh && dx, "vqb_resblock_bwd_data: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->precision != VQB_PREC_FP32) return resblock_bwd_tc(d, x, h, dy, w1, w2, dh, dx, st);
+  if (d->precision != VQB_PREC_FP32) return resblock_bwd_tc(d, x, h, dy, w1, w2, dh, dx, nullptr, nullptr, st);
   vqb_conv_desc c2{d->B, d->L, d->F, d->C, 3, 1, 1, 1, VQB_PREC_FP32};
   rc = conv1d_dgrad_fp32(&c2, dy, w2, h, nullptr, dh, st);  // dh = (h>0) * conv2^T(dy)
   if (rc) return rc;
   vqb_conv_desc c1{d->B, d->L, d->C, d->F, 3, 1, d->dilation, 1, VQB_PREC_FP32};
   return conv1d_dgrad_fp32(&c1, dh, w1, x, dy, dx, st);     // dx = (x>0) * conv1^T(dh) + dy
+}
+
+/* Sign-mask variants for the tensor-core precisions (resblock_tc.cu): the forward also writes xbits / hbits [B, L] (bit c of
+   word t = channel c of x / h at t is > 0), the data gradient reads those 8 bytes per position instead of the two fp32
+   tensors (x and h stay the operands of vqb_resblock_wgrad). */
+int vqb_resblock_fwd_masks(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1, const float* w2,
+                           const float* b2, float* h, float* y, uint32_t* xbits, uint32_t* hbits, void* stream) {
+  VQB_ARCH();
+  int rc = check_rb(d);
+  if (rc) return rc;
+  VQB_REQUIRE(x && w1 && w2 && h && y && xbits && hbits, "vqb_resblock_fwd_masks: NULL pointer");
+  VQB_REQUIRE(d->precision != VQB_PREC_FP32 && resblock_tc_supported(d),
+              "vqb_resblock_fwd_masks: tensor-core precisions and shapes only (vqb_resblock_supports)");
+  return resblock_fwd_tc(d, x, w1, b1, w2, b2, h, y, xbits, hbits, (cudaStream_t)stream);
+}
+
+int vqb_resblock_bwd_data_masks(const vqb_resblock_desc* d, const uint32_t* xbits, const uint32_t* hbits, const float* dy,
+                                const float* w1, const float* w2, float* dh, float* dx, void* stream) {
+  VQB_ARCH();
+  int rc = check_rb(d);
+  if (rc) return rc;
+  VQB_REQUIRE(xbits && hbits && dy && w1 && w2 && dh && dx, "vqb_resblock_bwd_data_masks: NULL pointer");
+  VQB_REQUIRE(d->precision != VQB_PREC_FP32 && resblock_tc_supported(d),
+              "vqb_resblock_bwd_data_masks: tensor-core precisions and shapes only (vqb_resblock_supports)");
+  return resblock_bwd_tc(d, nullptr, nullptr, dy, w1, w2, dh, dx, xbits, hbits, (cudaStream_t)stream);
 }
 
 /* both weight gradients of the block: dw1 / db1 from (ReLU(x), dh, dilation), dw2 / db2 from (ReLU(h), dy, 1).  The tensor-core

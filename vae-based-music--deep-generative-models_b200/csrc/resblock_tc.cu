@@ -40,6 +40,14 @@ struct RbTcParams {
   int sj2, si2, so2, flip2;
   int B, L, d1, d2, relu1, relu2;
   int tiles_x, total_tiles;  // time tiles per batch item, B * tiles_x
+  // Sign masks, one uint32 per time position (bit c = channel c is > 0).  The forward kernel can emit them for its input
+  // (xbits_out, from the residual operand of epilogue 2) and for its intermediate (hbits_out, epilogue 1), one uint16 per
+  // row and 16-channel half; the data-gradient kernel then takes them (m1bits = h > 0, m2bits = x > 0) instead of re-reading
+  // the two fp32 tensors: 392 instead of 640 bytes per position and no staged mask fetches.
+  uint16_t* xbits_out;
+  uint16_t* hbits_out;
+  const uint16_t* m1bits;
+  const uint16_t* m2bits;
 };
 
 // MODE 0: bf16   1: tf32   2: bf16x2 (operands split hi+lo, 3 MMAs per product, ~2^-16)   3: bf16x3 (hi+mid+lo, 6 MMAs,
@@ -343,6 +351,9 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB, TMA_>::NT, 3 - MB)
 
     float v[16], m[16];
     float4 f[4];
+    uint32_t mb1 = 0u, mb2 = 0u;  // this thread's row / half of the sign masks
+    if (p.m1bits && inrange) mb1 = p.m1bits[((size_t)boff + g) * 2 + half];
+    if (p.m2bits && inrange) mb2 = p.m2bits[((size_t)boff + g) * 2 + half];
     // ---- epilogue 1: TMEM -> (+bias, mask) -> out1 (global, owned rows) and act2(out1) -> A2 (shared)
     if (p.mask1) warp_fetch_rows(p.mask1, boff, s0 + i0, L, half, lane, f);
     mbar_wait(&bar[0], phase);
@@ -365,10 +376,22 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB, TMA_>::NT, 3 - MB)
         v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
       }
     }
-    if (p.mask1) {
+    if (p.m1bits) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = (mb1 >> c) & 1u ? v[c] : 0.f;
+    } else if (p.mask1) {
       warp_unpack_rows(f, stg, lane, m);
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] = m[c] > 0.f ? v[c] : 0.f;
+    }
+    if (p.hbits_out) {
+      const int j = i - p.d2;
+      if (j >= 0 && j < Rout && g < L) {
+        uint32_t hm = 0u;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) hm |= (uint32_t)(v[c] > 0.f) << c;
+        p.hbits_out[((size_t)boff + g) * 2 + half] = (uint16_t)hm;
+      }
     }
     if (Cfg::TMA) {
       const int j = i - p.d2;  // row of the stored box: global row t0 + j
@@ -453,7 +476,10 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB, TMA_>::NT, 3 - MB)
         v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
       }
     }
-    if (p.mask2) {
+    if (p.m2bits) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = (mb2 >> c) & 1u ? v[c] : 0.f;
+    } else if (p.mask2) {
       warp_unpack_rows(f, stg, lane, m);
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] = m[c] > 0.f ? v[c] : 0.f;
@@ -462,6 +488,15 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB, TMA_>::NT, 3 - MB)
       warp_unpack_rows(f2, stg, lane, m);
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] += m[c];
+      if (p.xbits_out) {  // forward: add2 is the block input x, this thread holds its row / half
+        const int j = i - p.d2;
+        if (j >= 0 && j < Rout && g < L) {
+          uint32_t xm = 0u;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) xm |= (uint32_t)(m[c] > 0.f) << c;
+          p.xbits_out[((size_t)boff + g) * 2 + half] = (uint16_t)xm;
+        }
+      }
     }
     if (Cfg::TMA) {
       const int j = i - p.d2;
@@ -550,13 +585,14 @@ bool resblock_tc_supported(const vqb_resblock_desc* d) {
 }
 
 int resblock_fwd_tc(const vqb_resblock_desc* d, const float* x, const float* w1, const float* b1, const float* w2,
-                    const float* b2, float* h, float* y, cudaStream_t st) {
+                    const float* b2, float* h, float* y, uint32_t* xbits, uint32_t* hbits, cudaStream_t st) {
   if (!resblock_tc_supported(d))
     return set_err(VQB_ERR_UNIMPLEMENTED, "tensor-core residual block: C=F=32, dilation<=32, precision bf16|tf32 only (got C=%d F=%d dil=%d prec=%d)",
                    d->C, d->F, d->dilation, d->precision);
   if (d->B == 0 || d->L == 0) return VQB_OK;
   RbTcParams p{};
   p.in1 = x; p.out1 = h; p.add2 = x; p.out2 = y;
+  p.xbits_out = reinterpret_cast<uint16_t*>(xbits); p.hbits_out = reinterpret_cast<uint16_t*>(hbits);
   p.w1 = w1; p.bias1 = b1; p.sj1 = 32 * 32; p.si1 = 32; p.so1 = 1; p.flip1 = 0;   // B[n=co][k=ci] = W1[j][ci][co]
   p.w2 = w2; p.bias2 = b2; p.sj2 = 32 * 32; p.si2 = 32; p.so2 = 1; p.flip2 = 0;
   p.B = d->B; p.L = d->L; p.d1 = d->dilation; p.d2 = 1; p.relu1 = 1; p.relu2 = 1;
@@ -564,12 +600,16 @@ int resblock_fwd_tc(const vqb_resblock_desc* d, const float* x, const float* w1,
 }
 
 int resblock_bwd_tc(const vqb_resblock_desc* d, const float* x, const float* h, const float* dy, const float* w1,
-                    const float* w2, float* dh, float* dx, cudaStream_t st) {
+                    const float* w2, float* dh, float* dx, const uint32_t* xbits, const uint32_t* hbits, cudaStream_t st) {
   if (!resblock_tc_supported(d))
     return set_err(VQB_ERR_UNIMPLEMENTED, "tensor-core residual block backward: unsupported shape / precision");
   if (d->B == 0 || d->L == 0) return VQB_OK;
   RbTcParams p{};
   p.in1 = dy; p.mask1 = h; p.out1 = dh; p.mask2 = x; p.add2 = dy; p.out2 = dx;
+  if (xbits && hbits) {  // sign masks from the forward kernel replace the two fp32 tensors
+    p.mask1 = nullptr; p.mask2 = nullptr;
+    p.m1bits = reinterpret_cast<const uint16_t*>(hbits); p.m2bits = reinterpret_cast<const uint16_t*>(xbits);
+  }
   // stage 1 = conv2^T: dA[t][f] = sum_j sum_c W2[j][f][c] dy[t + (1-j)*1][c]  -> tap n = 2-j, B[n=f][k=c]
   p.w1 = w2; p.sj1 = 32 * 32; p.si1 = 1; p.so1 = 32; p.flip1 = 1;
   // stage 2 = conv1^T with the block's dilation

@@ -190,6 +190,35 @@ def resblock_fwd(x, w1, b1, w2, b2, dilation, precision=0):
     return y, h
 
 
+def resblock_fwd_masks(x, w1, b1, w2, b2, dilation, precision):
+    """resblock_fwd that also returns the sign masks of x and h (int32 [B, L], bit c = channel c > 0) for
+    resblock_bwd_data_masks.  Tensor-core precisions / shapes only (resblock_precision(...) != 0)."""
+    for t, n in ((x, "x"), (w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2")):
+        _chk(t, n)
+    B, L, Cc = x.shape
+    Fc = w1.shape[2]
+    if w1.shape[1] != Cc or w2.shape[1] != Fc or w2.shape[2] != Cc:
+        raise ValueError(f"ResnetConv1DBlock: kernel shapes {tuple(w1.shape)}, {tuple(w2.shape)} do not fit input {tuple(x.shape)}")
+    h, y = empty(B, L, Fc), empty(B, L, Cc)
+    xbits = torch.empty(B, L, dtype=torch.int32, device=_lib.device())
+    hbits = torch.empty(B, L, dtype=torch.int32, device=_lib.device())
+    d = ResblockDesc(B, L, Cc, Fc, dilation, precision)
+    call("vqb_resblock_fwd_masks", C.byref(d), ptr(x), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(h), ptr(y), ptr(xbits),
+         ptr(hbits), _lib.stream())
+    return y, h, xbits, hbits
+
+
+def resblock_bwd_data_masks(xbits, hbits, dy, w1, w2, dilation, precision):
+    _chk(dy, "dy")
+    B, L, Cc = dy.shape
+    Fc = w1.shape[2]
+    dh, dx = empty(B, L, Fc), empty(B, L, Cc)
+    d = ResblockDesc(B, L, Cc, Fc, dilation, precision)
+    call("vqb_resblock_bwd_data_masks", C.byref(d), ptr(xbits), ptr(hbits), ptr(dy), ptr(w1), ptr(w2), ptr(dh), ptr(dx),
+         _lib.stream())
+    return dx, dh
+
+
 def resblock_bwd_data(x, h, dy, w1, w2, dilation, precision=0):
     _chk(dy, "dy")
     B, L, Cc = x.shape

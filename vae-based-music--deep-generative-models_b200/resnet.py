@@ -38,11 +38,23 @@ class ResnetConv1DBlock(layers.Layer):
         d = self.dilation
         prec = ops.resblock_precision(self.input_dim, self.filters, d, self.precision)
         # y = x + conv2(relu(conv1(relu(x))))   (resnet.py:11-18,29)
-        y, h = ops.resblock_fwd(x, conv1.kernel.value, conv1.bias.value, conv2.kernel.value, conv2.bias.value, d, prec)
+        from .keras_compat import GradientTape
+        taping = GradientTape.current() is not None
+        xbits = hbits = None
+        if prec != _lib.PREC_FP32 and taping:
+            # tensor-core path under a tape: the forward also emits the sign masks of x and h (8 bytes per position), which is
+            # all the data gradient needs of them (x and h themselves stay the operands of the weight gradients)
+            y, h, xbits, hbits = ops.resblock_fwd_masks(x, conv1.kernel.value, conv1.bias.value, conv2.kernel.value,
+                                                        conv2.bias.value, d, prec)
+        else:
+            y, h = ops.resblock_fwd(x, conv1.kernel.value, conv1.bias.value, conv2.kernel.value, conv2.bias.value, d, prec)
 
         def bwd(g, needs):
             dy = g[0].contiguous()
-            dx, dh = ops.resblock_bwd_data(x, h, dy, conv1.kernel.value, conv2.kernel.value, d, prec)
+            if xbits is not None:
+                dx, dh = ops.resblock_bwd_data_masks(xbits, hbits, dy, conv1.kernel.value, conv2.kernel.value, d, prec)
+            else:
+                dx, dh = ops.resblock_bwd_data(x, h, dy, conv1.kernel.value, conv2.kernel.value, d, prec)
             # both weight gradients in one call (one launch on the tensor-core paths): tape.gradient wrt the four variables
             write_grad(conv1.kernel, lambda buf1: write_grad(conv2.kernel, lambda buf2: ops.resblock_wgrad(
                 x, h, dy, dh, buf1, grad_buffer(conv1.bias), buf2, grad_buffer(conv2.bias), d, prec)))
