@@ -674,10 +674,11 @@ __global__ void __launch_bounds__(256) conv_in1_wgrad_kernel(const float* __rest
   for (int j = 0; j <= IN1_MAXK; ++j) acc[j] = 0.f;
   const long r0 = ((long)blockIdx.x * 8 + warp) * rpw;
   const long r1 = r0 + rpw < rows ? r0 + rpw : rows;
+  long b = r0 / Lo;                  // one 64-bit division per warp, not per row
+  int t = (int)(r0 - b * Lo) - 1;
 #pragma unroll 4
   for (long row = r0; row < r1; ++row) {
-    const long b = row / Lo;
-    const int t = (int)(row - b * Lo);
+    if (++t == Lo) { t = 0; ++b; }
     const int g = t * stride + lane - padL;
     const float xv = (lane < k && g >= 0 && g < L) ? x[b * L + g] : 0.f;
     const float d = lane < Co ? dy[row * Co + lane] : 0.f;

@@ -171,13 +171,14 @@ __global__ void __launch_bounds__(256) tail_bwd_kernel(const float* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) tail_finish_kernel(const float* __restrict__ partial, int nparts,
+__global__ void __launch_bounds__(1024) tail_finish_kernel(const float* __restrict__ partial, int nparts,
                                                           const float* __restrict__ x, const float* __restrict__ dr,
                                                           const float* __restrict__ wt, const float* __restrict__ bt,
                                                           const float* __restrict__ wf, int B, int L, int C, int Cm,
                                                           float* __restrict__ dwt, float* __restrict__ dbt,
                                                           float* __restrict__ dwf, float* __restrict__ dbf) {
   __shared__ float dG[TAIL_PART];
+  __shared__ float dGq[4][TAIL_PART];  // quarter sums of the CTA partials
   __shared__ float dV[12][32];
   __shared__ float b0[32], b1[32], sc[8];  // sc: sdr, e0, e1, dc_0..2
   const int tid = threadIdx.x;
@@ -189,16 +190,23 @@ __global__ void __launch_bounds__(256) tail_finish_kernel(const float* __restric
   for (int e = tid; e < 4 * Cm * C; e += blockDim.x) wts[e] = wt[e];
   for (int e = tid; e < 3 * Cm; e += blockDim.x) wfs[e] = wf[e];
   for (int e = tid; e < Cm; e += blockDim.x) bts[e] = bt ? bt[e] : 0.f;
-  if (tid < TAIL_PART) {  // fixed-order sum over the CTA partials: 8 independent chains, coalesced across threads
-    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int p = 0;
-    for (; p + 8 <= nparts; p += 8) {
+  {  // fixed-order sum over the CTA partials: 4 thread groups take a quarter of the parts each (8 independent chains per
+     // thread, coalesced across threads), then the quarters are added in order: deterministic, 4x shorter than one group
+    const int grp = tid >> 8, col = tid & 255;
+    if (grp < 4 && col < TAIL_PART) {
+      const int per = (nparts + 3) / 4, p0 = grp * per, p1 = min(nparts, p0 + per);
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int p = p0;
+      for (; p + 8 <= p1; p += 8) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] += partial[(size_t)(p + u) * TAIL_PART + tid];
+        for (int u = 0; u < 8; ++u) a[u] += partial[(size_t)(p + u) * TAIL_PART + col];
+      }
+      for (; p < p1; ++p) a[0] += partial[(size_t)p * TAIL_PART + col];
+      dGq[grp][col] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     }
-    for (; p < nparts; ++p) a[0] += partial[(size_t)p * TAIL_PART + tid];
-    dG[tid] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
+  __syncthreads();
+  if (tid < TAIL_PART) dG[tid] = (dGq[0][tid] + dGq[1][tid]) + (dGq[2][tid] + dGq[3][tid]);
   // boundary rows: the terms the zero padding of y removes at t = 0 and t = 2L-1
   if (tid < 32) {
     float s0 = 0.f, s1 = 0.f;
@@ -321,7 +329,7 @@ int vqb_dec_tail_bwd(const vqb_tail_desc* d, const float* x, const float* drecon
   VQB_LAUNCH_CHECK();
   const size_t fsm = ((size_t)4 * d->C_mid * d->C_in + 4 * d->C_mid) * sizeof(float);
   VQB_REQUIRE(fsm <= 48 * 1024, "decoder tail: C_mid = %d too wide for the weight staging buffer", d->C_mid);
-  tail_finish_kernel<<<1, 256, fsm, st>>>(partial, grid, x, drecon, wt, bt, wf, d->L > 0 ? d->B : 0, d->L, d->C_in, d->C_mid,
+  tail_finish_kernel<<<1, 1024, fsm, st>>>(partial, grid, x, drecon, wt, bt, wf, d->L > 0 ? d->B : 0, d->L, d->C_in, d->C_mid,
                                         dwt, dbt, dwf, dbf);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
