@@ -318,3 +318,37 @@ def test_conditioner_decoder_conv_block(gpu, prec, tol):
     gmax = max(float(t.abs().max()) for t in gwant)
     for got, w in zip(g, gwant):
         assert float((got.cpu() - w).abs().max()) <= tol * gmax
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_level_streams_do_not_change_the_step(gpu, graph):
+    """`VQVAE.use_level_streams`: level 1 (encoder -> VQ -> decoder, forward and backward) on a side CUDA stream, eagerly and
+    inside the captured graphs.  SMALL_VQ_VAE, batch 4, fp16x2: the gradients of the first step are bit-identical with and
+    without the streams (same kernels, same inputs; only the overlap differs), and three steps later the weights still agree
+    (the VQ statistics use shared-memory float atomics, so later steps are equal up to amplified rounding, not bit for bit).  Repeated
+    to give a cross-stream race a chance to show."""
+    V = gpu
+    rng = np.random.Generator(np.random.PCG64(5))
+    x = torch.tensor(rng.uniform(0, 1, size=(4, 28160, 1)).astype(np.float32)).cuda()
+    res = []
+    for streams in (False, True, True):
+        V.keras_compat.reset_name_counters()
+        V.set_seed(0)
+        m = V.VQVAE((28160, 1), **V.SMALL_VQ_VAE)
+        m.use_cuda_graph = graph
+        m.use_level_streams = streams
+        m.set_precision("fp16x2")
+        m.compile(optimizer=V.keras.optimizers.Adam())
+        m.train_step((x, None))
+        torch.cuda.synchronize()
+        g1 = m._packed.grads.clone()
+        for _ in range(3):
+            logs = m.train_step((x, None))
+        torch.cuda.synchronize()
+        res.append((g1, m._packed.params.clone(), float(logs["loss"])))
+    for r in res[1:]:
+        assert torch.equal(r[0], res[0][0]), "first-step gradients differ"
+        # later steps: equal up to the amplification of rounding-level differences (Adam's first steps move every weight by
+        # ~lr whatever the gradient's size; cf. test_small_vqvae_training_trajectory)
+        assert rel_err(r[1], res[0][1]) < 2e-2
+        assert abs(r[2] - res[0][2]) <= 5e-2 * abs(res[0][2])

@@ -474,8 +474,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
     const int lanes = 256 / C, nt = lanes * C;
     const int c = threadIdx.x % C, rl = threadIdx.x / C;
     float s = 0.f;
-    if (threadIdx.x < nt)
-      for (long r = r0 + rl; r < r1; r += lanes) s += x[r * C + c];
+    if (threadIdx.x < nt) {  // four independent chains keep four loads in flight per thread (fixed order: deterministic)
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      long r = r0 + rl;
+      for (; r + 3 * lanes < r1; r += 4 * lanes) {
+        s0 += x[r * C + c]; s1 += x[(r + lanes) * C + c]; s2 += x[(r + 2 * lanes) * C + c]; s3 += x[(r + 3 * lanes) * C + c];
+      }
+      for (; r < r1; r += lanes) s0 += x[r * C + c];
+      s = (s0 + s1) + (s2 + s3);
+    }
     red[threadIdx.x] = threadIdx.x < nt ? s : 0.f;
     __syncthreads();
     if (threadIdx.x < C) {

@@ -163,10 +163,40 @@ class Scalar:
 
 
 class _Node:
-    __slots__ = ("inputs", "outputs", "bwd")
+    __slots__ = ("inputs", "outputs", "bwd", "stream")
 
-    def __init__(self, inputs, outputs, bwd):
-        self.inputs, self.outputs, self.bwd = inputs, outputs, bwd
+    def __init__(self, inputs, outputs, bwd, stream=None):
+        self.inputs, self.outputs, self.bwd, self.stream = inputs, outputs, bwd, stream
+
+
+_node_stream = None  # side CUDA stream the ops being recorded run on (None = the caller's stream)
+
+
+class on_stream:
+    """Runs a self-contained part of the computation (one level's encoder -> VQ -> decoder: nothing but the input batch and
+    read-only parameters is shared with the rest) on a side CUDA stream, and tags the tape nodes recorded inside so that
+    `GradientTape.gradient` replays their backward on the same stream.  The caller forks the stream (`stream.wait_stream`)
+    before and joins it (`current.wait_stream(stream)`) after; works eagerly and under CUDA-graph capture alike.
+    A `None` stream makes it a no-op."""
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        global _node_stream
+        self._prev = _node_stream
+        if self.stream is not None:
+            _node_stream = self.stream
+            self._ctx = torch.cuda.stream(self.stream)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        global _node_stream
+        if self.stream is not None:
+            self._ctx.__exit__(*exc)
+        _node_stream = self._prev
+        return False
 
 
 class GradientTape:
@@ -207,23 +237,55 @@ class GradientTape:
         return [v.grad if getattr(v, "_grad_written", False) else None for v in sources]
 
     def _backprop(self, grads, produced):
-        for node in reversed(self.nodes):
-            gouts = [grads.pop(id(o), None) for o in node.outputs]
-            if all(g is None for g in gouts):
-                continue
-            needs = [(not isinstance(i, Variable)) and id(i) in produced for i in node.inputs]
-            gins = node.bwd(gouts, needs)
-            for inp, g in zip(node.inputs, gins):
-                if g is None:
+        """Reverse sweep.  Nodes tagged with a side stream (`on_stream`) replay there.  A gradient tensor that crosses streams
+        makes the consumer's stream wait for the producer's and is `record_stream`ed, so that the caching allocator does not
+        hand its block to the producer's stream again while the consumer still reads it (also under graph capture, where the
+        reuse would be baked into the graph); side streams are joined into the caller's stream at the end."""
+        cuda = torch.cuda.is_available() and any(n.stream is not None for n in self.nodes)
+        main = torch.cuda.current_stream() if cuda else None
+        prod = {}     # id(gradient tensor) -> stream it was produced on
+        used = []
+
+        def sync_in(t, ns):
+            if cuda and isinstance(t, torch.Tensor):
+                ps = prod.get(id(t), main)
+                if ps is not ns:
+                    ns.wait_stream(ps)
+                    t.record_stream(ns)
+
+        try:
+            for node in reversed(self.nodes):
+                gouts = [grads.pop(id(o), None) for o in node.outputs]
+                if all(g is None for g in gouts):
                     continue
-                k = id(inp)
-                grads[k] = g if k not in grads else grads[k] + g
+                needs = [(not isinstance(i, Variable)) and id(i) in produced for i in node.inputs]
+                ns = node.stream if node.stream is not None else main
+                if node.stream is not None and node.stream not in used:
+                    node.stream.wait_stream(main)  # everything enqueued so far (the loss heads) precedes this level's sweep
+                    used.append(node.stream)
+                for g in gouts:
+                    sync_in(g, ns)
+                with on_stream(node.stream):
+                    gins = node.bwd(gouts, needs)
+                    for inp, g in zip(node.inputs, gins):
+                        if g is None:
+                            continue
+                        k = id(inp)
+                        if k in grads:
+                            sync_in(grads[k], ns)
+                            g = grads[k] + g
+                        grads[k] = g
+                        if cuda and isinstance(g, torch.Tensor):
+                            prod[id(g)] = ns
+        finally:
+            for s in used:
+                main.wait_stream(s)
 
 
 def record(inputs, outputs, bwd):
     t = GradientTape.current()
     if t is not None:
-        t.nodes.append(_Node(list(inputs), list(outputs), bwd))
+        t.nodes.append(_Node(list(inputs), list(outputs), bwd, _node_stream))
 
 
 def grad_buffer(v: Variable) -> torch.Tensor:

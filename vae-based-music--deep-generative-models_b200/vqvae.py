@@ -28,7 +28,7 @@ from .VectorQuantizer import VectorQuantizer
 from .data_utils import STFT_ARGS, MultiSpectralLoss, norm, spectral  # noqa: F401
 from .encdec import Decoder, Encoder, print_dec_layer  # noqa: F401
 from .keras_compat import (GradientTape, Input, MeanSquaredError, Model, Packed, Scalar, convert_to_tensor, metrics,
-                           reduce_mean)
+                           on_stream, reduce_mean)
 
 
 def get_vqvae(input_shape, encoder, decoder, vq, level=0):
@@ -76,6 +76,8 @@ class VQVAE(Model):
         # ---- implementation state --------------------------------------------------------------------------
         self.train_step_training = True   # see module docstring
         self.use_cuda_graph = _lib.is_native() or _lib._BACKEND is None
+        self.use_level_streams = True     # levels >= 1 on side CUDA streams inside train_step (see _forward_backward)
+        self._level_streams = []
         self.spectral_weight = 1.0        # parity tests may switch the torch-side loss head off (0.0)
         self._graphs = {}
         self._pack_variables()
@@ -147,9 +149,14 @@ class VQVAE(Model):
         return out
 
     # ------------------------------------------------------------------------------------------------------
-    def _level_losses(self, level, x, training):
-        """One level of the loss computation shared by train_step / test_step / call (vqvae.py:121-131)."""
-        reconstructions = self.vqvaes[level](x) if training is None else self.vqvaes[level](x, training=training)
+    def _level_losses(self, level, x, training, stream=None):
+        """One level of the loss computation shared by train_step / test_step / call (vqvae.py:121-131).  `stream`: side CUDA
+        stream for the level's encoder -> VQ -> decoder (already forked by the caller); the loss head runs on the caller's."""
+        with on_stream(stream):
+            reconstructions = self.vqvaes[level](x) if training is None else self.vqvaes[level](x, training=training)
+        if stream is not None:
+            torch.cuda.current_stream().wait_stream(stream)
+            reconstructions.record_stream(torch.cuda.current_stream())  # allocated on `stream`, read by the loss head here
         reconstruction_loss = reduce_mean(self.loss_fn(x, reconstructions))
         spectral_loss = reduce_mean(self._multispectral_loss(x, reconstructions)) if self.spectral_weight else Scalar()
         commit_loss = sum(self.vqvaes[level].losses)
@@ -159,10 +166,20 @@ class VQVAE(Model):
         """The tape part of train_step (vqvae.py:113-143)."""
         commit_losses, recon_losses, spectral_losses, level_losses = [], [], [], []
         total_loss = Scalar()
+        # The levels are independent models on the same batch: levels >= 1 run their encoder -> VQ -> decoder (forward and,
+        # through the tape's stream tags, backward) on side streams, so that their many small-grid kernels (the deep stages:
+        # 14 to 110 tiles for 148 SMs) fill in next to level 0's.  Forked here, before level 0 is enqueued.
+        streams = [None] * self.levels
+        if self.use_level_streams and self.levels > 1 and _lib.device().type == "cuda":
+            if len(self._level_streams) < self.levels - 1:
+                self._level_streams = [torch.cuda.Stream(device=_lib.device()) for _ in range(self.levels - 1)]
+            for l in range(1, self.levels):
+                streams[l] = self._level_streams[l - 1]
+                streams[l].wait_stream(torch.cuda.current_stream())
         with GradientTape() as tape:
             for level in range(self.levels):  # bottom to top
                 _, reconstruction_loss, spectral_loss, commit_loss = self._level_losses(
-                    level, x, self.train_step_training)
+                    level, x, self.train_step_training, streams[level])
                 level_loss = reconstruction_loss + commit_loss + spectral_loss
                 commit_losses.append(commit_loss)
                 recon_losses.append(reconstruction_loss)
@@ -221,7 +238,7 @@ class VQVAE(Model):
 
     def _graph_train_step(self, raw):
         key = (tuple(raw.shape), vdist.world_size(), self.train_step_training, self.spectral_weight,
-               getattr(self, "precision", "fp32"))
+               getattr(self, "precision", "fp32"), self.use_level_streams)
         st = self._graphs.get(key)
         world = vdist.world_size()
         if st is not None:
