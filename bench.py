@@ -121,7 +121,21 @@ def cpu_reference_run(steps, warmup, batch):
                        f"samples, torch CPU fp32, {cores} threads")
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line of this run, on the real stdout."""
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
+
+
 def main():
+    # stdout carries exactly one JSON line: file descriptor 1 is pointed at stderr for everything else (NCCL prints its
+    # version banner to stdout when NCCL_DEBUG is set, libraries print warnings), the line itself goes to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -158,7 +172,7 @@ def main():
                                                          "oracle port of the reference's CPU path)"},
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import numpy as np
@@ -250,7 +264,7 @@ def main():
         r = cpu_reference_run(1, 1, args.cpu_batch)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"]}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -279,19 +293,22 @@ def roofline_section(V, pk, precision="fp32"):
     w1 = torch.randn(3, C, C, device="cuda", generator=g) * 0.1
     w2 = torch.randn(3, C, C, device="cuda", generator=g) * 0.1
     b1 = torch.zeros(C, device="cuda"); b2 = torch.zeros(C, device="cuda")
+    # what train_step launches under a tape: on the tensor-core paths the forward also writes the two sign-mask words per
+    # position for the data gradient (+8 B on 384)
+    fwd = ops.resblock_fwd_masks if P else ops.resblock_fwd
     for i in range(4):
-        ops.resblock_fwd(xs[i % 2], w1, b1, w2, b2, d, P)
+        fwd(xs[i % 2], w1, b1, w2, b2, d, P)
     torch.cuda.synchronize()
     n = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n):
-        ops.resblock_fwd(xs[i % 2], w1, b1, w2, b2, d, P)
+        fwd(xs[i % 2], w1, b1, w2, b2, d, P)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     flops = 2.0 * B * L * (3 * C * C) * 2          # two k=3 C->C convolutions
-    bytes_alg = B * L * C * 4 * 3.0                # read x, write h (kept for backward), write y
+    bytes_alg = B * L * (C * 4 * 3.0 + (8.0 if P else 0.0))  # read x, write h (kept for backward), write y (+ 2 mask words)
     tf = flops / (ms * 1e-3) / 1e12
     gbs = bytes_alg / (ms * 1e-3) / 1e9
     kname = "vqb_resblock_fwd [32,14080,32] dil 1 (" + ("fp32 path: 2 x tgc_kernel" if precision == "fp32" else "rb_tc_kernel, tcgen05 " + precision) + ")"
@@ -299,7 +316,7 @@ def roofline_section(V, pk, precision="fp32"):
                          "frac": gbs / pk["hbm"], "traffic": ncu_traffic("rb_fwd_" + precision),
                          "peak_source": pk["src"] + " HBM copy bandwidth", "ms_per_launch": ms,
                          "algorithmic_bytes_per_launch": bytes_alg,
-                         "algorithmic_bytes_per_unit": "384 B per time position (SURVEY 8d / DESIGN 4)"},
+                         "algorithmic_bytes_per_unit": "384 B per time position (SURVEY 8d / DESIGN 4) + 8 B of sign masks on the tensor-core paths"},
             "roofline_tensor": {"bound": "tensor", "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                                 "frac": tf / pk["tf_burst"], "flop_per_launch": flops,
                                 "note": "algorithmic FLOP of the two convolutions; the tensor pipe is not the limiter of this block"}}

@@ -1,4 +1,4 @@
-"""Runs one hot kernel a few times (for `ncu --set full -k regex:...`).  Usage: python tools/bench_kernel.py resblock_fwd|resblock_bwd|wgrad|vq [precision]"""
+"""Runs one hot kernel a few times (for `ncu --set full -k regex:...`).  Usage: python tools/bench_kernel.py resblock_fwd[_masks]|resblock_bwd[_masks]|wgrad|resblock_wgrad|vq [precision]"""
 import os
 import sys
 
@@ -20,6 +20,7 @@ w2 = torch.randn(3, C, C, device="cuda", generator=g) * 0.1
 b1 = torch.zeros(C, device="cuda"); b2 = torch.zeros(C, device="cuda")
 y, h = ops.resblock_fwd(xs[0], w1, b1, w2, b2, 1, P)
 dw, db = ops.empty(3, C, C), ops.empty(C)
+dw2, db2 = ops.empty(3, C, C), ops.empty(C)
 if what.endswith("_masks"):
     _, _, xb, hb = ops.resblock_fwd_masks(xs[0], w1, b1, w2, b2, 1, P)
 n = int(os.environ.get("N", "6"))
@@ -35,6 +36,8 @@ def one(i):
         ops.resblock_bwd_data_masks(xb, hb, dy, w1, w2, int(os.environ.get("DIL", "1")), P)
     elif what == "resblock_bwd":
         ops.resblock_bwd_data(xs[i % 2], h, dy, w1, w2, int(os.environ.get("DIL", "1")), P)
+    elif what == "resblock_wgrad":
+        ops.resblock_wgrad(xs[i % 2], h, dy, xs[(i + 1) % 2], dw, db, dw2, db2, int(os.environ.get("DIL", "1")), P)
     elif what == "wgrad":
         ops.conv1d_wgrad(xs[i % 2], dy, dw, db, 1, 1, True, P)
     elif what == "vq":

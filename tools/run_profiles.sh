@@ -17,8 +17,9 @@ full() {  # name, kernel regex, skip, command...
   $NCU --set full --import-source on -k regex:$rx -s $skip -c 1 -f -o $O/prof_$name "$@" > $O/ncu_$name.log 2>&1
 }
 full rb_fwd_$P rb_tc_kernel 4 python tools/bench_kernel.py resblock_fwd $P
-full rb_bwd_$P rb_tc_kernel 4 python tools/bench_kernel.py resblock_bwd $P
-DIL=27 full rb_bwd_d27_$P rb_tc_kernel 4 python tools/bench_kernel.py resblock_bwd $P
+full rb_fwd_masks_$P rb_tc_kernel 5 python tools/bench_kernel.py resblock_fwd_masks $P
+full rb_bwd_masks_$P rb_tc_kernel 5 python tools/bench_kernel.py resblock_bwd_masks $P
+DIL=27 full rb_bwd_masks_d27_$P rb_tc_kernel 5 python tools/bench_kernel.py resblock_bwd_masks $P
 full wgrad_$P wgrad_tc_kernel 4 python tools/bench_kernel.py wgrad $P
 full vq_search vq2_kernel 2 python tools/profile_vq.py
 full vq_finish vq_finish_smem_kernel 2 python tools/profile_vq.py
