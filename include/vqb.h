@@ -148,6 +148,14 @@ size_t vqb_resblock_wgrad_workspace_bytes(const vqb_resblock_desc* d);
 int vqb_resblock_wgrad(const vqb_resblock_desc* d, const float* x, const float* h, const float* dy, const float* dh,
                        float* dw1, float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes,
                        void* stream);
+/* ... of n blocks of the same shape in one call (1 <= n <= 4 for one launch on the tensor-core paths; e.g. the blocks of a
+ * DilatedResnet1D once its data-gradient chain is through).  Arrays of n pointers; d->dilation is ignored, dilations[i] is
+ * block i's.  db1[i] / db2[i] may be NULL. */
+size_t vqb_resblock_wgrad_batch_workspace_bytes(const vqb_resblock_desc* d, int32_t n);
+int vqb_resblock_wgrad_batch(const vqb_resblock_desc* d, int32_t n, const int32_t* dilations, const float* const* x,
+                             const float* const* h, const float* const* dy, const float* const* dh, float* const* dw1,
+                             float* const* db1, float* const* dw2, float* const* db2, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Decoder tail: the last Conv1DTranspose(C_mid, k=4, s=2) (encdec.py:67-68) and the final Conv1D(1, 3) (encdec.py:148)

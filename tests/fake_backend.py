@@ -278,6 +278,22 @@ class FakeBackend:
             _t(db2, (d.C,)).copy_(DY.sum((0, 1)))
         return 0
 
+    def vqb_resblock_wgrad_batch_workspace_bytes(self, dref, n):
+        return 16
+
+    def vqb_resblock_wgrad_batch(self, dref, n, dils, x, h, dy, dh, dw1, db1, dw2, db2, ws, wsn, stream):
+        import copy
+        P = C.POINTER(C.c_void_p)
+        arr = lambda a: C.cast(a, P)
+        dl = C.cast(dils, C.POINTER(C.c_int32))
+        for i in range(n):
+            di = copy.copy(dref._obj)
+            di.dilation = dl[i]
+            rc = self.vqb_resblock_wgrad(C.byref(di), *[arr(a)[i] for a in (x, h, dy, dh, dw1, db1, dw2, db2)], ws, wsn, stream)
+            if rc:
+                return rc
+        return 0
+
     def vqb_resblock_bwd_data(self, dref, x, h, dy, w1, w2, dh, dx, stream):
         d = _d(dref)
         X = _t(x, (d.B, d.L, d.C)); H = _t(h, (d.B, d.L, d.F)); DY = _t(dy, (d.B, d.L, d.C))

@@ -202,6 +202,41 @@ def test_resblock_wgrad_matches_two_conv_wgrads(gpu, prec, B, L, d):
     assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3", "fp16x2"])
+@pytest.mark.parametrize("B,L,nblk", [(2, 1000, 4), (3, 881, 3), (1, 1, 2), (32, 110, 4), (4, 3520, 4), (2, 300, 5)])
+def test_resblock_wgrad_batching(gpu, prec, B, L, nblk):
+    """Inside a reduce_begin() / reduce_flush() window ops.resblock_wgrad collects the blocks of a stack and launches them
+    together (vqb_resblock_wgrad_batch: up to 4 blocks = 8 problems share the grid of one tcgen05 wgrad launch; a 5th block
+    starts the next batch).  Every block's four gradients must match the oracle's autograd, and a second pass must be bit
+    identical (fixed CTA split, fixed-order reductions)."""
+    ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
+    g = torch.Generator().manual_seed(11 * L + nblk)
+    dil = [27, 9, 3, 1, 27][:nblk]
+    blocks = []
+    for i in range(nblk):
+        x, h = torch.randn(B, L, 32, generator=g), torch.randn(B, L, 32, generator=g)
+        dy, dh = torch.randn(B, L, 32, generator=g), torch.randn(B, L, 32, generator=g)
+        w1 = torch.zeros(3, 32, 32, requires_grad=True); b1 = torch.zeros(32, requires_grad=True)
+        w2 = torch.zeros(3, 32, 32, requires_grad=True); b2 = torch.zeros(32, requires_grad=True)
+        g1 = torch.autograd.grad(O.conv1d(torch.relu(x), w1, b1, 1, dil[i]), (w1, b1), dh)
+        g2 = torch.autograd.grad(O.conv1d(torch.relu(h), w2, b2, 1, 1), (w2, b2), dy)
+        blocks.append(((x.cuda(), h.cuda(), dy.cuda(), dh.cuda()), (*g1, *g2)))
+    runs = []
+    for _ in range(2):
+        outs = [[ops.empty(3, 32, 32), ops.empty(32), ops.empty(3, 32, 32), ops.empty(32)] for _ in range(nblk)]
+        ops.reduce_begin()
+        for i, (t, _) in enumerate(blocks):
+            ops.resblock_wgrad(*t, *outs[i], dil[i], P)
+        ops.reduce_flush()
+        torch.cuda.synchronize()
+        runs.append(outs)
+    tol = 2e-5 if prec == "fp32" else TOL["bf16x3"]
+    for i, (_, want) in enumerate(blocks):
+        for got, w in zip(runs[0][i], want):
+            assert rel(got, w) < tol, (prec, i, rel(got, w))
+        assert all(torch.equal(a, b) for a, b in zip(runs[0][i], runs[1][i]))
+
+
 @pytest.mark.parametrize("N,K,kind", [(28160, 512, "normal"), (3520, 512, "init"), (1 << 16, 2048, "normal"), (4096, 512, "nearties"),
                                       (440, 512, "normal"), (1000, 256, "normal"), (129, 1024, "normal")])
 def test_vq_search_tc_is_exact(gpu, N, K, kind):

@@ -71,6 +71,8 @@ SIGNATURES = {
     "vqb_resblock_bwd_data_masks": (C.c_int, [_RD, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vqb_resblock_wgrad_workspace_bytes": (C.c_size_t, [_RD]),
     "vqb_resblock_wgrad": (C.c_int, [_RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vqb_resblock_wgrad_batch_workspace_bytes": (C.c_size_t, [_RD, C.c_int32]),
+    "vqb_resblock_wgrad_batch": (C.c_int, [_RD, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_dec_tail_supports": (C.c_int, [_TD]),
     "vqb_dec_tail_fwd": (C.c_int, [_TD, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vqb_dec_tail_bwd_workspace_bytes": (C.c_size_t, [_TD]),

@@ -56,9 +56,10 @@ bool wgrad_tc_supported(const vqb_conv_desc* d);
 size_t wgrad_tc_workspace_bytes(const vqb_conv_desc* d);
 int conv1d_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, void* ws,
                     size_t ws_bytes, cudaStream_t st);
-size_t resblock_wgrad_tc_workspace_bytes(const vqb_conv_desc* d);
-int resblock_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* h, const float* dy, const float* dh, float* dw1,
-                      float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t resblock_wgrad_tc_workspace_bytes(const vqb_conv_desc* d, int n);
+int resblock_wgrad_tc(const vqb_conv_desc* d, int n, const int* dilations, const float* const* x, const float* const* h,
+                      const float* const* dy, const float* const* dh, float* const* dw1, float* const* db1,
+                      float* const* dw2, float* const* db2, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // tensor-core stride-2 convolutions (conv_tc.cu)
 bool conv_tc_supported(const vqb_conv_desc* d);

@@ -94,7 +94,7 @@ size_t vqb_resblock_wgrad_workspace_bytes(const vqb_resblock_desc* d) {
   if (!d) return 0;
   vqb_conv_desc c1{d->B, d->L, d->C, d->F, 3, 1, d->dilation, 1, d->precision};
   vqb_conv_desc c2{d->B, d->L, d->F, d->C, 3, 1, 1, 1, d->precision};
-  if (d->precision != VQB_PREC_FP32 && d->C == d->F && wgrad_tc_supported(&c1)) return resblock_wgrad_tc_workspace_bytes(&c1);
+  if (d->precision != VQB_PREC_FP32 && d->C == d->F && wgrad_tc_supported(&c1)) return resblock_wgrad_tc_workspace_bytes(&c1, 1);
   const size_t a = (vqb_conv1d_wgrad_workspace_bytes(&c1) + 255) & ~(size_t)255;
   return a + vqb_conv1d_wgrad_workspace_bytes(&c2);
 }
@@ -109,7 +109,7 @@ int vqb_resblock_wgrad(const vqb_resblock_desc* d, const float* x, const float* 
   vqb_conv_desc c1{d->B, d->L, d->C, d->F, 3, 1, d->dilation, 1, d->precision};
   vqb_conv_desc c2{d->B, d->L, d->F, d->C, 3, 1, 1, 1, d->precision};
   if (d->precision != VQB_PREC_FP32 && d->C == d->F && wgrad_tc_supported(&c1) && d->B > 0 && d->L > 0)
-    return resblock_wgrad_tc(&c1, x, h, dy, dh, dw1, db1, dw2, db2, workspace, workspace_bytes, (cudaStream_t)stream);
+    return resblock_wgrad_tc(&c1, 1, &d->dilation, &x, &h, &dy, &dh, &dw1, &db1, &dw2, &db2, workspace, workspace_bytes, (cudaStream_t)stream);
   const size_t a = (vqb_conv1d_wgrad_workspace_bytes(&c1) + 255) & ~(size_t)255;
   const size_t need = a + vqb_conv1d_wgrad_workspace_bytes(&c2);
   if (!workspace || workspace_bytes < need)
@@ -117,6 +117,38 @@ int vqb_resblock_wgrad(const vqb_resblock_desc* d, const float* x, const float* 
   rc = vqb_conv1d_wgrad(&c1, x, dh, dw1, db1, workspace, a, stream);
   if (rc) return rc;
   return vqb_conv1d_wgrad(&c2, h, dy, dw2, db2, (char*)workspace + a, workspace_bytes - a, stream);
+}
+
+/* the same for n blocks of one shape (1 <= n <= 4; e.g. the four blocks of a DilatedResnet1D once its data-gradient chain is
+   through): ONE launch on the tensor-core paths.  d->dilation is ignored, dilations[i] is block i's. */
+size_t vqb_resblock_wgrad_batch_workspace_bytes(const vqb_resblock_desc* d, int32_t n) {
+  if (!d || n < 1) return 0;
+  vqb_conv_desc c1{d->B, d->L, d->C, d->F, 3, 1, 1, 1, d->precision};
+  if (d->precision != VQB_PREC_FP32 && d->C == d->F && wgrad_tc_supported(&c1) && n <= 4) return resblock_wgrad_tc_workspace_bytes(&c1, n);
+  return (size_t)n * ((vqb_resblock_wgrad_workspace_bytes(d) + 255) & ~(size_t)255);
+}
+
+int vqb_resblock_wgrad_batch(const vqb_resblock_desc* d, int32_t n, const int32_t* dilations, const float* const* x,
+                             const float* const* h, const float* const* dy, const float* const* dh, float* const* dw1,
+                             float* const* db1, float* const* dw2, float* const* db2, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  VQB_ARCH();
+  int rc = check_rb(d);
+  if (rc) return rc;
+  VQB_REQUIRE(n >= 1 && dilations && x && h && dy && dh && dw1 && db1 && dw2 && db2, "vqb_resblock_wgrad_batch: bad arguments");
+  vqb_conv_desc c1{d->B, d->L, d->C, d->F, 3, 1, 1, 1, d->precision};
+  if (d->precision != VQB_PREC_FP32 && d->C == d->F && wgrad_tc_supported(&c1) && d->B > 0 && d->L > 0 && n <= 4)
+    return resblock_wgrad_tc(&c1, n, dilations, x, h, dy, dh, dw1, db1, dw2, db2, workspace, workspace_bytes, (cudaStream_t)stream);
+  const size_t per = (vqb_resblock_wgrad_workspace_bytes(d) + 255) & ~(size_t)255;
+  if (!workspace || workspace_bytes < per * (size_t)n)
+    return set_err(VQB_ERR_WORKSPACE, "vqb_resblock_wgrad_batch workspace: need %zu bytes, got %zu", per * (size_t)n, workspace_bytes);
+  for (int i = 0; i < n; ++i) {
+    vqb_resblock_desc di = *d;
+    di.dilation = dilations[i];
+    rc = vqb_resblock_wgrad(&di, x[i], h[i], dy[i], dh[i], dw1[i], db1[i], dw2[i], db2[i], (char*)workspace + per * i, per, stream);
+    if (rc) return rc;
+  }
+  return VQB_OK;
 }
 
 }  // extern "C"

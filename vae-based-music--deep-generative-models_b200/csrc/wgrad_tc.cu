@@ -23,12 +23,15 @@ struct WgTcParams {
   const float* ot;  // other side   [B, L, 32]  (dy)
   float* partial;   // [CTAs of this problem][3*32*32 + 32]
   int B, L, dil, relu_ga, tiles_per_b, total_tiles;
-  // Second problem of the same [B, L] (the other convolution of a residual block: vqb_resblock_wgrad): the upper half of
-  // the grid works on it, so that one launch (one prologue, one drain) yields both weight gradients.  nprob = 1 or 2.
-  const float* ga2;
-  const float* ot2;
-  float* partial2;
-  int dil2, relu_ga2, nprob;
+  // Further problems of the same [B, L] (the other convolution of a residual block, the blocks of a whole DilatedResnet1D:
+  // vqb_resblock_wgrad / vqb_resblock_wgrad_batch): the grid is cut into nprob equal runs of CTAs, run q works on problem q,
+  // so that one launch (one prologue, one drain) yields all the weight gradients.  Problem 0 is the fields above.
+  static constexpr int MAXP = 8;
+  const float* gaq[MAXP];
+  const float* otq[MAXP];
+  float* partialq[MAXP];
+  int dilq[MAXP], reluq[MAXP];
+  int nprob;
 };
 
 // S = number of bf16 pieces each operand is split into (1: bf16, 2: bf16x2, 3: bf16x3 = fp32-grade products)
@@ -71,11 +74,12 @@ template <int S, int NT_>
 __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams pp) {
   using Cfg = WgCfg<S, NT_>;
   // CTA-local view: which problem, which slice of its tiles
-  const int half = pp.nprob == 2 ? (int)gridDim.x / 2 : (int)gridDim.x;
-  const bool second = (int)blockIdx.x >= half;
-  const int nblk = second ? (int)gridDim.x - half : half, bidx = second ? (int)blockIdx.x - half : (int)blockIdx.x;
-  WgTcParams p = pp;
-  if (second) { p.ga = pp.ga2; p.ot = pp.ot2; p.partial = pp.partial2; p.dil = pp.dil2; p.relu_ga = pp.relu_ga2; }
+  const int nblk = (int)gridDim.x / pp.nprob;  // the grid is nprob * nblk CTAs
+  const int prob = (int)blockIdx.x / nblk, bidx = (int)blockIdx.x - prob * nblk;
+  struct { const float* ga; const float* ot; float* partial; int B, L, dil, relu_ga, tiles_per_b, total_tiles; } p;
+  p.B = pp.B; p.L = pp.L; p.tiles_per_b = pp.tiles_per_b; p.total_tiles = pp.total_tiles;
+  if (prob == 0) { p.ga = pp.ga; p.ot = pp.ot; p.partial = pp.partial; p.dil = pp.dil; p.relu_ga = pp.relu_ga; }
+  else { p.ga = pp.gaq[prob]; p.ot = pp.otq[prob]; p.partial = pp.partialq[prob]; p.dil = pp.dilq[prob]; p.relu_ga = pp.reluq[prob]; }
   constexpr int NT = Cfg::NT, NA = Cfg::NA, NB = Cfg::NB, NSETS = Cfg::NSETS;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[2], empty[2], done;
@@ -308,31 +312,41 @@ static int launch_wg_any(int S, const WgTcParams& p, int grid, cudaStream_t st) 
                    : (S == 3 ? launch_wg<3>(p, grid, st) : S == 2 ? launch_wg<2>(p, grid, st) : launch_wg<1>(p, grid, st));
 }
 
-// Both weight gradients of a residual block (resnet.py:13-17) in ONE launch: problem 0 = conv1 (act(x), dh, dilation d),
-// problem 1 = conv2 (act(h), dy, dilation 1).  d describes conv1 (k 3, 32 -> 32, dilation, relu_in).
-size_t resblock_wgrad_tc_workspace_bytes(const vqb_conv_desc* d) { return 2 * wgrad_tc_workspace_bytes(d); }
+// The weight gradients of n residual blocks of the same [B, L, 32] (resnet.py:13-17; n = 1: one block, n = 4: a whole
+// DilatedResnet1D) in ONE launch: problem 2i = conv1 of block i (act(x), dh, its dilation), problem 2i + 1 = conv2
+// (act(h), dy, dilation 1).  d describes the shape (k 3, 32 -> 32); its dilation field is ignored.
+size_t resblock_wgrad_tc_workspace_bytes(const vqb_conv_desc* d, int n) { return (size_t)2 * n * wgrad_tc_workspace_bytes(d); }
 
-int resblock_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* h, const float* dy, const float* dh, float* dw1,
-                      float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, cudaStream_t st) {
-  const size_t need = resblock_wgrad_tc_workspace_bytes(d);
+int resblock_wgrad_tc(const vqb_conv_desc* d, int n, const int* dilations, const float* const* x, const float* const* h,
+                      const float* const* dy, const float* const* dh, float* const* dw1, float* const* db1,
+                      float* const* dw2, float* const* db2, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (n < 1 || 2 * n > WgTcParams::MAXP) return set_err(VQB_ERR_INVALID, "residual-block wgrad: 1..%d blocks per launch (got %d)", WgTcParams::MAXP / 2, n);
+  const size_t need = resblock_wgrad_tc_workspace_bytes(d, n);
   if (!ws || ws_bytes < need) return set_err(VQB_ERR_WORKSPACE, "residual-block wgrad workspace: need %zu bytes, got %zu", need, ws_bytes);
   constexpr int PART = WgCfg<1>::PART;
   WgTcParams p{};
-  int g = wgrad_tc_grid(d, &p.tiles_per_b);  // CTAs a single problem would get
-  g = g > 1 ? (g + 1) / 2 : 1;               // ... per problem here: 2 g <= number of SMs (+1)
-  p.B = d->B; p.L = d->L; p.total_tiles = d->B * p.tiles_per_b; p.nprob = 2;
+  const int np = 2 * n;
+  int g = wgrad_tc_grid(d, &p.tiles_per_b);  // CTAs a single problem would get (<= number of SMs)
+  p.B = d->B; p.L = d->L; p.total_tiles = d->B * p.tiles_per_b; p.nprob = np;
+  const int full = g;
+  g = full / np > 0 ? full / np : 1;         // ... per problem here
   if (g > p.total_tiles) g = p.total_tiles;
-  p.ga = x; p.ot = dh; p.dil = d->dilation; p.relu_ga = 1; p.partial = (float*)ws;
-  p.ga2 = h; p.ot2 = dy; p.dil2 = 1; p.relu_ga2 = 1; p.partial2 = (float*)ws + (size_t)g * PART;
-  int rc = launch_wg_any(wg_split(d->precision), p, 2 * g, st);
+  for (int q = 0; q < np; ++q) {
+    const int i = q >> 1;
+    const bool c2 = q & 1;
+    p.gaq[q] = c2 ? h[i] : x[i]; p.otq[q] = c2 ? dy[i] : dh[i]; p.dilq[q] = c2 ? 1 : dilations[i]; p.reluq[q] = 1;
+    p.partialq[q] = (float*)ws + (size_t)q * g * PART;
+  }
+  p.ga = p.gaq[0]; p.ot = p.otq[0]; p.dil = p.dilq[0]; p.relu_ga = 1; p.partial = p.partialq[0];
+  int rc = launch_wg_any(wg_split(d->precision), p, np * g, st);
   if (rc) return rc;
-  float* outs[2][2] = {{dw1, db1}, {dw2, db2}};
-  for (int q = 0; q < 2; ++q) {
-    float* part = q ? p.partial2 : p.partial;
-    reduce_chunks_strided(part, g, PART, 0, 3 * 32 * 32, outs[q][0], st);
+  for (int q = 0; q < np; ++q) {
+    float* dw = (q & 1) ? dw2[q >> 1] : dw1[q >> 1];
+    float* db = (q & 1) ? db2[q >> 1] : db1[q >> 1];
+    reduce_chunks_strided(p.partialq[q], g, PART, 0, 3 * 32 * 32, dw, st);
     VQB_LAUNCH_CHECK();
-    if (outs[q][1]) {
-      reduce_chunks_strided(part, g, PART, 3 * 32 * 32, 32, outs[q][1], st);
+    if (db) {
+      reduce_chunks_strided(p.partialq[q], g, PART, 3 * 32 * 32, 32, db, st);
       VQB_LAUNCH_CHECK();
     }
   }

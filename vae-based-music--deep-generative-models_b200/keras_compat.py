@@ -245,6 +245,7 @@ class GradientTape:
         main = torch.cuda.current_stream() if cuda else None
         prod = {}     # id(gradient tensor) -> stream it was produced on
         used = []
+        last_ns = main
 
         def sync_in(t, ns):
             if cuda and isinstance(t, torch.Tensor):
@@ -260,6 +261,9 @@ class GradientTape:
                     continue
                 needs = [(not isinstance(i, Variable)) and id(i) in produced for i in node.inputs]
                 ns = node.stream if node.stream is not None else main
+                if ns is not last_ns:
+                    ops.wg_flush()  # leftovers of the previous stream's queue (launched on that stream)
+                    last_ns = ns
                 if node.stream is not None and node.stream not in used:
                     node.stream.wait_stream(main)  # everything enqueued so far (the loss heads) precedes this level's sweep
                     used.append(node.stream)
@@ -278,6 +282,7 @@ class GradientTape:
                         if cuda and isinstance(g, torch.Tensor):
                             prod[id(g)] = ns
         finally:
+            ops.wg_flush()  # queued block weight gradients go out on their own stream BEFORE it is joined
             for s in used:
                 main.wait_stream(s)
 

@@ -2,6 +2,7 @@
 name the stream; every computation below is one or more `vqb_*` calls into libvqvae_b200.so."""
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import torch
@@ -40,6 +41,7 @@ def reduce_begin():
 def reduce_flush():
     """Launch all queued reductions as a few batched kernels (vqb_reduce_flush)."""
     global _deferred
+    wg_flush()
     call("vqb_reduce_flush", _lib.stream())
     _deferred = None
 
@@ -231,11 +233,57 @@ def resblock_bwd_data(x, h, dy, w1, w2, dilation, precision=0):
 
 
 # ------------------------------------------------------------------------------------------------- VQ
+_wg_queue = []      # residual-block weight-gradient problems waiting for their stack mates (same shape, same stream)
+WG_BATCH = 4        # blocks per launch: a DilatedResnet1D of the reference models (vqb_resblock_wgrad_batch takes <= 4)
+
+
+def _wg_key(x, h, precision):
+    dev = _lib.device()
+    st = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
+    return (tuple(x.shape), h.shape[2], precision, st.cuda_stream if st is not None else 0), st
+
+
+def wg_flush():
+    """Launch the queued residual-block weight gradients: one vqb_resblock_wgrad_batch call for up to WG_BATCH blocks."""
+    global _wg_queue
+    q, _wg_queue = _wg_queue, []
+    if not q:
+        return
+    key, stream, items = q[0][0], q[0][1], [it[2] for it in q]
+    (B, L, Cc), Fc, precision, _ = key
+    n = len(items)
+    # on the stream the problems were queued on (their operands were produced there), whatever the current one is
+    with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+        if n == 1:
+            x, h, dy, dh, dw1, db1, dw2, db2, dil = items[0]
+            _resblock_wgrad_now(x, h, dy, dh, dw1, db1, dw2, db2, dil, precision)
+            return
+        d = ResblockDesc(B, L, Cc, Fc, 1, precision)
+        arr = lambda k: (C.c_void_p * n)(*[ptr(it[k]) for it in items])
+        dils = (C.c_int32 * n)(*[it[8] for it in items])
+        ws = _ws(_lib.lib().vqb_resblock_wgrad_batch_workspace_bytes(C.byref(d), n))
+        call("vqb_resblock_wgrad_batch", C.byref(d), n, C.cast(dils, C.c_void_p),
+             *[C.cast(arr(k), C.c_void_p) for k in range(8)], ptr(ws), ws.numel(), _lib.stream())
+
+
 def resblock_wgrad(x, h, dy, dh, dw1, db1, dw2, db2, dilation, precision=0):
-    """Both weight (+ bias) gradients of a residual block in one call (vqb_resblock_wgrad): conv1 from (ReLU(x), dh, dilation),
-    conv2 from (ReLU(h), dy, 1).  One kernel launch in the tensor-core precisions."""
+    """Both weight (+ bias) gradients of a residual block (vqb_resblock_wgrad): conv1 from (ReLU(x), dh, dilation), conv2 from
+    (ReLU(h), dy, 1).  One kernel launch in the tensor-core precisions; inside a reduce_begin() / reduce_flush() window (a
+    backward pass) consecutive blocks of one shape on one stream are collected and launched together, WG_BATCH at a time
+    (vqb_resblock_wgrad_batch: the per-launch fixed cost of the persistent kernel is paid once per DilatedResnet1D)."""
     for t, n in ((x, "x"), (h, "h"), (dy, "dy"), (dh, "dh"), (dw1, "dw1"), (db1, "db1"), (dw2, "dw2"), (db2, "db2")):
         _chk(t, n)
+    if _deferred is None or precision == 0 or WG_BATCH <= 1:
+        return _resblock_wgrad_now(x, h, dy, dh, dw1, db1, dw2, db2, dilation, precision)
+    key, stream = _wg_key(x, h, precision)
+    if _wg_queue and _wg_queue[0][0] != key:
+        wg_flush()
+    _wg_queue.append((key, stream, (x, h, dy, dh, dw1, db1, dw2, db2, dilation)))
+    if len(_wg_queue) >= WG_BATCH:
+        wg_flush()
+
+
+def _resblock_wgrad_now(x, h, dy, dh, dw1, db1, dw2, db2, dilation, precision=0):
     B, L, Cc = x.shape
     d = ResblockDesc(B, L, Cc, h.shape[2], dilation, precision)
     ws = _ws(_lib.lib().vqb_resblock_wgrad_workspace_bytes(C.byref(d)))

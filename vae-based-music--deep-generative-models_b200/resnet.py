@@ -55,8 +55,14 @@ class ResnetConv1DBlock(layers.Layer):
                 dx, dh = ops.resblock_bwd_data_masks(xbits, hbits, dy, conv1.kernel.value, conv2.kernel.value, d, prec)
             else:
                 dx, dh = ops.resblock_bwd_data(x, h, dy, conv1.kernel.value, conv2.kernel.value, d, prec)
-            # both weight gradients in one call (one launch on the tensor-core paths): tape.gradient wrt the four variables
-            write_grad(conv1.kernel, lambda buf1: write_grad(conv2.kernel, lambda buf2: ops.resblock_wgrad(
+            # both weight gradients in one call (one launch on the tensor-core paths; ops.resblock_wgrad may hold it back to
+            # launch the blocks of a stack together): tape.gradient wrt the four variables
+            if getattr(conv1.kernel, "_grad_written", False) or getattr(conv2.kernel, "_grad_written", False):
+                ops.wg_flush()  # a block used twice under one tape accumulates: needs its gradient now (write_grad)
+                wg = ops._resblock_wgrad_now
+            else:
+                wg = ops.resblock_wgrad
+            write_grad(conv1.kernel, lambda buf1: write_grad(conv2.kernel, lambda buf2: wg(
                 x, h, dy, dh, buf1, grad_buffer(conv1.bias), buf2, grad_buffer(conv2.bias), d, prec)))
             conv1.bias._grad_written = True
             conv2.bias._grad_written = True
