@@ -466,7 +466,7 @@ int reduce_flush(cudaStream_t st) {
 void reduce_begin() { g_rq.active = true; g_rq.n = 0; }
 
 // column sums of a [rows, C] matrix (Conv1DTranspose bias gradient): partial[block][c]
-constexpr int COLSUM_ROWS = 2048;
+constexpr int COLSUM_ROWS = 256;  // rows per CTA: small, so that a [28160, 64] matrix still spreads over ~110 CTAs
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long rows, int C, float* __restrict__ partial) {
   __shared__ float red[256];
   const long r0 = (long)blockIdx.x * COLSUM_ROWS, r1 = min(r0 + (long)COLSUM_ROWS, rows);
