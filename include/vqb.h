@@ -116,7 +116,8 @@ int vqb_conv1d_transpose_wgrad(const vqb_conv_desc* d, const float* x, const flo
 /* ------------------------------------------------------------------------------------------------------------
  * Fused pre-activation residual block  (replaces ResnetConv1DBlock.call, resnet.py:11-18,29:
  *   y = x + Conv1D_k3(ReLU(Conv1D_k3,dil(ReLU(x)))), both SAME, C -> F -> C channels)
- * h [B,L,F] receives the first conv's output (pre-ReLU); the backward pass needs it, so it is always written.
+ * h [B,L,F] receives the first conv's output (pre-ReLU) for the backward pass; on the tensor-core precisions h may be NULL
+ * (inference): the intermediate then never leaves the SM (256 instead of 384 bytes per position).
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct vqb_resblock_desc {
   int32_t B, L, C, F, dilation;

@@ -166,8 +166,9 @@ def test_resblock_sign_mask_variants(gpu, prec, B, L, d):
     y0, h0 = ops.resblock_fwd(x, w1, b1, w2, b2, d, P)
     xb = hb = None
     y1, h1, xb, hb = ops.resblock_fwd_masks(x, w1, b1, w2, b2, d, P)
+    y2, h2 = ops.resblock_fwd(x, w1, b1, w2, b2, d, P, want_h=False)  # inference form: h is not stored
     torch.cuda.synchronize()
-    assert torch.equal(y0, y1) and torch.equal(h0, h1)
+    assert torch.equal(y0, y1) and torch.equal(h0, h1) and h2 is None and torch.equal(y0, y2)
     sh = torch.arange(32, device="cuda")
     assert torch.equal(((xb.long().unsqueeze(-1) >> sh) & 1).bool(), x > 0)
     assert torch.equal(((hb.long().unsqueeze(-1) >> sh) & 1).bool(), h1 > 0)

@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--windows", type=int, default=8)
     ap.add_argument("--log2-window", type=int, default=20)
     ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--precision", default="bf16x3")
+    ap.add_argument("--precision", default="fp16x2")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:

@@ -38,9 +38,11 @@ int vqb_resblock_fwd(const vqb_resblock_desc* d, const float* x, const float* w1
   VQB_ARCH();
   int rc = check_rb(d);
   if (rc) return rc;
-  VQB_REQUIRE(x && w1 && w2 && h && y, "vqb_resblock_fwd: NULL pointer");
+  VQB_REQUIRE(x && w1 && w2 && y, "vqb_resblock_fwd: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  // h may be NULL on the tensor-core paths (inference: the intermediate is not needed outside the kernel and is not stored)
   if (d->precision != VQB_PREC_FP32) return resblock_fwd_tc(d, x, w1, b1, w2, b2, h, y, nullptr, nullptr, st);
+  VQB_REQUIRE(h, "vqb_resblock_fwd: the fp32 path needs h (it is the input of its second kernel)");
   vqb_conv_desc c1{d->B, d->L, d->C, d->F, 3, 1, d->dilation, 1, VQB_PREC_FP32};
   rc = conv1d_fwd_fp32(&c1, x, w1, b1, nullptr, h, st);
   if (rc) return rc;

@@ -179,14 +179,16 @@ def resblock_precision(C_, F_, dilation, precision):
     return precision if _lib.lib().vqb_resblock_supports(C.byref(d)) else 0
 
 
-def resblock_fwd(x, w1, b1, w2, b2, dilation, precision=0):
+def resblock_fwd(x, w1, b1, w2, b2, dilation, precision=0, want_h=True):
+    """(y, h).  want_h=False (inference, tensor-core precisions only): the intermediate is not stored, h is None."""
     for t, n in ((x, "x"), (w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2")):
         _chk(t, n)
     B, L, Cc = x.shape
     Fc = w1.shape[2]
     if w1.shape[1] != Cc or w2.shape[1] != Fc or w2.shape[2] != Cc:
         raise ValueError(f"ResnetConv1DBlock: kernel shapes {tuple(w1.shape)}, {tuple(w2.shape)} do not fit input {tuple(x.shape)}")
-    h, y = empty(B, L, Fc), empty(B, L, Cc)
+    h = empty(B, L, Fc) if (want_h or precision == 0) else None
+    y = empty(B, L, Cc)
     d = ResblockDesc(B, L, Cc, Fc, dilation, precision)
     call("vqb_resblock_fwd", C.byref(d), ptr(x), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(h), ptr(y), _lib.stream())
     return y, h

@@ -46,8 +46,9 @@ class ResnetConv1DBlock(layers.Layer):
             # all the data gradient needs of them (x and h themselves stay the operands of the weight gradients)
             y, h, xbits, hbits = ops.resblock_fwd_masks(x, conv1.kernel.value, conv1.bias.value, conv2.kernel.value,
                                                         conv2.bias.value, d, prec)
-        else:
-            y, h = ops.resblock_fwd(x, conv1.kernel.value, conv1.bias.value, conv2.kernel.value, conv2.bias.value, d, prec)
+        else:  # no tape (inference): nobody needs h, the tensor-core kernel does not store it
+            y, h = ops.resblock_fwd(x, conv1.kernel.value, conv1.bias.value, conv2.kernel.value, conv2.bias.value, d, prec,
+                                    want_h=taping)
 
         def bwd(g, needs):
             dy = g[0].contiguous()
