@@ -1,4 +1,4 @@
-"""Measures, on the GPU, how far each arithmetic mode (fp32 / tf32 / bf16 contractions) is from the fp32 oracle on the
+"""Measures, on the GPU, how far each arithmetic mode (fp32, fp16x2, bf16x3, bf16x2, tf32, bf16) is from the fp32 oracle on the
 SMALL_VQ_VAE forward + gradients at batch 2 (the quantities the north star bounds at 1e-3 relative in fp32).
 Writes gpurun_out/precision_report.json.  Test infrastructure (uses the oracle)."""
 import json
@@ -28,7 +28,7 @@ def main():
             "recon": float((res[l]["recon"].double() - res64[l]["recon"]).abs().max() / res64[l]["recon"].abs().max()),
             "grad_max_rel_to_largest": max(float((a.double() - b).abs().max()) for a, b in zip(grads[l], grads64[l])) / gm,
             "idx_mismatch": int((res[l]["idx"] != res64[l]["idx"]).sum())}
-    for prec in (sys.argv[1:] or ("fp32", "bf16x3", "bf16x2", "tf32", "bf16")):
+    for prec in (sys.argv[1:] or ("fp32", "fp16x2", "bf16x3", "bf16x2", "tf32", "bf16")):
         V.keras_compat.reset_name_counters(); V.set_seed(0)
         m = V.VQVAE((28160, 1), **V.SMALL_VQ_VAE)
         m.use_cuda_graph = False

@@ -97,6 +97,7 @@ size_t vqb_resblock_wgrad_workspace_bytes(const vqb_resblock_desc* d) {
   vqb_conv_desc c1{d->B, d->L, d->C, d->F, 3, 1, d->dilation, 1, d->precision};
   vqb_conv_desc c2{d->B, d->L, d->F, d->C, 3, 1, 1, 1, d->precision};
   if (d->precision != VQB_PREC_FP32 && d->C == d->F && wgrad_tc_supported(&c1)) return resblock_wgrad_tc_workspace_bytes(&c1, 1);
+  c1.precision = c2.precision = VQB_PREC_FP32;  // no tensor-core weight-gradient kernel for this shape / mode (e.g. tf32)
   const size_t a = (vqb_conv1d_wgrad_workspace_bytes(&c1) + 255) & ~(size_t)255;
   return a + vqb_conv1d_wgrad_workspace_bytes(&c2);
 }
@@ -112,6 +113,7 @@ int vqb_resblock_wgrad(const vqb_resblock_desc* d, const float* x, const float* 
   vqb_conv_desc c2{d->B, d->L, d->F, d->C, 3, 1, 1, 1, d->precision};
   if (d->precision != VQB_PREC_FP32 && d->C == d->F && wgrad_tc_supported(&c1) && d->B > 0 && d->L > 0)
     return resblock_wgrad_tc(&c1, 1, &d->dilation, &x, &h, &dy, &dh, &dw1, &db1, &dw2, &db2, workspace, workspace_bytes, (cudaStream_t)stream);
+  c1.precision = c2.precision = VQB_PREC_FP32;  // shapes / modes without a tensor-core weight-gradient kernel: exact fp32
   const size_t a = (vqb_conv1d_wgrad_workspace_bytes(&c1) + 255) & ~(size_t)255;
   const size_t need = a + vqb_conv1d_wgrad_workspace_bytes(&c2);
   if (!workspace || workspace_bytes < need)
