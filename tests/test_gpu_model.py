@@ -352,3 +352,27 @@ def test_level_streams_do_not_change_the_step(gpu, graph):
         # ~lr whatever the gradient's size; cf. test_small_vqvae_training_trajectory)
         assert rel_err(r[1], res[0][1]) < 2e-2
         assert abs(r[2] - res[0][2]) <= 5e-2 * abs(res[0][2])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16", "bf16x2", "bf16x3", "fp16x2"])
+def test_every_precision_mode_trains(gpu, prec):
+    """Every arithmetic mode through the whole training path (sign-mask residual blocks, batched block weight gradients, level
+    streams, eager step + graph capture + replay): SMALL_VQ_VAE on two short windows; the first-step losses agree with the
+    exact-fp32 mode within the mode's accuracy and stay finite."""
+    V = gpu
+    T = 2816
+    x = torch.tensor(np.random.Generator(np.random.PCG64(2)).uniform(0, 1, size=(2, T, 1)).astype(np.float32)).cuda()
+    first = {}
+    for p in ("fp32", prec):
+        V.keras_compat.reset_name_counters()
+        V.set_seed(0)
+        m = V.VQVAE((T, 1), **V.SMALL_VQ_VAE)
+        m.set_precision(p)
+        m.compile(optimizer=V.keras.optimizers.Adam())
+        logs = [{k: float(v) for k, v in m.train_step((x, None)).items()} for _ in range(3)]
+        torch.cuda.synchronize()
+        assert all(np.isfinite(l["loss"]) for l in logs), (p, logs)
+        first[p] = logs[0]
+    tol = {"fp32": 1e-6, "tf32": 2e-2, "bf16": 5e-2, "bf16x2": 1e-3, "bf16x3": 1e-3, "fp16x2": 1e-3}[prec]
+    for k in ("[0]recon_loss", "[1]recon_loss", "[0]spectral_loss", "[1]spectral_loss"):
+        assert abs(first[prec][k] - first["fp32"][k]) <= tol * abs(first["fp32"][k]) + 1e-7, (prec, k, first[prec][k], first["fp32"][k])
