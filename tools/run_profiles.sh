@@ -11,6 +11,8 @@ python bench.py --precision $P > $O/bench_final.json 2> $O/bench_final.err || ta
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_final_ref.json 2> $O/bench_final_ref.err
 NCU="ncu --clock-control none"
 $NCU --profile-from-start off --metrics gpu__time_duration.sum --csv --log-file $O/launches_$P.csv python tools/profile_step.py $P > $O/ncu_step.log 2>&1
+# the same pass over the bench command itself (eager first step, capture, graph replays: kernel nodes are listed one by one)
+$NCU --metrics gpu__time_duration.sum --csv --log-file $O/launches_bench_$P.csv -c 2500 python bench.py --precision $P --steps 2 --warmup 3 --no-cpu-baseline --no-roofline > $O/ncu_bench.log 2>&1
 full() {  # name, kernel regex, skip, command...
   local name=$1 rx=$2 skip=$3; shift 3
   "$@" > /dev/null 2>&1 || { echo "plain run of $name failed"; return; }
