@@ -165,11 +165,14 @@ __device__ __forceinline__ void stage8(uint8_t* tile, int r, int o, const float4
 // (A variant with a dedicated MMA-issuing warp and mbarrier-only hand-offs measured slower: 17 warps cap the register
 // file at 96 per thread; so did epilogues that access their rows in global memory directly instead of through the
 // per-warp staging transposes: 32 lines per access instruction saturate the L1 pipeline.)
-template <int MODE, int MB, bool TMA_>
+// D1MAX: largest stage-1 dilation this instantiation stages (sizes the register prefetch of the input tile: 3 instead of 4
+// 8-channel units per thread at 128-row tiles when d1 <= 9, i.e. everywhere but the forward of the dilation-27 blocks)
+template <int MODE, int MB, bool TMA_, int D1MAX>
 __global__ void __launch_bounds__(RbCfg<MODE, MB, TMA_>::NT, 3 - MB)
     rb_tc_kernel(const RbTcParams p, const __grid_constant__ CUtensorMap tm_out1, const __grid_constant__ CUtensorMap tm_out2) {
+  static_assert(D1MAX <= RbCfg<MODE, MB, TMA_>::DMAX, "D1MAX");
   using Cfg = RbCfg<MODE, MB, TMA_>;
-  constexpr int NT = Cfg::NT, NU = Cfg::NU;
+  constexpr int NT = Cfg::NT, NU = ((Cfg::R + 2 * D1MAX) * 4 + Cfg::NCV - 1) / Cfg::NCV;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // the swizzled output images must start on a 1024-byte boundary
   uint8_t* smem = Cfg::TMA ? smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
@@ -523,12 +526,12 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB, TMA_>::NT, 3 - MB)
   if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
-template <int MODE, int MB, bool TMA_>
+template <int MODE, int MB, bool TMA_, int D1MAX = 32>
 static int launch_rb(const RbTcParams& p, cudaStream_t st) {
   using Cfg = RbCfg<MODE, MB, TMA_>;
   static bool attr_set = false;
   if (!attr_set) {
-    VQB_CUDA(cudaFuncSetAttribute(rb_tc_kernel<MODE, MB, TMA_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    VQB_CUDA(cudaFuncSetAttribute(rb_tc_kernel<MODE, MB, TMA_, D1MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -550,7 +553,7 @@ static int launch_rb(const RbTcParams& p, cudaStream_t st) {
     if ((p.out1 && !tma::make_rows_map(&tm1, p.out1, p.B, p.L, Rout)) || !tma::make_rows_map(&tm2, p.out2, p.B, p.L, Rout))
       return set_err(VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed for a [%d, %d, 32] fp32 tensor (box rows %d)", p.B, p.L, Rout);
   }
-  VQB_CUDA(launch_pdl(rb_tc_kernel<MODE, MB, TMA_>, dim3(grid), dim3(Cfg::NT), (size_t)Cfg::SMEM, st, q, tm1, tm2));
+  VQB_CUDA(launch_pdl(rb_tc_kernel<MODE, MB, TMA_, D1MAX>, dim3(grid), dim3(Cfg::NT), (size_t)Cfg::SMEM, st, q, tm1, tm2));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
@@ -574,7 +577,9 @@ static int dispatch_rb(int precision, const RbTcParams& p, cudaStream_t st) {
     case VQB_PREC_BF16X2: return half_tiles ? launch_rb<2, 1, false>(p, st) : launch_rb<2, 2, false>(p, st);
     case VQB_PREC_BF16X3: return launch_rb<3, 2, false>(p, st);
     case VQB_PREC_FP16X2:
-      return use_tma ? launch_rb<4, 2, true>(p, st) : half_tiles ? launch_rb<4, 1, false>(p, st) : launch_rb<4, 2, false>(p, st);
+      return use_tma ? launch_rb<4, 2, true>(p, st)
+                     : half_tiles ? (p.d1 <= 9 ? launch_rb<4, 1, false, 9>(p, st) : launch_rb<4, 1, false>(p, st))
+                                  : launch_rb<4, 2, false>(p, st);
   }
   return set_err(VQB_ERR_INVALID, "unknown precision %d", precision);
 }
