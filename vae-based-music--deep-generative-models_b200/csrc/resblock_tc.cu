@@ -167,9 +167,27 @@ __device__ __forceinline__ void stage8(uint8_t* tile, int r, int o, const float4
 // per-warp staging transposes: 32 lines per access instruction saturate the L1 pipeline.)
 // D1MAX: largest stage-1 dilation this instantiation stages (sizes the register prefetch of the input tile: 3 instead of 4
 // 8-channel units per thread at 128-row tiles when d1 <= 9, i.e. everywhere but the forward of the dilation-27 blocks)
-template <int MODE, int MB, bool TMA_, int D1MAX>
+// KIND: which of the runtime flags are known at compile time (the kernel is instruction-issue bound: every uniform branch and
+// dead path costs issue slots).  0 = generic; 1 = training forward (ReLU before both stages, residual add, h stored, both
+// sign-mask words written, no input masks); 2 = data gradient from sign-mask words (no ReLU, masks from m1bits / m2bits).
+template <int KIND>
+__device__ __forceinline__ RbTcParams rb_specialize(RbTcParams q) {
+  if (KIND == 1) {
+    q.relu1 = 1; q.relu2 = 1; q.mask1 = nullptr; q.mask2 = nullptr; q.m1bits = nullptr; q.m2bits = nullptr;
+    __builtin_assume(q.out1 != nullptr); __builtin_assume(q.add2 != nullptr);
+    __builtin_assume(q.xbits_out != nullptr); __builtin_assume(q.hbits_out != nullptr);
+  } else if (KIND == 2) {
+    q.relu1 = 0; q.relu2 = 0; q.mask1 = nullptr; q.mask2 = nullptr; q.xbits_out = nullptr; q.hbits_out = nullptr;
+    __builtin_assume(q.out1 != nullptr); __builtin_assume(q.add2 != nullptr);
+    __builtin_assume(q.m1bits != nullptr); __builtin_assume(q.m2bits != nullptr);
+  }
+  return q;
+}
+
+template <int MODE, int MB, bool TMA_, int D1MAX, int KIND>
 __global__ void __launch_bounds__(RbCfg<MODE, MB, TMA_>::NT, 3 - MB)
-    rb_tc_kernel(const RbTcParams p, const __grid_constant__ CUtensorMap tm_out1, const __grid_constant__ CUtensorMap tm_out2) {
+    rb_tc_kernel(const RbTcParams pp, const __grid_constant__ CUtensorMap tm_out1, const __grid_constant__ CUtensorMap tm_out2) {
+  const RbTcParams p = rb_specialize<KIND>(pp);
   static_assert(D1MAX <= RbCfg<MODE, MB, TMA_>::DMAX, "D1MAX");
   using Cfg = RbCfg<MODE, MB, TMA_>;
   constexpr int NT = Cfg::NT, NU = ((Cfg::R + 2 * D1MAX) * 4 + Cfg::NCV - 1) / Cfg::NCV;
@@ -526,12 +544,12 @@ __global__ void __launch_bounds__(RbCfg<MODE, MB, TMA_>::NT, 3 - MB)
   if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
-template <int MODE, int MB, bool TMA_, int D1MAX = 32>
+template <int MODE, int MB, bool TMA_, int D1MAX = 32, int KIND = 0>
 static int launch_rb(const RbTcParams& p, cudaStream_t st) {
   using Cfg = RbCfg<MODE, MB, TMA_>;
   static bool attr_set = false;
   if (!attr_set) {
-    VQB_CUDA(cudaFuncSetAttribute(rb_tc_kernel<MODE, MB, TMA_, D1MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    VQB_CUDA(cudaFuncSetAttribute(rb_tc_kernel<MODE, MB, TMA_, D1MAX, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -553,7 +571,7 @@ static int launch_rb(const RbTcParams& p, cudaStream_t st) {
     if ((p.out1 && !tma::make_rows_map(&tm1, p.out1, p.B, p.L, Rout)) || !tma::make_rows_map(&tm2, p.out2, p.B, p.L, Rout))
       return set_err(VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed for a [%d, %d, 32] fp32 tensor (box rows %d)", p.B, p.L, Rout);
   }
-  VQB_CUDA(launch_pdl(rb_tc_kernel<MODE, MB, TMA_, D1MAX>, dim3(grid), dim3(Cfg::NT), (size_t)Cfg::SMEM, st, q, tm1, tm2));
+  VQB_CUDA(launch_pdl(rb_tc_kernel<MODE, MB, TMA_, D1MAX, KIND>, dim3(grid), dim3(Cfg::NT), (size_t)Cfg::SMEM, st, q, tm1, tm2));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
@@ -577,9 +595,20 @@ static int dispatch_rb(int precision, const RbTcParams& p, cudaStream_t st) {
     case VQB_PREC_BF16X2: return half_tiles ? launch_rb<2, 1, false>(p, st) : launch_rb<2, 2, false>(p, st);
     case VQB_PREC_BF16X3: return launch_rb<3, 2, false>(p, st);
     case VQB_PREC_FP16X2:
-      return use_tma ? launch_rb<4, 2, true>(p, st)
-                     : half_tiles ? (p.d1 <= 9 ? launch_rb<4, 1, false, 9>(p, st) : launch_rb<4, 1, false>(p, st))
-                                  : launch_rb<4, 2, false>(p, st);
+      if (use_tma) return launch_rb<4, 2, true>(p, st);
+      {  // the two shapes of a training step get their own instantiation (rb_specialize)
+        const bool fwd_train = p.relu1 && p.relu2 && !p.mask1 && !p.mask2 && !p.m1bits && !p.m2bits && p.out1 && p.add2 &&
+                               p.xbits_out && p.hbits_out;
+        const bool bwd_bits = !p.relu1 && !p.relu2 && !p.mask1 && !p.mask2 && p.m1bits && p.m2bits && p.out1 && p.add2 &&
+                              !p.xbits_out && !p.hbits_out;
+        if (fwd_train)
+          return half_tiles ? (p.d1 <= 9 ? launch_rb<4, 1, false, 9, 1>(p, st) : launch_rb<4, 1, false, 32, 1>(p, st))
+                            : launch_rb<4, 2, false, 32, 1>(p, st);
+        if (bwd_bits)
+          return half_tiles ? launch_rb<4, 1, false, 9, 2>(p, st) : launch_rb<4, 2, false, 32, 2>(p, st);
+      }
+      return half_tiles ? (p.d1 <= 9 ? launch_rb<4, 1, false, 9>(p, st) : launch_rb<4, 1, false>(p, st))
+                        : launch_rb<4, 2, false>(p, st);
   }
   return set_err(VQB_ERR_INVALID, "unknown precision %d", precision);
 }
