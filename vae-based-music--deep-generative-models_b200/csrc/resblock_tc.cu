@@ -169,7 +169,8 @@ __device__ __forceinline__ void stage8(uint8_t* tile, int r, int o, const float4
 // 8-channel units per thread at 128-row tiles when d1 <= 9, i.e. everywhere but the forward of the dilation-27 blocks)
 // KIND: which of the runtime flags are known at compile time (the kernel is instruction-issue bound: every uniform branch and
 // dead path costs issue slots).  0 = generic; 1 = training forward (ReLU before both stages, residual add, h stored, both
-// sign-mask words written, no input masks); 2 = data gradient from sign-mask words (no ReLU, masks from m1bits / m2bits).
+// sign-mask words written, no input masks); 2 = data gradient from sign-mask words (no ReLU, masks from m1bits / m2bits);
+// 3 = inference forward (h not stored, no mask words).
 template <int KIND>
 __device__ __forceinline__ RbTcParams rb_specialize(RbTcParams q) {
   if (KIND == 1) {
@@ -180,6 +181,10 @@ __device__ __forceinline__ RbTcParams rb_specialize(RbTcParams q) {
     q.relu1 = 0; q.relu2 = 0; q.mask1 = nullptr; q.mask2 = nullptr; q.xbits_out = nullptr; q.hbits_out = nullptr;
     __builtin_assume(q.out1 != nullptr); __builtin_assume(q.add2 != nullptr);
     __builtin_assume(q.m1bits != nullptr); __builtin_assume(q.m2bits != nullptr);
+  } else if (KIND == 3) {  // inference forward: nothing kept for a backward pass
+    q.relu1 = 1; q.relu2 = 1; q.mask1 = nullptr; q.mask2 = nullptr; q.m1bits = nullptr; q.m2bits = nullptr;
+    q.out1 = nullptr; q.xbits_out = nullptr; q.hbits_out = nullptr;
+    __builtin_assume(q.add2 != nullptr);
   }
   return q;
 }
@@ -606,6 +611,11 @@ static int dispatch_rb(int precision, const RbTcParams& p, cudaStream_t st) {
                             : launch_rb<4, 2, false, 32, 1>(p, st);
         if (bwd_bits)
           return half_tiles ? launch_rb<4, 1, false, 9, 2>(p, st) : launch_rb<4, 2, false, 32, 2>(p, st);
+        const bool fwd_infer = p.relu1 && p.relu2 && !p.mask1 && !p.mask2 && !p.m1bits && !p.m2bits && !p.out1 && p.add2 &&
+                               !p.xbits_out && !p.hbits_out;
+        if (fwd_infer)
+          return half_tiles ? (p.d1 <= 9 ? launch_rb<4, 1, false, 9, 3>(p, st) : launch_rb<4, 1, false, 32, 3>(p, st))
+                            : launch_rb<4, 2, false, 32, 3>(p, st);
       }
       return half_tiles ? (p.d1 <= 9 ? launch_rb<4, 1, false, 9>(p, st) : launch_rb<4, 1, false>(p, st))
                         : launch_rb<4, 2, false>(p, st);
