@@ -253,3 +253,45 @@ def test_resblock_sign_mask_variants_on_the_test_double(cpu_backend):
     dx0, dh0 = ops.resblock_bwd_data(x, h0, dy, w1, w2, 3, 0)
     dx1, dh1 = ops.resblock_bwd_data_masks(xb, hb, dy, w1, w2, 3, 0)
     assert torch.equal(dx0, dx1) and torch.equal(dh0, dh1)
+
+
+def test_block_weight_gradient_queue(cpu_backend):
+    """ops.resblock_wgrad inside a reduce_begin() / reduce_flush() window (a backward pass) holds the blocks of a stack back and
+    hands them to vqb_resblock_wgrad_batch four at a time; a change of shape flushes the queue; outside the window and in
+    fp32 every call is immediate.  Host logic on the CPU double: the batched results equal the immediate ones."""
+    V = cpu_backend
+    ops, P = V.ops, V._lib.PREC_FP16X2
+    g = torch.Generator().manual_seed(3)
+
+    def block(B, L):
+        t = [torch.randn(B, L, 32, generator=g) for _ in range(4)]
+        return t, [torch.empty(3, 32, 32), torch.empty(32), torch.empty(3, 32, 32), torch.empty(32)]
+
+    blocks = [block(2, 50) for _ in range(5)] + [block(1, 20)]
+    dil = [27, 9, 3, 1, 27, 3]
+    want = []
+    for (t, _), d in zip(blocks, dil):
+        o = [torch.empty(3, 32, 32), torch.empty(32), torch.empty(3, 32, 32), torch.empty(32)]
+        ops.resblock_wgrad(*t, *o, d, P)        # no window: immediate
+        assert not ops._wg_queue
+        want.append(o)
+    calls = []
+    real = V._lib._BACKEND.vqb_resblock_wgrad_batch
+    V._lib._BACKEND.vqb_resblock_wgrad_batch = lambda dref, n, *a: (calls.append(n), real(dref, n, *a))[1]
+    try:
+        ops.reduce_begin()
+        for i, ((t, o), d) in enumerate(zip(blocks, dil)):
+            ops.resblock_wgrad(*t, *o, d, P)
+            assert len(ops._wg_queue) == [1, 2, 3, 0, 1, 1][i]   # full batch after 4; the new shape flushes the single leftover
+        ops.reduce_flush()
+    finally:
+        V._lib._BACKEND.vqb_resblock_wgrad_batch = real
+    assert calls == [4] and not ops._wg_queue  # batches of one go through vqb_resblock_wgrad
+    for (_, o), w in zip(blocks, want):
+        for a, b in zip(o, w):
+            assert torch.equal(a, b)
+    ops.reduce_begin()
+    t, o = blocks[0]
+    ops.resblock_wgrad(*t, *o, 1, 0)            # fp32: never queued
+    assert not ops._wg_queue
+    ops.reduce_flush()
