@@ -12,7 +12,29 @@ using namespace vqb::tc;
 
 struct Probe {
   int a_mn, b_mn, N, plane_a, plane_b, nacc, reps, shift;
+  int swz;     // 1: both operands K-major in the 128-byte-swizzled layout (rows of 128 B, 8-row groups of 1024 B)
+  int a_tmem;  // 1: A operand read from tensor memory (.ts form: tcgen05.mma [d], [a], bdesc, idesc)
+  int M;       // 0 = 128
 };
+
+// K-major operand in the SWIZZLE_128B layout: SBO = 1024 (next 8 rows), LBO unused, layout_type 2 (bits 61..63)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// A from tensor memory
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(Probe p, long long* out) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -31,9 +53,30 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Probe p, long long* out) 
     uint8_t* A = smem;
     uint8_t* B = smem + 100 * 1024;
     // K-major: LBO = plane pitch (next 16 bytes of K), SBO = 128 (next 8 rows);  MN-major: LBO = 128, SBO = plane pitch
-    const uint64_t ad0 = p.a_mn ? smem_desc(smem_u32(A), 128, p.plane_a) : smem_desc(smem_u32(A), p.plane_a, 128);
-    const uint64_t bd0 = p.b_mn ? smem_desc(smem_u32(B), 128, p.plane_b) : smem_desc(smem_u32(B), p.plane_b, 128);
-    const uint32_t idesc = instr_desc(FMT_BF16, 128, p.N, p.a_mn != 0, p.b_mn != 0);
+    const uint32_t A1k = (smem_u32(A) + 1023u) & ~1023u, B1k = (smem_u32(B) + 1023u) & ~1023u;  // swizzle atoms: 1024-byte aligned
+    const uint64_t ad0 = p.swz ? smem_desc_sw128(A1k) : p.a_mn ? smem_desc(smem_u32(A), 128, p.plane_a) : smem_desc(smem_u32(A), p.plane_a, 128);
+    const uint64_t bd0 = p.swz ? smem_desc_sw128(B1k) : p.b_mn ? smem_desc(smem_u32(B), 128, p.plane_b) : smem_desc(smem_u32(B), p.plane_b, 128);
+    const uint32_t idesc = instr_desc(FMT_BF16, p.M ? p.M : 128, p.N, p.a_mn != 0, p.b_mn != 0);
+    if (p.a_tmem) {  // A = 128 lanes x 8 columns of tensor memory (K = 16 halves), accumulators behind it
+      const uint32_t ta = tmem + 480;
+      for (int i = 0; i < 16; ++i) mma_ts(tmem, ta, bd0, idesc, 1);
+      commit(&bar);
+      mbar_wait(&bar, 0);
+      const long long t0 = clock64();
+#pragma unroll 1
+      for (int i = 0; i < p.reps; i += 6) {
+        mma_ts(tmem + (0 % p.nacc) * p.N, ta, bd0, idesc, 1);
+        mma_ts(tmem + (1 % p.nacc) * p.N, ta, bd0, idesc, 1);
+        mma_ts(tmem + (2 % p.nacc) * p.N, ta, bd0, idesc, 1);
+        mma_ts(tmem + (3 % p.nacc) * p.N, ta, bd0, idesc, 1);
+        mma_ts(tmem + (4 % p.nacc) * p.N, ta, bd0, idesc, 1);
+        mma_ts(tmem + (5 % p.nacc) * p.N, ta, bd0, idesc, 1);
+      }
+      commit(&bar);
+      mbar_wait(&bar, 1);
+      const long long t1 = clock64();
+      if (blockIdx.x == 0) out[0] = t1 - t0;
+    } else {
     // warm-up
     for (int i = 0; i < 16; ++i) mma<false>(tmem, ad0, bd0, idesc, 1);
     commit(&bar);
@@ -56,6 +99,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Probe p, long long* out) 
     mbar_wait(&bar, 1);
     const long long t1 = clock64();
     if (blockIdx.x == 0) out[0] = t1 - t0;
+    }
   }
   __syncthreads();
   if (tid < 32) tmem_dealloc(tmem, 512);
@@ -88,6 +132,24 @@ int main() {
       {"MN-major A / K-major B  N=96", {1, 0, 96, PX, PW, 3, reps, 3}},
       {"K-major A / MN-major B  N=96", {0, 1, 96, PK, PD, 3, reps, 1}},
       {"MN-major A / MN-major B N=256", {1, 1, 256, PX, PD, 1, reps, 3}},
+      // round 2: 128-byte-swizzled K-major operands (the TMA-native layout) ...
+      {"SW128 K-major A / SW128 K-major B  N=32", {0, 0, 32, 0, 0, 1, reps, 2, 1, 0, 0}},
+      {"SW128 K-major A / SW128 K-major B  N=64", {0, 0, 64, 0, 0, 1, reps, 2, 1, 0, 0}},
+      {"SW128 K-major A / SW128 K-major B  N=96", {0, 0, 96, 0, 0, 1, reps, 2, 1, 0, 0}},
+      {"SW128 K-major A / SW128 K-major B  N=128", {0, 0, 128, 0, 0, 1, reps, 2, 1, 0, 0}},
+      {"SW128 K-major A / SW128 K-major B  N=256", {0, 0, 256, 0, 0, 1, reps, 2, 1, 0, 0}},
+      // ... M = 64 (half the A bytes per instruction) ...
+      {"K-major A / K-major B  M=64 N=32", {0, 0, 32, PK, PW, 1, reps, 1, 0, 0, 64}},
+      {"K-major A / K-major B  M=64 N=64", {0, 0, 64, PK, PW, 1, reps, 1, 0, 0, 64}},
+      {"K-major A / K-major B  M=64 N=256", {0, 0, 256, PK, 256 * 16, 1, reps, 1, 0, 0, 64}},
+      // ... and the A operand in tensor memory (.ts): no shared-memory read of A at all
+      {"A in TMEM / K-major B  N=32", {0, 0, 32, PK, PW, 1, reps, 1, 0, 1, 0}},
+      {"A in TMEM / K-major B  N=64", {0, 0, 64, PK, PW, 1, reps, 1, 0, 1, 0}},
+      {"A in TMEM / K-major B  N=96", {0, 0, 96, PK, PW, 1, reps, 1, 0, 1, 0}},
+      {"A in TMEM / K-major B  N=128", {0, 0, 128, PK, 128 * 16, 1, reps, 1, 0, 1, 0}},
+      {"A in TMEM / K-major B  N=256", {0, 0, 256, PK, 256 * 16, 1, reps, 1, 0, 1, 0}},
+      {"A in TMEM / SW128 K-major B  N=64", {0, 0, 64, 0, 0, 1, reps, 1, 1, 1, 0}},
+      {"A in TMEM / K-major B  M=64 N=64", {0, 0, 64, PK, PW, 1, reps, 1, 0, 1, 64}},
   };
   for (auto& c : cases) {
     probe_kernel<<<4, 128, 200 * 1024>>>(c.p, d);
