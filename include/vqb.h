@@ -268,6 +268,11 @@ int vqb_mse(const float* x, const float* r, int64_t n, float loss_scale, const f
  * p -= lr_t*m/(sqrt(v)+eps) */
 int vqb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
                   float eps, float grad_scale, const int64_t* step_counter, void* stream);
+/* The same step with the learning rate read from device memory (lr_dev[0], fp32) when the kernel runs: a captured CUDA
+ * graph then follows `optimizer.learning_rate = ...` / LearningRateSchedule objects (src/callback/vae_monitor.py trains
+ * with an lr scheduler) without re-capture. */
+int vqb_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float b1, float b2,
+                      float eps, float grad_scale, const int64_t* step_counter, void* stream);
 int vqb_increment(int64_t* counter, void* stream);
 
 #ifdef __cplusplus

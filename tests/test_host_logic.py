@@ -295,3 +295,69 @@ def test_block_weight_gradient_queue(cpu_backend):
     ops.resblock_wgrad(*t, *o, 1, 0)            # fp32: never queued
     assert not ops._wg_queue
     ops.reduce_flush()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# regressions for the round-1 review findings
+def test_evaluate_scores_every_batch_against_its_own_target(cpu_backend):
+    """The |STFT| of the target is cached per step, keyed on the tensor OBJECT (+ version): two different batches that happen
+    to live at the same address (a recycled allocator block on the GPU; one reused numpy buffer here) must not share it."""
+    V = cpu_backend
+    m, spec, weights, vq, x = build_tiny(V)
+    rng = np.random.default_rng(5)
+    x2 = rng.uniform(0, 1, size=x.shape).astype(np.float32)
+    want = []
+    for xb in (x, x2):
+        ref = O.forward_losses(spec, weights, vq, torch.tensor(xb))
+        want.append([float(ref[l]["spec_loss"]) for l in range(spec.levels)])
+    buf = torch.empty(x.shape, dtype=torch.float32)  # ONE buffer, filled with two batches in turn
+    got = []
+    for xb in (x, x2):
+        buf.copy_(torch.tensor(xb))
+        _, losses = m(buf, training=False)
+        got.append([float(s) for s in losses["spec_losses"]])
+    np.testing.assert_allclose(got, want, rtol=2e-4)
+    assert abs(got[0][0] - got[1][0]) > 1e-4  # the two batches really differ
+
+
+def test_adam_learning_rate_is_live_and_accepts_schedules(cpu_backend):
+    """`optimizer.learning_rate` is read at every update (it lives in a device scalar the kernel reads, so a captured
+    train_step follows it too), and may be a callable step -> lr (Keras LearningRateSchedule)."""
+    V = cpu_backend
+    K = V.keras
+    p0 = np.ones(8, np.float32)
+    g = np.full(8, 0.5, np.float32)
+
+    def run(lr, steps):
+        v = K.Variable(p0.copy(), name="p")
+        opt = K.optimizers.Adam(learning_rate=lr(0) if callable(lr) else lr)
+        opt.learning_rate = lr
+        out = []
+        for _ in range(steps):
+            opt.apply_gradients([(torch.tensor(g), v)])
+            out.append(v.numpy().copy())
+        return out, opt
+
+    const, _ = run(1e-2, 3)
+    sched, opt = run(lambda step: 1e-2 if step < 1 else 0.0, 3)
+    np.testing.assert_allclose(sched[0], const[0])
+    assert np.array_equal(sched[1], sched[0]) and np.array_equal(sched[2], sched[0])  # lr = 0 from the second update on
+    assert opt.iterations == 3 and opt._host_iterations == 3
+    # reassigning a plain number takes effect on the next update
+    v = K.Variable(p0.copy(), name="q")
+    opt = K.optimizers.Adam(learning_rate=1e-2)
+    opt.apply_gradients([(torch.tensor(g), v)])
+    a = v.numpy().copy()
+    opt.learning_rate = 0.0
+    opt.apply_gradients([(torch.tensor(g), v)])
+    assert np.array_equal(v.numpy(), a)
+
+
+def test_compile_drops_captured_graphs_and_step_flags_are_scoped(cpu_backend):
+    V = cpu_backend
+    m, spec, weights, vq, x = build_tiny(V)
+    m._graphs["stale"] = object()
+    m.compile(optimizer=V.keras.optimizers.Adam())
+    assert m._graphs == {}
+    m.train_step((x, None))
+    assert all(not q.defer_ema and not q.skip_metric_update for q in m.vqs)

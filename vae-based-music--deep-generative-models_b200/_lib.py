@@ -95,6 +95,7 @@ SIGNATURES = {
     "vqb_mse": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, _P, _P]),
+    "vqb_adam_step_dev": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
     "vqb_increment": (C.c_int, [_P, _P]),
 }
 

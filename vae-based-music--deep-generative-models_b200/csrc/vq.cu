@@ -393,11 +393,13 @@ __global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ x, c
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                   float* __restrict__ v, long n, float lr, float b1, float b2, float eps,
+                                                   float* __restrict__ v, long n, float lr, const float* __restrict__ lr_dev,
+                                                   float b1, float b2, float eps,
                                                    float gs, const int64_t* __restrict__ step) {
   __shared__ float lr_s;
   if (threadIdx.x == 0) {
     const double t = (double)(step[0] + 1);
+    if (lr_dev) lr = lr_dev[0];  // learning rate kept in device memory: survives CUDA-graph capture, follows schedules
     lr_s = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
   }
   __syncthreads();
@@ -590,7 +592,19 @@ int vqb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
   if (n == 0) return VQB_OK;
   int nb = cdiv(n, 256);
   if (nb > 148 * 16) nb = 148 * 16;
-  adam_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps, grad_scale, step_counter);
+  adam_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, nullptr, b1, b2, eps, grad_scale, step_counter);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+int vqb_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float b1, float b2,
+                      float eps, float grad_scale, const int64_t* step_counter, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(p && g && m && v && lr_dev && step_counter && n >= 0, "vqb_adam_step_dev: bad argument");
+  if (n == 0) return VQB_OK;
+  int nb = cdiv(n, 256);
+  if (nb > 148 * 16) nb = 148 * 16;
+  adam_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, lr_dev, b1, b2, eps, grad_scale, step_counter);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

@@ -885,8 +885,13 @@ class Adam:
     variables are slices of one packed buffer, otherwise one kernel per variable."""
 
     def __init__(self, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, name="Adam"):
+        # learning_rate: a number, or a callable step -> number (keras LearningRateSchedule, e.g. the reference's CustomSchedule,
+        # src/transformer/multi_head_attention.py:82); may be reassigned at any time, also after train_step was captured
         self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
         self._iterations = None
+        self._host_iterations = 0  # mirror of the device counter (no synchronisation needed to evaluate a schedule)
+        self._lr_dev = None        # the learning rate the kernels read: one fp32 in device memory
+        self._lr_host = None       # the value last written to it
         self._slots = {}
         self.grad_scale = 1.0  # 1/world_size under data parallelism (gradients arrive summed)
 
@@ -899,16 +904,46 @@ class Adam:
             self._iterations = ops.zeros(1, dtype=torch.int64)
         return self._iterations
 
+    def current_lr(self):
+        """learning rate of the NEXT update (schedules are evaluated at the number of updates applied so far, as Keras does)"""
+        lr = self.learning_rate
+        return float(lr(self._host_iterations)) if callable(lr) else float(lr)
+
+    def refresh_lr(self):
+        """Writes current_lr() into the device scalar the Adam kernel reads.  Called before every update — eager ones and
+        replays of a captured train_step alike (the copy itself is never part of a capture)."""
+        if self._lr_dev is None:
+            self._lr_dev = ops.zeros(1)
+        lr = self.current_lr()
+        if self._lr_host != lr:
+            self._lr_dev.fill_(lr)
+            self._lr_host = lr
+        return self._lr_dev
+
+    def step_done(self):
+        """bookkeeping of one applied update whose kernels ran from a CUDA-graph replay"""
+        self._host_iterations += 1
+
     def _slot(self, key, like):
         if key not in self._slots:
             self._slots[key] = (torch.zeros_like(like), torch.zeros_like(like))
         return self._slots[key]
 
+    def _lr_for_launch(self):
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        if capturing:  # the replay path refreshes the scalar before every replay
+            if self._lr_dev is None:
+                raise RuntimeError("Adam: refresh_lr() must run once before the update is captured into a CUDA graph")
+            return self._lr_dev
+        return self.refresh_lr()
+
     def apply_flat(self, params, grads):
         m, v = self._slot(("flat", params.data_ptr()), params)
-        ops.adam_step(params, grads, m, v, self.learning_rate, self.beta_1, self.beta_2, self.epsilon,
-                      self.grad_scale, self._counter())
+        ops.adam_step_dev(params, grads, m, v, self._lr_for_launch(), self.beta_1, self.beta_2, self.epsilon,
+                          self.grad_scale, self._counter())
         ops.increment(self._counter())
+        if not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
+            self._host_iterations += 1
 
     def apply_gradients(self, grads_and_vars):
         gv = [(g, v) for g, v in grads_and_vars if g is not None]
@@ -921,11 +956,14 @@ class Adam:
                 v is pv and g is v.grad for (g, v), pv in zip(gv, packed.vars)):
             self.apply_flat(packed.params, packed.grads)
             return
+        lr_dev = self._lr_for_launch()
         for g, v in gv:
             m, s = self._slot(id(v), v.value)
-            ops.adam_step(v.value, g.contiguous(), m, s, self.learning_rate, self.beta_1, self.beta_2, self.epsilon,
-                          self.grad_scale, self._counter())
+            ops.adam_step_dev(v.value, g.contiguous(), m, s, lr_dev, self.beta_1, self.beta_2, self.epsilon,
+                              self.grad_scale, self._counter())
         ops.increment(self._counter())
+        if not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
+            self._host_iterations += 1
 
 
 class Packed:

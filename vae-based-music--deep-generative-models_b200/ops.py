@@ -367,6 +367,12 @@ def adam_step(p, g, m, v, lr, b1, b2, eps, grad_scale, step_counter):
          float(grad_scale), ptr(step_counter), _lib.stream())
 
 
+def adam_step_dev(p, g, m, v, lr_dev, b1, b2, eps, grad_scale, step_counter):
+    """adam_step with the learning rate in a one-element device tensor (read when the kernel runs)."""
+    call("vqb_adam_step_dev", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(lr_dev), float(b1), float(b2), float(eps),
+         float(grad_scale), ptr(step_counter), _lib.stream())
+
+
 def increment(counter):
     call("vqb_increment", ptr(counter), _lib.stream())
 

@@ -18,6 +18,7 @@ What is different underneath:
 """
 from __future__ import annotations
 
+import contextlib
 from itertools import chain
 
 import numpy as np
@@ -117,6 +118,12 @@ class VQVAE(Model):
         self._graphs = {}
         return self
 
+    def compile(self, optimizer=None, **kw):
+        """vqvae.py:362.  A captured train_step has the optimizer's slot / counter / learning-rate buffers baked in by address:
+        a new optimizer invalidates the captures (the learning rate itself lives in device memory and may change freely)."""
+        super(VQVAE, self).compile(optimizer=optimizer, **kw)
+        self._graphs = {}
+
     def _all_trackers(self):
         return self.metrics + list(chain.from_iterable(vq.metrics for vq in self.vqs))
 
@@ -199,15 +206,31 @@ class VQVAE(Model):
             vq.defer_ema = world > 1
             vq.shard = (world, vdist.rank())
         self.optimizer.grad_scale = 1.0 / world
-        if self.use_cuda_graph and _lib.device().type == "cuda":
-            return self._graph_train_step(raw)
-        x = convert_to_tensor(raw)
-        grads, tvars, losses = self._forward_backward(x)
-        losses = self._exchange(losses, world)
+        try:
+            if self.use_cuda_graph and _lib.device().type == "cuda":
+                return self._graph_train_step(raw)
+            x = convert_to_tensor(raw)
+            grads, tvars, losses = self._forward_backward(x)
+            losses = self._exchange(losses, world)
+            for vq in self.vqs:
+                vq.apply_ema()
+            self.optimizer.apply_gradients(zip(grads, tvars))
+            return self.update_metrics(*losses)
+        finally:
+            for vq in self.vqs:  # a later direct call (`model(x, training=True)`, `vq(x)`) applies its own EMA again
+                vq.defer_ema = False
+
+    @contextlib.contextmanager
+    def _vq_metrics_in_step_vector(self):
+        """Inside the graph path the VQ usage / entropy metrics travel in the step vector (`_step_vector`), so the layers must
+        not also update their trackers one by one — for the duration of that step only."""
         for vq in self.vqs:
-            vq.apply_ema()
-        self.optimizer.apply_gradients(zip(grads, tvars))
-        return self.update_metrics(*losses)
+            vq.skip_metric_update = True
+        try:
+            yield
+        finally:
+            for vq in self.vqs:
+                vq.skip_metric_update = False
 
     def _exchange(self, losses, world):
         """Data parallelism: ONE all-reduce of [gradients | EMA statistics + restart rows | loss scalars]."""
@@ -233,12 +256,12 @@ class VQVAE(Model):
                  *level_losses, *recon_losses, *commit_losses, *spectral_losses]
         vec = [p.tensor().reshape(1) for p in parts]
         for vq in self.vqs:
-            vec.append(vq._metrics_buf if vq._metrics_buf is not None else ops.zeros(3))
+            vec.append(vq._metrics_buf if (vq._metrics_buf is not None and self.train_step_training) else ops.zeros(3))
         return torch.cat(vec)
 
     def _graph_train_step(self, raw):
         key = (tuple(raw.shape), vdist.world_size(), self.train_step_training, self.spectral_weight,
-               getattr(self, "precision", "fp32"), self.use_level_streams)
+               getattr(self, "precision", "fp32"), self.use_level_streams, id(self.optimizer))
         st = self._graphs.get(key)
         world = vdist.world_size()
         if st is not None:
@@ -249,50 +272,58 @@ class VQVAE(Model):
             x = convert_to_tensor(raw)
             # first step for this shape: run it eagerly (it is a real training step and doubles as warm-up)
             self._graphs[key] = {"graph": None, "x": x.clone()}
-            for vq in self.vqs:
-                vq.skip_metric_update = True
-            grads, tvars, losses = self._forward_backward(x)
-            losses = self._exchange(losses, world)
-            for vq in self.vqs:
-                vq.apply_ema()
-            self.optimizer.apply_gradients(zip(grads, tvars))
-            vec = self._step_vector(losses)
-            return self._accumulate(vec)
-        if st["graph"] is None:
-            torch.cuda.synchronize()
-            pool = torch.cuda.graph_pool_handle()
-            ga = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga, pool=pool):
-                grads, tvars, losses = self._forward_backward(st["x"])
-                if world > 1:
-                    level_losses, recon_losses, commit_losses, spectral_losses = losses
-                    self._comm_scalars.copy_(torch.cat(
-                        [s.tensor().reshape(1) for s in (*recon_losses, *commit_losses, *spectral_losses)]))
-            st["ga"] = ga
-            gb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gb, pool=pool):
-                if world > 1:
-                    L = self.levels
-                    sc = self._comm_scalars / world
-                    rec = [Scalar.leaf(sc[i:i + 1]) for i in range(L)]
-                    com = [Scalar.leaf(sc[L + i:L + i + 1]) for i in range(L)]
-                    spe = [Scalar.leaf(sc[2 * L + i:2 * L + i + 1]) for i in range(L)]
-                    losses = ([rec[i] + com[i] + spe[i] for i in range(L)], rec, com, spe)
+            with self._vq_metrics_in_step_vector():
+                grads, tvars, losses = self._forward_backward(x)
+                losses = self._exchange(losses, world)
                 for vq in self.vqs:
                     vq.apply_ema()
                 self.optimizer.apply_gradients(zip(grads, tvars))
-                st["vec"] = self._step_vector(losses)
-            st["gb"] = gb
-            st["graph"] = True
+                vec = self._step_vector(losses)
+            return self._accumulate(vec)
+        if st["graph"] is None:
+            with self._vq_metrics_in_step_vector():
+                self._capture(st, world)
+        self.optimizer.refresh_lr()  # the captured Adam kernel reads the learning rate from device memory
         st["ga"].replay()
         if world > 1:
             vdist.all_reduce_sum(self._packed.comm)
         st["gb"].replay()
+        self.optimizer.step_done()
         return self._accumulate(st["vec"])
+
+    def _capture(self, st, world):
+        """Captures graph A (forward + backward of every level) and graph B (EMA + Adam + metric vector) for st["x"]."""
+        torch.cuda.synchronize()
+        self.optimizer.refresh_lr()
+        pool = torch.cuda.graph_pool_handle()
+        ga = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga, pool=pool):
+            grads, tvars, losses = self._forward_backward(st["x"])
+            if world > 1:
+                level_losses, recon_losses, commit_losses, spectral_losses = losses
+                self._comm_scalars.copy_(torch.cat(
+                    [s.tensor().reshape(1) for s in (*recon_losses, *commit_losses, *spectral_losses)]))
+        st["ga"] = ga
+        gb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gb, pool=pool):
+            if world > 1:
+                L = self.levels
+                sc = self._comm_scalars / world
+                rec = [Scalar.leaf(sc[i:i + 1]) for i in range(L)]
+                com = [Scalar.leaf(sc[L + i:L + i + 1]) for i in range(L)]
+                spe = [Scalar.leaf(sc[2 * L + i:2 * L + i + 1]) for i in range(L)]
+                losses = ([rec[i] + com[i] + spe[i] for i in range(L)], rec, com, spe)
+            for vq in self.vqs:
+                vq.apply_ema()
+            self.optimizer.apply_gradients(zip(grads, tvars))
+            st["vec"] = self._step_vector(losses)
+        st["gb"] = gb
+        st["graph"] = True
 
     def _accumulate(self, vec):
         self._metric_totals += vec
-        for m in self._all_trackers():
+        ema_ran = bool(self.train_step_training)  # the VQ usage / entropy entries of `vec` are fresh only after an EMA update
+        for m in (self._all_trackers() if ema_ran else self.metrics):
             m._count += 1
         return self._metric_dict()
 
