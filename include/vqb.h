@@ -141,6 +141,39 @@ int vqb_resblock_fwd_masks(const vqb_resblock_desc* d, const float* x, const flo
 int vqb_resblock_bwd_data_masks(const vqb_resblock_desc* d, const uint32_t* xbits, const uint32_t* hbits, const float* dy,
                                 const float* w1, const float* w2, float* dh, float* dx, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused DilatedResnet1D  (replaces DilatedResnet1D.call, resnet.py:40-59: a Sequential of n ResnetConv1DBlocks whose first
+ * convolutions have dilations[0..n-1], in execution order — growing for encoders, reversed for decoders, resnet.py:44-55)
+ * as ONE launch: the input tile is fetched by TMA, all 2n convolutions run on the tensor cores with the activation staying
+ * in shared / tensor memory, only what the caller asks for goes back to HBM (TMA stores).
+ *   vqb_resstack_fwd       y[n-1] = stack(x).  Inference: h = xbits = hbits = NULL and y[i < n-1] = NULL: 256 bytes per
+ *                          position for the WHOLE stack.  Under a tape: h[i] (first convolution's output of block i), y[i]
+ *                          (block outputs = inputs of the next block) and the sign masks xbits[i] / hbits[i] (as
+ *                          vqb_resblock_fwd_masks) are all written — the operands of the weight gradients and of
+ *                          vqb_resstack_bwd_data.
+ *   vqb_resstack_bwd_data  given dy = gradient at y[n-1]: dx[i] = gradient at the input of block i, dh[i] = gradient at the
+ *                          output of block i's first convolution (both needed by vqb_resblock_wgrad_batch), blocks n-1 .. 0
+ *                          chained on chip.
+ * vqb_resstack_supports: 1 when the fused kernel exists for (C, n_blocks, dilations, precision) — C = 32, n <= 4,
+ * dilations <= 32, VQB_PREC_FP16X2 — else 0 and callers compose vqb_resblock_* (the functions below return
+ * VQB_ERR_UNIMPLEMENTED).  The workspace holds the packed operand images of the 2n weight tensors.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define VQB_RESSTACK_MAX_BLOCKS 4
+typedef struct vqb_resstack_desc {
+  int32_t B, L, C;
+  int32_t n_blocks;
+  int32_t dilations[VQB_RESSTACK_MAX_BLOCKS];
+  int32_t precision;
+} vqb_resstack_desc;
+int vqb_resstack_supports(const vqb_resstack_desc* d);
+size_t vqb_resstack_workspace_bytes(const vqb_resstack_desc* d);
+int vqb_resstack_fwd(const vqb_resstack_desc* d, const float* x, const float* const* w1, const float* const* b1,
+                     const float* const* w2, const float* const* b2, float* const* h, float* const* y,
+                     uint32_t* const* xbits, uint32_t* const* hbits, void* workspace, size_t workspace_bytes, void* stream);
+int vqb_resstack_bwd_data(const vqb_resstack_desc* d, const float* dy, const float* const* w1, const float* const* w2,
+                          const uint32_t* const* xbits, const uint32_t* const* hbits, float* const* dh, float* const* dx,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Both weight gradients of the block in one call (tensor-core precisions: one launch):
  *   dw1[3, C, F] = sum ReLU(x)[t + (j-1) dilation] dh[t],  db1[F] = sum dh   (dilated conv, resnet.py:13-15)
  *   dw2[3, F, C] = sum ReLU(h)[t + (j-1)] dy[t],           db2[C] = sum dy   (second conv, resnet.py:17)

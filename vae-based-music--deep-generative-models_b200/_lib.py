@@ -32,6 +32,11 @@ class ResblockDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "L", "C", "F", "dilation", "precision")]
 
 
+class ResstackDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("n_blocks", C.c_int32),
+                ("dilations", C.c_int32 * 4), ("precision", C.c_int32)]
+
+
 class VQDesc(C.Structure):
     _fields_ = [("N", C.c_int64), ("D", C.c_int32), ("K", C.c_int32), ("beta", C.c_float),
                 ("precision", C.c_int32)]
@@ -45,6 +50,7 @@ TAIL_GBUF = 272  # VQB_TAIL_GBUF
 
 _P = C.c_void_p
 _CD, _RD, _VD, _TD = C.POINTER(ConvDesc), C.POINTER(ResblockDesc), C.POINTER(VQDesc), C.POINTER(TailDesc)
+_SD = C.POINTER(ResstackDesc)
 
 # name -> (restype, argtypes); mirrors include/vqb.h one to one
 SIGNATURES = {
@@ -73,6 +79,10 @@ SIGNATURES = {
     "vqb_resblock_wgrad": (C.c_int, [_RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_resblock_wgrad_batch_workspace_bytes": (C.c_size_t, [_RD, C.c_int32]),
     "vqb_resblock_wgrad_batch": (C.c_int, [_RD, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vqb_resstack_supports": (C.c_int, [_SD]),
+    "vqb_resstack_workspace_bytes": (C.c_size_t, [_SD]),
+    "vqb_resstack_fwd": (C.c_int, [_SD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vqb_resstack_bwd_data": (C.c_int, [_SD, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_dec_tail_supports": (C.c_int, [_TD]),
     "vqb_dec_tail_fwd": (C.c_int, [_TD, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vqb_dec_tail_bwd_workspace_bytes": (C.c_size_t, [_TD]),

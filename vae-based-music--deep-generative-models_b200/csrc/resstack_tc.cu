@@ -1,0 +1,586 @@
+// resstack_tc.cu — a whole DilatedResnet1D (resnet.py:40-59: up to 4 pre-activation residual blocks = 8 k=3 32->32
+// convolutions) and its data-gradient chain as ONE persistent, warp-specialised tcgen05 kernel.
+//
+//   per tile of R = 384 time rows (3 M blocks of 128) of one batch item, halo H = sum(dilation_i + 1) rows per side:
+//     producer warp : TMA-loads the raw fp32 [R, 32] input rows (3-D tensor map, rows outside [0, L) arrive as zeros = the
+//                     SAME padding) and, per convolution, the pre-packed fp16x2 operand image of its weights (bulk copy)
+//     issuer warp   : per convolution and M block 12 tcgen05.mma (3 taps = the SAME operand tile addressed with a row shift of
+//                     (tap-1)*dilation, 2 K steps, 2 piece instructions N = 64 + N = 32), accumulators in tensor memory
+//     12 epilogue warps (thread = tile row = TMEM lane, all 32 channels): TMEM -> registers, scale / bias / sign mask /
+//                     residual (kept in registers across the whole stack), -> the next convolution's operand rows in
+//                     shared memory (ReLU, power-of-two scale, fp16 hi / lo split), and — only where the caller wants a
+//                     tensor back — a swizzled row image that leaves through a TMA store
+//   hand-offs are mbarriers per M block: the MMAs of convolution k+1 on block mb start as soon as the epilogues of blocks
+//   mb-1 .. mb+1 of convolution k are through, so the tensor pipe works on one M block while the epilogue warps of the others
+//   convert; operand tiles ping-pong between two buffers (X, Y); the raw input of the NEXT tile lands in Y while the last
+//   epilogue of the current one runs.
+//
+// Arithmetic = the fp16x2 mode of resblock_tc.cu (operands scaled by a power of two and split into two fp16 pieces, three
+// piece products, fp32 accumulation).  Operand scales: exact maximum of the tile input (one reduction per tile), then for every
+// convolution the bound  L1(W) * max|input| (+ max|residual|) + max|bias|  with max|input| the EXACT maximum of the previous
+// convolution's output (published through shared memory by its epilogues, complete by the time it is needed because the
+// epilogue of convolution k waits for all epilogues of k-1, which finish under the MMAs of k anyway).
+//
+// Three instantiations: KIND 0 inference forward (stores y only: 256 B per position for the whole stack), KIND 1 training
+// forward (stores h_i, y_i and both sign masks per block), KIND 2 data gradient (masks from the sign words, stores dh_i, dx_i).
+#include <string.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+#include "tma.cuh"
+
+namespace vqb {
+
+using namespace tc;
+
+constexpr int RS_MAXC = 2 * VQB_RESSTACK_MAX_BLOCKS;  // convolutions per launch
+
+struct RsCfg {
+  static constexpr int MB = 3, R = 128 * MB, G = 32;
+  static constexpr int NP = 4;                          // 16-byte planes (8 fp16 channels each) per piece
+  static constexpr int PLANE = (R + 2 * G) * 16 + 32;   // bytes; +32 de-aliases the planes' banks
+  static constexpr int TILE = NP * PLANE;               // one piece of an operand tile
+  static constexpr int OPB = 2 * TILE;                  // operand buffer: hi piece, lo piece
+  static constexpr int NW = 64, WPLANE = NW * 16, WTAP = NP * WPLANE, WCONV = 3 * WTAP;  // weight image: [tap][plane][hi 32 | lo 32 rows][16 B]
+  static constexpr int META = 36;                       // floats per convolution: weight scale, L1 bound, max|bias|, -, bias[32]
+  static constexpr int WREC = WCONV + 256;              // packed record in global memory: image + META floats (padded)
+  static constexpr int IMG = 128 * 128;                 // one M block of fp32 rows
+  static constexpr int OFF_Y = 0;
+  static constexpr int OFF_OUT = ((OPB + 1023) / 1024) * 1024;
+  static constexpr int OFF_X = OFF_OUT + MB * IMG;
+  static constexpr int OFF_W = OFF_X + OPB;
+  static constexpr int OFF_META = OFF_W + 2 * WCONV;
+  static constexpr int OFF_AMAX = OFF_META + RS_MAXC * META * 4;
+  static constexpr int OFF_BAR = OFF_AMAX + 2 * 16 * 4;
+  static constexpr int NBAR = 3 * MB + 8;
+  static constexpr int OFF_TSLOT = OFF_BAR + NBAR * 8;
+  static constexpr int SMEM = OFF_TSLOT + 16 + 1024;    // + slack for the 1024-byte alignment of the base
+  static constexpr int NEPI = 4 * MB;                   // epilogue warps
+  static constexpr int NT = (NEPI + 2) * 32;            // + issuer warp + producer warp
+  static constexpr int TCOLS = 256;                     // MB * NW = 192 accumulator columns
+  static_assert(OFF_X % 16 == 0 && OFF_W % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
+  static_assert(SMEM <= 232448, "shared memory");
+};
+
+struct RsParams {
+  const uint8_t* wpack;                // nconv records of RsCfg::WREC bytes (rs_pack_kernel)
+  int B, L, nconv, H, Rout, tiles_x, total_tiles;
+  int dil[RS_MAXC];
+  int store[RS_MAXC];                  // 1: the output of convolution k is stored (tensor maps out[k][*])
+  uint32_t* bits_in0;                  // KIND 1: sign mask of the chain input
+  uint32_t* bits_out[RS_MAXC];         // KIND 1: sign mask of the output of convolution k (or NULL)
+  const uint32_t* bits_mask[RS_MAXC];  // KIND 2: sign mask applied to the output of convolution k
+};
+struct RsMaps {
+  CUtensorMap in;                      // box {32, 128, 1}
+  CUtensorMap out[RS_MAXC][2];         // [k][0]: box of 128 - H rows (first / last M block), [k][1]: 128 rows (middle)
+};
+
+struct RsPackParams {
+  const float* w[RS_MAXC];
+  const float* bias[RS_MAXC];
+  int sj[RS_MAXC], si[RS_MAXC], so[RS_MAXC], flip[RS_MAXC];
+  uint8_t* out;
+};
+
+// One block per convolution: element (tap j, in-channel k, out-channel n) at w[jj*sj + k*si + n*so] (jj = flip ? 2-j : j) ->
+// fp16 hi / lo pieces of w * 2^s in the operand image, plus the numbers the epilogues need: the scale, the exact worst-case
+// gain  max_n sum_{j,k} |w|  (L1 bound) and the bias.
+__global__ void __launch_bounds__(256) rs_pack_kernel(const RsPackParams p) {
+  const int c = blockIdx.x, tid = threadIdx.x;
+  __shared__ float l1p[8][32];
+  __shared__ uint32_t mx;
+  if (tid == 0) mx = 0u;
+  __syncthreads();
+  float wv[12];
+  uint32_t m = 0u;
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    const int e = tid + q * 256, n = e & 31, k = (e >> 5) & 31, j = e >> 10;
+    wv[q] = p.w[c][(size_t)(p.flip[c] ? 2 - j : j) * p.sj[c] + (size_t)k * p.si[c] + (size_t)n * p.so[c]];
+    m = max(m, absbits(wv[q]));
+  }
+  // L1 norms per output channel n = lane (all 12 elements of a thread share n): per-warp partials, summed in fixed order
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < 12; ++q) s += fabsf(wv[q]);
+  l1p[tid >> 5][tid & 31] = s;
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((tid & 31) == 0) atomicMax(&mx, m);
+  __syncthreads();
+  const float sw = pow2_scale(__uint_as_float(mx));
+  uint8_t* img = p.out + (size_t)c * RsCfg::WREC;
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    const int e = tid + q * 256, n = e & 31, k = (e >> 5) & 31, j = e >> 10;
+    uint8_t* a = img + j * RsCfg::WTAP + (k >> 3) * RsCfg::WPLANE + n * 16 + (k & 7) * 2;
+    const __half hi = __float2half_rn(wv[q] * sw);
+    const __half lo = __float2half_rn(wv[q] * sw - __half2float(hi));
+    *reinterpret_cast<__half*>(a) = hi;
+    *reinterpret_cast<__half*>(a + 32 * 16) = lo;
+  }
+  float* meta = reinterpret_cast<float*>(img + RsCfg::WCONV);
+  if (tid < 32) {
+    float l = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) l += l1p[w][tid];
+    l = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, 16)); l = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, 8));
+    l = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, 4)); l = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, 2));
+    l = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, 1));
+    const float b = p.bias[c] ? p.bias[c][tid] : 0.f;
+    uint32_t bm = __reduce_max_sync(0xffffffffu, absbits(b));
+    meta[4 + tid] = b;
+    if (tid == 0) { meta[0] = sw; meta[1] = l * 1.0001f; meta[2] = __uint_as_float(bm); meta[3] = 0.f; }
+  }
+}
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_rows_l2(const CUtensorMap* tm, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(0), "r"(c1), "r"(c2) : "memory");
+}
+// 16 fp32 columns of this thread's TMEM lane, without the wait (tmem_ld_wait() below covers any number of them)
+__device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 12 MMAs of one convolution on one M block: taps x K steps x (hi-activation x [W_hi | W_lo], lo-activation x W_hi)
+__device__ __forceinline__ void rs_issue(uint32_t tacc, uint32_t a_base, int row0, int dil, uint32_t w_base) {
+  const uint64_t ad0 = smem_desc(a_base + (uint32_t)row0 * 16u, RsCfg::PLANE, 128);  // row0 = first row of tap 0
+  const uint64_t bd0 = smem_desc(w_base, RsCfg::WPLANE, 128);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+      for (int sa = 0; sa < 2; ++sa) {
+        const uint32_t idesc = instr_desc(FMT_F16, 128, 32 * (2 - sa), false, false);
+        const uint64_t bd = bd0 + (uint64_t)((j * RsCfg::WTAP + kk * 2 * RsCfg::WPLANE) >> 4);
+        const uint64_t ad = ad0 + (uint64_t)((sa * RsCfg::TILE + kk * 2 * RsCfg::PLANE) >> 4) + (uint64_t)(j * dil);
+        mma<false>(tacc, ad, bd, idesc, acc);
+        acc = 1;
+      }
+}
+
+// 8 channels o*8 .. o*8+7 of operand row `prow` (physical row, guard rows included): hi and lo chunk
+__device__ __forceinline__ void rs_stage8(uint8_t* op, int prow, int o, const float* v, float scale) {
+  uint4 pc[2];
+  split8_f16(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), scale, pc);
+  *reinterpret_cast<uint4*>(op + o * RsCfg::PLANE + prow * 16) = pc[0];
+  *reinterpret_cast<uint4*>(op + RsCfg::TILE + o * RsCfg::PLANE + prow * 16) = pc[1];
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(RsCfg::NT, 1) rs_kernel(const RsParams p, const __grid_constant__ RsMaps maps) {
+  using Cfg = RsCfg;
+  constexpr bool FWD = KIND != 2;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* Y = smem + Cfg::OFF_Y;      // operand buffer 1 (odd convolutions read it); also receives the raw fp32 input tile
+  uint8_t* OUT = smem + Cfg::OFF_OUT;  // MB swizzled row images for the TMA stores
+  uint8_t* X = smem + Cfg::OFF_X;      // operand buffer 0
+  uint8_t* W = smem + Cfg::OFF_W;      // two weight slots
+  float* meta = reinterpret_cast<float*>(smem + Cfg::OFF_META);
+  uint32_t* amax = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_AMAX);  // [2][16]: per tile parity, [k] = max |input of convolution k|
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* mma_done = bars;               // [MB]  accumulators of (k, mb) complete
+  uint64_t* ready = bars + Cfg::MB;        // [MB]  operand rows of M block mb written (and its accumulator drained)
+  uint64_t* w_full = bars + 2 * Cfg::MB;   // [2]
+  uint64_t* w_empty = w_full + 2;          // [2]
+  uint64_t* allepi = w_empty + 2;          // every epilogue warp is through a phase
+  uint64_t* in_full = allepi + 1;
+  uint64_t* y_empty = in_full + 1;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_TSLOT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nconv = p.nconv, L = p.L;
+
+  if (warp == 0) tmem_alloc(tslot, Cfg::TCOLS);
+  if (tid == 32) {
+    for (int i = 0; i < Cfg::MB; ++i) { mbar_init(&mma_done[i], 1); mbar_init(&ready[i], 4); }
+    mbar_init(&w_full[0], 1); mbar_init(&w_full[1], 1); mbar_init(&w_empty[0], 1); mbar_init(&w_empty[1], 1);
+    mbar_init(allepi, Cfg::NEPI); mbar_init(in_full, 1); mbar_init(y_empty, 1);
+    fence_mbar_init();
+  }
+  // operand buffer X: zero once (its guard rows are never written again); Y's guard rows are re-zeroed per tile, because the
+  // raw input tile passes through Y
+  for (int e = tid; e < Cfg::OPB / 16; e += Cfg::NT) reinterpret_cast<uint4*>(X)[e] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 32) amax[tid] = 0u;
+  pdl_launch_dependents();
+  pdl_wait();  // the packed weights come from the kernel in front of this one
+  for (int e = tid; e < nconv * Cfg::META; e += Cfg::NT)
+    meta[e] = reinterpret_cast<const float*>(p.wpack + (size_t)(e / Cfg::META) * Cfg::WREC + Cfg::WCONV)[e % Cfg::META];
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tslot;
+
+  if (warp == Cfg::NEPI + 1) {
+    // ------------------------------------------------------------------------------------------- producer
+    if (elect_one()) {
+      uint32_t wuse[2] = {0u, 0u};
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+        const int b = tile / p.tiles_x;
+        const int g0 = (tile - b * p.tiles_x) * p.Rout - p.H;
+        if (ti > 0) mbar_wait(y_empty, (uint32_t)(ti - 1) & 1u);  // the last convolution of the previous tile has read Y
+        tma::expect_tx(in_full, Cfg::R * 128);
+#pragma unroll
+        for (int j = 0; j < Cfg::MB; ++j) tma::load_rows(&maps.in, Y + j * Cfg::IMG, in_full, g0 + j * 128, b);
+        const int next = tile + gridDim.x;
+        if (next < p.total_tiles) {  // the next tile's rows: into L2 now, so that its load is short when its turn comes
+          const int nb = next / p.tiles_x;
+          const int ng0 = (next - nb * p.tiles_x) * p.Rout - p.H;
+#pragma unroll
+          for (int j = 0; j < Cfg::MB; ++j) prefetch_rows_l2(&maps.in, ng0 + j * 128, nb);
+        }
+        for (int k = 0; k < nconv; ++k) {
+          const int s = k & 1;
+          if (wuse[s] > 0) mbar_wait(&w_empty[s], (wuse[s] - 1u) & 1u);
+          tma::expect_tx(&w_full[s], Cfg::WCONV);
+          bulk_g2s(W + s * Cfg::WCONV, p.wpack + (size_t)k * Cfg::WREC, Cfg::WCONV, &w_full[s]);
+          ++wuse[s];
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == Cfg::NEPI) {
+    // --------------------------------------------------------------------------------------------- issuer
+    if (elect_one()) {
+      uint32_t rdy[Cfg::MB], wf[2] = {0u, 0u};
+#pragma unroll
+      for (int i = 0; i < Cfg::MB; ++i) rdy[i] = 0u;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int k = 0; k < nconv; ++k) {
+          const int s = k & 1;
+          mbar_wait(&w_full[s], wf[s] & 1u); ++wf[s];
+          const uint32_t a_base = smem_u32(s ? Y : X);
+          const int dil = p.dil[k];
+#pragma unroll
+          for (int mb = 0; mb < Cfg::MB; ++mb) {
+            // rows mb*128 - dil .. mb*128 + 127 + dil of the operand: M blocks mb-1, mb, mb+1 (waited for in order)
+            if (mb == 0) {
+              mbar_wait(&ready[0], rdy[0] & 1u); ++rdy[0];
+              if (Cfg::MB > 1) { mbar_wait(&ready[1], rdy[1] & 1u); ++rdy[1]; }
+            } else if (mb + 1 < Cfg::MB) {
+              mbar_wait(&ready[mb + 1], rdy[mb + 1] & 1u); ++rdy[mb + 1];
+            }
+            fence_after_sync();
+            rs_issue(tmem + mb * Cfg::NW, a_base, Cfg::G + mb * 128 - dil, dil, smem_u32(W + s * Cfg::WCONV));
+            commit(&mma_done[mb]);
+          }
+          commit(&w_empty[s]);
+          if (k == nconv - 1) commit(y_empty);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------------------------------ epilogues
+    const int mb = warp >> 2, qd = warp & 3;
+    const int r = warp * 32 + lane;  // tile row = TMEM lane (mb * 128 + qd * 32 + lane)
+    const uint32_t taddr = tmem + (((uint32_t)qd * 32u) << 16) + (uint32_t)(mb * Cfg::NW);
+    // rows of this M block that belong to the tile's output: [lo, hi); image row j = r - lo
+    const int lo = max(mb * 128, p.H), hi = min(mb * 128 + 128, Cfg::R - p.H);
+    const bool own = r >= lo && r < hi;
+    const int jrow = r - lo;
+    uint8_t* img = OUT + mb * Cfg::IMG;
+    const bool leader = qd == 0 && lane == 0;  // issues this M block's TMA stores (bulk groups are per thread)
+    const int mapsel = (mb == 0 || mb == Cfg::MB - 1) ? 0 : 1;
+    uint32_t md = 0u, ae = 0u;
+    float res[32];
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      const int par = ti & 1;
+      uint32_t* am = amax + par * 16;
+      const int b = tile / p.tiles_x;
+      const int g0 = (tile - b * p.tiles_x) * p.Rout - p.H;
+      const int g = g0 + r;
+      const bool inrange = g >= 0 && g < L;
+      const size_t grow = (size_t)b * L + (size_t)(inrange ? g : 0);
+      // ---- input phase: raw fp32 row -> residual registers, tile maximum, first operand
+      mbar_wait(in_full, (uint32_t)ti & 1u);
+      {
+        const uint8_t* raw = Y + (r >> 7) * Cfg::IMG;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 f = *reinterpret_cast<const float4*>(raw + tma::swz(r & 127, c));
+          res[4 * c] = f.x; res[4 * c + 1] = f.y; res[4 * c + 2] = f.z; res[4 * c + 3] = f.w;
+        }
+      }
+      uint32_t m = 0u;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) m = max(m, absbits(res[c]));
+      m = __reduce_max_sync(0xffffffffu, m);
+      if (lane == 0) atomicMax(&am[0], m);
+      if (KIND == 1 && p.bits_in0 && own && inrange) {
+        uint32_t w = 0u;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) w |= (uint32_t)(res[c] > 0.f) << c;
+        p.bits_in0[grow] = w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(allepi);
+      mbar_wait(allepi, ae & 1u); ++ae;
+      if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) amax[(par ^ 1) * 16 + i] = 0u;  // the other parity: next tile
+      }
+      // Y's guard rows (overwritten by the raw tile): 2 * G rows x 8 chunk columns
+      for (int e = tid; e < 2 * Cfg::G * 8; e += Cfg::NEPI * 32) {
+        const int q = e / (2 * Cfg::G), gr = e % (2 * Cfg::G);
+        const int prow = gr < Cfg::G ? gr : Cfg::R + gr;
+        *reinterpret_cast<uint4*>(Y + (q >> 2) * Cfg::TILE + (q & 3) * Cfg::PLANE + prow * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      float sa = pow2_scale(__uint_as_float(am[0]));  // scale of the operand the NEXT convolution reads
+      {
+        float t[8];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) t[c] = FWD ? fmaxf(res[o * 8 + c], 0.f) : res[o * 8 + c];
+          rs_stage8(X, Cfg::G + r, o, t, sa);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready[mb]);
+
+      for (int k = 0; k < nconv; ++k) {
+        const int stage = k & 1;
+        const float* mt = meta + k * Cfg::META;
+        uint32_t mword = 0xffffffffu;
+        if (KIND == 2) mword = inrange ? p.bits_mask[k][grow] : 0u;
+        mbar_wait(&mma_done[mb], md & 1u); ++md;
+        fence_after_sync();
+        uint32_t ra[16], rb[16], rc[16], rd[16];
+        tmem_ld16_nw(taddr, ra); tmem_ld16_nw(taddr + 32, rb); tmem_ld16_nw(taddr + 16, rc); tmem_ld16_nw(taddr + 48, rd);
+        if (k > 0) { mbar_wait(allepi, ae & 1u); ++ae; }  // all epilogues of convolution k-1: am[k] is final
+        const float amax_in = __uint_as_float(am[k]);
+        const float amax_res = stage ? __uint_as_float(am[k - 1]) : 0.f;
+        const float inv = pow2_inv(sa) * pow2_inv(mt[0]);
+        const float bound = fmaf(mt[1], amax_in, mt[2]) + amax_res;
+        const float sa_next = pow2_scale(bound);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          v[c] = fmaf(__uint_as_float(ra[c]) + __uint_as_float(rb[c]), inv, mt[4 + c]);
+          v[16 + c] = fmaf(__uint_as_float(rc[c]) + __uint_as_float(rd[c]), inv, mt[20 + c]);
+        }
+        if (KIND == 2) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = (mword >> c) & 1u ? v[c] : 0.f;
+        }
+        if (stage) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { v[c] += res[c]; }
+        }
+        if (!inrange) {  // rows outside [0, L) are the next convolution's zero padding
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = 0.f;
+        }
+        if (stage) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) res[c] = v[c];
+        }
+        const bool last = k == nconv - 1;
+        if (!last) {
+          uint32_t mm = 0u;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) mm = max(mm, absbits(v[c]));
+          mm = __reduce_max_sync(0xffffffffu, mm);
+          if (lane == 0) atomicMax(&am[k + 1], mm);
+        }
+        if (KIND == 1 && p.bits_out[k] && own && inrange) {
+          uint32_t w = 0u;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) w |= (uint32_t)(v[c] > 0.f) << c;
+          p.bits_out[k][grow] = w;
+        }
+        if (p.store[k]) {
+          if (leader) tma::wait_read();   // the image's previous store has been read out of shared memory
+          bar_sync(1 + mb, 128);
+          if (own) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(img + tma::swz(jrow, c)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
+          fence_proxy_async();
+          bar_sync(1 + mb, 128);
+          if (leader) {
+            tma::store_rows(&maps.out[k][mapsel], img, g0 + lo, b);
+            tma::commit_group();
+          }
+        }
+        if (!last) {
+          uint8_t* op = stage ? X : Y;  // convolution k+1 reads buffer (k+1) & 1
+          float t[8];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) t[c] = FWD ? fmaxf(v[o * 8 + c], 0.f) : v[o * 8 + c];
+            rs_stage8(op, Cfg::G + r, o, t, sa_next);
+          }
+          sa = sa_next;
+          fence_proxy_async();
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(allepi); mbar_arrive(&ready[mb]); }
+        } else {
+          fence_before_sync();  // orders this tile's TMEM reads before the arrivals of the next tile's input phase
+        }
+      }
+    }
+    if (leader) tma::wait_all();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------- host side
+bool resstack_tc_supported(const vqb_resstack_desc* d) {
+  if (!d || d->C != 32 || d->precision != VQB_PREC_FP16X2 || d->n_blocks < 1 || d->n_blocks > VQB_RESSTACK_MAX_BLOCKS) return false;
+  int H = 0;
+  for (int i = 0; i < d->n_blocks; ++i) {
+    if (d->dilations[i] < 1 || d->dilations[i] > RsCfg::G - 1) return false;
+    H += d->dilations[i] + 1;
+  }
+  return H <= 64;
+}
+
+size_t resstack_tc_workspace_bytes(const vqb_resstack_desc* d) { return (size_t)RS_MAXC * RsCfg::WREC + 256; }
+
+template <int KIND>
+static int launch_rs(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VQB_CUDA(cudaFuncSetAttribute(rs_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, RsCfg::SMEM));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    VQB_CUDA(cudaGetDevice(&dev));
+    VQB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  VQB_CUDA(launch_pdl(rs_kernel<KIND>, dim3(grid), dim3(RsCfg::NT), (size_t)RsCfg::SMEM, st, p, maps));
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+// kind 0 / 1: forward (h == NULL -> inference), kind 2: data gradient
+int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const float* const* w1, const float* const* b1,
+                const float* const* w2, const float* const* b2, float* const* o1, float* const* o2, uint32_t* const* xbits,
+                uint32_t* const* hbits, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!resstack_tc_supported(d))
+    return set_err(VQB_ERR_UNIMPLEMENTED, "fused residual stack: C = 32, 1..%d blocks, dilations < %d, fp16x2 only", VQB_RESSTACK_MAX_BLOCKS, RsCfg::G);
+  if (d->B == 0 || d->L == 0) return VQB_OK;
+  const size_t need = resstack_tc_workspace_bytes(d);
+  uint8_t* wsp = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  if (!ws || ws_bytes < need) return set_err(VQB_ERR_WORKSPACE, "vqb_resstack workspace: need %zu bytes, got %zu", need, ws_bytes);
+  const int n = d->n_blocks, nconv = 2 * n;
+  RsPackParams pk{};
+  RsParams p{};
+  alignas(64) RsMaps maps;  // filled per call, copied into the launch parameters
+  memset(&maps, 0, sizeof(maps));
+  pk.out = wsp;
+  p.wpack = wsp;
+  p.B = d->B; p.L = d->L; p.nconv = nconv;
+  int H = 0;
+  for (int i = 0; i < n; ++i) H += d->dilations[i] + 1;
+  p.H = H; p.Rout = RsCfg::R - 2 * H;
+  p.tiles_x = cdiv(d->L, p.Rout);
+  p.total_tiles = p.tiles_x * d->B;
+  float* outs[RS_MAXC];
+  for (int k = 0; k < nconv; ++k) {
+    const int stage = k & 1;
+    if (kind != 2) {  // forward: block i = k / 2: conv1 (dilation d_i, bias b1) then conv2 (dilation 1, bias b2)
+      const int i = k >> 1;
+      pk.w[k] = stage ? w2[i] : w1[i];
+      pk.bias[k] = stage ? (b2 ? b2[i] : nullptr) : (b1 ? b1[i] : nullptr);
+      pk.sj[k] = 32 * 32; pk.si[k] = 32; pk.so[k] = 1; pk.flip[k] = 0;   // B[n = co][k = ci] = W[j][ci][co]
+      p.dil[k] = stage ? 1 : d->dilations[i];
+      outs[k] = stage ? (o2 ? o2[i] : nullptr) : (o1 ? o1[i] : nullptr);
+      p.bits_out[k] = kind == 1 ? (stage ? (i + 1 < n ? xbits[i + 1] : nullptr) : hbits[i]) : nullptr;
+    } else {          // data gradient: blocks n-1 .. 0: conv2^T (dilation 1, mask h > 0) then conv1^T (dilation d_i, mask x > 0)
+      const int i = n - 1 - (k >> 1);
+      pk.w[k] = stage ? w1[i] : w2[i];
+      pk.bias[k] = nullptr;
+      pk.sj[k] = 32 * 32; pk.si[k] = 1; pk.so[k] = 32; pk.flip[k] = 1;   // transposed, taps flipped
+      p.dil[k] = stage ? d->dilations[i] : 1;
+      outs[k] = stage ? o2[i] : o1[i];                                    // dx[i] / dh[i]
+      p.bits_mask[k] = stage ? xbits[i] : hbits[i];
+    }
+    p.store[k] = outs[k] != nullptr;
+  }
+  if (kind == 1) p.bits_in0 = xbits[0];
+  if (!p.store[nconv - 1]) return set_err(VQB_ERR_INVALID, "vqb_resstack: the output of the last block must be given");
+  if (!tma::make_rows_map(&maps.in, in, d->B, d->L, 128))
+    return set_err(VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the [%d, %d, 32] input", d->B, d->L);
+  for (int k = 0; k < nconv; ++k)
+    if (p.store[k]) {
+      if (!tma::make_rows_map(&maps.out[k][0], outs[k], d->B, d->L, 128 - H) || !tma::make_rows_map(&maps.out[k][1], outs[k], d->B, d->L, 128))
+        return set_err(VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed for an output of the residual stack");
+    }
+  rs_pack_kernel<<<nconv, 256, 0, st>>>(pk);
+  VQB_LAUNCH_CHECK();
+  switch (kind) {
+    case 0: return launch_rs<0>(p, maps, st);
+    case 1: return launch_rs<1>(p, maps, st);
+    default: return launch_rs<2>(p, maps, st);
+  }
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" {
+
+int vqb_resstack_supports(const vqb_resstack_desc* d) { return resstack_tc_supported(d) ? 1 : 0; }
+
+size_t vqb_resstack_workspace_bytes(const vqb_resstack_desc* d) { return d ? resstack_tc_workspace_bytes(d) : 0; }
+
+int vqb_resstack_fwd(const vqb_resstack_desc* d, const float* x, const float* const* w1, const float* const* b1,
+                     const float* const* w2, const float* const* b2, float* const* h, float* const* y,
+                     uint32_t* const* xbits, uint32_t* const* hbits, void* workspace, size_t workspace_bytes, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(d && x && w1 && w2 && y, "vqb_resstack_fwd: NULL pointer");
+  VQB_REQUIRE(d->B >= 0 && d->L >= 0, "vqb_resstack_fwd: bad shape B=%d L=%d", d->B, d->L);
+  const bool train = h != nullptr;
+  if (train) {
+    VQB_REQUIRE(xbits && hbits, "vqb_resstack_fwd: h given without xbits / hbits (training forward stores all of them)");
+    for (int i = 0; i < d->n_blocks && i < VQB_RESSTACK_MAX_BLOCKS; ++i)
+      VQB_REQUIRE(h[i] && y[i] && xbits[i] && hbits[i], "vqb_resstack_fwd: training forward needs h, y, xbits, hbits of block %d", i);
+  }
+  return resstack_tc(train ? 1 : 0, d, x, w1, b1, w2, b2, h, y, xbits, hbits, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int vqb_resstack_bwd_data(const vqb_resstack_desc* d, const float* dy, const float* const* w1, const float* const* w2,
+                          const uint32_t* const* xbits, const uint32_t* const* hbits, float* const* dh, float* const* dx,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(d && dy && w1 && w2 && xbits && hbits && dh && dx, "vqb_resstack_bwd_data: NULL pointer");
+  VQB_REQUIRE(d->B >= 0 && d->L >= 0, "vqb_resstack_bwd_data: bad shape B=%d L=%d", d->B, d->L);
+  for (int i = 0; i < d->n_blocks && i < VQB_RESSTACK_MAX_BLOCKS; ++i)
+    VQB_REQUIRE(xbits[i] && hbits[i] && dh[i] && dx[i], "vqb_resstack_bwd_data: xbits, hbits, dh, dx of block %d", i);
+  return resstack_tc(2, d, dy, w1, nullptr, w2, nullptr, dh, dx, const_cast<uint32_t* const*>(xbits),
+                     const_cast<uint32_t* const*>(hbits), workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

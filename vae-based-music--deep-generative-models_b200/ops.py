@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, ResblockDesc, TailDesc, VQDesc, call, ptr
+from ._lib import ConvDesc, ResblockDesc, ResstackDesc, TailDesc, VQDesc, call, ptr
 
 F32 = torch.float32
 
@@ -232,6 +232,69 @@ def resblock_bwd_data(x, h, dy, w1, w2, dilation, precision=0):
     call("vqb_resblock_bwd_data", C.byref(d), ptr(x), ptr(h), ptr(dy), ptr(w1), ptr(w2), ptr(dh), ptr(dx),
          _lib.stream())
     return dx, dh
+
+
+# ------------------------------------------------------------------------------------------- resstack
+RESSTACK_MAX = 4  # VQB_RESSTACK_MAX_BLOCKS
+
+
+def _sdesc(B, L, Cc, dilations, precision):
+    d = ResstackDesc()
+    d.B, d.L, d.C, d.n_blocks, d.precision = B, L, Cc, len(dilations), precision
+    for i, v in enumerate(dilations[:RESSTACK_MAX]):
+        d.dilations[i] = int(v)
+    return d
+
+
+def resstack_supported(Cc, dilations, precision):
+    """True if libvqvae_b200 runs these residual blocks (first-convolution dilations, in execution order) as ONE fused launch."""
+    if precision == 0 or not 1 <= len(dilations) <= RESSTACK_MAX:
+        return False
+    return bool(_lib.lib().vqb_resstack_supports(C.byref(_sdesc(1, 1, Cc, list(dilations), precision))))
+
+
+def _parr(ts):
+    return C.cast((C.c_void_p * len(ts))(*[ptr(t) for t in ts]), C.c_void_p)
+
+
+def resstack_fwd(x, w1s, b1s, w2s, b2s, dilations, precision, train):
+    """A chain of len(dilations) residual blocks in one launch (vqb_resstack_fwd).  Returns (ys, hs, xbits, hbits): under a
+    tape (`train`) every block's h, output and sign masks (lists of n tensors), else ys = [None, ..., y_last] and hs, xbits,
+    hbits = None (nothing but the stack's output is written)."""
+    _chk(x, "x")
+    for t in (*w1s, *b1s, *w2s, *b2s):
+        _chk(t, "weight")
+    B, L, Cc = x.shape
+    n = len(dilations)
+    d = _sdesc(B, L, Cc, list(dilations), precision)
+    ws = _ws(_lib.lib().vqb_resstack_workspace_bytes(C.byref(d)))
+    if train:
+        ys = [empty(B, L, Cc) for _ in range(n)]
+        hs = [empty(B, L, Cc) for _ in range(n)]
+        xb = [torch.empty(B, L, dtype=torch.int32, device=_lib.device()) for _ in range(n)]
+        hb = [torch.empty(B, L, dtype=torch.int32, device=_lib.device()) for _ in range(n)]
+        call("vqb_resstack_fwd", C.byref(d), ptr(x), _parr(w1s), _parr(b1s), _parr(w2s), _parr(b2s), _parr(hs), _parr(ys),
+             _parr(xb), _parr(hb), ptr(ws), ws.numel(), _lib.stream())
+        return ys, hs, xb, hb
+    ys = [None] * (n - 1) + [empty(B, L, Cc)]
+    call("vqb_resstack_fwd", C.byref(d), ptr(x), _parr(w1s), _parr(b1s), _parr(w2s), _parr(b2s), None, _parr(ys), None, None,
+         ptr(ws), ws.numel(), _lib.stream())
+    return ys, None, None, None
+
+
+def resstack_bwd_data(dy, w1s, w2s, xbits, hbits, dilations, precision):
+    """Data gradients of the chain (vqb_resstack_bwd_data): returns (dxs, dhs), dxs[i] = gradient at the input of block i,
+    dhs[i] = gradient at the output of its first convolution."""
+    _chk(dy, "dy")
+    B, L, Cc = dy.shape
+    n = len(dilations)
+    d = _sdesc(B, L, Cc, list(dilations), precision)
+    ws = _ws(_lib.lib().vqb_resstack_workspace_bytes(C.byref(d)))
+    dhs = [empty(B, L, Cc) for _ in range(n)]
+    dxs = [empty(B, L, Cc) for _ in range(n)]
+    call("vqb_resstack_bwd_data", C.byref(d), ptr(dy), _parr(w1s), _parr(w2s), _parr(xbits), _parr(hbits), _parr(dhs),
+         _parr(dxs), ptr(ws), ws.numel(), _lib.stream())
+    return dxs, dhs
 
 
 # ------------------------------------------------------------------------------------------------- VQ
