@@ -391,6 +391,9 @@ class FakeBackend:
         O.adam_step([P], [G * gs], [M], [V], t, lr, b1, b2, eps)
         return 0
 
+    def vqb_resstack_supports(self, d):
+        return 0  # the CPU double composes residual blocks one by one
+
     def vqb_adam_step_dev(self, p, g, m, v, n, lr_dev, b1, b2, eps, gs, step, stream):
         return self.vqb_adam_step(p, g, m, v, n, float(_t(lr_dev, (1,))[0]), b1, b2, eps, gs, step, stream)
 

@@ -1,4 +1,5 @@
-"""Runs one hot kernel a few times (for `ncu --set full -k regex:...`).  Usage: python tools/bench_kernel.py resblock_fwd[_masks]|resblock_bwd[_masks]|wgrad|resblock_wgrad|vq [precision]"""
+"""Runs one hot kernel a few times (for `ncu --set full -k regex:...`).  Usage: python tools/bench_kernel.py resblock_fwd[_masks]|resblock_bwd[_masks]|wgrad|resblock_wgrad|vq|stack_infer|stack_train|stack_bwd [precision]
+stack_*: the fused DilatedResnet1D kernel (4 blocks, dilations 1,3,9,27; DILS=27,9,3,1 to reverse) — one launch per call."""
 import os
 import sys
 
@@ -23,6 +24,12 @@ dw, db = ops.empty(3, C, C), ops.empty(C)
 dw2, db2 = ops.empty(3, C, C), ops.empty(C)
 if what.endswith("_masks"):
     _, _, xb, hb = ops.resblock_fwd_masks(xs[0], w1, b1, w2, b2, 1, P)
+if what.startswith("stack"):
+    dils = tuple(int(v) for v in os.environ.get("DILS", "1,3,9,27").split(","))
+    W1 = [torch.randn(3, C, C, device="cuda", generator=g) * 0.1 for _ in dils]
+    W2 = [torch.randn(3, C, C, device="cuda", generator=g) * 0.1 for _ in dils]
+    Bz = [torch.zeros(C, device="cuda") for _ in dils]
+    _, _, sxb, shb = ops.resstack_fwd(xs[0], W1, Bz, W2, Bz, dils, P, True)
 n = int(os.environ.get("N", "6"))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -34,6 +41,12 @@ def one(i):
         ops.resblock_fwd_masks(xs[i % 2], w1, b1, w2, b2, 1, P)
     elif what == "resblock_bwd_masks":
         ops.resblock_bwd_data_masks(xb, hb, dy, w1, w2, int(os.environ.get("DIL", "1")), P)
+    elif what == "stack_infer":
+        ops.resstack_fwd(xs[i % 2], W1, Bz, W2, Bz, dils, P, False)
+    elif what == "stack_train":
+        ops.resstack_fwd(xs[i % 2], W1, Bz, W2, Bz, dils, P, True)
+    elif what == "stack_bwd":
+        ops.resstack_bwd_data(dy, W1, W2, sxb, shb, dils, P)
     elif what == "resblock_bwd":
         ops.resblock_bwd_data(xs[i % 2], h, dy, w1, w2, int(os.environ.get("DIL", "1")), P)
     elif what == "resblock_wgrad":
@@ -49,9 +62,20 @@ def one(i):
 for i in range(4):
     one(i)
 torch.cuda.synchronize()
-e0.record()
-for i in range(n):
-    one(i)
-e1.record()
+if os.environ.get("GRAPH", "0") == "1":  # device time without the host side of the calls: n calls captured, replayed
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for i in range(n):
+            one(i)
+    gr.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    gr.replay()
+    e1.record()
+else:
+    e0.record()
+    for i in range(n):
+        one(i)
+    e1.record()
 torch.cuda.synchronize()
 print(what, prec, f"B={B} L={L}", "ms per call", e0.elapsed_time(e1) / n)

@@ -23,7 +23,10 @@
 //
 // Three instantiations: KIND 0 inference forward (stores y only: 256 B per position for the whole stack), KIND 1 training
 // forward (stores h_i, y_i and both sign masks per block), KIND 2 data gradient (masks from the sign words, stores dh_i, dx_i).
+#include <stdlib.h>
 #include <string.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -55,7 +58,7 @@ struct RsCfg {
   static constexpr int NBAR = 3 * MB + 8;
   static constexpr int OFF_TSLOT = OFF_BAR + NBAR * 8;
   static constexpr int SMEM = OFF_TSLOT + 16 + 1024;    // + slack for the 1024-byte alignment of the base
-  static constexpr int NEPI = 4 * MB;                   // epilogue warps
+  static constexpr int NEPI = 8 * MB;                   // epilogue warps: two threads per tile row (16 channels each)
   static constexpr int NT = (NEPI + 2) * 32;            // + issuer warp + producer warp
   static constexpr int TCOLS = 256;                     // MB * NW = 192 accumulator columns
   static_assert(OFF_X % 16 == 0 && OFF_W % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
@@ -70,6 +73,7 @@ struct RsParams {
   uint32_t* bits_in0;                  // KIND 1: sign mask of the chain input
   uint32_t* bits_out[RS_MAXC];         // KIND 1: sign mask of the output of convolution k (or NULL)
   const uint32_t* bits_mask[RS_MAXC];  // KIND 2: sign mask applied to the output of convolution k
+  long long* trace;                    // TRACE builds: clock64 stamps of CTA 0's second tile, [role 0..3][k 0..8][event 0..7]
 };
 struct RsMaps {
   CUtensorMap in;                      // box {32, 128, 1}
@@ -153,15 +157,20 @@ __device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// 12 MMAs of one convolution on one M block: taps x K steps x (hi-activation x [W_hi | W_lo], lo-activation x W_hi)
-__device__ __forceinline__ void rs_issue(uint32_t tacc, uint32_t a_base, int row0, int dil, uint32_t w_base) {
+// MMAs of one convolution on one M block for taps [j0, j1): per tap 2 K steps x (hi-activation x [W_hi | W_lo], lo-activation x
+// W_hi).  Tap j reads operand rows shifted by (j - 1) * dil: taps 0 and 1 need the rows of M blocks mb - 1 and mb only, tap 2
+// those of mb + 1 — the issuer starts a block's taps 0, 1 before the next block's epilogue is through.
+__device__ __forceinline__ void rs_issue(uint32_t tacc, uint32_t a_base, int row0, int dil, uint32_t w_base, int j0, int j1) {
   const uint64_t ad0 = smem_desc(a_base + (uint32_t)row0 * 16u, RsCfg::PLANE, 128);  // row0 = first row of tap 0
   const uint64_t bd0 = smem_desc(w_base, RsCfg::WPLANE, 128);
-  uint32_t acc = 0;
 #pragma unroll
-  for (int j = 0; j < 3; ++j)
+  for (int j = 0; j < 3; ++j) {
+    if (j < j0 || j >= j1) continue;
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
@@ -169,20 +178,51 @@ __device__ __forceinline__ void rs_issue(uint32_t tacc, uint32_t a_base, int row
         const uint32_t idesc = instr_desc(FMT_F16, 128, 32 * (2 - sa), false, false);
         const uint64_t bd = bd0 + (uint64_t)((j * RsCfg::WTAP + kk * 2 * RsCfg::WPLANE) >> 4);
         const uint64_t ad = ad0 + (uint64_t)((sa * RsCfg::TILE + kk * 2 * RsCfg::PLANE) >> 4) + (uint64_t)(j * dil);
-        mma<false>(tacc, ad, bd, idesc, acc);
-        acc = 1;
+        mma<false>(tacc, ad, bd, idesc, (j | kk | sa) ? 1u : 0u);
       }
+  }
 }
 
-// 8 channels o*8 .. o*8+7 of operand row `prow` (physical row, guard rows included): hi and lo chunk
-__device__ __forceinline__ void rs_stage8(uint8_t* op, int prow, int o, const float* v, float scale) {
-  uint4 pc[2];
-  split8_f16(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), scale, pc);
-  *reinterpret_cast<uint4*>(op + o * RsCfg::PLANE + prow * 16) = pc[0];
-  *reinterpret_cast<uint4*>(op + RsCfg::TILE + o * RsCfg::PLANE + prow * 16) = pc[1];
+// fp32 -> two fp16 pieces by TRUNCATION: hi = the value with its mantissa cut to fp16's 10 bits (one LOP3; exactly
+// representable, so the conversion is exact), lo = rn_f16(x - hi) (exact difference, 13 bits rounded to 11): 2^-22 relative,
+// one instruction per element less than the round-to-nearest split of tc.cuh (no fp16 -> fp32 unpack).  RELU folds the
+// activation into the two conversions (cvt.rn.relu): for x < 0 both hi and x - hi are <= 0 and come out as +0, for x >= 0
+// both are >= 0 and pass unchanged — no separate max.
+template <bool RELU>
+__device__ __forceinline__ uint32_t rs_cvt2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+// 8 channels (already scaled) -> hi chunk, lo chunk; hm accumulates max |hi| (packed halves)
+template <bool RELU>
+__device__ __forceinline__ void rs_split8(const float* t, uint4& hi, uint4& lo, __half2& hm) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = t[2 * i], b = t[2 * i + 1];
+    const float ah = __uint_as_float(__float_as_uint(a) & 0xffffe000u), bh = __uint_as_float(__float_as_uint(b) & 0xffffe000u);
+    h[i] = rs_cvt2<RELU>(ah, bh);
+    l[i] = rs_cvt2<RELU>(a - ah, b - bh);
+    hm = __hmax2(hm, __habs2(*reinterpret_cast<const __half2*>(&h[i])));
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// max of the two halves -> fp32 bits of an upper bound of max |operand| in true scale (inv = 1 / operand scale)
+__device__ __forceinline__ uint32_t rs_hmax_bits(__half2 hm, float inv) {
+  const float2 f = __half22float2(hm);
+  return __float_as_uint(fmaxf(f.x, f.y) * inv * 1.002f);
 }
 
-template <int KIND>
+// TRACE: time stamps of the pipeline (tools/trace_stack.py): role 0 = issuer, 1 + mb = first epilogue warp of M block mb
+#define RS_TR(role, k, ev)                                                                                   \
+  do {                                                                                                       \
+    if (TRACE && p.trace && blockIdx.x == 0 && ti == 1 && lane == 0) p.trace[((role) * 9 + (k)) * 8 + (ev)] = clock64(); \
+  } while (0)
+
+template <int KIND, bool TRACE = false>
 __global__ void __launch_bounds__(RsCfg::NT, 1) rs_kernel(const RsParams p, const __grid_constant__ RsMaps maps) {
   using Cfg = RsCfg;
   constexpr bool FWD = KIND != 2;
@@ -209,7 +249,7 @@ __global__ void __launch_bounds__(RsCfg::NT, 1) rs_kernel(const RsParams p, cons
 
   if (warp == 0) tmem_alloc(tslot, Cfg::TCOLS);
   if (tid == 32) {
-    for (int i = 0; i < Cfg::MB; ++i) { mbar_init(&mma_done[i], 1); mbar_init(&ready[i], 4); }
+    for (int i = 0; i < Cfg::MB; ++i) { mbar_init(&mma_done[i], 1); mbar_init(&ready[i], 8); }
     mbar_init(&w_full[0], 1); mbar_init(&w_full[1], 1); mbar_init(&w_empty[0], 1); mbar_init(&w_empty[1], 1);
     mbar_init(allepi, Cfg::NEPI); mbar_init(in_full, 1); mbar_init(y_empty, 1);
     fence_mbar_init();
@@ -263,24 +303,24 @@ __global__ void __launch_bounds__(RsCfg::NT, 1) rs_kernel(const RsParams p, cons
       uint32_t rdy[Cfg::MB], wf[2] = {0u, 0u};
 #pragma unroll
       for (int i = 0; i < Cfg::MB; ++i) rdy[i] = 0u;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
         for (int k = 0; k < nconv; ++k) {
           const int s = k & 1;
           mbar_wait(&w_full[s], wf[s] & 1u); ++wf[s];
+          RS_TR(0, k, 0);
           const uint32_t a_base = smem_u32(s ? Y : X);
           const int dil = p.dil[k];
 #pragma unroll
           for (int mb = 0; mb < Cfg::MB; ++mb) {
-            // rows mb*128 - dil .. mb*128 + 127 + dil of the operand: M blocks mb-1, mb, mb+1 (waited for in order)
-            if (mb == 0) {
-              mbar_wait(&ready[0], rdy[0] & 1u); ++rdy[0];
-              if (Cfg::MB > 1) { mbar_wait(&ready[1], rdy[1] & 1u); ++rdy[1]; }
-            } else if (mb + 1 < Cfg::MB) {
-              mbar_wait(&ready[mb + 1], rdy[mb + 1] & 1u); ++rdy[mb + 1];
-            }
-            fence_after_sync();
-            rs_issue(tmem + mb * Cfg::NW, a_base, Cfg::G + mb * 128 - dil, dil, smem_u32(W + s * Cfg::WCONV));
+            const uint32_t tacc = tmem + mb * Cfg::NW, wb = smem_u32(W + s * Cfg::WCONV);
+            const int row0 = Cfg::G + mb * 128 - dil;
+            if (mb == 0) { mbar_wait(&ready[0], rdy[0] & 1u); ++rdy[0]; fence_after_sync(); RS_TR(0, k, 1); }
+            rs_issue(tacc, a_base, row0, dil, wb, 0, 2);   // taps -1, 0: rows of M blocks mb - 1, mb
+            if (mb + 1 < Cfg::MB) { mbar_wait(&ready[mb + 1], rdy[mb + 1] & 1u); ++rdy[mb + 1]; fence_after_sync(); RS_TR(0, k, 2 + mb); }
+            rs_issue(tacc, a_base, row0, dil, wb, 2, 3);   // tap +1: rows of M block mb + 1 as well
             commit(&mma_done[mb]);
+            RS_TR(0, k, 4 + mb);
           }
           commit(&w_empty[s]);
           if (k == nconv - 1) commit(y_empty);
@@ -290,47 +330,150 @@ __global__ void __launch_bounds__(RsCfg::NT, 1) rs_kernel(const RsParams p, cons
     __syncwarp();
   } else {
     // ------------------------------------------------------------------------------------------ epilogues
-    const int mb = warp >> 2, qd = warp & 3;
-    const int r = warp * 32 + lane;  // tile row = TMEM lane (mb * 128 + qd * 32 + lane)
-    const uint32_t taddr = tmem + (((uint32_t)qd * 32u) << 16) + (uint32_t)(mb * Cfg::NW);
+    // thread = (tile row, 16-channel half): warp w -> M block w / 8, TMEM lane quadrant w % 4, half (w / 4) % 2
+    const int mb = warp >> 3, qd = warp & 3, half = (warp >> 2) & 1;
+    const int r = mb * 128 + qd * 32 + lane;  // tile row = TMEM lane
+    const uint32_t taddr = tmem + (((uint32_t)qd * 32u) << 16) + (uint32_t)(mb * Cfg::NW + half * 16);
     // rows of this M block that belong to the tile's output: [lo, hi); image row j = r - lo
     const int lo = max(mb * 128, p.H), hi = min(mb * 128 + 128, Cfg::R - p.H);
     const bool own = r >= lo && r < hi;
     const int jrow = r - lo;
     uint8_t* img = OUT + mb * Cfg::IMG;
-    const bool leader = qd == 0 && lane == 0;  // issues this M block's TMA stores (bulk groups are per thread)
+    uint32_t imgc[4];  // this thread's four 16-byte chunks of its image row (shared-memory addresses)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) imgc[c] = smem_u32(img) + tma::swz(jrow & 127, half * 4 + c);
+    const bool leader = (warp & 7) == 0 && lane == 0;  // issues this M block's TMA stores (bulk groups are per thread)
+    const bool tr = (warp & 7) == 0;
     const int mapsel = (mb == 0 || mb == Cfg::MB - 1) ? 0 : 1;
+    // this thread's operand chunks: planes 2 * half, 2 * half + 1 of row G + r, hi piece (lo piece: + TILE)
+    const uint32_t opoff = (uint32_t)(half * 2 * Cfg::PLANE + (Cfg::G + r) * 16);
+    const uint32_t xrow = smem_u32(X) + opoff, yrow = smem_u32(Y) + opoff;
     uint32_t md = 0u, ae = 0u;
-    float res[32];
-    int ti = 0;
+    float res[16];
+    float sa = 1.f, rbound = 0.f;
+    bool inrange = false;
+    size_t grow = 0;
+    int g0 = 0, b = 0, ti = 0;
+    uint32_t* am = amax;
+
+    // relu(v) (forward) or v -> hi / lo operand rows of buffer `op`, scaled by `scale`; returns max |hi| as packed halves
+    auto write_operand = [&](uint32_t oprow, const float* v, float scale) {
+      __half2 hm = __float2half2_rn(0.f);
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        float t[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) t[c] = v[o * 8 + c] * scale;
+        uint4 ph, pl;
+        rs_split8<FWD>(t, ph, pl, hm);
+        sts128(oprow + o * Cfg::PLANE, ph);
+        sts128(oprow + o * Cfg::PLANE + Cfg::TILE, pl);
+      }
+      return hm;
+    };
+
+    // epilogue of convolution k (STAGE = k & 1: 0 = first convolution of a block, 1 = second: residual add)
+    auto epilogue = [&](int k, auto stage_tag) {
+      constexpr int STAGE = decltype(stage_tag)::value;
+      const float* mt = meta + k * Cfg::META;
+      uint32_t mword = 0xffffu;
+      if (KIND == 2) mword = inrange ? (uint32_t)reinterpret_cast<const uint16_t*>(p.bits_mask[k])[grow] : 0u;
+      mbar_wait(&mma_done[mb], md & 1u); ++md;
+      fence_after_sync();
+      if (tr) RS_TR(1 + mb, k, 0);
+      uint32_t ra[16], rb[16];
+      tmem_ld16_nw(taddr, ra); tmem_ld16_nw(taddr + 32, rb);
+      const float inv = pow2_inv(sa) * pow2_inv(mt[0]);
+      const float* bias = mt + 4 + half * 16;
+      tmem_ld_wait();
+      if (tr) RS_TR(1 + mb, k, 1);
+      float v[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = fmaf(__uint_as_float(ra[c]) + __uint_as_float(rb[c]), inv, bias[c]);
+      if (KIND == 2) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = (mword >> c) & 1u ? v[c] : 0.f;
+      }
+      if (STAGE) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { res[c] += v[c]; v[c] = res[c]; }
+      }
+      const bool last = k == nconv - 1;
+      if (KIND == 1 && p.bits_out[k] && own && inrange) {
+        uint32_t w = 0u;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) w |= (uint32_t)(v[c] > 0.f) << c;
+        reinterpret_cast<uint16_t*>(p.bits_out[k])[grow] = (uint16_t)w;
+      }
+      if (p.store[k]) {
+        if (leader) tma::wait_read();   // the image's previous store has been read out of shared memory
+        bar_sync(1 + mb, 256);
+        if (own) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            sts128(imgc[c], make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3])));
+        }
+        fence_proxy_async();
+        bar_sync(1 + mb, 256);
+        if (leader) {
+          tma::store_rows(&maps.out[k][mapsel], img, g0 + lo, b);
+          tma::commit_group();
+        }
+      }
+      if (tr) RS_TR(1 + mb, k, 2);
+      // every phase of `allepi` is observed by every warp (parity waits must not fall a phase behind)
+      if (k > 0) { mbar_wait(allepi, ae & 1u); ++ae; }
+      if (tr) RS_TR(1 + mb, k, 3);
+      if (!last) {
+        // scale of this convolution's output as the next operand: am[k] = max |operand k| (all epilogues of k-1 are through)
+        float bound = fmaf(mt[1], __uint_as_float(am[k]), mt[2]);
+        if (STAGE) { bound += rbound; rbound = bound; }
+        const float sa_next = pow2_scale(bound);
+        // rows outside [0, L) are the next convolution's zero padding: scale 0
+        const __half2 hm = write_operand(STAGE ? xrow : yrow, v, inrange ? sa_next : 0.f);  // convolution k+1 reads buffer (k+1) & 1
+        uint32_t mm = rs_hmax_bits(hm, pow2_inv(sa_next));
+        mm = __reduce_max_sync(0xffffffffu, mm);
+        if (lane == 0) atomicMax(&am[k + 1], mm);
+        sa = sa_next;
+        if (tr) RS_TR(1 + mb, k, 4);
+        fence_proxy_async();
+        fence_before_sync();
+        __syncwarp();
+        if (tr) RS_TR(1 + mb, k, 5);
+        if (lane == 0) { mbar_arrive(allepi); mbar_arrive(&ready[mb]); }
+      } else {
+        fence_before_sync();  // orders this tile's TMEM reads before the arrivals of the next tile's input phase
+      }
+    };
+
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const int par = ti & 1;
-      uint32_t* am = amax + par * 16;
-      const int b = tile / p.tiles_x;
-      const int g0 = (tile - b * p.tiles_x) * p.Rout - p.H;
+      am = amax + par * 16;
+      b = tile / p.tiles_x;
+      g0 = (tile - b * p.tiles_x) * p.Rout - p.H;
       const int g = g0 + r;
-      const bool inrange = g >= 0 && g < L;
-      const size_t grow = (size_t)b * L + (size_t)(inrange ? g : 0);
+      inrange = g >= 0 && g < L;
+      grow = ((size_t)b * L + (size_t)(inrange ? g : 0)) * 2 + half;  // index of this thread's 16-bit mask word
       // ---- input phase: raw fp32 row -> residual registers, tile maximum, first operand
       mbar_wait(in_full, (uint32_t)ti & 1u);
       {
         const uint8_t* raw = Y + (r >> 7) * Cfg::IMG;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 f = *reinterpret_cast<const float4*>(raw + tma::swz(r & 127, c));
+        for (int c = 0; c < 4; ++c) {
+          const float4 f = *reinterpret_cast<const float4*>(raw + tma::swz(r & 127, half * 4 + c));
           res[4 * c] = f.x; res[4 * c + 1] = f.y; res[4 * c + 2] = f.z; res[4 * c + 3] = f.w;
         }
       }
       uint32_t m = 0u;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) m = max(m, absbits(res[c]));
+      for (int c = 0; c < 16; ++c) m = max(m, absbits(res[c]));
       m = __reduce_max_sync(0xffffffffu, m);
       if (lane == 0) atomicMax(&am[0], m);
       if (KIND == 1 && p.bits_in0 && own && inrange) {
         uint32_t w = 0u;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) w |= (uint32_t)(res[c] > 0.f) << c;
-        p.bits_in0[grow] = w;
+        for (int c = 0; c < 16; ++c) w |= (uint32_t)(res[c] > 0.f) << c;
+        reinterpret_cast<uint16_t*>(p.bits_in0)[grow] = (uint16_t)w;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(allepi);
@@ -340,109 +483,21 @@ __global__ void __launch_bounds__(RsCfg::NT, 1) rs_kernel(const RsParams p, cons
         for (int i = 0; i < 16; ++i) amax[(par ^ 1) * 16 + i] = 0u;  // the other parity: next tile
       }
       // Y's guard rows (overwritten by the raw tile): 2 * G rows x 8 chunk columns
-      for (int e = tid; e < 2 * Cfg::G * 8; e += Cfg::NEPI * 32) {
-        const int q = e / (2 * Cfg::G), gr = e % (2 * Cfg::G);
+      if (tid < 2 * Cfg::G * 8) {
+        const int q = tid / (2 * Cfg::G), gr = tid % (2 * Cfg::G);
         const int prow = gr < Cfg::G ? gr : Cfg::R + gr;
         *reinterpret_cast<uint4*>(Y + (q >> 2) * Cfg::TILE + (q & 3) * Cfg::PLANE + prow * 16) = make_uint4(0u, 0u, 0u, 0u);
       }
-      float sa = pow2_scale(__uint_as_float(am[0]));  // scale of the operand the NEXT convolution reads
-      {
-        float t[8];
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) t[c] = FWD ? fmaxf(res[o * 8 + c], 0.f) : res[o * 8 + c];
-          rs_stage8(X, Cfg::G + r, o, t, sa);
-        }
-      }
+      rbound = __uint_as_float(am[0]);  // bound of |residual stream|: exact for the tile input, then additive per block
+      sa = pow2_scale(rbound);          // scale of the operand the NEXT convolution reads
+      write_operand(xrow, res, sa);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ready[mb]);
 
-      for (int k = 0; k < nconv; ++k) {
-        const int stage = k & 1;
-        const float* mt = meta + k * Cfg::META;
-        uint32_t mword = 0xffffffffu;
-        if (KIND == 2) mword = inrange ? p.bits_mask[k][grow] : 0u;
-        mbar_wait(&mma_done[mb], md & 1u); ++md;
-        fence_after_sync();
-        uint32_t ra[16], rb[16], rc[16], rd[16];
-        tmem_ld16_nw(taddr, ra); tmem_ld16_nw(taddr + 32, rb); tmem_ld16_nw(taddr + 16, rc); tmem_ld16_nw(taddr + 48, rd);
-        if (k > 0) { mbar_wait(allepi, ae & 1u); ++ae; }  // all epilogues of convolution k-1: am[k] is final
-        const float amax_in = __uint_as_float(am[k]);
-        const float amax_res = stage ? __uint_as_float(am[k - 1]) : 0.f;
-        const float inv = pow2_inv(sa) * pow2_inv(mt[0]);
-        const float bound = fmaf(mt[1], amax_in, mt[2]) + amax_res;
-        const float sa_next = pow2_scale(bound);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          v[c] = fmaf(__uint_as_float(ra[c]) + __uint_as_float(rb[c]), inv, mt[4 + c]);
-          v[16 + c] = fmaf(__uint_as_float(rc[c]) + __uint_as_float(rd[c]), inv, mt[20 + c]);
-        }
-        if (KIND == 2) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] = (mword >> c) & 1u ? v[c] : 0.f;
-        }
-        if (stage) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) { v[c] += res[c]; }
-        }
-        if (!inrange) {  // rows outside [0, L) are the next convolution's zero padding
-#pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] = 0.f;
-        }
-        if (stage) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) res[c] = v[c];
-        }
-        const bool last = k == nconv - 1;
-        if (!last) {
-          uint32_t mm = 0u;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) mm = max(mm, absbits(v[c]));
-          mm = __reduce_max_sync(0xffffffffu, mm);
-          if (lane == 0) atomicMax(&am[k + 1], mm);
-        }
-        if (KIND == 1 && p.bits_out[k] && own && inrange) {
-          uint32_t w = 0u;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) w |= (uint32_t)(v[c] > 0.f) << c;
-          p.bits_out[k][grow] = w;
-        }
-        if (p.store[k]) {
-          if (leader) tma::wait_read();   // the image's previous store has been read out of shared memory
-          bar_sync(1 + mb, 128);
-          if (own) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<float4*>(img + tma::swz(jrow, c)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          }
-          fence_proxy_async();
-          bar_sync(1 + mb, 128);
-          if (leader) {
-            tma::store_rows(&maps.out[k][mapsel], img, g0 + lo, b);
-            tma::commit_group();
-          }
-        }
-        if (!last) {
-          uint8_t* op = stage ? X : Y;  // convolution k+1 reads buffer (k+1) & 1
-          float t[8];
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) t[c] = FWD ? fmaxf(v[o * 8 + c], 0.f) : v[o * 8 + c];
-            rs_stage8(op, Cfg::G + r, o, t, sa_next);
-          }
-          sa = sa_next;
-          fence_proxy_async();
-          fence_before_sync();
-          __syncwarp();
-          if (lane == 0) { mbar_arrive(allepi); mbar_arrive(&ready[mb]); }
-        } else {
-          fence_before_sync();  // orders this tile's TMEM reads before the arrivals of the next tile's input phase
-        }
+      for (int k = 0; k < nconv; k += 2) {
+        epilogue(k, std::integral_constant<int, 0>());
+        epilogue(k + 1, std::integral_constant<int, 1>());
       }
     }
     if (leader) tma::wait_all();
@@ -464,11 +519,11 @@ bool resstack_tc_supported(const vqb_resstack_desc* d) {
 
 size_t resstack_tc_workspace_bytes(const vqb_resstack_desc* d) { return (size_t)RS_MAXC * RsCfg::WREC + 256; }
 
-template <int KIND>
+template <int KIND, bool TRACE = false>
 static int launch_rs(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    VQB_CUDA(cudaFuncSetAttribute(rs_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, RsCfg::SMEM));
+    VQB_CUDA(cudaFuncSetAttribute(rs_kernel<KIND, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RsCfg::SMEM));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -478,7 +533,7 @@ static int launch_rs(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
     VQB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  VQB_CUDA(launch_pdl(rs_kernel<KIND>, dim3(grid), dim3(RsCfg::NT), (size_t)RsCfg::SMEM, st, p, maps));
+  VQB_CUDA(launch_pdl(rs_kernel<KIND, TRACE>, dim3(grid), dim3(RsCfg::NT), (size_t)RsCfg::SMEM, st, p, maps));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
@@ -539,6 +594,10 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
     }
   rs_pack_kernel<<<nconv, 256, 0, st>>>(pk);
   VQB_LAUNCH_CHECK();
+  if (kind == 0 && getenv("VQB_RS_TRACE")) {  // profiling aid: address of a device buffer of 4 * 9 * 8 int64 (tools/trace_stack.py)
+    p.trace = reinterpret_cast<long long*>(strtoull(getenv("VQB_RS_TRACE"), nullptr, 0));
+    return launch_rs<0, true>(p, maps, st);
+  }
   switch (kind) {
     case 0: return launch_rs<0>(p, maps, st);
     case 1: return launch_rs<1>(p, maps, st);

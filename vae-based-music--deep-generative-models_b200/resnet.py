@@ -56,21 +56,33 @@ class ResnetConv1DBlock(layers.Layer):
                 dx, dh = ops.resblock_bwd_data_masks(xbits, hbits, dy, conv1.kernel.value, conv2.kernel.value, d, prec)
             else:
                 dx, dh = ops.resblock_bwd_data(x, h, dy, conv1.kernel.value, conv2.kernel.value, d, prec)
-            # both weight gradients in one call (one launch on the tensor-core paths; ops.resblock_wgrad may hold it back to
-            # launch the blocks of a stack together): tape.gradient wrt the four variables
-            if getattr(conv1.kernel, "_grad_written", False) or getattr(conv2.kernel, "_grad_written", False):
-                ops.wg_flush()  # a block used twice under one tape accumulates: needs its gradient now (write_grad)
-                wg = ops._resblock_wgrad_now
-            else:
-                wg = ops.resblock_wgrad
-            write_grad(conv1.kernel, lambda buf1: write_grad(conv2.kernel, lambda buf2: wg(
-                x, h, dy, dh, buf1, grad_buffer(conv1.bias), buf2, grad_buffer(conv2.bias), d, prec)))
-            conv1.bias._grad_written = True
-            conv2.bias._grad_written = True
+            self._weight_gradients(x, h, dy, dh, prec)
             return [dx if needs[0] else None]
 
         record([input_tensor], [y], bwd)
         return y
+
+    def _convs(self, in_shape=None):
+        conv1, conv2 = self.model.layers[1], self.model.layers[3]
+        if not conv1.built and in_shape is not None:
+            conv1.build(tuple(in_shape)); conv1.built = True
+            conv2.build(tuple(in_shape[:-1]) + (self.filters,)); conv2.built = True
+        return conv1, conv2
+
+    def _weight_gradients(self, x, h, dy, dh, prec):
+        """both weight gradients in one call (one launch on the tensor-core paths; ops.resblock_wgrad may hold it back to launch
+        the blocks of a stack together): tape.gradient wrt the four variables"""
+        conv1, conv2 = self._convs()
+        d = self.dilation
+        if getattr(conv1.kernel, "_grad_written", False) or getattr(conv2.kernel, "_grad_written", False):
+            ops.wg_flush()  # a block used twice under one tape accumulates: needs its gradient now (write_grad)
+            wg = ops._resblock_wgrad_now
+        else:
+            wg = ops.resblock_wgrad
+        write_grad(conv1.kernel, lambda buf1: write_grad(conv2.kernel, lambda buf2: wg(
+            x, h, dy, dh, buf1, grad_buffer(conv1.bias), buf2, grad_buffer(conv2.bias), d, prec)))
+        conv1.bias._grad_written = True
+        conv2.bias._grad_written = True
 
 
 class DilatedResnet1D(layers.Layer):
@@ -87,5 +99,49 @@ class DilatedResnet1D(layers.Layer):
             blocks = blocks[::-1]
         self.model = Sequential(blocks)
 
+        self.use_fused_stack = True  # one launch per <= 4 blocks where libvqvae_b200 has the fused kernel (vqb_resstack_*)
+
     def call(self, input, **kwargs):
-        return self.model(input)
+        x = input
+        blocks = self.model.layers
+        if _is_symbolic(x) or not self.use_fused_stack or not blocks:
+            return self.model(x)
+        prec = blocks[0].precision
+        C_ = blocks[0].input_dim
+        if (x.shape[-1] != C_ or any(b.precision != prec or b.input_dim != C_ or b.filters != C_ for b in blocks)
+                or not ops.resstack_supported(C_, [b.dilation for b in blocks[:ops.RESSTACK_MAX]], prec)):
+            return self.model(x)
+        # resnet.py:51-59 as fused launches: chains of up to RESSTACK_MAX blocks, the activation staying on chip inside a chain
+        for i in range(0, len(blocks), ops.RESSTACK_MAX):
+            chunk = blocks[i:i + ops.RESSTACK_MAX]
+            if not ops.resstack_supported(C_, [b.dilation for b in chunk], prec):
+                for b in chunk:
+                    x = b(x)
+                continue
+            x = self._fused_chain(chunk, x, prec)
+        return x
+
+    @staticmethod
+    def _fused_chain(chunk, x_in, prec):
+        from .keras_compat import GradientTape
+        x = x_in if x_in.is_contiguous() else x_in.contiguous()
+        convs = [b._convs(x.shape) for b in chunk]
+        w1 = [c1.kernel.value for c1, _ in convs]; b1 = [c1.bias.value for c1, _ in convs]
+        w2 = [c2.kernel.value for _, c2 in convs]; b2 = [c2.bias.value for _, c2 in convs]
+        dils = [b.dilation for b in chunk]
+        taping = GradientTape.current() is not None
+        ys, hs, xbits, hbits = ops.resstack_fwd(x, w1, b1, w2, b2, dils, prec, train=taping)
+        y = ys[-1]
+        if not taping:
+            return y
+
+        def bwd(g, needs):
+            dy = g[0].contiguous()
+            dxs, dhs = ops.resstack_bwd_data(dy, w1, w2, xbits, hbits, dils, prec)
+            n = len(chunk)
+            for i in reversed(range(n)):  # operands of the weight gradients: block input, h, gradient at its output, dh
+                chunk[i]._weight_gradients(x if i == 0 else ys[i - 1], hs[i], dy if i == n - 1 else dxs[i + 1], dhs[i], prec)
+            return [dxs[0] if needs[0] else None]
+
+        record([x_in], [y], bwd)
+        return y
