@@ -148,6 +148,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run train_step eagerly (profiling)")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train (default): BASELINE.json configs[1] / [2]; infer: configs[4] (8 windows x 2^20 samples, encode -> "
+                         "quantize -> decode, windows spread over the GPUs) as the headline line")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): --batch windows per GPU; strong: the global batch stays --batch windows, split over the GPUs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the `infer` and `strong` sections of the default line")
     ap.add_argument("--precision", default="fp16x2", choices=["fp32", "tf32", "bf16", "bf16x2", "bf16x3", "fp16x2"],
                     help="fp16x2 (default): fp32-grade two-piece fp16 split in the residual blocks (see PRECISION_NOTE); bf16x3: fp32 operands split into 3 bf16 pieces = all 24 mantissa bits, piece products on "
                          "tcgen05, fp32 accumulation (meets the fp32 parity contract, tests/test_gpu_model.py); fp32: exact "
@@ -199,16 +205,38 @@ def main():
     lib = V._lib.lib()
     assert V._lib.is_native()
 
-    V.set_seed(0)
-    model = V.VQVAE((T_WINDOW, 1), **V.SMALL_VQ_VAE)
-    if world > 1:  # identical initial weights / codebooks on every rank
-        V.dist.broadcast(model._packed.params, 0)
-        for vq in model.vqs:
-            for v in (vq.embeddings, vq.m_t, vq.N_t):
-                V.dist.broadcast(v.value, 0)
-    model.compile(optimizer=V.keras.optimizers.Adam())
-    model.use_cuda_graph = not args.no_graph
-    model.set_precision(args.precision)
+    def make_model():
+        V.set_seed(0)
+        m = V.VQVAE((T_WINDOW, 1), **V.SMALL_VQ_VAE)
+        if world > 1:  # identical initial weights / codebooks on every rank
+            V.dist.broadcast(m._packed.params, 0)
+            for vq in m.vqs:
+                for v in (vq.embeddings, vq.m_t, vq.N_t):
+                    V.dist.broadcast(v.value, 0)
+        m.compile(optimizer=V.keras.optimizers.Adam())
+        m.use_cuda_graph = not args.no_graph
+        m.set_precision(args.precision)
+        return m
+
+    if args.workload == "infer":  # configs[4] as the headline
+        with ClockSampler(local) as clk:
+            sec = infer_section(V, world, rank, args.precision, iters=max(args.steps // 4, 3))["infer"]
+        if rank == 0:
+            config["workload"] = sec["workload"]
+            config["parallelism"] = f"replicas x{world}"
+            emit({"metric": sec["metric"], "value": sec["value"], "unit": sec["unit"], "n_gpus": world, "steps": max(args.steps // 4, 3),
+                  "warmup": 2, "ms_per_step": sec["ms_per_pass"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                  "dtype": DTYPE[args.precision], "data": "synthetic", "config": config, "clocks": clk.summary()})
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    if args.scaling == "strong":
+        if args.batch % world:
+            raise SystemExit(f"--scaling strong: the global batch {args.batch} is not divisible by {world} GPUs")
+        config["global_batch"] = args.batch
+        args.batch //= world
+        config["workload"] = config["workload"].replace("32 windows x", f"{args.batch} windows x") + " [strong scaling: global batch fixed]"
+    model = make_model()
     config["precision"] = args.precision
     config["precision_note"] = PRECISION_NOTE[args.precision]
     rng = np.random.Generator(np.random.PCG64(1000 + rank))
@@ -257,6 +285,14 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    extra = {}
+    if not args.no_extra and args.scaling == "weak":
+        del model  # its graphs hold ~5 GB of activations
+        torch.cuda.empty_cache()
+        if world > 1 and 32 % world == 0:   # the same job with the global batch fixed at 32 windows
+            extra.update(strong_section(V, make_model, world, rank, 32, min(args.steps, 10)))
+            torch.cuda.empty_cache()
+        extra.update(infer_section(V, world, rank, args.precision))  # configs[4]
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -265,8 +301,8 @@ def main():
     samples = args.batch * T_WINDOW * world
     pk = peaks()
     line = {"metric": METRIC, "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": DTYPE[args.precision], "data": "synthetic", "config": config,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": DTYPE[args.precision], "data": "synthetic", "config": config, **extra,
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
@@ -287,86 +323,220 @@ def main():
 
 
 def ncu_traffic(name):
-    """DRAM bytes (read + write) of one launch from the committed `ncu --set full` capture (profiles/r1_ncu.json)."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r1_ncu.json")))[name]["traffic_bytes"]
-    except Exception:
-        return None
+    """DRAM bytes (read + write) of one launch from the committed `ncu --set full` captures (profiles/r2_ncu.json, r1_ncu.json)."""
+    for f in ("r2_ncu.json", "r1_ncu.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", f)))[name]["traffic_bytes"]
+        except Exception:
+            continue
+    return None
+
+
+def device_ms(fn, n=20, warm=3):
+    """Average device time of one call of `fn(i)`: n calls captured into a CUDA graph and replayed between two CUDA events on
+    the launching stream (the host side of the calls — ctypes, tensor-map encoding, allocations — is not in the number, as it
+    is not in a captured train_step either).  Inputs alternate (i % 2) and exceed the L2 per call."""
+    import torch
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(n):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
 
 
 def roofline_section(V, pk, precision="fp32"):
-    """The dominant kernel timed ALONE with CUDA events on its launch stream: the fused residual-block forward at the
-    largest stage of the model ([32, 14080, 32], dilation 1) — 208 of the model's 242 forward convolutions are inside
-    such blocks, and the block kernels (forward + data gradient) are the largest share of the step (profiles/).
-    After fusion the block is HBM-bound: 384 algorithmic bytes per time position (read x, write h for the backward pass,
-    write y) against 12 288 FLOP, i.e. 26 us of HBM time vs 3.4 us of bf16 tensor time at this shape (20 us with the 6
-    piece products of bf16x3).  Two input buffers are alternated; inputs + outputs per launch (173 MB) exceed the L2."""
+    """The dominant kernels timed ALONE (CUDA events on their launch stream, graph replays) at the largest stage of the model,
+    [32, 14080, 32]: after round 2 the residual stacks run as ONE launch per DilatedResnet1D (vqb_resstack_fwd under a tape,
+    vqb_resstack_bwd_data; 40 % of the step) next to the batched weight-gradient kernel (22 %).
+    Algorithmic work of a stack (4 blocks = 8 k=3 32->32 convolutions): 49 152 FLOP and 256 B (read x, write y) per time
+    position — with the activations on chip the stack is TENSOR-bound by SURVEY 8d, so `roofline` is quoted on the tensor
+    roofline; the HBM view (algorithmic 256 B and the bytes the training variants really write: `design_bytes`) rides along.
+    `roofline` = the lower of the two training kernels."""
     import torch
     ops = V.ops
     P = V._lib.PRECISIONS[precision]
-    B, L, C, d = 32, 14080, 32, 1
+    B, L, C = 32, 14080, 32
+    dils = (1, 3, 9, 27)
     g = torch.Generator(device="cuda").manual_seed(0)
     xs = [torch.randn(B, L, C, device="cuda", generator=g) for _ in range(2)]
-    w1 = torch.randn(3, C, C, device="cuda", generator=g) * 0.1
-    w2 = torch.randn(3, C, C, device="cuda", generator=g) * 0.1
-    b1 = torch.zeros(C, device="cuda"); b2 = torch.zeros(C, device="cuda")
-    # what train_step launches under a tape: on the tensor-core paths the forward also writes the two sign-mask words per
-    # position for the data gradient (+8 B on 384)
+    dy = torch.randn(B, L, C, device="cuda", generator=g)
+    W1 = [torch.randn(3, C, C, device="cuda", generator=g) * 0.1 for _ in dils]
+    W2 = [torch.randn(3, C, C, device="cuda", generator=g) * 0.1 for _ in dils]
+    Bz = [torch.zeros(C, device="cuda") for _ in dils]
+    pos = B * L
+    flop_stack = 2.0 * pos * (3 * C * C) * 2 * len(dils)
+    kernels = []
+
+    def entry(name, ms, flop, alg_b, design_b, traffic_key=None):
+        tf, gbs = flop / (ms * 1e-3) / 1e12, alg_b / (ms * 1e-3) / 1e9
+        e = {"kernel": name, "ms_per_launch": ms, "tflops": tf, "frac_tensor": tf / pk["tf_sust"], "gbs_algorithmic": gbs,
+             "frac_hbm_algorithmic": gbs / pk["hbm"], "gbs_design": design_b / (ms * 1e-3) / 1e9,
+             "frac_hbm_design": design_b / (ms * 1e-3) / 1e9 / pk["hbm"], "flop_per_launch": flop,
+             "algorithmic_bytes_per_launch": alg_b, "design_bytes_per_launch": design_b,
+             "traffic": ncu_traffic(traffic_key) if traffic_key else None}
+        kernels.append(e)
+        return e
+
+    fused = bool(P) and ops.resstack_supported(C, dils, P)
+    if fused:
+        _, hs, xb, hb = ops.resstack_fwd(xs[0], W1, Bz, W2, Bz, dils, P, True)
+        n = len(dils)
+        t_inf = device_ms(lambda i: ops.resstack_fwd(xs[i % 2], W1, Bz, W2, Bz, dils, P, False))
+        t_trn = device_ms(lambda i: ops.resstack_fwd(xs[i % 2], W1, Bz, W2, Bz, dils, P, True))
+        t_bwd = device_ms(lambda i: ops.resstack_bwd_data(dy, W1, W2, xb, hb, dils, P))
+        e_inf = entry("rs_kernel<0>: vqb_resstack_fwd, inference (4 blocks, dilations 1,3,9,27) [32,14080,32]", t_inf, flop_stack,
+                      pos * 256.0, pos * 256.0, "rs_infer")
+        e_trn = entry("rs_kernel<1>: vqb_resstack_fwd under a tape (stores h_i, y_i, sign masks)", t_trn, flop_stack, pos * 256.0,
+                      pos * (128.0 + n * (256.0 + 8.0)), "rs_train")
+        e_bwd = entry("rs_kernel<2>: vqb_resstack_bwd_data (stores dh_i, dx_i)", t_bwd, flop_stack, pos * 256.0,
+                      pos * (128.0 + n * (256.0 + 8.0)), "rs_bwd")
+        dom = min((e_trn, e_bwd), key=lambda e: e["frac_tensor"])
+    # the per-block kernels (round 1's hot kernels; still the path of the other precisions)
+    w1, w2, b0 = W1[0], W2[0], Bz[0]
     fwd = ops.resblock_fwd_masks if P else ops.resblock_fwd
-    for i in range(4):
-        fwd(xs[i % 2], w1, b1, w2, b2, d, P)
-    torch.cuda.synchronize()
-    n = 20
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(n):
-        fwd(xs[i % 2], w1, b1, w2, b2, d, P)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    flops = 2.0 * B * L * (3 * C * C) * 2          # two k=3 C->C convolutions
-    bytes_alg = B * L * (C * 4 * 3.0 + (8.0 if P else 0.0))  # read x, write h (kept for backward), write y (+ 2 mask words)
-    tf = flops / (ms * 1e-3) / 1e12
-    gbs = bytes_alg / (ms * 1e-3) / 1e9
-    kname = "vqb_resblock_fwd [32,14080,32] dil 1 (" + ("fp32 path: 2 x tgc_kernel" if precision == "fp32" else "rb_tc_kernel, tcgen05 " + precision) + ")"
-    return {"roofline": {"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
-                         "frac": gbs / pk["hbm"], "traffic": ncu_traffic("rb_fwd_" + precision),
-                         "peak_source": pk["src"] + " HBM copy bandwidth", "ms_per_launch": ms,
-                         "algorithmic_bytes_per_launch": bytes_alg,
-                         "algorithmic_bytes_per_unit": "384 B per time position (SURVEY 8d / DESIGN 4) + 8 B of sign masks on the tensor-core paths"},
-            "roofline_tensor": {"bound": "tensor", "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
-                                "frac": tf / pk["tf_burst"], "flop_per_launch": flops,
-                                "note": "algorithmic FLOP of the two convolutions; the tensor pipe is not the limiter of this block"}}
+    t_bf = device_ms(lambda i: fwd(xs[i % 2], w1, b0, w2, b0, 1, P))
+    flop_blk = 2.0 * pos * (3 * C * C) * 2
+    e_bf = entry("vqb_resblock_fwd" + ("_masks" if P else "") + " (one block, dilation 1)", t_bf, flop_blk, pos * 256.0,
+                 pos * (384.0 + (8.0 if P else 0.0)), "rb_fwd_" + precision)
+    if P:
+        _, hh, xb1, hb1 = ops.resblock_fwd_masks(xs[0], w1, b0, w2, b0, 1, P)
+        t_bb = device_ms(lambda i: ops.resblock_bwd_data_masks(xb1, hb1, dy, w1, w2, 1, P))
+        entry("vqb_resblock_bwd_data_masks (one block, dilation 1)", t_bb, flop_blk, pos * 256.0, pos * 392.0, "rb_bwd_" + precision)
+    if not fused:
+        dom = min(kernels, key=lambda e: e["frac_hbm_algorithmic"])
+        return {"roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["gbs_algorithmic"], "peak": pk["hbm"],
+                             "unit": "GB/s", "frac": dom["frac_hbm_algorithmic"], "traffic": dom["traffic"],
+                             "peak_source": pk["src"] + " HBM copy bandwidth", "ms_per_launch": dom["ms_per_launch"],
+                             "algorithmic_bytes_per_unit": "256 B per time position (read x, write y)",
+                             "design_bytes_per_launch": dom["design_bytes_per_launch"]},
+                "roofline_kernels": kernels}
+    return {"roofline": {"kernel": dom["kernel"], "bound": "tensor", "achieved": dom["tflops"], "peak": pk["tf_sust"],
+                         "unit": "TFLOP/s", "frac": dom["frac_tensor"], "traffic": dom["traffic"],
+                         "peak_source": pk["src"] + " bf16 matmul, sustained", "ms_per_launch": dom["ms_per_launch"],
+                         "algorithmic_flop_per_unit": "49 152 FLOP per time position (8 convolutions x 2*3*32*32), fp32-equivalent: "
+                                                      "the fp16x2 arithmetic issues 3 piece products per FLOP counted here",
+                         "hbm": {"algorithmic_bytes_per_unit": "256 B per time position for the whole stack (read x, write y)",
+                                 "achieved_algorithmic": dom["gbs_algorithmic"], "frac_algorithmic": dom["frac_hbm_algorithmic"],
+                                 "design_bytes_per_launch": dom["design_bytes_per_launch"],
+                                 "achieved_design": dom["gbs_design"], "frac_design": dom["frac_hbm_design"], "peak": pk["hbm"]}},
+            "roofline_kernels": kernels}
 
 
 def vq_section(V, pk):
-    """BASELINE.json's second metric: VectorQuantizer latents/s (configs[3]: 2^20 latents x 512 codes x 64 dims, forward =
-    indices + gather + straight-through output + commitment loss + batch statistics), against its HBM roofline
-    (520 algorithmic bytes per latent: x 256 + q_st 256 + idx 8)."""
+    """BASELINE.json's second metric: VectorQuantizer latents/s (configs[3]: 2^20 latents x K in {512, 2048} x 64 dims, forward =
+    indices + gather + straight-through output + commitment loss + batch statistics).  Roofline per SURVEY 8d:
+    max(520 B [264 B with bf16 I/O] per latent / HBM, 2 K D FLOP / bf16 tensor peak)."""
     import torch
     ops = V.ops
-    N, D, K = 1 << 20, 64, 512
+    N, D = 1 << 20, 64
     g = torch.Generator(device="cuda").manual_seed(0)
     xs = [torch.randn(N, D, device="cuda", generator=g) for _ in range(2)]  # 2 x 268 MB alternate: not L2 resident
-    E = torch.randn(D, K, device="cuda", generator=g)
-    mb, nb = ops.empty(D, K), ops.empty(K)
     P = V._lib.PRECISIONS["bf16"]  # tensor-core search with exact fp32 re-ranking: same indices as the fp32 search
-    for i in range(3):
-        ops.vq_fwd(xs[i % 2], E, 0.25, True, False, mb, nb, P)
+    sweep = []
+    for K in (512, 2048):
+        E = torch.randn(D, K, device="cuda", generator=g)
+        mb, nb = ops.empty(D, K), ops.empty(K)
+        for io in ("fp32", "bf16"):
+            if io == "bf16" and not getattr(ops, "VQ_BF16_IO", False):
+                sweep.append({"K": K, "io": io, "unavailable": "bf16 I/O for the VectorQuantizer is not implemented (fp32 activations end to end)"})
+                continue
+            kw = {"io_bf16": True} if io == "bf16" else {}
+            xin = [x.to(torch.bfloat16) for x in xs] if io == "bf16" else xs
+            ms = device_ms(lambda i: ops.vq_fwd(xin[i % 2], E, 0.25, True, False, mb, nb, P, **kw), n=10)
+            per = 264 if io == "bf16" else 520
+            t_hbm, t_mma = N * per / (pk["hbm"] * 1e9), N * 2.0 * K * D / (pk["tf_sust"] * 1e12)
+            bound = "hbm" if t_hbm >= t_mma else "tensor"
+            sweep.append({"K": K, "io": io, "ms": ms, "latents_per_s": N / (ms * 1e-3), "bound": bound,
+                          "roofline_ms": max(t_hbm, t_mma) * 1e3, "frac": max(t_hbm, t_mma) * 1e3 / ms,
+                          "algorithmic_bytes_per_unit": per, "flop_per_unit": 2 * K * D})
+    head = sweep[0]
+    return {"vq": {"metric": "VQ latents/sec", "workload": "VectorQuantizer forward, 2^20 latents x 512 codes x 64 dims, fp32 I/O, exact fp32 indices",
+                   "value": head["latents_per_s"], "unit": "latents/s", "ms": head["ms"],
+                   "roofline": {"bound": head["bound"], "achieved": N * 520 / (head["ms"] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                "frac": head["frac"], "algorithmic_bytes_per_unit": 520}},
+            "vq_sweep": sweep}
+
+
+def infer_section(V, world, rank, precision, windows=8, log2_window=20, iters=3):
+    """BASELINE.json configs[4]: SMALL_VQ_VAE encode -> quantize -> decode of both levels over `windows` windows of 2^20 samples.
+    Windows are independent: rank r takes windows r, r + world, ... (replicas only, no collective on the data path; strong
+    scaling: the job is the same 8 windows at every N).  Device time, max over ranks."""
+    import numpy as np
+    import torch
+    T = 1 << log2_window
+    V.set_seed(0)
+    m = V.VQVAE((T, 1), **V.SMALL_VQ_VAE)
+    m.set_precision(precision)
+    mine = list(range(rank, windows, world))
+    rng = np.random.Generator(np.random.PCG64(5))
+    x = torch.from_numpy(rng.uniform(0, 1, size=(windows, T, 1)).astype(np.float32))[mine].cuda()
+
+    def run():
+        codes = m.encode(x)
+        return codes, [m.decode(c, level=l) for l, c in enumerate(codes)]
+
+    ms = 0.0
+    if mine:
+        for _ in range(2):
+            run()
     torch.cuda.synchronize()
-    n = 10
+    if world > 1:
+        torch.distributed.barrier()
+    if mine:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            codes, recons = run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t[0])
+    del m, x
+    torch.cuda.empty_cache()
+    return {"infer": {"metric": "VQ-VAE encode->quantize->decode audio samples/sec (both levels)", "value": windows * T / (ms * 1e-3),
+                      "unit": "samples/s", "ms_per_pass": ms, "n_gpus": world, "scaling": "strong",
+                      "workload": f"{windows} windows x 2^{log2_window} samples (BASELINE.json configs[4]), encode + decode of levels 0 "
+                                  f"and 1, {len(list(range(0, windows, world)))} window(s) per GPU, replicas only"}}
+
+
+def strong_section(V, model_factory, world, rank, global_batch, steps):
+    """SURVEY 8d C3, strong scaling: the global batch stays 32 windows, every rank trains on 32 / N of them (same model, one
+    all-reduce per step).  Returns samples/s of the whole job (device time, max over ranks)."""
+    import numpy as np
+    import torch
+    per = global_batch // world
+    model = model_factory()
+    rng = np.random.Generator(np.random.PCG64(2000 + rank))
+    x = torch.from_numpy(rng.uniform(0, 1, size=(per, T_WINDOW, 1)).astype(np.float32)).cuda()
+    for _ in range(5):
+        model.train_step((x, None))
+    torch.distributed.barrier()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(n):
-        ops.vq_fwd(xs[i % 2], E, 0.25, True, False, mb, nb, P)
+    for _ in range(steps):
+        model.train_step((x, None))
     e1.record()
+    torch.distributed.barrier()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    t_hbm = N * 520 / (pk["hbm"] * 1e9)
-    return {"vq": {"metric": "VQ latents/sec", "workload": "VectorQuantizer forward, 2^20 latents x 512 codes x 64 dims, fp32 I/O, exact fp32 indices",
-                   "value": N / (ms * 1e-3), "unit": "latents/s", "ms": ms,
-                   "roofline": {"bound": "hbm", "achieved": N * 520 / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                                "frac": t_hbm * 1e3 / ms, "algorithmic_bytes_per_unit": 520}}}
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t[0])
+    return {"strong": {"metric": METRIC, "value": per * world * T_WINDOW / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+                       "scaling": "strong", "global_batch": per * world, "windows_per_gpu": per, "n_gpus": world}}
 
 
 if __name__ == "__main__":
