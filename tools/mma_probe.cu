@@ -105,6 +105,54 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Probe p, long long* out) 
   if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
+// Is the ~50 clk per small-N MMA a property of the tensor pipe or of the issuing thread?  NI threads (lane 0 of NI different warps)
+// issue reps / NI MMAs each into their own accumulators at the same time; the clock runs until all of them have completed.
+__global__ void __launch_bounds__(128, 1) probe_multi_kernel(int N, int reps, int ni, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t tslot;
+  __shared__ long long tstart[4], tend[4];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int e = tid; e < 200 * 1024 / 16; e += blockDim.x) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 32) tmem_alloc(&tslot, 512);
+  if (tid == 32) { for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1); fence_mbar_init(); }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tslot;
+  const int PK = (256 + 64) * 16 + 32, PW = 96 * 16;
+  if ((tid & 31) == 0 && warp < ni) {
+    uint8_t* A = smem + warp * 24 * 1024;
+    uint8_t* B = smem + 100 * 1024 + warp * 8 * 1024;
+    const uint64_t ad0 = smem_desc(smem_u32(A), PK, 128), bd0 = smem_desc(smem_u32(B), PW, 128);
+    const uint32_t idesc = instr_desc(FMT_BF16, 128, N, false, false);
+    const uint32_t dst = tmem + warp * 128;
+    for (int i = 0; i < 8; ++i) mma<false>(dst, ad0, bd0, idesc, 1);
+    commit(&bar[warp]);
+    mbar_wait(&bar[warp], 0);
+    tstart[warp] = clock64();
+#pragma unroll 1
+    for (int i = 0; i < reps / ni; i += 4) {
+      mma<false>(dst, ad0, bd0, idesc, 1);
+      mma<false>(dst, ad0 + 1, bd0, idesc, 1);
+      mma<false>(dst, ad0 + 2, bd0, idesc, 1);
+      mma<false>(dst, ad0, bd0, idesc, 1);
+    }
+    commit(&bar[warp]);
+    mbar_wait(&bar[warp], 1);
+    tend[warp] = clock64();
+  }
+  __syncthreads();
+  if (tid == 0 && blockIdx.x == 0) {
+    long long t0 = tstart[0], t1 = tend[0];
+    for (int i = 1; i < ni; ++i) { t0 = t0 < tstart[i] ? t0 : tstart[i]; t1 = t1 > tend[i] ? t1 : tend[i]; }
+    out[0] = t1 - t0;
+  }
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
 int main() {
   long long* d;
   cudaMalloc(&d, 8);
@@ -157,6 +205,17 @@ int main() {
     long long cyc = 0;
     cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
     printf("%-52s %8.1f clk / MMA   (%s)\n", c.name, (double)cyc / reps, cudaGetErrorString(e));
+  }
+  cudaFuncSetAttribute(probe_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  for (int N : {32, 64}) {
+    for (int ni : {1, 2, 4}) {
+      probe_multi_kernel<<<4, 128, 200 * 1024>>>(N, 480, ni, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long cyc = 0;
+      cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+      printf("K-major N=%d, %d issuing thread(s) (different warps), 480 MMAs in total      %8.1f clk / MMA   (%s)\n", N, ni,
+             (double)cyc / 480, cudaGetErrorString(e));
+    }
   }
   return 0;
 }

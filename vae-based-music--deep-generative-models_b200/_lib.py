@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libvqvae_b200.so")
+# VQB_LIB: another build of the same library (A/B timing of two kernel variants on one GPU box); default = the in-tree build
+LIB_PATH = os.environ.get("VQB_LIB") or os.path.join(_HERE, "csrc", "libvqvae_b200.so")
 
 PREC_FP32, PREC_TF32, PREC_BF16, PREC_BF16X2, PREC_BF16X3, PREC_FP16X2 = 0, 1, 2, 3, 4, 5
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "bf16x2": PREC_BF16X2, "bf16x3": PREC_BF16X3,
