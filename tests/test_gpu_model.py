@@ -217,8 +217,10 @@ def test_small_vqvae_training_trajectory(gpu):
 def test_small_vqvae_fp32_grade_tensor_core_mode(gpu, prec):
     """precision "fp16x2": see tc.cuh (two scaled fp16 pieces in the residual blocks, bf16x3 elsewhere).  precision "bf16x3" — every fp32 operand split into 3 bf16 pieces (all 24 mantissa bits), piece products on tcgen05,
     fp32 accumulation in TMEM — against the fp32 oracle on SMALL_VQ_VAE (batch 2): identical code indices (up to the 1e-5
-    near-tie allowance), reconstructions and losses within 1e-3, gradient vector within 1e-3 of its largest entry per level
-    (single tensors can deviate more when a ReLU mask flips at |h| ~ 1e-6: the block is discontinuous there)."""
+    near-tie allowance), reconstructions and losses within 1e-3, and EVERY gradient tensor within 1e-3 of its own largest entry
+    (floored at 1e-3 of the level's largest gradient) — the same per-tensor rule as the exact-fp32 kernels in
+    test_small_vqvae_forward_and_gradients.  Measured margins: profiles/r2_precision_report.json (fp16x2 ~7e-5 / 2.4e-4 of the
+    allowance unit, bf16x3 3e-4 / 4e-4)."""
     V = gpu
     spec = O.ModelSpec(T=28160, **O.SMALL_VQ_VAE)
     weights, vq = O.init_model(spec, 0, bias_scale=0.02)
@@ -253,7 +255,7 @@ def test_small_vqvae_fp32_grade_tensor_core_mode(gpu, prec):
         gmax = max(float(t.abs().max()) for t in grads[l])
         for want in grads[l]:
             err = float((g[i].cpu() - want).abs().max())
-            assert err <= REL * gmax, (l, i, err, gmax)
+            assert err <= REL * max(float(want.abs().max()), 1e-3 * gmax), (l, i, err, float(want.abs().max()), gmax)
             i += 1
 
 
