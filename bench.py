@@ -389,11 +389,11 @@ def roofline_section(V, pk, precision="fp32"):
 
     fused = bool(P) and ops.resstack_supported(C, dils, P)
     if fused:
-        _, hs, xb, hb = ops.resstack_fwd(xs[0], W1, Bz, W2, Bz, dils, P, True)
+        _, hs, xb, hb, fws = ops.resstack_fwd(xs[0], W1, Bz, W2, Bz, dils, P, True)
         n = len(dils)
         t_inf = device_ms(lambda i: ops.resstack_fwd(xs[i % 2], W1, Bz, W2, Bz, dils, P, False))
         t_trn = device_ms(lambda i: ops.resstack_fwd(xs[i % 2], W1, Bz, W2, Bz, dils, P, True))
-        t_bwd = device_ms(lambda i: ops.resstack_bwd_data(dy, W1, W2, xb, hb, dils, P))
+        t_bwd = device_ms(lambda i: ops.resstack_bwd_data(dy, W1, W2, xb, hb, dils, P, fwd_ws=fws))  # as train_step runs it
         e_inf = entry("rs_kernel<0>: vqb_resstack_fwd, inference (4 blocks, dilations 1,3,9,27) [32,14080,32]", t_inf, flop_stack,
                       pos * 256.0, pos * 256.0, "rs_infer")
         e_trn = entry("rs_kernel<1>: vqb_resstack_fwd under a tape (stores h_i, y_i, sign masks)", t_trn, flop_stack, pos * 256.0,

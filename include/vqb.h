@@ -173,6 +173,12 @@ int vqb_resstack_fwd(const vqb_resstack_desc* d, const float* x, const float* co
 int vqb_resstack_bwd_data(const vqb_resstack_desc* d, const float* dy, const float* const* w1, const float* const* w2,
                           const uint32_t* const* xbits, const uint32_t* const* hbits, float* const* dh, float* const* dx,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* The same, running from the workspace of the vqb_resstack_fwd call (under a tape) of the same blocks and weights: that call
+ * packs the operand images of both directions, so the backward pass of a step needs no packing launch.  The caller keeps the
+ * forward's workspace alive and unmodified until this call has run (tape.gradient, vqvae.py:142-143). */
+int vqb_resstack_bwd_data_packed(const vqb_resstack_desc* d, const float* dy, const uint32_t* const* xbits,
+                                 const uint32_t* const* hbits, float* const* dh, float* const* dx, void* fwd_workspace,
+                                 size_t workspace_bytes, void* stream);
 
 /* Both weight gradients of the block in one call (tensor-core precisions: one launch):
  *   dw1[3, C, F] = sum ReLU(x)[t + (j-1) dilation] dh[t],  db1[F] = sum dh   (dilated conv, resnet.py:13-15)

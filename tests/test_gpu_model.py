@@ -21,6 +21,25 @@ def rel_err(got, want):
     return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-12))
 
 
+FLIP_TOL = 2e-5  # the residual kernels' output tolerance (tests/test_gpu_tc.py, test_gpu_stack.py): sign of |h| below it is undecided
+
+
+def check_gradients(g, grads, res):
+    """north star: gradients within 1e-3 relative.  Per tensor: |got - want| <= 1e-3 * max(|want|max, 1e-3 * largest gradient of
+    the level) — plus, for the first convolution of a residual block only, what ReLU masks flipping at numerically undecided
+    pre-activations can move (oracle.relu_flip_bounds: the sum of the pre-mask gradients where the ORACLE's own |h| is below the
+    kernels' output tolerance; a block's weight gradient is discontinuous there, so no arithmetic can do better)."""
+    i = 0
+    for l in range(len(grads)):
+        gmax = max(float(t.abs().max()) for t in grads[l])
+        fb = res[l].get("flip_bounds") or [0.0] * len(grads[l])
+        for j, want in enumerate(grads[l]):
+            err = float((g[i].cpu() - want).abs().max())
+            allowed = REL * max(float(want.abs().max()), 1e-3 * gmax)
+            assert err <= allowed + fb[j], (l, j, err, allowed, fb[j], float(want.abs().max()), gmax)
+            i += 1
+
+
 def load_into(m, weights, vq):
     for l in range(m.levels):
         for v, w in zip(m.vqvaes[l].trainable_variables, weights[l]):
@@ -107,7 +126,7 @@ def test_small_vqvae_forward_and_gradients(gpu):
     m = V.VQVAE((28160, 1), **V.SMALL_VQ_VAE)
     m.use_cuda_graph = False
     load_into(m, weights, vq)
-    res, grads = O.loss_and_grads(spec, weights, vq, torch.tensor(x))
+    res, grads = O.loss_and_grads(spec, weights, vq, torch.tensor(x), flip_tol=FLIP_TOL)
     with V.GradientTape() as tape:
         total = V.keras.Scalar()
         outs = []
@@ -129,11 +148,7 @@ def test_small_vqvae_forward_and_gradients(gpu):
         scale = (zt ** 2).sum(1) + (Et ** 2).sum(0)[d64.argmin(1)]  # magnitude of the reference's fp32 expression
         ok = (srt[:, 1] - srt[:, 0]) > 1e-5 * scale
         assert int(((idx != res[l]["idx"]) & ok).sum()) == 0
-        gmax = max(float(t.abs().max()) for t in grads[l])
-        for want in grads[l]:
-            err = float((g[i].cpu() - want).abs().max())
-            assert err <= REL * max(float(want.abs().max()), 1e-3 * gmax), (l, i, err)
-            i += 1
+    check_gradients(g, grads, res)
 
 
 def test_full_size_properties(gpu):
@@ -230,7 +245,7 @@ def test_small_vqvae_fp32_grade_tensor_core_mode(gpu, prec):
     m.use_cuda_graph = False
     m.set_precision(prec)
     load_into(m, weights, vq)
-    res, grads = O.loss_and_grads(spec, weights, vq, torch.tensor(x))
+    res, grads = O.loss_and_grads(spec, weights, vq, torch.tensor(x), flip_tol=FLIP_TOL)
     with V.GradientTape() as tape:
         total = V.keras.Scalar()
         outs = []
@@ -252,11 +267,7 @@ def test_small_vqvae_fp32_grade_tensor_core_mode(gpu, prec):
         scale = (zt ** 2).sum(1) + (Et ** 2).sum(0)[d64.argmin(1)]
         ok = (srt[:, 1] - srt[:, 0]) > 1e-5 * scale
         assert int(((idx != res[l]["idx"]) & ok).sum()) == 0
-        gmax = max(float(t.abs().max()) for t in grads[l])
-        for want in grads[l]:
-            err = float((g[i].cpu() - want).abs().max())
-            assert err <= REL * max(float(want.abs().max()), 1e-3 * gmax), (l, i, err, float(want.abs().max()), gmax)
-            i += 1
+    check_gradients(g, grads, res)
 
 
 def test_long_window_inference_is_time_tiling_consistent(gpu):

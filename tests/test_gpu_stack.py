@@ -57,7 +57,7 @@ def test_resstack_inference_forward(gpu, B, L, dils):
     x, ws = make(rng, B, L, len(dils))
     _, ys_ref, _, _ = oracle_stack(x, ws, dils)
     W = [[dev(a) for a in blk] for blk in ws]
-    ys, hs, xb, hb = ops.resstack_fwd(dev(x), [w[0] for w in W], [w[1] for w in W], [w[2] for w in W], [w[3] for w in W],
+    ys, hs, xb, hb, fws = ops.resstack_fwd(dev(x), [w[0] for w in W], [w[1] for w in W], [w[2] for w in W], [w[3] for w in W],
                                       dils, P, train=False)
     torch.cuda.synchronize()
     assert hs is None and all(y is None for y in ys[:-1])
@@ -75,7 +75,7 @@ def test_resstack_training_forward_and_data_gradient(gpu, B, L, dils):
     dy = rng.normal(size=(B, L, 32)).astype(np.float32)
     hs_ref, ys_ref, gx_ref, gh_ref = oracle_stack(x, ws, dils, dy)
     W = [[dev(a) for a in blk] for blk in ws]
-    ys, hs, xb, hb = ops.resstack_fwd(dev(x), [w[0] for w in W], [w[1] for w in W], [w[2] for w in W], [w[3] for w in W],
+    ys, hs, xb, hb, fws = ops.resstack_fwd(dev(x), [w[0] for w in W], [w[1] for w in W], [w[2] for w in W], [w[3] for w in W],
                                       dils, P, train=True)
     torch.cuda.synchronize()
     ins_ref = [torch.tensor(x)] + [y.detach() for y in ys_ref[:-1]]
@@ -114,8 +114,8 @@ def test_resstack_full_size_matches_block_kernels(gpu, dils):
           torch.randn(3, C, C, device="cuda", generator=g) / 96 ** 0.5, torch.randn(C, device="cuda", generator=g) * 0.1]
          for _ in dils]
     dy = torch.randn(B, L, C, device="cuda", generator=g)
-    ys, hs, xb, hb = ops.resstack_fwd(x, [w[0] for w in W], [w[1] for w in W], [w[2] for w in W], [w[3] for w in W], dils, P, True)
-    yi, _, _, _ = ops.resstack_fwd(x, [w[0] for w in W], [w[1] for w in W], [w[2] for w in W], [w[3] for w in W], dils, P, False)
+    ys, hs, xb, hb, fws = ops.resstack_fwd(x, [w[0] for w in W], [w[1] for w in W], [w[2] for w in W], [w[3] for w in W], dils, P, True)
+    yi, _, _, _, _ = ops.resstack_fwd(x, [w[0] for w in W], [w[1] for w in W], [w[2] for w in W], [w[3] for w in W], dils, P, False)
     cur = x
     for i, d in enumerate(dils):
         y0, h0 = ops.resblock_fwd(cur, *W[i], d, 0)
@@ -124,6 +124,9 @@ def test_resstack_full_size_matches_block_kernels(gpu, dils):
     assert rel(yi[-1], cur) < TOL
     assert torch.equal(yi[-1], ys[-1])  # the inference and the training instantiation compute the same numbers
     dxs, dhs = ops.resstack_bwd_data(dy, [w[0] for w in W], [w[2] for w in W], xb, hb, dils, P)
+    # ... and from the operand images the training forward packed (vqb_resstack_bwd_data_packed: no packing launch): same bits
+    dxp, dhp = ops.resstack_bwd_data(dy, None, None, xb, hb, dils, P, fwd_ws=fws)
+    assert all(torch.equal(a, b) for a, b in zip(dxs + dhs, dxp + dhp))
     gcur = dy
     for i in reversed(range(len(dils))):
         xin = x if i == 0 else ys[i - 1]

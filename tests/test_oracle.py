@@ -212,3 +212,37 @@ def test_golden_fixtures_reproduce():
     res = O.forward_losses(spec, weights, vq, torch.tensor(x))
     for l in range(spec.levels):
         np.testing.assert_allclose(res[l]["recon"].numpy(), t[f"recon{l}"], rtol=1e-4, atol=1e-5)
+
+
+def test_relu_flip_bounds_cover_a_perturbed_block():
+    """oracle.relu_flip_bounds: a residual block's w1 / b1 gradients are discontinuous where h crosses 0.  Shifting h by less than
+    tol * max|h| (here: a tiny change of b1) may flip masks; the change of the gradients must stay inside the bound."""
+    rng = np.random.default_rng(0)
+    C, L, d = 8, 4000, 3
+    x = torch.tensor(rng.normal(size=(1, L, C)).astype(np.float32))
+    w1 = torch.tensor((rng.normal(size=(3, C, C)) / np.sqrt(3 * C)).astype(np.float32))
+    w2 = torch.tensor((rng.normal(size=(3, C, C)) / np.sqrt(3 * C)).astype(np.float32))
+    b2 = torch.zeros(C)
+    dy = torch.tensor(rng.normal(size=(1, L, C)).astype(np.float32))
+    tol = 1e-3
+
+    def grads(b1v):
+        p = [w1.clone().requires_grad_(True), b1v.clone().requires_grad_(True), w2.clone().requires_grad_(True), b2.clone().requires_grad_(True)]
+        O.TRACE = []
+        y = O.resblock(x, *p, d)
+        rec, O.TRACE = O.TRACE, None
+        allg = torch.autograd.grad((y * dy).sum(), p + [rec[0]["ah"]])
+        return p, rec, allg
+
+    b1 = torch.tensor((0.1 * rng.normal(size=C)).astype(np.float32))
+    p, rec, g0 = grads(b1)
+    bounds = O.relu_flip_bounds(rec, [g0[4]], 4, p, tol)
+    assert bounds[2] == 0.0 and bounds[3] == 0.0 and bounds[0] > 0 and bounds[1] > 0
+    hmax = float(rec[0]["h"].abs().max())
+    flips_seen = 0
+    for sign in (+1, -1):
+        p2, rec2, g1 = grads(b1 + sign * 0.5 * tol * hmax)
+        flips_seen += int(((rec2[0]["h"] > 0) != (rec[0]["h"] > 0)).sum())
+        assert float((g1[1] - g0[1]).abs().max()) <= bounds[1] * 1.01 + 1e-5     # b1
+        assert float((g1[0] - g0[0]).abs().max()) <= bounds[0] * 1.01 + 1e-4     # w1
+    assert flips_seen > 0  # the perturbation really crossed zeros

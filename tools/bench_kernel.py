@@ -29,7 +29,7 @@ if what.startswith("stack"):
     W1 = [torch.randn(3, C, C, device="cuda", generator=g) * 0.1 for _ in dils]
     W2 = [torch.randn(3, C, C, device="cuda", generator=g) * 0.1 for _ in dils]
     Bz = [torch.zeros(C, device="cuda") for _ in dils]
-    _, _, sxb, shb = ops.resstack_fwd(xs[0], W1, Bz, W2, Bz, dils, P, True)
+    _, _, sxb, shb, sws = ops.resstack_fwd(xs[0], W1, Bz, W2, Bz, dils, P, True)
 n = int(os.environ.get("N", "6"))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -46,7 +46,7 @@ def one(i):
     elif what == "stack_train":
         ops.resstack_fwd(xs[i % 2], W1, Bz, W2, Bz, dils, P, True)
     elif what == "stack_bwd":
-        ops.resstack_bwd_data(dy, W1, W2, sxb, shb, dils, P)
+        ops.resstack_bwd_data(dy, W1, W2, sxb, shb, dils, P, fwd_ws=sws if os.environ.get("PACKED", "1") == "1" else None)
     elif what == "resblock_bwd":
         ops.resblock_bwd_data(xs[i % 2], h, dy, w1, w2, int(os.environ.get("DIL", "1")), P)
     elif what == "resblock_wgrad":

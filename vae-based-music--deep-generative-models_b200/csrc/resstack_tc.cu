@@ -80,10 +80,10 @@ struct RsMaps {
   CUtensorMap out[RS_MAXC][2];         // [k][0]: box of 128 - H rows (first / last M block), [k][1]: 128 rows (middle)
 };
 
-struct RsPackParams {
-  const float* w[RS_MAXC];
-  const float* bias[RS_MAXC];
-  int sj[RS_MAXC], si[RS_MAXC], so[RS_MAXC], flip[RS_MAXC];
+struct RsPackParams {  // up to 2 * RS_MAXC records: a training forward also packs the images of its data-gradient chain
+  const float* w[2 * RS_MAXC];
+  const float* bias[2 * RS_MAXC];
+  int sj[2 * RS_MAXC], si[2 * RS_MAXC], so[2 * RS_MAXC], flip[2 * RS_MAXC];
   uint8_t* out;
 };
 
@@ -517,7 +517,7 @@ bool resstack_tc_supported(const vqb_resstack_desc* d) {
   return H <= 64;
 }
 
-size_t resstack_tc_workspace_bytes(const vqb_resstack_desc* d) { return (size_t)RS_MAXC * RsCfg::WREC + 256; }
+size_t resstack_tc_workspace_bytes(const vqb_resstack_desc* d) { return (size_t)2 * RS_MAXC * RsCfg::WREC + 256; }
 
 template <int KIND, bool TRACE = false>
 static int launch_rs(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
@@ -538,10 +538,12 @@ static int launch_rs(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
   return VQB_OK;
 }
 
-// kind 0 / 1: forward (h == NULL -> inference), kind 2: data gradient
+// kind 0 / 1: forward (h == NULL -> inference), kind 2: data gradient.  A training forward (kind 1) packs the operand images of
+// BOTH directions (records [0, nconv): forward, [nconv, 2 nconv): data gradient), so that the data gradient of the same step can
+// run from the same workspace without a packing launch of its own (`prepacked`).
 int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const float* const* w1, const float* const* b1,
                 const float* const* w2, const float* const* b2, float* const* o1, float* const* o2, uint32_t* const* xbits,
-                uint32_t* const* hbits, void* ws, size_t ws_bytes, cudaStream_t st) {
+                uint32_t* const* hbits, void* ws, size_t ws_bytes, cudaStream_t st, bool prepacked = false) {
   if (!resstack_tc_supported(d))
     return set_err(VQB_ERR_UNIMPLEMENTED, "fused residual stack: C = 32, 1..%d blocks, dilations < %d, fp16x2 only", VQB_RESSTACK_MAX_BLOCKS, RsCfg::G);
   if (d->B == 0 || d->L == 0) return VQB_OK;
@@ -554,7 +556,7 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
   alignas(64) RsMaps maps;  // filled per call, copied into the launch parameters
   memset(&maps, 0, sizeof(maps));
   pk.out = wsp;
-  p.wpack = wsp;
+  p.wpack = (kind == 2 && prepacked) ? wsp + (size_t)nconv * RsCfg::WREC : wsp;
   p.B = d->B; p.L = d->L; p.nconv = nconv;
   int H = 0;
   for (int i = 0; i < n; ++i) H += d->dilations[i] + 1;
@@ -592,8 +594,20 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
       if (!tma::make_rows_map(&maps.out[k][0], outs[k], d->B, d->L, 128 - H) || !tma::make_rows_map(&maps.out[k][1], outs[k], d->B, d->L, 128))
         return set_err(VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed for an output of the residual stack");
     }
-  rs_pack_kernel<<<nconv, 256, 0, st>>>(pk);
-  VQB_LAUNCH_CHECK();
+  int npack = nconv;
+  if (kind == 1) {  // + the data-gradient chain of the same blocks: n-1 .. 0, conv2^T then conv1^T, no bias
+    for (int k = 0; k < nconv; ++k) {
+      const int i = n - 1 - (k >> 1), stage = k & 1;
+      pk.w[nconv + k] = stage ? w1[i] : w2[i];
+      pk.bias[nconv + k] = nullptr;
+      pk.sj[nconv + k] = 32 * 32; pk.si[nconv + k] = 1; pk.so[nconv + k] = 32; pk.flip[nconv + k] = 1;
+    }
+    npack = 2 * nconv;
+  }
+  if (!(kind == 2 && prepacked)) {
+    rs_pack_kernel<<<npack, 256, 0, st>>>(pk);
+    VQB_LAUNCH_CHECK();
+  }
   if (kind == 0 && getenv("VQB_RS_TRACE")) {  // profiling aid: address of a device buffer of 4 * 9 * 8 int64 (tools/trace_stack.py)
     p.trace = reinterpret_cast<long long*>(strtoull(getenv("VQB_RS_TRACE"), nullptr, 0));
     return launch_rs<0, true>(p, maps, st);
@@ -640,6 +654,19 @@ int vqb_resstack_bwd_data(const vqb_resstack_desc* d, const float* dy, const flo
     VQB_REQUIRE(xbits[i] && hbits[i] && dh[i] && dx[i], "vqb_resstack_bwd_data: xbits, hbits, dh, dx of block %d", i);
   return resstack_tc(2, d, dy, w1, nullptr, w2, nullptr, dh, dx, const_cast<uint32_t* const*>(xbits),
                      const_cast<uint32_t* const*>(hbits), workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int vqb_resstack_bwd_data_packed(const vqb_resstack_desc* d, const float* dy, const uint32_t* const* xbits,
+                                 const uint32_t* const* hbits, float* const* dh, float* const* dx, void* fwd_workspace,
+                                 size_t workspace_bytes, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(d && dy && xbits && hbits && dh && dx && fwd_workspace, "vqb_resstack_bwd_data_packed: NULL pointer");
+  VQB_REQUIRE(d->B >= 0 && d->L >= 0, "vqb_resstack_bwd_data_packed: bad shape B=%d L=%d", d->B, d->L);
+  for (int i = 0; i < d->n_blocks && i < VQB_RESSTACK_MAX_BLOCKS; ++i)
+    VQB_REQUIRE(xbits[i] && hbits[i] && dh[i] && dx[i], "vqb_resstack_bwd_data_packed: xbits, hbits, dh, dx of block %d", i);
+  const float* none[VQB_RESSTACK_MAX_BLOCKS] = {nullptr, nullptr, nullptr, nullptr};  // weights are not read again
+  return resstack_tc(2, d, dy, none, nullptr, none, nullptr, dh, dx, const_cast<uint32_t* const*>(xbits),
+                     const_cast<uint32_t* const*>(hbits), fwd_workspace, workspace_bytes, (cudaStream_t)stream, true);
 }
 
 }  // extern "C"

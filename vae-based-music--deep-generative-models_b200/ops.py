@@ -258,9 +258,10 @@ def _parr(ts):
 
 
 def resstack_fwd(x, w1s, b1s, w2s, b2s, dilations, precision, train):
-    """A chain of len(dilations) residual blocks in one launch (vqb_resstack_fwd).  Returns (ys, hs, xbits, hbits): under a
-    tape (`train`) every block's h, output and sign masks (lists of n tensors), else ys = [None, ..., y_last] and hs, xbits,
-    hbits = None (nothing but the stack's output is written)."""
+    """A chain of len(dilations) residual blocks in one launch (vqb_resstack_fwd).  Returns (ys, hs, xbits, hbits, ws): under a
+    tape (`train`) every block's h, output and sign masks (lists of n tensors) and the workspace with the packed operand
+    images of both directions (hand it to resstack_bwd_data), else ys = [None, ..., y_last] and hs, xbits, hbits, ws = None
+    (nothing but the stack's output is written)."""
     _chk(x, "x")
     for t in (*w1s, *b1s, *w2s, *b2s):
         _chk(t, "weight")
@@ -275,23 +276,28 @@ def resstack_fwd(x, w1s, b1s, w2s, b2s, dilations, precision, train):
         hb = [torch.empty(B, L, dtype=torch.int32, device=_lib.device()) for _ in range(n)]
         call("vqb_resstack_fwd", C.byref(d), ptr(x), _parr(w1s), _parr(b1s), _parr(w2s), _parr(b2s), _parr(hs), _parr(ys),
              _parr(xb), _parr(hb), ptr(ws), ws.numel(), _lib.stream())
-        return ys, hs, xb, hb
+        return ys, hs, xb, hb, ws
     ys = [None] * (n - 1) + [empty(B, L, Cc)]
     call("vqb_resstack_fwd", C.byref(d), ptr(x), _parr(w1s), _parr(b1s), _parr(w2s), _parr(b2s), None, _parr(ys), None, None,
          ptr(ws), ws.numel(), _lib.stream())
-    return ys, None, None, None
+    return ys, None, None, None, None
 
 
-def resstack_bwd_data(dy, w1s, w2s, xbits, hbits, dilations, precision):
+def resstack_bwd_data(dy, w1s, w2s, xbits, hbits, dilations, precision, fwd_ws=None):
     """Data gradients of the chain (vqb_resstack_bwd_data): returns (dxs, dhs), dxs[i] = gradient at the input of block i,
-    dhs[i] = gradient at the output of its first convolution."""
+    dhs[i] = gradient at the output of its first convolution.  fwd_ws: the workspace returned by the resstack_fwd(train=True)
+    call of the same blocks and (unchanged) weights — the operand images packed there are reused (no packing launch)."""
     _chk(dy, "dy")
     B, L, Cc = dy.shape
     n = len(dilations)
     d = _sdesc(B, L, Cc, list(dilations), precision)
-    ws = _ws(_lib.lib().vqb_resstack_workspace_bytes(C.byref(d)))
     dhs = [empty(B, L, Cc) for _ in range(n)]
     dxs = [empty(B, L, Cc) for _ in range(n)]
+    if fwd_ws is not None:
+        call("vqb_resstack_bwd_data_packed", C.byref(d), ptr(dy), _parr(xbits), _parr(hbits), _parr(dhs), _parr(dxs),
+             ptr(fwd_ws), fwd_ws.numel(), _lib.stream())
+        return dxs, dhs
+    ws = _ws(_lib.lib().vqb_resstack_workspace_bytes(C.byref(d)))
     call("vqb_resstack_bwd_data", C.byref(d), ptr(dy), _parr(w1s), _parr(w2s), _parr(xbits), _parr(hbits), _parr(dhs),
          _parr(dxs), ptr(ws), ws.numel(), _lib.stream())
     return dxs, dhs

@@ -130,14 +130,14 @@ class DilatedResnet1D(layers.Layer):
         w2 = [c2.kernel.value for _, c2 in convs]; b2 = [c2.bias.value for _, c2 in convs]
         dils = [b.dilation for b in chunk]
         taping = GradientTape.current() is not None
-        ys, hs, xbits, hbits = ops.resstack_fwd(x, w1, b1, w2, b2, dils, prec, train=taping)
+        ys, hs, xbits, hbits, ws = ops.resstack_fwd(x, w1, b1, w2, b2, dils, prec, train=taping)
         y = ys[-1]
         if not taping:
             return y
 
         def bwd(g, needs):
             dy = g[0].contiguous()
-            dxs, dhs = ops.resstack_bwd_data(dy, w1, w2, xbits, hbits, dils, prec)
+            dxs, dhs = ops.resstack_bwd_data(dy, w1, w2, xbits, hbits, dils, prec, fwd_ws=ws)  # images packed by the forward
             n = len(chunk)
             for i in reversed(range(n)):  # operands of the weight gradients: block input, h, gradient at its output, dh
                 chunk[i]._weight_gradients(x if i == 0 else ys[i - 1], hs[i], dy if i == n - 1 else dxs[i + 1], dhs[i], prec)
