@@ -389,3 +389,58 @@ def test_every_precision_mode_trains(gpu, prec):
     tol = {"fp32": 1e-6, "tf32": 2e-2, "bf16": 5e-2, "bf16x2": 1e-3, "bf16x3": 1e-3, "fp16x2": 1e-3}[prec]
     for k in ("[0]recon_loss", "[1]recon_loss", "[0]spectral_loss", "[1]spectral_loss"):
         assert abs(first[prec][k] - first["fp32"][k]) <= tol * abs(first["fp32"][k]) + 1e-7, (prec, k, first[prec][k], first["fp32"][k])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16x2"])
+def test_time_tiled_long_window_inference(gpu, prec):
+    """BASELINE.json configs[4] shape class (long windows): encode / decode with chunk > 1 (halo time-tiling, `_halo(level)`)
+    against the one-pass call.  Exact-fp32 kernels: identical codes and audio (every output is the same FMA chain whatever the
+    tiling).  fp16x2: tile-dependent operand scales move values by ~2^-22, so a code may change only at a near-tie and the
+    audio agrees to the kernels' tolerance."""
+    V = gpu
+    T = 1 << 18
+    V.set_seed(0)
+    m = V.VQVAE((T, 1), **V.SMALL_VQ_VAE)
+    m.set_precision(prec)
+    x = torch.from_numpy(np.random.default_rng(1).uniform(0, 1, size=(1, T, 1)).astype(np.float32)).cuda()
+    for level in range(2):
+        one = m.encode_level(x, level)
+        tiled = m.encode_level(x, level, chunk=3)
+        assert tiled.shape == one.shape == (1, T // (32 if level == 0 else 256))
+        if prec == "fp32":
+            assert torch.equal(tiled, one)
+        else:
+            assert float((tiled != one).float().mean()) < 2e-3
+        y1 = m.decode_level(one, level)
+        y2 = m.decode_level(one, level, chunk=4)
+        assert y2.shape == y1.shape == (1, T, 1)
+        if prec == "fp32":
+            assert torch.equal(y1, y2)
+        else:
+            assert rel_err(y2, y1) < 1e-4
+
+
+def test_checkpoint_round_trip_on_device(gpu, tmp_path):
+    """save_weights -> a new model -> load_weights: identical variables, codes, and — with the optimizer's moments, step counter
+    and the restart-RNG steps restored — identical weights after one more (CUDA-graph) training step."""
+    V = gpu
+    m, spec, weights, vq, x = tiny_model(V, graph=False)
+    for q in m.vqs:
+        q.restart_ids = None  # device RNG: its step is part of the checkpoint
+    m.compile(optimizer=V.keras.optimizers.Adam())
+    for _ in range(3):
+        m.train_step((x, None))
+    m.save_weights(str(tmp_path / "ck"))
+    m2, *_ = tiny_model(V, graph=False)
+    for q in m2.vqs:
+        q.restart_ids = None
+    m2.compile(optimizer=V.keras.optimizers.Adam())
+    m2.load_weights(str(tmp_path / "ck"))
+    for a, b in zip(m.variables, m2.variables):
+        assert np.array_equal(a.numpy(), b.numpy()), a.name
+    for a, b in zip(m.encode(x), m2.encode(x)):
+        assert torch.equal(a, b)
+    assert m2.optimizer.iterations == 3
+    m.train_step((x, None)); m2.train_step((x, None))
+    for a, b in zip(m.variables, m2.variables):
+        assert np.array_equal(a.numpy(), b.numpy()), a.name

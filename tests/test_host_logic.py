@@ -361,3 +361,45 @@ def test_compile_drops_captured_graphs_and_step_flags_are_scoped(cpu_backend):
     assert m._graphs == {}
     m.train_step((x, None))
     assert all(not q.defer_ema and not q.skip_metric_update for q in m.vqs)
+
+
+def test_time_tiled_encode_decode_equals_one_pass(cpu_backend):
+    """encode_level / decode_level with chunk > 1 (vqvae.py:208,238: `chunk` is an unused TODO in the reference): pieces with
+    `_halo(level)` samples of context on either side give the codes / audio of the one-pass call."""
+    V = cpu_backend
+    kw = dict(levels=2, latent_dim=8, num_embeddings=16, down_depth=[2, 1], strides=[2, 2], dilation_factor=2, residual_width=4,
+              residual_depth=2)
+    T = 4096
+    m = V.VQVAE((T, 1), **kw)
+    assert m._halo(0) == (80, 4) and m._halo(1) == (192, 8)   # summed (k-1) * dilation * cumulative stride, rounded up to the hop
+    x = np.random.default_rng(0).uniform(0, 1, size=(2, T, 1)).astype(np.float32)
+    for level in range(2):
+        one = m.encode_level(x, level)
+        for chunk in (2, 3, 7):
+            assert torch.equal(m.encode_level(x, level, chunk=chunk), one), (level, chunk)
+        y = m.decode_level(one, level)
+        for chunk in (2, 5):
+            np.testing.assert_allclose(m.decode_level(one, level, chunk=chunk).numpy(), y.numpy(), rtol=0, atol=1e-6)
+    assert [tuple(c.shape) for c in m.encode(x, chunk=4)] == [(2, T // 4), (2, T // 8)]
+
+
+def test_checkpoint_carries_optimizer_and_restart_state(cpu_backend, tmp_path):
+    V = cpu_backend
+    m, spec, weights, vq, x = build_tiny(V)
+    m.compile(optimizer=V.keras.optimizers.Adam())
+    for _ in range(2):
+        m.train_step((x, None))
+    m.save_weights(str(tmp_path / "ck"))
+    m2, *_ = build_tiny(V, seed=5)
+    m2.compile(optimizer=V.keras.optimizers.Adam())
+    m2.load_weights(str(tmp_path / "ck"))
+    assert m2.optimizer.iterations == 2
+    # both continue identically: same weights after one more step (Adam moments and bias-correction step were restored)
+    m.train_step((x, None)); m2.train_step((x, None))
+    for a, b in zip(m.variables, m2.variables):
+        assert np.array_equal(a.numpy(), b.numpy()), a.name
+    # a file of another architecture is refused by NAME, not just by shape
+    m3 = V.VQVAE((TINY["T"], 1), **{**{k: (list(v) if isinstance(v, tuple) else v) for k, v in TINY.items() if k != "T"}, "levels": 1,
+                                     "down_depth": [3], "strides": [2]})
+    with pytest.raises(ValueError):
+        m3.load_weights(str(tmp_path / "ck"))

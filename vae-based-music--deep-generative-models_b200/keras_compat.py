@@ -21,6 +21,8 @@ import time
 from collections import defaultdict
 from typing import List, Optional, Sequence
 
+import re as _re
+
 import numpy as np
 import torch
 
@@ -812,12 +814,54 @@ class Model(Layer):
         return logs if return_dict else list(logs.values())
 
     def save_weights(self, path):
-        np.savez(path, **{f"{i:04d}|{v.name}": v.numpy() for i, v in enumerate(self.variables)})
+        """All variables (Keras `variables` order: conv kernels / biases, then the VQ state embeddings / m_t / N_t per level) plus
+        what a resumed run needs to continue bit for bit: the optimizer's Adam moments and step counter and the VQ layers'
+        restart-RNG step.  The file is a flat .npz keyed "index|variable name" (+ "opt|..." / "state|..." entries) — NOT the
+        tf.train.Checkpoint format of the reference's CheckpointManager (src/callback/vae_monitor.py:56-58)."""
+        out = {f"{i:04d}|{v.name}": v.numpy() for i, v in enumerate(self.variables)}
+        opt = getattr(self, "optimizer", None)
+        if opt is not None and getattr(opt, "_iterations", None) is not None:
+            out["opt|iterations"] = np.asarray(opt.iterations, np.int64)
+            packed = getattr(self, "_packed", None)
+            for key, (m, v) in opt._slots.items():
+                if packed is not None and key == ("flat", packed.params.data_ptr()):
+                    out["opt|flat|m"], out["opt|flat|v"] = m.cpu().numpy(), v.cpu().numpy()
+        for i, st in enumerate(self._extra_state()):
+            out[f"state|{i:03d}"] = st
+        np.savez(path, **out)
+
+    def _extra_state(self):
+        """numpy arrays of non-variable state to checkpoint (overridden where a model has any)"""
+        return []
+
+    def _set_extra_state(self, arrays):
+        pass
 
     def load_weights(self, path):
         data = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
-        keys = sorted(data.files)
-        self.set_weights([data[k] for k in keys])
+        wkeys = sorted(k for k in data.files if k[:4].isdigit())
+        vs = self.variables
+        if len(wkeys) != len(vs):
+            raise ValueError(f"{self.name}.load_weights: the file holds {len(wkeys)} variables, the model has {len(vs)}")
+        for k, v in zip(wkeys, vs):  # names are validated: equal shapes are not enough to accept a file
+            name = k.split("|", 1)[1]
+            # Keras uniquifies auto-generated layer names per process ("conv1d_48"): compare without that counter
+            if _re.sub(r"_\d+(?=/)", "", name) != _re.sub(r"_\d+(?=/)", "", v.name):
+                raise ValueError(f"{self.name}.load_weights: variable {k[:4]} is '{name}' in the file but '{v.name}' in the model")
+        self.set_weights([data[k] for k in wkeys])
+        opt = getattr(self, "optimizer", None)
+        packed = getattr(self, "_packed", None)
+        if opt is not None and "opt|iterations" in data.files:
+            opt._counter().fill_(int(data["opt|iterations"]))
+            opt._host_iterations = int(data["opt|iterations"])
+            if packed is not None and "opt|flat|m" in data.files:
+                m, v = opt._slot(("flat", packed.params.data_ptr()), packed.params)
+                m.copy_(torch.from_numpy(data["opt|flat|m"])); v.copy_(torch.from_numpy(data["opt|flat|v"]))
+        st = [data[k] for k in sorted(k for k in data.files if k.startswith("state|"))]
+        if st:
+            self._set_extra_state(st)
+        if hasattr(self, "_graphs"):
+            self._graphs = {}
 
 
 # ---------------------------------------------------------------------------------------------- metrics

@@ -47,6 +47,7 @@ class VQVAE(Model):
                  residual_depth=4, dilation_factor=1, train_variance=1.0, **kwargs):
         super(VQVAE, self).__init__(**kwargs)
         self.levels = levels
+        self._arch = (list(down_depth), list(strides), residual_depth, dilation_factor)  # for the halo of time-tiled inference
         self.train_variance = train_variance
         self.latent_dim = latent_dim
         self.num_embeddings = num_embeddings
@@ -123,6 +124,14 @@ class VQVAE(Model):
         a new optimizer invalidates the captures (the learning rate itself lives in device memory and may change freely)."""
         super(VQVAE, self).compile(optimizer=optimizer, **kw)
         self._graphs = {}
+
+    def _extra_state(self):
+        return [np.asarray(0 if vq._step is None else int(vq._step.item()), np.int64) for vq in self.vqs]
+
+    def _set_extra_state(self, arrays):
+        for vq, a in zip(self.vqs, arrays):
+            vq._buffers()
+            vq._step.fill_(int(a))
 
     def _all_trackers(self):
         return self.metrics + list(chain.from_iterable(vq.metrics for vq in self.vqs))
@@ -358,25 +367,74 @@ class VQVAE(Model):
         return recons, {"level_losses": level_losses, "recon_losses": recon_losses, "commit_losses": commit_losses,
                         "spec_losses": spectral_losses}
 
-    def encode_level(self, x, level, chunk=1):
-        enc_outputs = self.encoders[level](convert_to_tensor(x), training=False)
+    def _halo(self, level):
+        """(halo in input samples, hop) of level `level`: an upper bound of the receptive-field radius of its encoder (and of its
+        decoder, in output samples) — the summed extents (k - 1) * dilation * cumulative stride of all its convolutions —
+        rounded up to a multiple of the level's hop, so that tile boundaries keep the phase of every strided convolution."""
+        down_depth, strides, depth, factor = self._arch
+        per_stack = sum(2 * factor ** i + 2 for i in range(depth))  # one DilatedResnet1D: k=3 dilated + k=3 per block
+        j, ext = 1, 0
+        for n, st in zip(down_depth[:level + 1], strides[:level + 1]):
+            for _ in range(n):
+                ext += (2 * st - 1) * j
+                j *= st
+                ext += per_stack * j
+            ext += 2 * j
+        return -(-ext // j) * j, j
+
+    def _encode_once(self, x, level):
+        enc_outputs = self.encoders[level](x, training=False)
         latent_output, latent_codes = self.vqs[level](enc_outputs, training=False)
         return latent_codes.view(enc_outputs.shape[:-1])  # (N, T_downsampled) int64
 
-    def encode(self, x, start_level=0, end_level=None):
+    def encode_level(self, x, level, chunk=1):
+        """codes (N, T / hop) of one level (vqvae.py:208-219).  chunk > 1 (a TODO in the reference, which ignores the argument)
+        time-tiles a long window: the T samples are encoded in `chunk` pieces, each with `_halo(level)` samples of real context
+        on either side, and only the codes of the piece itself are kept — the same codes as the one-pass call (every code
+        depends on inputs inside the halo only), with the activation memory of a piece instead of the whole window."""
+        x = convert_to_tensor(x)
+        T = x.shape[1]
+        halo, hop = self._halo(level)
+        if chunk <= 1 or T % hop or T <= hop * chunk:
+            return self._encode_once(x, level)
+        seg = -(-(T // hop) // chunk) * hop
+        parts = []
+        for s0 in range(0, T, seg):
+            a, b, e = max(s0 - halo, 0), min(s0 + seg + halo, T), min(s0 + seg, T)
+            codes = self._encode_once(x[:, a:b].contiguous(), level)
+            parts.append(codes[:, (s0 - a) // hop:(e - a) // hop])
+        return torch.cat(parts, dim=1)
+
+    def encode(self, x, start_level=0, end_level=None, chunk=1):
         """list of code tensors for levels [start_level, end_level)  (vqvae.py:221-236)"""
         if end_level is None:
             end_level = self.levels
-        return [self.encode_level(x, i) for i in range(start_level, end_level)]
+        return [self.encode_level(x, i, chunk) for i in range(start_level, end_level)]
 
-    def decode_level(self, zq, level, chunk=1):
-        """zq (N, T) int64 codes -> (N, T * hop, 1)  (vqvae.py:238-251): codebook gather + decoder."""
+    def _decode_once(self, zq, level):
         level_vq = self.vqs[level]
-        quantized = ops.gather_codes(level_vq.embeddings.value, convert_to_tensor(zq, torch.int64))
+        quantized = ops.gather_codes(level_vq.embeddings.value, zq)
         return self.decoders[level](quantized, training=False)
 
-    def decode(self, zq, level=0):
-        return self.decode_level(zq, level)
+    def decode_level(self, zq, level, chunk=1):
+        """zq (N, T) int64 codes -> (N, T * hop, 1)  (vqvae.py:238-251): codebook gather + decoder; chunk > 1 time-tiles the code
+        sequence the same way as encode_level (halo in latent positions)."""
+        zq = convert_to_tensor(zq, torch.int64)
+        Tl = zq.shape[1]
+        halo, hop = self._halo(level)
+        hl = halo // hop
+        if chunk <= 1 or Tl <= chunk:
+            return self._decode_once(zq, level)
+        seg = -(-Tl // chunk)
+        parts = []
+        for s0 in range(0, Tl, seg):
+            a, b, e = max(s0 - hl, 0), min(s0 + seg + hl, Tl), min(s0 + seg, Tl)
+            y = self._decode_once(zq[:, a:b].contiguous(), level)
+            parts.append(y[:, (s0 - a) * hop:(e - a) * hop])
+        return torch.cat(parts, dim=1)
+
+    def decode(self, zq, level=0, chunk=1):
+        return self.decode_level(zq, level, chunk)
 
     def update_metrics(self, level_losses, recon_losses, commit_losses, spectral_losses):
         self.total_loss_tracker.update_state(sum(level_losses))
