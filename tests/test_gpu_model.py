@@ -443,4 +443,7 @@ def test_checkpoint_round_trip_on_device(gpu, tmp_path):
     assert m2.optimizer.iterations == 3
     m.train_step((x, None)); m2.train_step((x, None))
     for a, b in zip(m.variables, m2.variables):
-        assert np.array_equal(a.numpy(), b.numpy()), a.name
+        if a.trainable:
+            assert np.array_equal(a.numpy(), b.numpy()), a.name
+        else:  # VQ state: the per-code sums are accumulated with shared-memory atomics (order, hence the last bit, varies per run)
+            np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=2e-6, atol=1e-7, err_msg=a.name)
