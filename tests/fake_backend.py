@@ -359,12 +359,22 @@ class FakeBackend:
     def vqb_restart_ids(self, N, K, seed, step, ids, stream):
         s = int(_t(step, (1,), np.int64)[0]) if step is not None else 0
         Nt = N if N >= K else N * (-(-K // N))
-        h1 = _mix(seed ^ _mix(s)); h2 = _mix(h1)
-        a = 1 + h1 % (Nt - 1) if Nt > 1 else 1
-        while np.gcd(a, Nt) != 1:
-            a = 1 if a + 1 >= Nt else a + 1
-        c = h2 % Nt
-        _t(ids, (K,), np.int64).copy_(torch.tensor([(a * i + c) % Nt for i in range(K)], dtype=torch.int64))
+        key = _mix(seed ^ _mix(s))
+        hb = 1
+        while (1 << (2 * hb)) < Nt:
+            hb += 1
+        mask = (1 << hb) - 1
+
+        def perm(v):  # the kernel's 4-round Feistel permutation, cycle-walked into [0, Nt)
+            while True:
+                L, R = v >> hb, v & mask
+                for r in range(4):
+                    L, R = R, L ^ (_mix(R ^ key ^ (((r + 1) * 0x9E3779B97F4A7C15) & ((1 << 64) - 1))) & mask)
+                v = (L << hb) | R
+                if v < Nt:
+                    return v
+
+        _t(ids, (K,), np.int64).copy_(torch.tensor([perm(i) for i in range(K)], dtype=torch.int64))
         return 0
 
     def vqb_gather_codes(self, E, D, K, idx, n, out, stream):

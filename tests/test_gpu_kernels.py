@@ -227,6 +227,14 @@ def test_restart_rows(gpu):
         Nt = N if N >= K else N * (-(-K // N))
         assert ids.min() >= 0 and ids.max() < Nt and len(set(ids.tolist())) == K  # K distinct rows of the tiled batch
     a = ops.restart_ids(28160, 512, 1234, step).cpu().numpy()
+    # a pseudo-random sample, not an arithmetic progression: the gaps between consecutive ids vary (tf.random.shuffle stand-in)
+    assert len(set(np.diff(a).tolist())) > 400
+    # the CPU double of the ABI (tests/fake_backend.py) implements the same permutation: host-logic tests see the device's picks
+    from tests.fake_backend import FakeBackend
+    import ctypes as C
+    buf = np.zeros(512, np.int64); st0 = np.zeros(1, np.int64)
+    FakeBackend().vqb_restart_ids(28160, 512, 1234, st0.ctypes.data, buf.ctypes.data, None)
+    assert np.array_equal(buf, a)
     ops.increment(step)
     b = ops.restart_ids(28160, 512, 1234, step).cpu().numpy()
     assert not np.array_equal(a, b) and np.array_equal(a, ops.restart_ids(28160, 512, 1234, ops.zeros(1, dtype=torch.int64)).cpu().numpy())

@@ -345,21 +345,33 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   return z ^ (z >> 31);
 }
 
+// K distinct pseudo-random rows of the (tiled) batch = the first K entries of a keyed pseudo-random PERMUTATION of [0, Nt):
+// a 4-round Feistel network over the smallest even-width bit domain covering Nt, cycle-walked into range (a permutation
+// restricted by cycle-walking stays a permutation).  Every id is an independent-looking draw, so the restart rows are a
+// uniform sample of the batch like tf.random.shuffle(...)[:K] (VectorQuantizer.py:137) — not an arithmetic progression, whose
+// rows are equally spaced and, for a small stride, neighbouring frames of one clip.  Same ids on every rank (seed, step).
+__device__ __forceinline__ uint64_t feistel_perm(uint64_t v, int hb, uint64_t key) {
+  const uint64_t mask = (1ull << hb) - 1ull;
+  uint64_t L = v >> hb, R = v & mask;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const uint64_t t = L ^ (splitmix64(R ^ key ^ ((uint64_t)(r + 1) * 0x9E3779B97F4A7C15ull)) & mask);
+    L = R;
+    R = t;
+  }
+  return (L << hb) | R;
+}
+
 __global__ void restart_ids_kernel(long N, int K, uint64_t seed, const int64_t* __restrict__ step, int64_t* __restrict__ ids) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K) return;
   const uint64_t Nt = N >= K ? (uint64_t)N : (uint64_t)N * (uint64_t)((K + N - 1) / N);
-  const uint64_t h1 = splitmix64(seed ^ splitmix64((uint64_t)(step ? step[0] : 0)));
-  const uint64_t h2 = splitmix64(h1);
-  uint64_t a = Nt > 1 ? 1 + h1 % (Nt - 1) : 1;
-  for (;;) {  // smallest a' >= a coprime with Nt
-    uint64_t u = a, v = Nt;
-    while (v) { const uint64_t t = u % v; u = v; v = t; }
-    if (u == 1) break;
-    a = a + 1 >= Nt ? 1 : a + 1;
-  }
-  const uint64_t c = h2 % Nt;
-  ids[i] = (int64_t)((a % Nt * ((uint64_t)i % Nt) + c) % Nt);
+  const uint64_t key = splitmix64(seed ^ splitmix64((uint64_t)(step ? step[0] : 0)));
+  int hb = 1;
+  while ((1ull << (2 * hb)) < Nt) ++hb;  // domain 2^(2 hb) >= Nt, < 4 Nt: fewer than 4 walks expected
+  uint64_t v = (uint64_t)i;
+  do { v = feistel_perm(v, hb, key); } while (v >= Nt);
+  ids[i] = (int64_t)v;
 }
 
 __global__ void gather_codes_kernel(const float* __restrict__ E, int D, int K, const int64_t* __restrict__ idx, long n,

@@ -293,39 +293,64 @@ class VQVAE(Model):
             with self._vq_metrics_in_step_vector():
                 self._capture(st, world)
         self.optimizer.refresh_lr()  # the captured Adam kernel reads the learning rate from device memory
-        st["ga"].replay()
-        if world > 1:
-            vdist.all_reduce_sum(self._packed.comm)
-        st["gb"].replay()
+        if st.get("gone") is not None:   # single process: the whole step is one graph launch
+            st["gone"].replay()
+        else:
+            st["ga"].replay()
+            if world > 1:
+                vdist.all_reduce_sum(self._packed.comm)
+            st["gb"].replay()
         self.optimizer.step_done()
         return self._accumulate(st["vec"])
 
+    def _tail(self, grads, tvars, losses, world):
+        """what follows the exchange: reduced loss scalars, EMA codebook update, Adam, the metric vector"""
+        if world > 1:
+            L = self.levels
+            sc = self._comm_scalars / world
+            rec = [Scalar.leaf(sc[i:i + 1]) for i in range(L)]
+            com = [Scalar.leaf(sc[L + i:L + i + 1]) for i in range(L)]
+            spe = [Scalar.leaf(sc[2 * L + i:2 * L + i + 1]) for i in range(L)]
+            losses = ([rec[i] + com[i] + spe[i] for i in range(L)], rec, com, spe)
+        for vq in self.vqs:
+            vq.apply_ema()
+        self.optimizer.apply_gradients(zip(grads, tvars))
+        return self._step_vector(losses)
+
+    def _head(self, x, world):
+        grads, tvars, losses = self._forward_backward(x)
+        if world > 1:
+            level_losses, recon_losses, commit_losses, spectral_losses = losses
+            self._comm_scalars.copy_(torch.cat(
+                [s.tensor().reshape(1) for s in (*recon_losses, *commit_losses, *spectral_losses)]))
+        return grads, tvars, losses
+
     def _capture(self, st, world):
-        """Captures graph A (forward + backward of every level) and graph B (EMA + Adam + metric vector) for st["x"]."""
+        """Captures train_step for st["x"].  One process: ONE graph (forward + backward of every level, EMA + Adam + metric
+        vector).  Data parallel: graph A (forward + backward), the NCCL all-reduce of [gradients | EMA statistics | loss scalars]
+        issued by torch.distributed between the replays, graph B (EMA + Adam + metrics).  (Capturing the collective into the
+        step graph was tried in round 2 and hung at the first replay on 2 GPUs — ProcessGroupNCCL's side-stream / watchdog
+        interplay under capture with the level streams — so it stays outside; it costs two graph launches and one host-side
+        enqueue per step, 0.1 ms of a 7.9 ms step at 8 GPUs.)"""
         torch.cuda.synchronize()
         self.optimizer.refresh_lr()
         pool = torch.cuda.graph_pool_handle()
+        st["gone"] = None
+        if world == 1:
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1, pool=pool):
+                grads, tvars, losses = self._head(st["x"], world)
+                st["vec"] = self._tail(grads, tvars, losses, world)
+            st["gone"] = g1
+            st["graph"] = True
+            return
         ga = torch.cuda.CUDAGraph()
         with torch.cuda.graph(ga, pool=pool):
-            grads, tvars, losses = self._forward_backward(st["x"])
-            if world > 1:
-                level_losses, recon_losses, commit_losses, spectral_losses = losses
-                self._comm_scalars.copy_(torch.cat(
-                    [s.tensor().reshape(1) for s in (*recon_losses, *commit_losses, *spectral_losses)]))
+            grads, tvars, losses = self._head(st["x"], world)
         st["ga"] = ga
         gb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gb, pool=pool):
-            if world > 1:
-                L = self.levels
-                sc = self._comm_scalars / world
-                rec = [Scalar.leaf(sc[i:i + 1]) for i in range(L)]
-                com = [Scalar.leaf(sc[L + i:L + i + 1]) for i in range(L)]
-                spe = [Scalar.leaf(sc[2 * L + i:2 * L + i + 1]) for i in range(L)]
-                losses = ([rec[i] + com[i] + spe[i] for i in range(L)], rec, com, spe)
-            for vq in self.vqs:
-                vq.apply_ema()
-            self.optimizer.apply_gradients(zip(grads, tvars))
-            st["vec"] = self._step_vector(losses)
+            st["vec"] = self._tail(grads, tvars, losses, world)
         st["gb"] = gb
         st["graph"] = True
 
