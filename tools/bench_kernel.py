@@ -30,6 +30,9 @@ if what.startswith("stack"):
     W2 = [torch.randn(3, C, C, device="cuda", generator=g) * 0.1 for _ in dils]
     Bz = [torch.zeros(C, device="cuda") for _ in dils]
     _, _, sxb, shb, sws = ops.resstack_fwd(xs[0], W1, Bz, W2, Bz, dils, P, True)
+w4 = torch.randn(4, C, C, device="cuda", generator=g) * 0.1
+dw4 = ops.empty(4, C, C)
+dyh = dy[:, :L // 2].contiguous()
 n = int(os.environ.get("N", "6"))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -47,6 +50,10 @@ def one(i):
         ops.resstack_fwd(xs[i % 2], W1, Bz, W2, Bz, dils, P, True)
     elif what == "stack_bwd":
         ops.resstack_bwd_data(dy, W1, W2, sxb, shb, dils, P, fwd_ws=sws if os.environ.get("PACKED", "1") == "1" else None)
+    elif what == "conv_down":      # Conv1D(32, 4, strides=2) 32 -> 32 (conv_tc_kernel): the encoder's down-sampling convolution
+        ops.conv1d_fwd(xs[i % 2], w4, b1, 2, 1, False, None, P)
+    elif what == "conv_down_wgrad":
+        ops.conv1d_wgrad(xs[i % 2], dy[:, :L // 2].contiguous() if False else dyh, dw4, db, 2, 1, False, P)
     elif what == "resblock_bwd":
         ops.resblock_bwd_data(xs[i % 2], h, dy, w1, w2, int(os.environ.get("DIL", "1")), P)
     elif what == "resblock_wgrad":
