@@ -77,7 +77,8 @@ struct RsParams {
 };
 struct RsMaps {
   CUtensorMap in;                      // box {32, 128, 1}
-  CUtensorMap out[RS_MAXC][2];         // [k][0]: box of 128 - H rows (first / last M block), [k][1]: 128 rows (middle)
+  CUtensorMap out[RS_MAXC][2];         // per-warp slices {16 channels, rows}: [k][1]: 32 rows, [k][0]: the partial quadrant at the
+                                       // two ends of a tile's output rows (32 - H % 32 rows)
 };
 
 struct RsPackParams {  // up to 2 * RS_MAXC records: a training forward also packs the images of its data-gradient chain
@@ -334,17 +335,18 @@ __global__ void __launch_bounds__(RsCfg::NT, 1) rs_kernel(const RsParams p, cons
     const int mb = warp >> 3, qd = warp & 3, half = (warp >> 2) & 1;
     const int r = mb * 128 + qd * 32 + lane;  // tile row = TMEM lane
     const uint32_t taddr = tmem + (((uint32_t)qd * 32u) << 16) + (uint32_t)(mb * Cfg::NW + half * 16);
-    // rows of this M block that belong to the tile's output: [lo, hi); image row j = r - lo
-    const int lo = max(mb * 128, p.H), hi = min(mb * 128 + 128, Cfg::R - p.H);
-    const bool own = r >= lo && r < hi;
-    const int jrow = r - lo;
-    uint8_t* img = OUT + mb * Cfg::IMG;
+    // Output slices: a warp stores the rows of its quadrant that lie inside the tile's output rows [H, R - H) — 32, or the partial
+    // count at the two ends of that range, or none — and its 16 channels as ONE TMA box from its own 2 KB image (rows of 64 B,
+    // 64-byte swizzle): warp-local hand-off only (__syncwarp), no block-wide barrier on the store path.
+    const int q0 = mb * 128 + qd * 32;
+    const int srow = max(q0, p.H), snum = max(min(q0 + 32, Cfg::R - p.H) - srow, 0);
+    const bool own = r >= srow && r < srow + snum;
+    const uint32_t img = smem_u32(OUT) + (uint32_t)warp * 2048u;
     uint32_t imgc[4];  // this thread's four 16-byte chunks of its image row (shared-memory addresses)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) imgc[c] = smem_u32(img) + tma::swz(jrow & 127, half * 4 + c);
-    const bool leader = (warp & 7) == 0 && lane == 0;  // issues this M block's TMA stores (bulk groups are per thread)
+    for (int c = 0; c < 4; ++c) imgc[c] = img + tma::swz64((r - srow) & 31, c);
+    const int mapsel = snum == 32 ? 1 : 0;
     const bool tr = (warp & 7) == 0;
-    const int mapsel = (mb == 0 || mb == Cfg::MB - 1) ? 0 : 1;
     // this thread's operand chunks: planes 2 * half, 2 * half + 1 of row G + r, hi piece (lo piece: + TILE)
     const uint32_t opoff = (uint32_t)(half * 2 * Cfg::PLANE + (Cfg::G + r) * 16);
     const uint32_t xrow = smem_u32(X) + opoff, yrow = smem_u32(Y) + opoff;
@@ -405,18 +407,18 @@ __global__ void __launch_bounds__(RsCfg::NT, 1) rs_kernel(const RsParams p, cons
         for (int c = 0; c < 16; ++c) w |= (uint32_t)(v[c] > 0.f) << c;
         reinterpret_cast<uint16_t*>(p.bits_out[k])[grow] = (uint16_t)w;
       }
-      if (p.store[k]) {
-        if (leader) tma::wait_read();   // the image's previous store has been read out of shared memory
-        bar_sync(1 + mb, 256);
+      if (p.store[k] && snum > 0) {
+        if (lane == 0) tma::wait_read();   // the image's previous store has been read out of shared memory
+        __syncwarp();
         if (own) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             sts128(imgc[c], make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3])));
         }
         fence_proxy_async();
-        bar_sync(1 + mb, 256);
-        if (leader) {
-          tma::store_rows(&maps.out[k][mapsel], img, g0 + lo, b);
+        __syncwarp();
+        if (lane == 0) {
+          tma::store_box(&maps.out[k][mapsel], img, half * 16, g0 + srow, b);
           tma::commit_group();
         }
       }
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(RsCfg::NT, 1) rs_kernel(const RsParams p, cons
         epilogue(k + 1, std::integral_constant<int, 1>());
       }
     }
-    if (leader) tma::wait_all();
+    if (lane == 0) tma::wait_all();
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
@@ -591,7 +593,8 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
     return set_err(VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the [%d, %d, 32] input", d->B, d->L);
   for (int k = 0; k < nconv; ++k)
     if (p.store[k]) {
-      if (!tma::make_rows_map(&maps.out[k][0], outs[k], d->B, d->L, 128 - H) || !tma::make_rows_map(&maps.out[k][1], outs[k], d->B, d->L, 128))
+      const int part = 32 - H % 32;  // rows of the partial quadrant at either end of a tile's output rows
+      if (!tma::make_slice_map(&maps.out[k][0], outs[k], d->B, d->L, part) || !tma::make_slice_map(&maps.out[k][1], outs[k], d->B, d->L, 32))
         return set_err(VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed for an output of the residual stack");
     }
   int npack = nconv;
