@@ -153,6 +153,57 @@ __global__ void __launch_bounds__(128, 1) probe_multi_kernel(int N, int reps, in
   if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
+// Tensor-memory read rate: nw warps (lane quadrant = warp % 4) each issue reps tcgen05.ld.32x32b.x32 (4 KB per instruction: 32
+// lanes x 32 columns x 4 B), waited for in groups of 4.  Bytes per clock per SM.
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int SHAPE>
+__global__ void __launch_bounds__(512, 1) probe_tmem_ld_kernel(int reps, long long* out) {
+  __shared__ uint32_t tslot;
+  __shared__ long long t0s[16], t1s[16];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tslot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t taddr = tslot + ((uint32_t)(warp & 3) * 32u << 16) + (uint32_t)((warp >> 2) * 32);
+  float acc = 0.f;
+  float v[32];
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < reps; ++i) {
+    if (SHAPE == 0) tmem_ld32(taddr, v); else tmem_ld_16x256b_x8(taddr, v);
+    acc += v[i & 31];
+  }
+  const long long t1 = clock64();
+  if ((tid & 31) == 0) { t0s[warp] = t0; t1s[warp] = t1; }
+  __syncthreads();
+  if (tid == 0 && blockIdx.x == 0) {
+    long long a = t0s[0], b = t1s[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = a < t0s[w] ? a : t0s[w]; b = b > t1s[w] ? b : t1s[w]; }
+    out[0] = b - a;
+    out[1] = (long long)acc;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tslot, 512);
+}
+
 int main() {
   long long* d;
   cudaMalloc(&d, 8);
@@ -206,6 +257,15 @@ int main() {
     cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
     printf("%-52s %8.1f clk / MMA   (%s)\n", c.name, (double)cyc / reps, cudaGetErrorString(e));
   }
+  for (int shape : {0, 1})
+    for (int nw : {1, 4, 8, 16}) {
+      if (shape == 0) probe_tmem_ld_kernel<0><<<4, nw * 32>>>(2000, d); else probe_tmem_ld_kernel<1><<<4, nw * 32>>>(2000, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long cyc = 0;
+      cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+      printf("tcgen05.ld.%s, %2d warps x 2000 loads (4 KB each)                        %8.1f B / clk / SM   (%s)\n",
+             shape ? "16x256b.x8 " : "32x32b.x32 ", nw, (double)nw * 2000 * 4096 / (double)cyc, cudaGetErrorString(e));
+    }
   cudaFuncSetAttribute(probe_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   for (int N : {32, 64}) {
     for (int ni : {1, 2, 4}) {

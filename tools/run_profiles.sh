@@ -22,10 +22,10 @@ full() {  # name, kernel regex, skip, command...
   timeout 300 $NCU --set full --import-source on -k regex:$rx -s $skip -c 1 -f -o $O/prof_$name "$@" > $O/ncu_$name.log 2>&1
 }
 export N=4
-full rs_infer "rs_kernel<0" 3 python tools/bench_kernel.py stack_infer $P
-full rs_train "rs_kernel<1" 4 python tools/bench_kernel.py stack_train $P
-full rs_bwd "rs_kernel<2" 3 python tools/bench_kernel.py stack_bwd $P
-DILS=27,9,3,1 full rs_train_rev "rs_kernel<1" 4 python tools/bench_kernel.py stack_train $P
+full rs_infer rs_kernel 3 python tools/bench_kernel.py stack_infer $P
+full rs_train rs_kernel 4 python tools/bench_kernel.py stack_train $P
+full rs_bwd rs_kernel 3 python tools/bench_kernel.py stack_bwd $P
+DILS=27,9,3,1 full rs_train_rev rs_kernel 4 python tools/bench_kernel.py stack_train $P
 full wgrad_$P wgrad_tc_kernel 4 python tools/bench_kernel.py resblock_wgrad $P
 full conv_tc conv_tc_kernel 2 python tools/bench_kernel.py conv_down $P
 full wgrad4_tc wgrad4_tc_kernel 2 python tools/bench_kernel.py conv_down_wgrad $P

@@ -157,7 +157,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // Not there yet: wait with a suspend-time hint, so that the thread sleeps in hardware until the phase completes (or the
   // hint expires) instead of spinning — a spinning warp takes issue slots from the warps it is waiting for (in the residual
   // stack kernel almost half of all executed instructions were such polls before the hint was added).
-  const long long t0 = clock64();
+  // The watchdog (a wait longer than ~2 s of SM clocks is a pipeline bug: trap instead of hanging the GPU) reads the clock only
+  // every 4096 polls: the poll loop itself is 3 instructions, and polling warps share issue slots with the working ones.
+  long long t0 = 0;
+  uint32_t spins = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
@@ -167,7 +170,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity), "r"(0x989680u)
         : "memory");
     if (ok) return;
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if ((++spins & 0xfffu) == 0u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000ll) __trap();
+    }
   }
 }
 // one arrival (release semantics: this thread's earlier shared-memory writes are visible to whoever observes the phase)
