@@ -77,6 +77,9 @@ class VQVAE(Model):
 
         # ---- implementation state --------------------------------------------------------------------------
         self.train_step_training = True   # see module docstring
+        self.test_step_training = None    # what test_step passes as `training`: None = the literal call `self.vqvaes[level](x)`
+                                          # (vqvae.py:158), resolved by keras_compat like Keras 2.7 (-> False: no EMA in evaluate);
+                                          # True if your Keras lets the VectorQuantizer's own default win
         self.use_cuda_graph = _lib.is_native() or _lib._BACKEND is None
         self.use_level_streams = True     # levels >= 1 on side CUDA streams inside train_step (see _forward_backward)
         self._level_streams = []
@@ -367,7 +370,7 @@ class VQVAE(Model):
         commit_losses, recon_losses, spectral_losses, level_losses = [], [], [], []
         for level in range(self.levels):  # bottom to top
             # the reference calls self.vqvaes[level](x) (vqvae.py:158); Keras resolves that to training=False
-            _, reconstruction_loss, spectral_loss, commit_loss = self._level_losses(level, x, None)
+            _, reconstruction_loss, spectral_loss, commit_loss = self._level_losses(level, x, self.test_step_training)
             level_loss = reconstruction_loss + commit_loss + spectral_loss
             commit_losses.append(commit_loss)
             recon_losses.append(reconstruction_loss)
