@@ -49,8 +49,17 @@ CASES = [(2, 1000, (1, 3, 9, 27)), (2, 1000, (27, 9, 3, 1)), (3, 881, (1, 3, 9, 
          (2, 297, (1, 3)), (1, 1, (1,)), (4, 3520, (9, 27)), (1, 600, (3, 3, 3, 3)), (2, 440, (1, 1, 1))]
 
 
+@pytest.fixture(params=["auto", "3", "4"])
+def tile_rows(request, monkeypatch):
+    """the stack kernel has two tile heights picked per call (resstack_tc.cu: use_rs4): 384 rows (rs_kernel) and 512 rows with an
+    in-place operand buffer (rs4_kernel); VQB_RS_MB forces one, so every case below runs on both"""
+    if request.param != "auto":
+        monkeypatch.setenv("VQB_RS_MB", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("B,L,dils", CASES)
-def test_resstack_inference_forward(gpu, B, L, dils):
+def test_resstack_inference_forward(gpu, tile_rows, B, L, dils):
     ops, P = gpu.ops, gpu._lib.PRECISIONS["fp16x2"]
     assert ops.resstack_supported(32, dils, P)
     rng = np.random.default_rng(L + sum(dils))
@@ -65,7 +74,7 @@ def test_resstack_inference_forward(gpu, B, L, dils):
 
 
 @pytest.mark.parametrize("B,L,dils", CASES)
-def test_resstack_training_forward_and_data_gradient(gpu, B, L, dils):
+def test_resstack_training_forward_and_data_gradient(gpu, tile_rows, B, L, dils):
     """Under a tape the forward writes every block's h, output and sign masks; the data-gradient chain reads the masks and
     writes every block's dh / dx (the operands of vqb_resblock_wgrad_batch)."""
     ops, P = gpu.ops, gpu._lib.PRECISIONS["fp16x2"]
@@ -103,7 +112,7 @@ def test_resstack_training_forward_and_data_gradient(gpu, B, L, dils):
 
 
 @pytest.mark.parametrize("dils", [(1, 3, 9, 27), (27, 9, 3, 1)])
-def test_resstack_full_size_matches_block_kernels(gpu, dils):
+def test_resstack_full_size_matches_block_kernels(gpu, tile_rows, dils):
     """[32, 14080, 32] (the largest stage of SMALL_VQ_VAE at batch 32): the fused stack against the chain of per-block fp16x2
     launches and the exact-fp32 CUDA-core kernels."""
     ops, P = gpu.ops, gpu._lib.PRECISIONS["fp16x2"]
@@ -136,7 +145,7 @@ def test_resstack_full_size_matches_block_kernels(gpu, dils):
 
 
 @pytest.mark.parametrize("xs,ws,bs", [(1e-6, 1.0, 0.0), (3e4, 1.0, 0.1), (1.0, 1e-3, 1e-5), (1e-3, 8.0, 10.0), (0.0, 1.0, 0.3)])
-def test_resstack_is_scale_free(gpu, xs, ws, bs):
+def test_resstack_is_scale_free(gpu, tile_rows, xs, ws, bs):
     """operand scales are chosen per tile and convolution from exact maxima and L1 bounds: magnitudes far outside fp16's range,
     growing or shrinking through the stack, and an all-zero input must all stay fp32-grade"""
     ops, P = gpu.ops, gpu._lib.PRECISIONS["fp16x2"]

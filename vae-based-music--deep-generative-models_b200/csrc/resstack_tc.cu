@@ -508,6 +508,328 @@ __global__ void __launch_bounds__(RsCfg::NT, 1) rs_kernel(const RsParams p, cons
   if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
+// ================================================================================================================
+// rs4_kernel — the same stack as rs_kernel with 512-row tiles (4 M blocks: 424 instead of 296 of every tile's rows are output
+// rows at halo 44, and the kernel is bound per row it reads out of tensor memory).  What makes 512 rows fit:
+//   * ONE operand buffer, rewritten in place: the epilogue of (convolution k, M block mb) writes the operand rows of
+//     convolution k+1 over those of k.  Safe because every MMA of k that reads rows of block mb — its own three taps, tap +1 of
+//     block mb-1 (head rows) and tap -1 of block mb+1 (tail rows) — is issued before the commit that releases the block
+//     (issue order per convolution: t-1(0) t0(0) | t-1(1) t+1(0) commit0 | t0(1) | t-1(2) t+1(1) commit1 | ...);
+//     the raw fp32 input tile of the next tile lands in the same buffer once the last convolution's MMAs are through;
+//   * one thread per row (16 epilogue warps), which works through its 32 channels as two 16-channel halves.
+// ================================================================================================================
+struct Rs4Cfg {
+  static constexpr int MB = 4, R = 128 * MB, G = 32;
+  static constexpr int NP = 4;
+  static constexpr int PLANE = (R + 2 * G) * 16 + 32;
+  static constexpr int TILE = NP * PLANE;
+  static constexpr int OPB = 2 * TILE;
+  static constexpr int NW = RsCfg::NW, WPLANE = RsCfg::WPLANE, WTAP = RsCfg::WTAP, WCONV = RsCfg::WCONV, META = RsCfg::META, WREC = RsCfg::WREC;
+  static constexpr int IMG = 128 * 128;
+  static constexpr int NEPI = 4 * MB;
+  static constexpr int OFF_OP = 0;
+  static constexpr int OFF_OUT = ((OPB + 1023) / 1024) * 1024;
+  static constexpr int OFF_W = OFF_OUT + NEPI * 4096;
+  static constexpr int OFF_META = OFF_W + 2 * WCONV;
+  static constexpr int OFF_AMAX = OFF_META + RS_MAXC * META * 4;
+  static constexpr int OFF_BAR = OFF_AMAX + 2 * 16 * 4;
+  static constexpr int NBAR = 2 * MB + 8;
+  static constexpr int OFF_TSLOT = OFF_BAR + NBAR * 8;
+  static constexpr int SMEM = OFF_TSLOT + 16 + 1024;
+  static constexpr int NT = (NEPI + 2) * 32;
+  static constexpr int TCOLS = 256;
+  static_assert(OFF_W % 16 == 0 && OFF_BAR % 8 == 0 && R * 128 <= OPB, "layout");
+  static_assert(SMEM <= 232448, "shared memory");
+};
+
+// one tap of one M block: 2 K steps x (hi-activation x [W_hi | W_lo], lo-activation x W_hi)
+__device__ __forceinline__ void rs4_tap(uint32_t tacc, uint32_t a_base, int row0, int dil, uint32_t w_base, int j, bool first) {
+  const uint64_t ad0 = smem_desc(a_base + (uint32_t)row0 * 16u, Rs4Cfg::PLANE, 128);  // row0 = first row of tap 0
+  const uint64_t bd0 = smem_desc(w_base, Rs4Cfg::WPLANE, 128);
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+    for (int sa = 0; sa < 2; ++sa) {
+      const uint32_t idesc = instr_desc(FMT_F16, 128, 32 * (2 - sa), false, false);
+      const uint64_t bd = bd0 + (uint64_t)((j * Rs4Cfg::WTAP + kk * 2 * Rs4Cfg::WPLANE) >> 4);
+      const uint64_t ad = ad0 + (uint64_t)((sa * Rs4Cfg::TILE + kk * 2 * Rs4Cfg::PLANE) >> 4) + (uint64_t)(j * dil);
+      mma<false>(tacc, ad, bd, idesc, (first && kk == 0 && sa == 0) ? 0u : 1u);
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(Rs4Cfg::NT, 1) rs4_kernel(const RsParams p, const __grid_constant__ RsMaps maps) {
+  using Cfg = Rs4Cfg;
+  constexpr bool FWD = KIND != 2;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* OP = smem + Cfg::OFF_OP;    // the operand buffer (all convolutions, in place); also receives the raw fp32 input tile
+  uint8_t* OUT = smem + Cfg::OFF_OUT;  // one 4 KB swizzled row image per epilogue warp
+  uint8_t* W = smem + Cfg::OFF_W;
+  float* meta = reinterpret_cast<float*>(smem + Cfg::OFF_META);
+  uint32_t* amax = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_AMAX);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* mma_done = bars;
+  uint64_t* ready = bars + Cfg::MB;
+  uint64_t* w_full = bars + 2 * Cfg::MB;
+  uint64_t* w_empty = w_full + 2;
+  uint64_t* allepi = w_empty + 2;
+  uint64_t* in_full = allepi + 1;
+  uint64_t* op_empty = in_full + 1;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_TSLOT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nconv = p.nconv, L = p.L;
+
+  if (warp == 0) tmem_alloc(tslot, Cfg::TCOLS);
+  if (tid == 32) {
+    for (int i = 0; i < Cfg::MB; ++i) { mbar_init(&mma_done[i], 1); mbar_init(&ready[i], 4); }
+    mbar_init(&w_full[0], 1); mbar_init(&w_full[1], 1); mbar_init(&w_empty[0], 1); mbar_init(&w_empty[1], 1);
+    mbar_init(allepi, Cfg::NEPI); mbar_init(in_full, 1); mbar_init(op_empty, 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) amax[tid] = 0u;
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int e = tid; e < nconv * Cfg::META; e += Cfg::NT)
+    meta[e] = reinterpret_cast<const float*>(p.wpack + (size_t)(e / Cfg::META) * Cfg::WREC + Cfg::WCONV)[e % Cfg::META];
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tslot;
+
+  if (warp == Cfg::NEPI + 1) {
+    // ------------------------------------------------------------------------------------------- producer
+    if (elect_one()) {
+      uint32_t wuse[2] = {0u, 0u};
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+        const int b = tile / p.tiles_x;
+        const int g0 = (tile - b * p.tiles_x) * p.Rout - p.H;
+        if (ti > 0) mbar_wait(op_empty, (uint32_t)(ti - 1) & 1u);  // the last convolution of the previous tile has read the buffer
+        tma::expect_tx(in_full, Cfg::R * 128);
+#pragma unroll
+        for (int j = 0; j < Cfg::MB; ++j) tma::load_rows(&maps.in, OP + j * Cfg::IMG, in_full, g0 + j * 128, b);
+        const int next = tile + gridDim.x;
+        if (next < p.total_tiles) {
+          const int nb = next / p.tiles_x;
+          const int ng0 = (next - nb * p.tiles_x) * p.Rout - p.H;
+#pragma unroll
+          for (int j = 0; j < Cfg::MB; ++j) prefetch_rows_l2(&maps.in, ng0 + j * 128, nb);
+        }
+        for (int k = 0; k < nconv; ++k) {
+          const int s = k & 1;
+          if (wuse[s] > 0) mbar_wait(&w_empty[s], (wuse[s] - 1u) & 1u);
+          tma::expect_tx(&w_full[s], Cfg::WCONV);
+          bulk_g2s(W + s * Cfg::WCONV, p.wpack + (size_t)k * Cfg::WREC, Cfg::WCONV, &w_full[s]);
+          ++wuse[s];
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == Cfg::NEPI) {
+    // --------------------------------------------------------------------------------------------- issuer
+    if (elect_one()) {
+      uint32_t rdy[Cfg::MB], wf[2] = {0u, 0u};
+#pragma unroll
+      for (int i = 0; i < Cfg::MB; ++i) rdy[i] = 0u;
+      const uint32_t a_base = smem_u32(OP);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int k = 0; k < nconv; ++k) {
+          const int s = k & 1;
+          mbar_wait(&w_full[s], wf[s] & 1u); ++wf[s];
+          const int dil = p.dil[k];
+          const uint32_t wb = smem_u32(W + s * Cfg::WCONV);
+          auto tap = [&](int mb, int j, bool first) { rs4_tap(tmem + mb * Cfg::NW, a_base, Cfg::G + mb * 128 - dil, dil, wb, j, first); };
+          auto wait_ready = [&](int mb) { mbar_wait(&ready[mb], rdy[mb] & 1u); ++rdy[mb]; fence_after_sync(); };
+          // taps: 0 reads rows of blocks mb-1, mb; 1 of mb; 2 of mb, mb+1.  Every MMA that reads rows of block mb goes out before
+          // commit(mb): the block's epilogue overwrites those rows.
+          wait_ready(0);
+          tap(0, 0, true); tap(0, 1, false);
+#pragma unroll
+          for (int mb = 0; mb < Cfg::MB; ++mb) {
+            if (mb + 1 < Cfg::MB) {
+              wait_ready(mb + 1);
+              tap(mb + 1, 0, true);   // tail rows of block mb
+            }
+            tap(mb, 2, false);        // head rows of block mb+1 (operand of this convolution: not yet overwritten)
+            commit(&mma_done[mb]);
+            if (mb + 1 < Cfg::MB) tap(mb + 1, 1, false);
+          }
+          commit(&w_empty[s]);
+          if (k == nconv - 1) commit(op_empty);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------------------------------ epilogues
+    const int mb = warp >> 2, qd = warp & 3;
+    const int r = warp * 32 + lane;  // tile row = TMEM lane (mb * 128 + qd * 32 + lane)
+    const uint32_t taddr = tmem + (((uint32_t)qd * 32u) << 16) + (uint32_t)(mb * Cfg::NW);
+    const int q0 = warp * 32;
+    const int srow = max(q0, p.H), snum = max(min(q0 + 32, Cfg::R - p.H) - srow, 0);
+    const bool own = r >= srow && r < srow + snum;
+    const int jrow = (r - srow) & 31;
+    const uint32_t img = smem_u32(OUT) + (uint32_t)warp * 4096u;
+    const uint32_t imgrow = img + (uint32_t)jrow * 128u;
+    const uint32_t jx = (uint32_t)(jrow & 7);
+    const int mapsel = snum == 32 ? 1 : 0;
+    const uint32_t oprow = smem_u32(OP) + (uint32_t)((Cfg::G + r) * 16);
+    uint32_t md = 0u, ae = 0u;
+    float res[32];
+    float sa = 1.f, rbound = 0.f;
+    bool inrange = false;
+    size_t grow = 0;
+    int g0 = 0, b = 0, ti = 0;
+    uint32_t* am = amax;
+
+    // 16 channels (half hf) -> hi / lo operand chunks of planes 2 hf, 2 hf + 1
+    auto write_operand = [&](int hf, const float* v, float scale, __half2& hm) {
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        float t[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) t[c] = v[o * 8 + c] * scale;
+        uint4 ph, pl;
+        rs_split8<FWD>(t, ph, pl, hm);
+        sts128(oprow + (hf * 2 + o) * Cfg::PLANE, ph);
+        sts128(oprow + (hf * 2 + o) * Cfg::PLANE + Cfg::TILE, pl);
+      }
+    };
+
+    auto epilogue = [&](int k, auto stage_tag) {
+      constexpr int STAGE = decltype(stage_tag)::value;
+      const float* mt = meta + k * Cfg::META;
+      const bool last = k == nconv - 1;
+      const bool store = p.store[k] != 0 && snum > 0;
+      uint32_t mword = 0xffffffffu;
+      if (KIND == 2) mword = inrange ? p.bits_mask[k][grow] : 0u;
+      mbar_wait(&mma_done[mb], md & 1u); ++md;
+      fence_after_sync();
+      if (k > 0) { mbar_wait(allepi, ae & 1u); ++ae; }  // all epilogues of convolution k-1: am[k] is final
+      const float inv = pow2_inv(sa) * pow2_inv(mt[0]);
+      float bound = fmaf(mt[1], __uint_as_float(am[k]), mt[2]);
+      if (STAGE) { bound += rbound; rbound = bound; }
+      const float sa_next = pow2_scale(bound);
+      const float sa_row = inrange ? sa_next : 0.f;  // rows outside [0, L) are the next convolution's zero padding
+      if (store) {
+        if (lane == 0) tma::wait_read();   // the warp's image: its previous store has been read out of shared memory
+        __syncwarp();
+      }
+      __half2 hm = __float2half2_rn(0.f);
+      uint32_t bits = 0u;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t ra[16], rb[16];
+        tmem_ld16_nw(taddr + hf * 16, ra); tmem_ld16_nw(taddr + 32 + hf * 16, rb);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = fmaf(__uint_as_float(ra[c]) + __uint_as_float(rb[c]), inv, mt[4 + hf * 16 + c]);
+        if (KIND == 2) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] = (mword >> (hf * 16 + c)) & 1u ? v[c] : 0.f;
+        }
+        if (STAGE) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { res[hf * 16 + c] += v[c]; v[c] = res[hf * 16 + c]; }
+        }
+        if (KIND == 1) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) bits |= (uint32_t)(v[c] > 0.f) << (hf * 16 + c);
+        }
+        if (store && own) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            sts128(imgrow + ((((uint32_t)(hf * 4 + c)) ^ jx) << 4),
+                   make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3])));
+        }
+        if (!last) write_operand(hf, v, sa_row, hm);
+      }
+      if (KIND == 1 && p.bits_out[k] && own && inrange) p.bits_out[k][grow] = bits;
+      if (!last) {
+        uint32_t mm = rs_hmax_bits(hm, pow2_inv(sa_next));
+        mm = __reduce_max_sync(0xffffffffu, mm);
+        if (lane == 0) atomicMax(&am[k + 1], mm);
+        sa = sa_next;
+      }
+      fence_proxy_async();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if (store) {
+          tma::store_rows(&maps.out[k][mapsel], reinterpret_cast<const void*>(OUT + warp * 4096), g0 + srow, b);
+          tma::commit_group();
+        }
+        if (!last) { mbar_arrive(allepi); mbar_arrive(&ready[mb]); }
+      }
+    };
+
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      const int par = ti & 1;
+      am = amax + par * 16;
+      b = tile / p.tiles_x;
+      g0 = (tile - b * p.tiles_x) * p.Rout - p.H;
+      const int g = g0 + r;
+      inrange = g >= 0 && g < L;
+      grow = (size_t)b * L + (size_t)(inrange ? g : 0);
+      // ---- input phase: raw fp32 row -> residual registers, tile maximum, first operand (written over the raw tile: in place)
+      mbar_wait(in_full, (uint32_t)ti & 1u);
+      {
+        const uint8_t* raw = OP + (r >> 7) * Cfg::IMG;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 f = *reinterpret_cast<const float4*>(raw + tma::swz(r & 127, c));
+          res[4 * c] = f.x; res[4 * c + 1] = f.y; res[4 * c + 2] = f.z; res[4 * c + 3] = f.w;
+        }
+      }
+      uint32_t m = 0u;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) m = max(m, absbits(res[c]));
+      m = __reduce_max_sync(0xffffffffu, m);
+      if (lane == 0) atomicMax(&am[0], m);
+      if (KIND == 1 && p.bits_in0 && own && inrange) {
+        uint32_t w = 0u;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) w |= (uint32_t)(res[c] > 0.f) << c;
+        p.bits_in0[grow] = w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(allepi);
+      mbar_wait(allepi, ae & 1u); ++ae;   // every raw row is in registers: the buffer may be rewritten
+      if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) amax[(par ^ 1) * 16 + i] = 0u;
+      }
+      {  // guard rows (the raw tile passed over them): 2 * G rows x 8 chunk columns = one chunk per epilogue thread
+        const int q = tid / (2 * Cfg::G), gr = tid % (2 * Cfg::G);
+        const int prow = gr < Cfg::G ? gr : Cfg::R + gr;
+        *reinterpret_cast<uint4*>(OP + (q >> 2) * Cfg::TILE + (q & 3) * Cfg::PLANE + prow * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      rbound = __uint_as_float(am[0]);
+      sa = pow2_scale(rbound);
+      {
+        __half2 hm = __float2half2_rn(0.f);
+        write_operand(0, res, sa, hm);
+        write_operand(1, res + 16, sa, hm);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready[mb]);
+      for (int k = 0; k < nconv; k += 2) {
+        epilogue(k, std::integral_constant<int, 0>());
+        epilogue(k + 1, std::integral_constant<int, 1>());
+      }
+      // the last epilogue does not arrive on allepi: keep the phase count even with the arrivals (one wait per phase)
+    }
+    if (lane == 0) tma::wait_all();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
+}
+
 // ---------------------------------------------------------------------------------------------------------- host side
 bool resstack_tc_supported(const vqb_resstack_desc* d) {
   if (!d || d->C != 32 || d->precision != VQB_PREC_FP16X2 || d->n_blocks < 1 || d->n_blocks > VQB_RESSTACK_MAX_BLOCKS) return false;
@@ -540,6 +862,41 @@ static int launch_rs(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
   return VQB_OK;
 }
 
+template <int KIND>
+static int launch_rs4(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VQB_CUDA(cudaFuncSetAttribute(rs4_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Rs4Cfg::SMEM));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    VQB_CUDA(cudaGetDevice(&dev));
+    VQB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  VQB_CUDA(launch_pdl(rs4_kernel<KIND>, dim3(grid), dim3(Rs4Cfg::NT), (size_t)Rs4Cfg::SMEM, st, p, maps));
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+// 512-row tiles (rs4_kernel) or 384-row tiles (rs_kernel): the larger tile loses fewer rows to the halo (424 vs 296 output rows
+// per tile at halo 44) and wins as soon as every SM gets more than one tile; for one wave or less the shorter tile finishes
+// sooner (measured at B = 32: L >= 3520 -> 512 rows: 167 vs 196 us at L = 14080, 50 vs 62 us at 3520; L <= 1760 -> 384 rows:
+// 42 vs 46 us).  VQB_RS_MB=3|4 forces one of them (tuning / A-B timing).
+static bool use_rs4(const vqb_resstack_desc* d, int H) {
+  const char* e = getenv("VQB_RS_MB");
+  if (e) return atoi(e) == 4;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) num_sms = 148;
+  }
+  const long tiles4 = (long)cdiv(d->L, Rs4Cfg::R - 2 * H) * d->B;
+  return 2 * tiles4 > 3L * num_sms;
+}
+
 // kind 0 / 1: forward (h == NULL -> inference), kind 2: data gradient.  A training forward (kind 1) packs the operand images of
 // BOTH directions (records [0, nconv): forward, [nconv, 2 nconv): data gradient), so that the data gradient of the same step can
 // run from the same workspace without a packing launch of its own (`prepacked`).
@@ -562,7 +919,8 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
   p.B = d->B; p.L = d->L; p.nconv = nconv;
   int H = 0;
   for (int i = 0; i < n; ++i) H += d->dilations[i] + 1;
-  p.H = H; p.Rout = RsCfg::R - 2 * H;
+  const bool v4 = use_rs4(d, H);
+  p.H = H; p.Rout = (v4 ? Rs4Cfg::R : RsCfg::R) - 2 * H;
   p.tiles_x = cdiv(d->L, p.Rout);
   p.total_tiles = p.tiles_x * d->B;
   float* outs[RS_MAXC];
@@ -594,7 +952,9 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
   for (int k = 0; k < nconv; ++k)
     if (p.store[k]) {
       const int part = 32 - H % 32;  // rows of the partial quadrant at either end of a tile's output rows
-      if (!tma::make_slice_map(&maps.out[k][0], outs[k], d->B, d->L, part) || !tma::make_slice_map(&maps.out[k][1], outs[k], d->B, d->L, 32))
+      const bool ok = v4 ? tma::make_rows_map(&maps.out[k][0], outs[k], d->B, d->L, part) && tma::make_rows_map(&maps.out[k][1], outs[k], d->B, d->L, 32)
+                         : tma::make_slice_map(&maps.out[k][0], outs[k], d->B, d->L, part) && tma::make_slice_map(&maps.out[k][1], outs[k], d->B, d->L, 32);
+      if (!ok)
         return set_err(VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed for an output of the residual stack");
     }
   int npack = nconv;
@@ -614,6 +974,13 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
   if (kind == 0 && getenv("VQB_RS_TRACE")) {  // profiling aid: address of a device buffer of 4 * 9 * 8 int64 (tools/trace_stack.py)
     p.trace = reinterpret_cast<long long*>(strtoull(getenv("VQB_RS_TRACE"), nullptr, 0));
     return launch_rs<0, true>(p, maps, st);
+  }
+  if (v4) {
+    switch (kind) {
+      case 0: return launch_rs4<0>(p, maps, st);
+      case 1: return launch_rs4<1>(p, maps, st);
+      default: return launch_rs4<2>(p, maps, st);
+    }
   }
   switch (kind) {
     case 0: return launch_rs<0>(p, maps, st);
