@@ -518,8 +518,9 @@ __global__ void __launch_bounds__(RsCfg::NT, 1) rs_kernel(const RsParams p, cons
 //     the raw fp32 input tile of the next tile lands in the same buffer once the last convolution's MMAs are through;
 //   * one thread per row (16 epilogue warps), which works through its 32 channels as two 16-channel halves.
 // ================================================================================================================
-struct Rs4Cfg {
-  static constexpr int MB = 4, R = 128 * MB, G = 32;
+template <int MBv>
+struct Rs4CfgT {
+  static constexpr int MB = MBv, R = 128 * MB, G = 32;
   static constexpr int NP = 4;
   static constexpr int PLANE = (R + 2 * G) * 16 + 32;
   static constexpr int TILE = NP * PLANE;
@@ -537,29 +538,31 @@ struct Rs4Cfg {
   static constexpr int OFF_TSLOT = OFF_BAR + NBAR * 8;
   static constexpr int SMEM = OFF_TSLOT + 16 + 1024;
   static constexpr int NT = (NEPI + 2) * 32;
-  static constexpr int TCOLS = 256;
+  static constexpr int TCOLS = MB * NW <= 256 ? 256 : 512;
   static_assert(OFF_W % 16 == 0 && OFF_BAR % 8 == 0 && R * 128 <= OPB, "layout");
   static_assert(SMEM <= 232448, "shared memory");
 };
+using Rs4Cfg = Rs4CfgT<4>;
 
 // one tap of one M block: 2 K steps x (hi-activation x [W_hi | W_lo], lo-activation x W_hi)
+template <class Cfg4>
 __device__ __forceinline__ void rs4_tap(uint32_t tacc, uint32_t a_base, int row0, int dil, uint32_t w_base, int j, bool first) {
-  const uint64_t ad0 = smem_desc(a_base + (uint32_t)row0 * 16u, Rs4Cfg::PLANE, 128);  // row0 = first row of tap 0
-  const uint64_t bd0 = smem_desc(w_base, Rs4Cfg::WPLANE, 128);
+  const uint64_t ad0 = smem_desc(a_base + (uint32_t)row0 * 16u, Cfg4::PLANE, 128);  // row0 = first row of tap 0
+  const uint64_t bd0 = smem_desc(w_base, Cfg4::WPLANE, 128);
 #pragma unroll
   for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
     for (int sa = 0; sa < 2; ++sa) {
       const uint32_t idesc = instr_desc(FMT_F16, 128, 32 * (2 - sa), false, false);
-      const uint64_t bd = bd0 + (uint64_t)((j * Rs4Cfg::WTAP + kk * 2 * Rs4Cfg::WPLANE) >> 4);
-      const uint64_t ad = ad0 + (uint64_t)((sa * Rs4Cfg::TILE + kk * 2 * Rs4Cfg::PLANE) >> 4) + (uint64_t)(j * dil);
+      const uint64_t bd = bd0 + (uint64_t)((j * Cfg4::WTAP + kk * 2 * Cfg4::WPLANE) >> 4);
+      const uint64_t ad = ad0 + (uint64_t)((sa * Cfg4::TILE + kk * 2 * Cfg4::PLANE) >> 4) + (uint64_t)(j * dil);
       mma<false>(tacc, ad, bd, idesc, (first && kk == 0 && sa == 0) ? 0u : 1u);
     }
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(Rs4Cfg::NT, 1) rs4_kernel(const RsParams p, const __grid_constant__ RsMaps maps) {
-  using Cfg = Rs4Cfg;
+template <int KIND, int MBv>
+__global__ void __launch_bounds__(Rs4CfgT<MBv>::NT, 1) rs4_kernel(const RsParams p, const __grid_constant__ RsMaps maps) {
+  using Cfg = Rs4CfgT<MBv>;
   constexpr bool FWD = KIND != 2;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -641,7 +644,7 @@ __global__ void __launch_bounds__(Rs4Cfg::NT, 1) rs4_kernel(const RsParams p, co
           mbar_wait(&w_full[s], wf[s] & 1u); ++wf[s];
           const int dil = p.dil[k];
           const uint32_t wb = smem_u32(W + s * Cfg::WCONV);
-          auto tap = [&](int mb, int j, bool first) { rs4_tap(tmem + mb * Cfg::NW, a_base, Cfg::G + mb * 128 - dil, dil, wb, j, first); };
+          auto tap = [&](int mb, int j, bool first) { rs4_tap<Cfg>(tmem + mb * Cfg::NW, a_base, Cfg::G + mb * 128 - dil, dil, wb, j, first); };
           auto wait_ready = [&](int mb) { mbar_wait(&ready[mb], rdy[mb] & 1u); ++rdy[mb]; fence_after_sync(); };
           // taps: 0 reads rows of blocks mb-1, mb; 1 of mb; 2 of mb, mb+1.  Every MMA that reads rows of block mb goes out before
           // commit(mb): the block's epilogue overwrites those rows.
@@ -803,7 +806,7 @@ __global__ void __launch_bounds__(Rs4Cfg::NT, 1) rs4_kernel(const RsParams p, co
 #pragma unroll
         for (int i = 0; i < 16; ++i) amax[(par ^ 1) * 16 + i] = 0u;
       }
-      {  // guard rows (the raw tile passed over them): 2 * G rows x 8 chunk columns = one chunk per epilogue thread
+      if (tid < 2 * Cfg::G * 8) {  // guard rows (the raw tile passed over them): 2 * G rows x 8 chunk columns
         const int q = tid / (2 * Cfg::G), gr = tid % (2 * Cfg::G);
         const int prow = gr < Cfg::G ? gr : Cfg::R + gr;
         *reinterpret_cast<uint4*>(OP + (q >> 2) * Cfg::TILE + (q & 3) * Cfg::PLANE + prow * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -862,11 +865,11 @@ static int launch_rs(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
   return VQB_OK;
 }
 
-template <int KIND>
+template <int KIND, int MBv>
 static int launch_rs4(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    VQB_CUDA(cudaFuncSetAttribute(rs4_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Rs4Cfg::SMEM));
+    VQB_CUDA(cudaFuncSetAttribute(rs4_kernel<KIND, MBv>, cudaFuncAttributeMaxDynamicSharedMemorySize, Rs4CfgT<MBv>::SMEM));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -876,7 +879,7 @@ static int launch_rs4(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
     VQB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  VQB_CUDA(launch_pdl(rs4_kernel<KIND>, dim3(grid), dim3(Rs4Cfg::NT), (size_t)Rs4Cfg::SMEM, st, p, maps));
+  VQB_CUDA(launch_pdl(rs4_kernel<KIND, MBv>, dim3(grid), dim3(Rs4CfgT<MBv>::NT), (size_t)Rs4CfgT<MBv>::SMEM, st, p, maps));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
@@ -884,17 +887,19 @@ static int launch_rs4(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
 // 512-row tiles (rs4_kernel) or 384-row tiles (rs_kernel): the larger tile loses fewer rows to the halo (424 vs 296 output rows
 // per tile at halo 44) and wins as soon as every SM gets more than one tile; for one wave or less the shorter tile finishes
 // sooner (measured at B = 32: L >= 3520 -> 512 rows: 167 vs 196 us at L = 14080, 50 vs 62 us at 3520; L <= 1760 -> 384 rows:
-// 42 vs 46 us).  VQB_RS_MB=3|4 forces one of them (tuning / A-B timing).
-static bool use_rs4(const vqb_resstack_desc* d, int H) {
+// 42 vs 46 us; 640-row tiles — the same template with 5 M blocks, 80 registers per thread — measured no better than 512:
+// 116 / 167 / 190 us against 123 / 168 / 187 us for inference / tape forward / data gradient).  VQB_RS_MB=3|4 forces a tile
+// height (tuning / A-B timing).
+static int pick_mb(const vqb_resstack_desc* d, int H) {
   const char* e = getenv("VQB_RS_MB");
-  if (e) return atoi(e) == 4;
+  if (e) return atoi(e) == 4 ? 4 : 3;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) num_sms = 148;
   }
   const long tiles4 = (long)cdiv(d->L, Rs4Cfg::R - 2 * H) * d->B;
-  return 2 * tiles4 > 3L * num_sms;
+  return 2 * tiles4 > 3L * num_sms ? 4 : 3;
 }
 
 // kind 0 / 1: forward (h == NULL -> inference), kind 2: data gradient.  A training forward (kind 1) packs the operand images of
@@ -919,8 +924,9 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
   p.B = d->B; p.L = d->L; p.nconv = nconv;
   int H = 0;
   for (int i = 0; i < n; ++i) H += d->dilations[i] + 1;
-  const bool v4 = use_rs4(d, H);
-  p.H = H; p.Rout = (v4 ? Rs4Cfg::R : RsCfg::R) - 2 * H;
+  const int mbsel = pick_mb(d, H);
+  const bool v4 = mbsel >= 4;
+  p.H = H; p.Rout = 128 * mbsel - 2 * H;
   p.tiles_x = cdiv(d->L, p.Rout);
   p.total_tiles = p.tiles_x * d->B;
   float* outs[RS_MAXC];
@@ -975,13 +981,14 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
     p.trace = reinterpret_cast<long long*>(strtoull(getenv("VQB_RS_TRACE"), nullptr, 0));
     return launch_rs<0, true>(p, maps, st);
   }
-  if (v4) {
+  if (mbsel == 4) {
     switch (kind) {
-      case 0: return launch_rs4<0>(p, maps, st);
-      case 1: return launch_rs4<1>(p, maps, st);
-      default: return launch_rs4<2>(p, maps, st);
+      case 0: return launch_rs4<0, 4>(p, maps, st);
+      case 1: return launch_rs4<1, 4>(p, maps, st);
+      default: return launch_rs4<2, 4>(p, maps, st);
     }
   }
+
   switch (kind) {
     case 0: return launch_rs<0>(p, maps, st);
     case 1: return launch_rs<1>(p, maps, st);
