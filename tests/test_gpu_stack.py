@@ -173,3 +173,30 @@ def test_resstack_unsupported_shapes_are_refused(gpu):
     w = torch.zeros(3, 64, 64, device="cuda"); b = torch.zeros(64, device="cuda")
     with pytest.raises(L.VQBError):
         ops.resstack_fwd(x, [w], [b], [w], [b], (1,), P, False)
+
+
+@pytest.mark.parametrize("B,L", [(2, 1000), (32, 3520)])
+def test_resstack_is_independent_of_what_ran_before(gpu, tile_rows, B, L):
+    """The kernel keeps state across tiles in shared / tensor memory (operand buffer rewritten in place, guard rows, per-tile
+    maxima, accumulators): the result of a call must not depend on what the SMs processed before it — bit for bit, also after a
+    launch full of huge values and after a launch of another shape."""
+    ops, P = gpu.ops, gpu._lib.PRECISIONS["fp16x2"]
+    rng = np.random.default_rng(11)
+    dils = (1, 3, 9, 27)
+    x, wts = make(rng, B, L, 4)
+    W = [[dev(a) for a in blk] for blk in wts]
+    args = ([w[0] for w in W], [w[1] for w in W], [w[2] for w in W], [w[3] for w in W], dils, P)
+    xd = dev(x)
+    first = ops.resstack_fwd(xd, *args, True)
+    junk = torch.full((B, L + 777, 32), 3.0e30, device="cuda")
+    junk[:, ::3] = -1.0e-30
+    ops.resstack_fwd(junk, *args, False)
+    again = ops.resstack_fwd(xd, *args, True)
+    for a, b in zip(first[0] + first[1] + first[2] + first[3], again[0] + again[1] + again[2] + again[3]):
+        assert torch.equal(a, b)
+    dy = dev(rng.normal(size=(B, L, 32)).astype(np.float32))
+    g1 = ops.resstack_bwd_data(dy, None, None, first[2], first[3], dils, P, fwd_ws=first[4])
+    ops.resstack_fwd(junk, *args, False)
+    g2 = ops.resstack_bwd_data(dy, None, None, first[2], first[3], dils, P, fwd_ws=first[4])
+    for a, b in zip(g1[0] + g1[1], g2[0] + g2[1]):
+        assert torch.equal(a, b)

@@ -1,6 +1,6 @@
 """Pipeline time stamps of the fused residual-stack kernel (csrc/resstack_tc.cu, TRACE instantiation): clock64 at the hand-offs of
-CTA 0's second tile — issuer (weights there, operands ready, commits) and the first epilogue warp of every M block (accumulator
-ready, TMEM read, row work done, all-epilogues barrier passed, operand written, proxy fence done).
+CTA 0's second tile — issuer (weights there, commit of every M block) and the first epilogue warp of every M block (accumulator
+ready, all-epilogues barrier passed, row work done incl. operand rows, proxy fence done).
 Usage: python tools/trace_stack.py   (prints clocks relative to the issuer's first stamp)"""
 import os
 import sys
@@ -8,7 +8,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-buf = torch.zeros(4 * 9 * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(5 * 9 * 8, dtype=torch.int64, device="cuda")
 os.environ["VQB_RS_TRACE"] = hex(buf.data_ptr())
 import vqvae_b200 as V  # noqa: E402
 
@@ -23,13 +23,13 @@ Bz = [torch.zeros(C, device="cuda") for _ in dils]
 for _ in range(3):
     ops.resstack_fwd(x, W1, Bz, W2, Bz, dils, P, False)
 torch.cuda.synchronize()
-t = buf.cpu().view(4, 9, 8)
+t = buf.cpu().view(5, 9, 8)
 t0 = int(t[0, 0, 0])
-names = {0: ["w_full", "ready0", "ready1", "ready2", "commit0", "commit1", "commit2", "-"],
-         1: ["acc_ready", "tmem_read", "rows_done", "allepi", "operand", "fenced", "-", "-"]}
+names = {0: ["w_full", "commit0", "commit1", "commit2", "commit3", "-", "-", "-"],
+         1: ["acc_ready", "allepi", "rows_done", "fenced", "-", "-", "-", "-"]}
 for k in range(8):
     print(f"conv {k}")
-    for role in range(4):
+    for role in range(5):
         row = [int(v) - t0 if int(v) else None for v in t[role, k]]
         nm = names[0 if role == 0 else 1]
         print("   ", "issuer " if role == 0 else f"epi mb{role - 1}", " ".join(f"{n}={v}" for n, v in zip(nm, row) if v is not None))

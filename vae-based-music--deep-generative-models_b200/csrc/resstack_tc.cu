@@ -1,25 +1,32 @@
 // resstack_tc.cu — a whole DilatedResnet1D (resnet.py:40-59: up to 4 pre-activation residual blocks = 8 k=3 32->32
 // convolutions) and its data-gradient chain as ONE persistent, warp-specialised tcgen05 kernel.
 //
-//   per tile of R = 384 time rows (3 M blocks of 128) of one batch item, halo H = sum(dilation_i + 1) rows per side:
-//     producer warp : TMA-loads the raw fp32 [R, 32] input rows (3-D tensor map, rows outside [0, L) arrive as zeros = the
-//                     SAME padding) and, per convolution, the pre-packed fp16x2 operand image of its weights (bulk copy)
+//   per tile of R = 128 * MB time rows (MB = 4, or 3 for short sequences) of one batch item, halo H = sum(dilation_i + 1) rows
+//   per side (R - 2 H of the rows are output rows):
+//     producer warp : TMA-loads the raw fp32 [R, 32] input rows (3-D tensor map, 128-byte swizzle; rows outside [0, L) arrive as
+//                     zeros = the SAME padding; the next tile is prefetched into L2) and, per convolution, the pre-packed
+//                     fp16x2 operand image of its weights (bulk copy)
 //     issuer warp   : per convolution and M block 12 tcgen05.mma (3 taps = the SAME operand tile addressed with a row shift of
 //                     (tap-1)*dilation, 2 K steps, 2 piece instructions N = 64 + N = 32), accumulators in tensor memory
-//     12 epilogue warps (thread = tile row = TMEM lane, all 32 channels): TMEM -> registers, scale / bias / sign mask /
-//                     residual (kept in registers across the whole stack), -> the next convolution's operand rows in
-//                     shared memory (ReLU, power-of-two scale, fp16 hi / lo split), and — only where the caller wants a
-//                     tensor back — a swizzled row image that leaves through a TMA store
-//   hand-offs are mbarriers per M block: the MMAs of convolution k+1 on block mb start as soon as the epilogues of blocks
-//   mb-1 .. mb+1 of convolution k are through, so the tensor pipe works on one M block while the epilogue warps of the others
-//   convert; operand tiles ping-pong between two buffers (X, Y); the raw input of the NEXT tile lands in Y while the last
-//   epilogue of the current one runs.
+//     4 * MB epilogue warps (thread = tile row = TMEM lane; its 32 channels as two halves): TMEM -> registers, scale / bias /
+//                     sign mask / residual (kept in registers across the whole stack), -> the next convolution's operand row
+//                     (ReLU folded into a truncating hi / lo fp16 split, power-of-two scale), and — only where the caller
+//                     wants a tensor back — a swizzled row image that leaves as the warp's own TMA store
+//   ONE operand buffer, rewritten in place: the epilogue of (convolution k, M block mb) writes the operand rows of convolution
+//   k+1 over those of k.  Safe because every MMA of k that reads rows of block mb — its own three taps, tap +1 of block mb-1
+//   (head rows) and tap -1 of block mb+1 (tail rows) — is issued before the commit that releases the block (issue order per
+//   convolution: t-1(0) t0(0) | t-1(1) t+1(0) commit0 | t0(1) | t-1(2) t+1(1) commit1 | ...).  Hand-offs are mbarriers per M
+//   block, so the tensor pipe works on one block while the epilogue warps of the others convert; the raw input of the NEXT tile
+//   lands in the same buffer once the last convolution's MMAs are through, under the last epilogue.
 //
 // Arithmetic = the fp16x2 mode of resblock_tc.cu (operands scaled by a power of two and split into two fp16 pieces, three
 // piece products, fp32 accumulation).  Operand scales: exact maximum of the tile input (one reduction per tile), then for every
-// convolution the bound  L1(W) * max|input| (+ max|residual|) + max|bias|  with max|input| the EXACT maximum of the previous
-// convolution's output (published through shared memory by its epilogues, complete by the time it is needed because the
+// convolution the bound  L1(W) * max|input| (+ bound of the residual stream) + max|bias|  with max|input| the EXACT maximum of
+// the previous convolution's operand (published through shared memory by its epilogues, complete by the time it is needed: the
 // epilogue of convolution k waits for all epilogues of k-1, which finish under the MMAs of k anyway).
+//
+// What bounds it (profiles/README.md): tensor memory is read at 32 B/clk/SM, and the [hi | lo] accumulator blocks are 64 fp32
+// columns per row and convolution.
 //
 // Three instantiations: KIND 0 inference forward (stores y only: 256 B per position for the whole stack), KIND 1 training
 // forward (stores h_i, y_i and both sign masks per block), KIND 2 data gradient (masks from the sign words, stores dh_i, dx_i).
@@ -38,32 +45,13 @@ using namespace tc;
 
 constexpr int RS_MAXC = 2 * VQB_RESSTACK_MAX_BLOCKS;  // convolutions per launch
 
-struct RsCfg {
-  static constexpr int MB = 3, R = 128 * MB, G = 32;
+struct RsW {  // packed weight record of one convolution (rs_pack_kernel): operand image + what the epilogues need
   static constexpr int NP = 4;                          // 16-byte planes (8 fp16 channels each) per piece
-  static constexpr int PLANE = (R + 2 * G) * 16 + 32;   // bytes; +32 de-aliases the planes' banks
-  static constexpr int TILE = NP * PLANE;               // one piece of an operand tile
-  static constexpr int OPB = 2 * TILE;                  // operand buffer: hi piece, lo piece
-  static constexpr int NW = 64, WPLANE = NW * 16, WTAP = NP * WPLANE, WCONV = 3 * WTAP;  // weight image: [tap][plane][hi 32 | lo 32 rows][16 B]
-  static constexpr int META = 36;                       // floats per convolution: weight scale, L1 bound, max|bias|, -, bias[32]
-  static constexpr int WREC = WCONV + 256;              // packed record in global memory: image + META floats (padded)
-  static constexpr int IMG = 128 * 128;                 // one M block of fp32 rows
-  static constexpr int OFF_Y = 0;
-  static constexpr int OFF_OUT = ((OPB + 1023) / 1024) * 1024;
-  static constexpr int OFF_X = OFF_OUT + MB * IMG;
-  static constexpr int OFF_W = OFF_X + OPB;
-  static constexpr int OFF_META = OFF_W + 2 * WCONV;
-  static constexpr int OFF_AMAX = OFF_META + RS_MAXC * META * 4;
-  static constexpr int OFF_BAR = OFF_AMAX + 2 * 16 * 4;
-  static constexpr int NBAR = 3 * MB + 8;
-  static constexpr int OFF_TSLOT = OFF_BAR + NBAR * 8;
-  static constexpr int SMEM = OFF_TSLOT + 16 + 1024;    // + slack for the 1024-byte alignment of the base
-  static constexpr int NEPI = 8 * MB;                   // epilogue warps: two threads per tile row (16 channels each)
-  static constexpr int NT = (NEPI + 2) * 32;            // + issuer warp + producer warp
-  static constexpr int TCOLS = 256;                     // MB * NW = 192 accumulator columns
-  static_assert(OFF_X % 16 == 0 && OFF_W % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
-  static_assert(SMEM <= 232448, "shared memory");
+  static constexpr int NW = 64, WPLANE = NW * 16, WTAP = NP * WPLANE, WCONV = 3 * WTAP;  // image: [tap][plane][hi 32 | lo 32 rows][16 B]
+  static constexpr int META = 36;                       // floats: weight scale, L1 bound, max|bias|, -, bias[32]
+  static constexpr int WREC = WCONV + 256;              // record in global memory: image + META floats (padded)
 };
+using RsCfg = RsW;
 
 struct RsParams {
   const uint8_t* wpack;                // nconv records of RsCfg::WREC bytes (rs_pack_kernel)
@@ -73,11 +61,11 @@ struct RsParams {
   uint32_t* bits_in0;                  // KIND 1: sign mask of the chain input
   uint32_t* bits_out[RS_MAXC];         // KIND 1: sign mask of the output of convolution k (or NULL)
   const uint32_t* bits_mask[RS_MAXC];  // KIND 2: sign mask applied to the output of convolution k
-  long long* trace;                    // TRACE builds: clock64 stamps of CTA 0's second tile, [role 0..3][k 0..8][event 0..7]
+  long long* trace;                    // TRACE builds: clock64 stamps of CTA 0's second tile, [role 0..4][k 0..8][event 0..7]
 };
 struct RsMaps {
   CUtensorMap in;                      // box {32, 128, 1}
-  CUtensorMap out[RS_MAXC][2];         // per-warp slices {16 channels, rows}: [k][1]: 32 rows, [k][0]: the partial quadrant at the
+  CUtensorMap out[RS_MAXC][2];         // per-warp slices {32 channels, rows}: [k][1]: 32 rows, [k][0]: the partial quadrant at the
                                        // two ends of a tile's output rows (32 - H % 32 rows)
 };
 
@@ -139,7 +127,6 @@ __global__ void __launch_bounds__(256) rs_pack_kernel(const RsPackParams p) {
   }
 }
 
-__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -162,27 +149,6 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// MMAs of one convolution on one M block for taps [j0, j1): per tap 2 K steps x (hi-activation x [W_hi | W_lo], lo-activation x
-// W_hi).  Tap j reads operand rows shifted by (j - 1) * dil: taps 0 and 1 need the rows of M blocks mb - 1 and mb only, tap 2
-// those of mb + 1 — the issuer starts a block's taps 0, 1 before the next block's epilogue is through.
-__device__ __forceinline__ void rs_issue(uint32_t tacc, uint32_t a_base, int row0, int dil, uint32_t w_base, int j0, int j1) {
-  const uint64_t ad0 = smem_desc(a_base + (uint32_t)row0 * 16u, RsCfg::PLANE, 128);  // row0 = first row of tap 0
-  const uint64_t bd0 = smem_desc(w_base, RsCfg::WPLANE, 128);
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    if (j < j0 || j >= j1) continue;
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-      for (int sa = 0; sa < 2; ++sa) {
-        const uint32_t idesc = instr_desc(FMT_F16, 128, 32 * (2 - sa), false, false);
-        const uint64_t bd = bd0 + (uint64_t)((j * RsCfg::WTAP + kk * 2 * RsCfg::WPLANE) >> 4);
-        const uint64_t ad = ad0 + (uint64_t)((sa * RsCfg::TILE + kk * 2 * RsCfg::PLANE) >> 4) + (uint64_t)(j * dil);
-        mma<false>(tacc, ad, bd, idesc, (j | kk | sa) ? 1u : 0u);
-      }
-  }
-}
 
 // fp32 -> two fp16 pieces by TRUNCATION: hi = the value with its mantissa cut to fp16's 10 bits (one LOP3; exactly
 // representable, so the conversion is exact), lo = rn_f16(x - hi) (exact difference, 13 bits rounded to 11): 2^-22 relative,
@@ -217,309 +183,15 @@ __device__ __forceinline__ uint32_t rs_hmax_bits(__half2 hm, float inv) {
   return __float_as_uint(fmaxf(f.x, f.y) * inv * 1.002f);
 }
 
-// TRACE: time stamps of the pipeline (tools/trace_stack.py): role 0 = issuer, 1 + mb = first epilogue warp of M block mb
+// TRACE: clock64 stamps of the hand-offs of CTA 0's second tile (tools/trace_stack.py): role 0 = issuer, 1 + mb = first epilogue
+// warp of M block mb
 #define RS_TR(role, k, ev)                                                                                   \
   do {                                                                                                       \
     if (TRACE && p.trace && blockIdx.x == 0 && ti == 1 && lane == 0) p.trace[((role) * 9 + (k)) * 8 + (ev)] = clock64(); \
   } while (0)
 
-template <int KIND, bool TRACE = false>
-__global__ void __launch_bounds__(RsCfg::NT, 1) rs_kernel(const RsParams p, const __grid_constant__ RsMaps maps) {
-  using Cfg = RsCfg;
-  constexpr bool FWD = KIND != 2;
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* Y = smem + Cfg::OFF_Y;      // operand buffer 1 (odd convolutions read it); also receives the raw fp32 input tile
-  uint8_t* OUT = smem + Cfg::OFF_OUT;  // MB swizzled row images for the TMA stores
-  uint8_t* X = smem + Cfg::OFF_X;      // operand buffer 0
-  uint8_t* W = smem + Cfg::OFF_W;      // two weight slots
-  float* meta = reinterpret_cast<float*>(smem + Cfg::OFF_META);
-  uint32_t* amax = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_AMAX);  // [2][16]: per tile parity, [k] = max |input of convolution k|
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* mma_done = bars;               // [MB]  accumulators of (k, mb) complete
-  uint64_t* ready = bars + Cfg::MB;        // [MB]  operand rows of M block mb written (and its accumulator drained)
-  uint64_t* w_full = bars + 2 * Cfg::MB;   // [2]
-  uint64_t* w_empty = w_full + 2;          // [2]
-  uint64_t* allepi = w_empty + 2;          // every epilogue warp is through a phase
-  uint64_t* in_full = allepi + 1;
-  uint64_t* y_empty = in_full + 1;
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_TSLOT);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nconv = p.nconv, L = p.L;
-
-  if (warp == 0) tmem_alloc(tslot, Cfg::TCOLS);
-  if (tid == 32) {
-    for (int i = 0; i < Cfg::MB; ++i) { mbar_init(&mma_done[i], 1); mbar_init(&ready[i], 8); }
-    mbar_init(&w_full[0], 1); mbar_init(&w_full[1], 1); mbar_init(&w_empty[0], 1); mbar_init(&w_empty[1], 1);
-    mbar_init(allepi, Cfg::NEPI); mbar_init(in_full, 1); mbar_init(y_empty, 1);
-    fence_mbar_init();
-  }
-  // operand buffer X: zero once (its guard rows are never written again); Y's guard rows are re-zeroed per tile, because the
-  // raw input tile passes through Y
-  for (int e = tid; e < Cfg::OPB / 16; e += Cfg::NT) reinterpret_cast<uint4*>(X)[e] = make_uint4(0u, 0u, 0u, 0u);
-  if (tid < 32) amax[tid] = 0u;
-  pdl_launch_dependents();
-  pdl_wait();  // the packed weights come from the kernel in front of this one
-  for (int e = tid; e < nconv * Cfg::META; e += Cfg::NT)
-    meta[e] = reinterpret_cast<const float*>(p.wpack + (size_t)(e / Cfg::META) * Cfg::WREC + Cfg::WCONV)[e % Cfg::META];
-  fence_proxy_async();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = *tslot;
-
-  if (warp == Cfg::NEPI + 1) {
-    // ------------------------------------------------------------------------------------------- producer
-    if (elect_one()) {
-      uint32_t wuse[2] = {0u, 0u};
-      int ti = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
-        const int b = tile / p.tiles_x;
-        const int g0 = (tile - b * p.tiles_x) * p.Rout - p.H;
-        if (ti > 0) mbar_wait(y_empty, (uint32_t)(ti - 1) & 1u);  // the last convolution of the previous tile has read Y
-        tma::expect_tx(in_full, Cfg::R * 128);
-#pragma unroll
-        for (int j = 0; j < Cfg::MB; ++j) tma::load_rows(&maps.in, Y + j * Cfg::IMG, in_full, g0 + j * 128, b);
-        const int next = tile + gridDim.x;
-        if (next < p.total_tiles) {  // the next tile's rows: into L2 now, so that its load is short when its turn comes
-          const int nb = next / p.tiles_x;
-          const int ng0 = (next - nb * p.tiles_x) * p.Rout - p.H;
-#pragma unroll
-          for (int j = 0; j < Cfg::MB; ++j) prefetch_rows_l2(&maps.in, ng0 + j * 128, nb);
-        }
-        for (int k = 0; k < nconv; ++k) {
-          const int s = k & 1;
-          if (wuse[s] > 0) mbar_wait(&w_empty[s], (wuse[s] - 1u) & 1u);
-          tma::expect_tx(&w_full[s], Cfg::WCONV);
-          bulk_g2s(W + s * Cfg::WCONV, p.wpack + (size_t)k * Cfg::WREC, Cfg::WCONV, &w_full[s]);
-          ++wuse[s];
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == Cfg::NEPI) {
-    // --------------------------------------------------------------------------------------------- issuer
-    if (elect_one()) {
-      uint32_t rdy[Cfg::MB], wf[2] = {0u, 0u};
-#pragma unroll
-      for (int i = 0; i < Cfg::MB; ++i) rdy[i] = 0u;
-      int ti = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
-        for (int k = 0; k < nconv; ++k) {
-          const int s = k & 1;
-          mbar_wait(&w_full[s], wf[s] & 1u); ++wf[s];
-          RS_TR(0, k, 0);
-          const uint32_t a_base = smem_u32(s ? Y : X);
-          const int dil = p.dil[k];
-#pragma unroll
-          for (int mb = 0; mb < Cfg::MB; ++mb) {
-            const uint32_t tacc = tmem + mb * Cfg::NW, wb = smem_u32(W + s * Cfg::WCONV);
-            const int row0 = Cfg::G + mb * 128 - dil;
-            if (mb == 0) { mbar_wait(&ready[0], rdy[0] & 1u); ++rdy[0]; fence_after_sync(); RS_TR(0, k, 1); }
-            rs_issue(tacc, a_base, row0, dil, wb, 0, 2);   // taps -1, 0: rows of M blocks mb - 1, mb
-            if (mb + 1 < Cfg::MB) { mbar_wait(&ready[mb + 1], rdy[mb + 1] & 1u); ++rdy[mb + 1]; fence_after_sync(); RS_TR(0, k, 2 + mb); }
-            rs_issue(tacc, a_base, row0, dil, wb, 2, 3);   // tap +1: rows of M block mb + 1 as well
-            commit(&mma_done[mb]);
-            RS_TR(0, k, 4 + mb);
-          }
-          commit(&w_empty[s]);
-          if (k == nconv - 1) commit(y_empty);
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // ------------------------------------------------------------------------------------------ epilogues
-    // thread = (tile row, 16-channel half): warp w -> M block w / 8, TMEM lane quadrant w % 4, half (w / 4) % 2
-    const int mb = warp >> 3, qd = warp & 3, half = (warp >> 2) & 1;
-    const int r = mb * 128 + qd * 32 + lane;  // tile row = TMEM lane
-    const uint32_t taddr = tmem + (((uint32_t)qd * 32u) << 16) + (uint32_t)(mb * Cfg::NW + half * 16);
-    // Output slices: a warp stores the rows of its quadrant that lie inside the tile's output rows [H, R - H) — 32, or the partial
-    // count at the two ends of that range, or none — and its 16 channels as ONE TMA box from its own 2 KB image (rows of 64 B,
-    // 64-byte swizzle): warp-local hand-off only (__syncwarp), no block-wide barrier on the store path.
-    const int q0 = mb * 128 + qd * 32;
-    const int srow = max(q0, p.H), snum = max(min(q0 + 32, Cfg::R - p.H) - srow, 0);
-    const bool own = r >= srow && r < srow + snum;
-    const uint32_t img = smem_u32(OUT) + (uint32_t)warp * 2048u;
-    uint32_t imgc[4];  // this thread's four 16-byte chunks of its image row (shared-memory addresses)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) imgc[c] = img + tma::swz64((r - srow) & 31, c);
-    const int mapsel = snum == 32 ? 1 : 0;
-    const bool tr = (warp & 7) == 0;
-    // this thread's operand chunks: planes 2 * half, 2 * half + 1 of row G + r, hi piece (lo piece: + TILE)
-    const uint32_t opoff = (uint32_t)(half * 2 * Cfg::PLANE + (Cfg::G + r) * 16);
-    const uint32_t xrow = smem_u32(X) + opoff, yrow = smem_u32(Y) + opoff;
-    uint32_t md = 0u, ae = 0u;
-    float res[16];
-    float sa = 1.f, rbound = 0.f;
-    bool inrange = false;
-    size_t grow = 0;
-    int g0 = 0, b = 0, ti = 0;
-    uint32_t* am = amax;
-
-    // relu(v) (forward) or v -> hi / lo operand rows of buffer `op`, scaled by `scale`; returns max |hi| as packed halves
-    auto write_operand = [&](uint32_t oprow, const float* v, float scale) {
-      __half2 hm = __float2half2_rn(0.f);
-#pragma unroll
-      for (int o = 0; o < 2; ++o) {
-        float t[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) t[c] = v[o * 8 + c] * scale;
-        uint4 ph, pl;
-        rs_split8<FWD>(t, ph, pl, hm);
-        sts128(oprow + o * Cfg::PLANE, ph);
-        sts128(oprow + o * Cfg::PLANE + Cfg::TILE, pl);
-      }
-      return hm;
-    };
-
-    // epilogue of convolution k (STAGE = k & 1: 0 = first convolution of a block, 1 = second: residual add)
-    auto epilogue = [&](int k, auto stage_tag) {
-      constexpr int STAGE = decltype(stage_tag)::value;
-      const float* mt = meta + k * Cfg::META;
-      uint32_t mword = 0xffffu;
-      if (KIND == 2) mword = inrange ? (uint32_t)reinterpret_cast<const uint16_t*>(p.bits_mask[k])[grow] : 0u;
-      mbar_wait(&mma_done[mb], md & 1u); ++md;
-      fence_after_sync();
-      if (tr) RS_TR(1 + mb, k, 0);
-      uint32_t ra[16], rb[16];
-      tmem_ld16_nw(taddr, ra); tmem_ld16_nw(taddr + 32, rb);
-      const float inv = pow2_inv(sa) * pow2_inv(mt[0]);
-      const float* bias = mt + 4 + half * 16;
-      tmem_ld_wait();
-      if (tr) RS_TR(1 + mb, k, 1);
-      float v[16];
-#pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = fmaf(__uint_as_float(ra[c]) + __uint_as_float(rb[c]), inv, bias[c]);
-      if (KIND == 2) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = (mword >> c) & 1u ? v[c] : 0.f;
-      }
-      if (STAGE) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) { res[c] += v[c]; v[c] = res[c]; }
-      }
-      const bool last = k == nconv - 1;
-      if (KIND == 1 && p.bits_out[k] && own && inrange) {
-        uint32_t w = 0u;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) w |= (uint32_t)(v[c] > 0.f) << c;
-        reinterpret_cast<uint16_t*>(p.bits_out[k])[grow] = (uint16_t)w;
-      }
-      if (p.store[k] && snum > 0) {
-        if (lane == 0) tma::wait_read();   // the image's previous store has been read out of shared memory
-        __syncwarp();
-        if (own) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            sts128(imgc[c], make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3])));
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma::store_box(&maps.out[k][mapsel], img, half * 16, g0 + srow, b);
-          tma::commit_group();
-        }
-      }
-      if (tr) RS_TR(1 + mb, k, 2);
-      // every phase of `allepi` is observed by every warp (parity waits must not fall a phase behind)
-      if (k > 0) { mbar_wait(allepi, ae & 1u); ++ae; }
-      if (tr) RS_TR(1 + mb, k, 3);
-      if (!last) {
-        // scale of this convolution's output as the next operand: am[k] = max |operand k| (all epilogues of k-1 are through)
-        float bound = fmaf(mt[1], __uint_as_float(am[k]), mt[2]);
-        if (STAGE) { bound += rbound; rbound = bound; }
-        const float sa_next = pow2_scale(bound);
-        // rows outside [0, L) are the next convolution's zero padding: scale 0
-        const __half2 hm = write_operand(STAGE ? xrow : yrow, v, inrange ? sa_next : 0.f);  // convolution k+1 reads buffer (k+1) & 1
-        uint32_t mm = rs_hmax_bits(hm, pow2_inv(sa_next));
-        mm = __reduce_max_sync(0xffffffffu, mm);
-        if (lane == 0) atomicMax(&am[k + 1], mm);
-        sa = sa_next;
-        if (tr) RS_TR(1 + mb, k, 4);
-        fence_proxy_async();
-        fence_before_sync();
-        __syncwarp();
-        if (tr) RS_TR(1 + mb, k, 5);
-        if (lane == 0) { mbar_arrive(allepi); mbar_arrive(&ready[mb]); }
-      } else {
-        fence_before_sync();  // orders this tile's TMEM reads before the arrivals of the next tile's input phase
-      }
-    };
-
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
-      const int par = ti & 1;
-      am = amax + par * 16;
-      b = tile / p.tiles_x;
-      g0 = (tile - b * p.tiles_x) * p.Rout - p.H;
-      const int g = g0 + r;
-      inrange = g >= 0 && g < L;
-      grow = ((size_t)b * L + (size_t)(inrange ? g : 0)) * 2 + half;  // index of this thread's 16-bit mask word
-      // ---- input phase: raw fp32 row -> residual registers, tile maximum, first operand
-      mbar_wait(in_full, (uint32_t)ti & 1u);
-      {
-        const uint8_t* raw = Y + (r >> 7) * Cfg::IMG;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 f = *reinterpret_cast<const float4*>(raw + tma::swz(r & 127, half * 4 + c));
-          res[4 * c] = f.x; res[4 * c + 1] = f.y; res[4 * c + 2] = f.z; res[4 * c + 3] = f.w;
-        }
-      }
-      uint32_t m = 0u;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) m = max(m, absbits(res[c]));
-      m = __reduce_max_sync(0xffffffffu, m);
-      if (lane == 0) atomicMax(&am[0], m);
-      if (KIND == 1 && p.bits_in0 && own && inrange) {
-        uint32_t w = 0u;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) w |= (uint32_t)(res[c] > 0.f) << c;
-        reinterpret_cast<uint16_t*>(p.bits_in0)[grow] = (uint16_t)w;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(allepi);
-      mbar_wait(allepi, ae & 1u); ++ae;
-      if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) amax[(par ^ 1) * 16 + i] = 0u;  // the other parity: next tile
-      }
-      // Y's guard rows (overwritten by the raw tile): 2 * G rows x 8 chunk columns
-      if (tid < 2 * Cfg::G * 8) {
-        const int q = tid / (2 * Cfg::G), gr = tid % (2 * Cfg::G);
-        const int prow = gr < Cfg::G ? gr : Cfg::R + gr;
-        *reinterpret_cast<uint4*>(Y + (q >> 2) * Cfg::TILE + (q & 3) * Cfg::PLANE + prow * 16) = make_uint4(0u, 0u, 0u, 0u);
-      }
-      rbound = __uint_as_float(am[0]);  // bound of |residual stream|: exact for the tile input, then additive per block
-      sa = pow2_scale(rbound);          // scale of the operand the NEXT convolution reads
-      write_operand(xrow, res, sa);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ready[mb]);
-
-      for (int k = 0; k < nconv; k += 2) {
-        epilogue(k, std::integral_constant<int, 0>());
-        epilogue(k + 1, std::integral_constant<int, 1>());
-      }
-    }
-    if (lane == 0) tma::wait_all();
-  }
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
-}
-
-// ================================================================================================================
-// rs4_kernel — the same stack as rs_kernel with 512-row tiles (4 M blocks: 424 instead of 296 of every tile's rows are output
-// rows at halo 44, and the kernel is bound per row it reads out of tensor memory).  What makes 512 rows fit:
-//   * ONE operand buffer, rewritten in place: the epilogue of (convolution k, M block mb) writes the operand rows of
-//     convolution k+1 over those of k.  Safe because every MMA of k that reads rows of block mb — its own three taps, tap +1 of
-//     block mb-1 (head rows) and tap -1 of block mb+1 (tail rows) — is issued before the commit that releases the block
-//     (issue order per convolution: t-1(0) t0(0) | t-1(1) t+1(0) commit0 | t0(1) | t-1(2) t+1(1) commit1 | ...);
-//     the raw fp32 input tile of the next tile lands in the same buffer once the last convolution's MMAs are through;
-//   * one thread per row (16 epilogue warps), which works through its 32 channels as two 16-channel halves.
-// ================================================================================================================
 template <int MBv>
-struct Rs4CfgT {
+struct RsTileCfg {
   static constexpr int MB = MBv, R = 128 * MB, G = 32;
   static constexpr int NP = 4;
   static constexpr int PLANE = (R + 2 * G) * 16 + 32;
@@ -542,27 +214,27 @@ struct Rs4CfgT {
   static_assert(OFF_W % 16 == 0 && OFF_BAR % 8 == 0 && R * 128 <= OPB, "layout");
   static_assert(SMEM <= 232448, "shared memory");
 };
-using Rs4Cfg = Rs4CfgT<4>;
+using RsCfg4 = RsTileCfg<4>;
 
 // one tap of one M block: 2 K steps x (hi-activation x [W_hi | W_lo], lo-activation x W_hi)
-template <class Cfg4>
-__device__ __forceinline__ void rs4_tap(uint32_t tacc, uint32_t a_base, int row0, int dil, uint32_t w_base, int j, bool first) {
-  const uint64_t ad0 = smem_desc(a_base + (uint32_t)row0 * 16u, Cfg4::PLANE, 128);  // row0 = first row of tap 0
-  const uint64_t bd0 = smem_desc(w_base, Cfg4::WPLANE, 128);
+template <class CfgT>
+__device__ __forceinline__ void rs_tap(uint32_t tacc, uint32_t a_base, int row0, int dil, uint32_t w_base, int j, bool first) {
+  const uint64_t ad0 = smem_desc(a_base + (uint32_t)row0 * 16u, CfgT::PLANE, 128);  // row0 = first row of tap 0
+  const uint64_t bd0 = smem_desc(w_base, CfgT::WPLANE, 128);
 #pragma unroll
   for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
     for (int sa = 0; sa < 2; ++sa) {
       const uint32_t idesc = instr_desc(FMT_F16, 128, 32 * (2 - sa), false, false);
-      const uint64_t bd = bd0 + (uint64_t)((j * Cfg4::WTAP + kk * 2 * Cfg4::WPLANE) >> 4);
-      const uint64_t ad = ad0 + (uint64_t)((sa * Cfg4::TILE + kk * 2 * Cfg4::PLANE) >> 4) + (uint64_t)(j * dil);
+      const uint64_t bd = bd0 + (uint64_t)((j * CfgT::WTAP + kk * 2 * CfgT::WPLANE) >> 4);
+      const uint64_t ad = ad0 + (uint64_t)((sa * CfgT::TILE + kk * 2 * CfgT::PLANE) >> 4) + (uint64_t)(j * dil);
       mma<false>(tacc, ad, bd, idesc, (first && kk == 0 && sa == 0) ? 0u : 1u);
     }
 }
 
-template <int KIND, int MBv>
-__global__ void __launch_bounds__(Rs4CfgT<MBv>::NT, 1) rs4_kernel(const RsParams p, const __grid_constant__ RsMaps maps) {
-  using Cfg = Rs4CfgT<MBv>;
+template <int KIND, int MBv, bool TRACE = false>
+__global__ void __launch_bounds__(RsTileCfg<MBv>::NT, 1) rs_kernel(const RsParams p, const __grid_constant__ RsMaps maps) {
+  using Cfg = RsTileCfg<MBv>;
   constexpr bool FWD = KIND != 2;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -638,13 +310,15 @@ __global__ void __launch_bounds__(Rs4CfgT<MBv>::NT, 1) rs4_kernel(const RsParams
 #pragma unroll
       for (int i = 0; i < Cfg::MB; ++i) rdy[i] = 0u;
       const uint32_t a_base = smem_u32(OP);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
         for (int k = 0; k < nconv; ++k) {
           const int s = k & 1;
           mbar_wait(&w_full[s], wf[s] & 1u); ++wf[s];
+          RS_TR(0, k, 0);
           const int dil = p.dil[k];
           const uint32_t wb = smem_u32(W + s * Cfg::WCONV);
-          auto tap = [&](int mb, int j, bool first) { rs4_tap<Cfg>(tmem + mb * Cfg::NW, a_base, Cfg::G + mb * 128 - dil, dil, wb, j, first); };
+          auto tap = [&](int mb, int j, bool first) { rs_tap<Cfg>(tmem + mb * Cfg::NW, a_base, Cfg::G + mb * 128 - dil, dil, wb, j, first); };
           auto wait_ready = [&](int mb) { mbar_wait(&ready[mb], rdy[mb] & 1u); ++rdy[mb]; fence_after_sync(); };
           // taps: 0 reads rows of blocks mb-1, mb; 1 of mb; 2 of mb, mb+1.  Every MMA that reads rows of block mb goes out before
           // commit(mb): the block's epilogue overwrites those rows.
@@ -658,6 +332,7 @@ __global__ void __launch_bounds__(Rs4CfgT<MBv>::NT, 1) rs4_kernel(const RsParams
             }
             tap(mb, 2, false);        // head rows of block mb+1 (operand of this convolution: not yet overwritten)
             commit(&mma_done[mb]);
+            RS_TR(0, k, 1 + mb);
             if (mb + 1 < Cfg::MB) tap(mb + 1, 1, false);
           }
           commit(&w_empty[s]);
@@ -711,7 +386,9 @@ __global__ void __launch_bounds__(Rs4CfgT<MBv>::NT, 1) rs4_kernel(const RsParams
       if (KIND == 2) mword = inrange ? p.bits_mask[k][grow] : 0u;
       mbar_wait(&mma_done[mb], md & 1u); ++md;
       fence_after_sync();
+      if (qd == 0) RS_TR(1 + mb, k, 0);
       if (k > 0) { mbar_wait(allepi, ae & 1u); ++ae; }  // all epilogues of convolution k-1: am[k] is final
+      if (qd == 0) RS_TR(1 + mb, k, 1);
       const float inv = pow2_inv(sa) * pow2_inv(mt[0]);
       float bound = fmaf(mt[1], __uint_as_float(am[k]), mt[2]);
       if (STAGE) { bound += rbound; rbound = bound; }
@@ -758,9 +435,11 @@ __global__ void __launch_bounds__(Rs4CfgT<MBv>::NT, 1) rs4_kernel(const RsParams
         if (lane == 0) atomicMax(&am[k + 1], mm);
         sa = sa_next;
       }
+      if (qd == 0) RS_TR(1 + mb, k, 2);
       fence_proxy_async();
       fence_before_sync();
       __syncwarp();
+      if (qd == 0) RS_TR(1 + mb, k, 3);
       if (lane == 0) {
         if (store) {
           tma::store_rows(&maps.out[k][mapsel], reinterpret_cast<const void*>(OUT + warp * 4096), g0 + srow, b);
@@ -806,8 +485,8 @@ __global__ void __launch_bounds__(Rs4CfgT<MBv>::NT, 1) rs4_kernel(const RsParams
 #pragma unroll
         for (int i = 0; i < 16; ++i) amax[(par ^ 1) * 16 + i] = 0u;
       }
-      if (tid < 2 * Cfg::G * 8) {  // guard rows (the raw tile passed over them): 2 * G rows x 8 chunk columns
-        const int q = tid / (2 * Cfg::G), gr = tid % (2 * Cfg::G);
+      for (int e = tid; e < 2 * Cfg::G * 8; e += Cfg::NEPI * 32) {  // guard rows (the raw tile passed over them): 2 G rows x 8 chunk columns
+        const int q = e / (2 * Cfg::G), gr = e % (2 * Cfg::G);
         const int prow = gr < Cfg::G ? gr : Cfg::R + gr;
         *reinterpret_cast<uint4*>(OP + (q >> 2) * Cfg::TILE + (q & 3) * Cfg::PLANE + prow * 16) = make_uint4(0u, 0u, 0u, 0u);
       }
@@ -838,7 +517,7 @@ bool resstack_tc_supported(const vqb_resstack_desc* d) {
   if (!d || d->C != 32 || d->precision != VQB_PREC_FP16X2 || d->n_blocks < 1 || d->n_blocks > VQB_RESSTACK_MAX_BLOCKS) return false;
   int H = 0;
   for (int i = 0; i < d->n_blocks; ++i) {
-    if (d->dilations[i] < 1 || d->dilations[i] > RsCfg::G - 1) return false;
+    if (d->dilations[i] < 1 || d->dilations[i] > RsCfg4::G - 1) return false;
     H += d->dilations[i] + 1;
   }
   return H <= 64;
@@ -846,11 +525,11 @@ bool resstack_tc_supported(const vqb_resstack_desc* d) {
 
 size_t resstack_tc_workspace_bytes(const vqb_resstack_desc* d) { return (size_t)2 * RS_MAXC * RsCfg::WREC + 256; }
 
-template <int KIND, bool TRACE = false>
+template <int KIND, int MBv, bool TRACE = false>
 static int launch_rs(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    VQB_CUDA(cudaFuncSetAttribute(rs_kernel<KIND, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RsCfg::SMEM));
+    VQB_CUDA(cudaFuncSetAttribute(rs_kernel<KIND, MBv, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RsTileCfg<MBv>::SMEM));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -860,36 +539,16 @@ static int launch_rs(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
     VQB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  VQB_CUDA(launch_pdl(rs_kernel<KIND, TRACE>, dim3(grid), dim3(RsCfg::NT), (size_t)RsCfg::SMEM, st, p, maps));
+  VQB_CUDA(launch_pdl(rs_kernel<KIND, MBv, TRACE>, dim3(grid), dim3(RsTileCfg<MBv>::NT), (size_t)RsTileCfg<MBv>::SMEM, st, p, maps));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
 
-template <int KIND, int MBv>
-static int launch_rs4(const RsParams& p, const RsMaps& maps, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    VQB_CUDA(cudaFuncSetAttribute(rs4_kernel<KIND, MBv>, cudaFuncAttributeMaxDynamicSharedMemorySize, Rs4CfgT<MBv>::SMEM));
-    attr_set = true;
-  }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    VQB_CUDA(cudaGetDevice(&dev));
-    VQB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  VQB_CUDA(launch_pdl(rs4_kernel<KIND, MBv>, dim3(grid), dim3(Rs4CfgT<MBv>::NT), (size_t)Rs4CfgT<MBv>::SMEM, st, p, maps));
-  VQB_LAUNCH_CHECK();
-  return VQB_OK;
-}
-
-// 512-row tiles (rs4_kernel) or 384-row tiles (rs_kernel): the larger tile loses fewer rows to the halo (424 vs 296 output rows
-// per tile at halo 44) and wins as soon as every SM gets more than one tile; for one wave or less the shorter tile finishes
-// sooner (measured at B = 32: L >= 3520 -> 512 rows: 167 vs 196 us at L = 14080, 50 vs 62 us at 3520; L <= 1760 -> 384 rows:
-// 42 vs 46 us; 640-row tiles — the same template with 5 M blocks, 80 registers per thread — measured no better than 512:
-// 116 / 167 / 190 us against 123 / 168 / 187 us for inference / tape forward / data gradient).  VQB_RS_MB=3|4 forces a tile
-// height (tuning / A-B timing).
+// Tile height: 512 rows (4 M blocks) or 384.  The larger tile loses fewer rows to the halo (424 vs 296 output rows per tile at halo
+// 44) and wins as soon as every SM gets more than one tile; for one wave or less the shorter tile finishes sooner (measured at
+// B = 32, forward under a tape: L = 14080: 167 vs 190 us, 3520: 50 vs 58 us; L = 1760: 42 vs 39 us).  640-row tiles (5 M blocks,
+// 80 registers per thread) measured no better than 512 (116 / 167 / 190 us against 123 / 168 / 187 us for inference / tape
+// forward / data gradient).  VQB_RS_MB=3|4 forces a tile height (tuning / A-B timing).
 static int pick_mb(const vqb_resstack_desc* d, int H) {
   const char* e = getenv("VQB_RS_MB");
   if (e) return atoi(e) == 4 ? 4 : 3;
@@ -898,7 +557,7 @@ static int pick_mb(const vqb_resstack_desc* d, int H) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) num_sms = 148;
   }
-  const long tiles4 = (long)cdiv(d->L, Rs4Cfg::R - 2 * H) * d->B;
+  const long tiles4 = (long)cdiv(d->L, RsCfg4::R - 2 * H) * d->B;
   return 2 * tiles4 > 3L * num_sms ? 4 : 3;
 }
 
@@ -909,7 +568,7 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
                 const float* const* w2, const float* const* b2, float* const* o1, float* const* o2, uint32_t* const* xbits,
                 uint32_t* const* hbits, void* ws, size_t ws_bytes, cudaStream_t st, bool prepacked = false) {
   if (!resstack_tc_supported(d))
-    return set_err(VQB_ERR_UNIMPLEMENTED, "fused residual stack: C = 32, 1..%d blocks, dilations < %d, fp16x2 only", VQB_RESSTACK_MAX_BLOCKS, RsCfg::G);
+    return set_err(VQB_ERR_UNIMPLEMENTED, "fused residual stack: C = 32, 1..%d blocks, dilations < %d, fp16x2 only", VQB_RESSTACK_MAX_BLOCKS, RsCfg4::G);
   if (d->B == 0 || d->L == 0) return VQB_OK;
   const size_t need = resstack_tc_workspace_bytes(d);
   uint8_t* wsp = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
@@ -925,7 +584,6 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
   int H = 0;
   for (int i = 0; i < n; ++i) H += d->dilations[i] + 1;
   const int mbsel = pick_mb(d, H);
-  const bool v4 = mbsel >= 4;
   p.H = H; p.Rout = 128 * mbsel - 2 * H;
   p.tiles_x = cdiv(d->L, p.Rout);
   p.total_tiles = p.tiles_x * d->B;
@@ -958,9 +616,7 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
   for (int k = 0; k < nconv; ++k)
     if (p.store[k]) {
       const int part = 32 - H % 32;  // rows of the partial quadrant at either end of a tile's output rows
-      const bool ok = v4 ? tma::make_rows_map(&maps.out[k][0], outs[k], d->B, d->L, part) && tma::make_rows_map(&maps.out[k][1], outs[k], d->B, d->L, 32)
-                         : tma::make_slice_map(&maps.out[k][0], outs[k], d->B, d->L, part) && tma::make_slice_map(&maps.out[k][1], outs[k], d->B, d->L, 32);
-      if (!ok)
+      if (!tma::make_rows_map(&maps.out[k][0], outs[k], d->B, d->L, part) || !tma::make_rows_map(&maps.out[k][1], outs[k], d->B, d->L, 32))
         return set_err(VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed for an output of the residual stack");
     }
   int npack = nconv;
@@ -977,22 +633,21 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
     rs_pack_kernel<<<npack, 256, 0, st>>>(pk);
     VQB_LAUNCH_CHECK();
   }
-  if (kind == 0 && getenv("VQB_RS_TRACE")) {  // profiling aid: address of a device buffer of 4 * 9 * 8 int64 (tools/trace_stack.py)
+  if (kind == 0 && mbsel == 4 && getenv("VQB_RS_TRACE")) {  // profiling aid: address of a device buffer of 5 * 9 * 8 int64 (tools/trace_stack.py)
     p.trace = reinterpret_cast<long long*>(strtoull(getenv("VQB_RS_TRACE"), nullptr, 0));
-    return launch_rs<0, true>(p, maps, st);
+    return launch_rs<0, 4, true>(p, maps, st);
   }
   if (mbsel == 4) {
     switch (kind) {
-      case 0: return launch_rs4<0, 4>(p, maps, st);
-      case 1: return launch_rs4<1, 4>(p, maps, st);
-      default: return launch_rs4<2, 4>(p, maps, st);
+      case 0: return launch_rs<0, 4>(p, maps, st);
+      case 1: return launch_rs<1, 4>(p, maps, st);
+      default: return launch_rs<2, 4>(p, maps, st);
     }
   }
-
   switch (kind) {
-    case 0: return launch_rs<0>(p, maps, st);
-    case 1: return launch_rs<1>(p, maps, st);
-    default: return launch_rs<2>(p, maps, st);
+    case 0: return launch_rs<0, 3>(p, maps, st);
+    case 1: return launch_rs<1, 3>(p, maps, st);
+    default: return launch_rs<2, 3>(p, maps, st);
   }
 }
 

@@ -40,29 +40,6 @@ static inline bool make_rows_map(CUtensorMap* m, const float* base, int B, int L
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// tensor map of the same [B, L, 32] fp32 tensor with box {16 channels, box_rows rows, 1}: rows of 64 bytes in the shared-memory
-// image, 64-byte swizzle (16-byte chunk index XOR (row / 2) % 4, see swz64) — the per-warp output slices of the residual-stack
-// kernel (a warp stores its 32 rows x 16 channels with one bulk-tensor store of its own, no block-wide hand-off)
-static inline bool make_slice_map(CUtensorMap* m, const float* base, int B, int L, int box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn || !base) return false;
-  const cuuint64_t dims[3] = {32, (cuuint64_t)L, (cuuint64_t)B};
-  const cuuint64_t strides[2] = {128, (cuuint64_t)L * 128};
-  const cuuint32_t box[3] = {16, (cuuint32_t)box_rows, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-// byte offset of 16-byte chunk `c` (0..3) of row `j` in a 512-byte-aligned, 64-byte-swizzled image of 64-byte rows
-__device__ __forceinline__ uint32_t swz64(int j, int c) { return (uint32_t)(j * 64 + ((c ^ ((j >> 1) & 3)) << 4)); }
-// shared -> global with an explicit first coordinate (channel offset)
-__device__ __forceinline__ void store_box(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm), "r"(smem_src),
-               "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-
 // byte offset of 16-byte chunk `c` (0..7) of row `j` in a 1024-byte-aligned, 128-byte-swizzled image of 128-byte rows
 __device__ __forceinline__ uint32_t swz(int j, int c) { return (uint32_t)(j * 128 + ((c ^ (j & 7)) << 4)); }
 
