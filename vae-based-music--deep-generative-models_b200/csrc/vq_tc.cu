@@ -264,6 +264,15 @@ struct Vq2Params {
   int* flist;           // their row numbers (any order)
   long N, ntiles;
   int K, nchunks;
+  // Codebooks beyond the resident 512 codes are searched in passes of <= 512 codes (same kernel, the x tiles are re-read): pass
+  // `code0 / 512` scans codes [code0, code0 + 256 * nchunks), merges its (best, second, index) with the state the previous
+  // passes left per row (st_*) and, unless it is the last pass, writes the state back; the last pass decides.
+  int code0, first_pass, last_pass, Ktot;
+  float* st_m1;
+  float* st_m2;
+  int* st_i1;
+  float* fbest;         // exact pass over code blocks (vq2_exact_kernel): running exact minimum per flagged row
+  int* fk;
 };
 
 __global__ void vq2_pack_codebook_kernel(const float* __restrict__ E, int K, const float* __restrict__ ee,
@@ -311,64 +320,74 @@ __device__ __forceinline__ void bar_scan() { asm volatile("bar.sync 1, %0;" ::"n
 constexpr int V2_EX_THREADS = 512;
 constexpr int V2_EX_ROWS = 4;
 __global__ void __launch_bounds__(V2_EX_THREADS, 1) vq2_exact_kernel(const Vq2Params p) {
-  extern __shared__ __align__(16) float esm[];  // [K][65] codebook, [64][4] x rows (row-interleaved), [4][16] warp results
-  float* xs = esm + (((size_t)p.K * 65 + 3) & ~(size_t)3);
+  extern __shared__ __align__(16) float esm[];  // [KB][65] codebook block, [64][4] x rows (row-interleaved), [4][16] warp results
+  const int KB = p.K;                           // codes per block staged in shared memory (<= 512); p.Ktot codes in all
+  float* xs = esm + (((size_t)KB * 65 + 3) & ~(size_t)3);
   float* wbest = xs + VT_D * V2_EX_ROWS;
   int* wk = reinterpret_cast<int*>(wbest + V2_EX_ROWS * 16);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nf = p.fcount[0];
   if ((int)blockIdx.x * V2_EX_ROWS >= nf) return;
-  for (int e = tid; e < p.K * VT_D; e += V2_EX_THREADS) esm[(e >> 6) * 65 + (e & 63)] = p.Et[e];
-  for (int f0 = blockIdx.x * V2_EX_ROWS; f0 < nf; f0 += gridDim.x * V2_EX_ROWS) {
-    __syncthreads();  // codebook staged / previous rows' buffers consumed
-    if (tid < VT_D * V2_EX_ROWS) {
-      const int rr = tid >> 6, d = tid & 63;
-      xs[d * V2_EX_ROWS + rr] = f0 + rr < nf ? p.x[(long)p.flist[f0 + rr] * VT_D + d] : 0.f;
-    }
-    __syncthreads();
-    float xx[V2_EX_ROWS] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-    for (int d = 0; d < VT_D; ++d) {
-      const float4 xv = *reinterpret_cast<const float4*>(xs + d * V2_EX_ROWS);
-      xx[0] = fmaf(xv.x, xv.x, xx[0]); xx[1] = fmaf(xv.y, xv.y, xx[1]);
-      xx[2] = fmaf(xv.z, xv.z, xx[2]); xx[3] = fmaf(xv.w, xv.w, xx[3]);
-    }
-    float best[V2_EX_ROWS] = {INFINITY, INFINITY, INFINITY, INFINITY};
-    int bk[V2_EX_ROWS] = {0, 0, 0, 0};
-    for (int k = tid; k < p.K; k += V2_EX_THREADS) {
-      const float* er = esm + (size_t)k * 65;
-      float acc[V2_EX_ROWS] = {0.f, 0.f, 0.f, 0.f};
+  const int nblocks = (p.Ktot + KB - 1) / KB;
+  for (int cb = 0; cb < nblocks; ++cb) {
+    const int c0 = cb * KB, kn = min(KB, p.Ktot - c0);
+    __syncthreads();  // the previous block's codebook has been consumed
+    for (int e = tid; e < kn * VT_D; e += V2_EX_THREADS) esm[(e >> 6) * 65 + (e & 63)] = p.Et[(size_t)c0 * VT_D + e];
+    for (int f0 = blockIdx.x * V2_EX_ROWS; f0 < nf; f0 += gridDim.x * V2_EX_ROWS) {
+      __syncthreads();  // codebook staged / previous rows' buffers consumed
+      if (tid < VT_D * V2_EX_ROWS) {
+        const int rr = tid >> 6, d = tid & 63;
+        xs[d * V2_EX_ROWS + rr] = f0 + rr < nf ? p.x[(long)p.flist[f0 + rr] * VT_D + d] : 0.f;
+      }
+      __syncthreads();
+      float xx[V2_EX_ROWS] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
       for (int d = 0; d < VT_D; ++d) {
         const float4 xv = *reinterpret_cast<const float4*>(xs + d * V2_EX_ROWS);
-        const float e = er[d];
-        acc[0] = fmaf(xv.x, e, acc[0]); acc[1] = fmaf(xv.y, e, acc[1]);
-        acc[2] = fmaf(xv.z, e, acc[2]); acc[3] = fmaf(xv.w, e, acc[3]);
+        xx[0] = fmaf(xv.x, xv.x, xx[0]); xx[1] = fmaf(xv.y, xv.y, xx[1]);
+        xx[2] = fmaf(xv.z, xv.z, xx[2]); xx[3] = fmaf(xv.w, xv.w, xx[3]);
       }
-      const float e2 = p.ee[k];
+      float best[V2_EX_ROWS] = {INFINITY, INFINITY, INFINITY, INFINITY};
+      int bk[V2_EX_ROWS] = {0, 0, 0, 0};
+      for (int k = tid; k < kn; k += V2_EX_THREADS) {
+        const float* er = esm + (size_t)k * 65;
+        float acc[V2_EX_ROWS] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+        for (int d = 0; d < VT_D; ++d) {
+          const float4 xv = *reinterpret_cast<const float4*>(xs + d * V2_EX_ROWS);
+          const float e = er[d];
+          acc[0] = fmaf(xv.x, e, acc[0]); acc[1] = fmaf(xv.y, e, acc[1]);
+          acc[2] = fmaf(xv.z, e, acc[2]); acc[3] = fmaf(xv.w, e, acc[3]);
+        }
+        const float e2 = p.ee[c0 + k];
+#pragma unroll
+        for (int rr = 0; rr < V2_EX_ROWS; ++rr) {
+          const float dist = __fsub_rn(__fadd_rn(xx[rr], e2), 2.f * acc[rr]);
+          if (dist < best[rr]) { best[rr] = dist; bk[rr] = c0 + k; }
+        }
+      }
 #pragma unroll
       for (int rr = 0; rr < V2_EX_ROWS; ++rr) {
-        const float dist = __fsub_rn(__fadd_rn(xx[rr], e2), 2.f * acc[rr]);
-        if (dist < best[rr]) { best[rr] = dist; bk[rr] = k; }
-      }
-    }
 #pragma unroll
-    for (int rr = 0; rr < V2_EX_ROWS; ++rr) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float od = __shfl_xor_sync(0xffffffffu, best[rr], o);
-        const int ok = __shfl_xor_sync(0xffffffffu, bk[rr], o);
-        if (od < best[rr] || (od == best[rr] && ok < bk[rr])) { best[rr] = od; bk[rr] = ok; }
+        for (int o = 16; o > 0; o >>= 1) {
+          const float od = __shfl_xor_sync(0xffffffffu, best[rr], o);
+          const int ok = __shfl_xor_sync(0xffffffffu, bk[rr], o);
+          if (od < best[rr] || (od == best[rr] && ok < bk[rr])) { best[rr] = od; bk[rr] = ok; }
+        }
+        if (lane == 0) { wbest[rr * 16 + warp] = best[rr]; wk[rr * 16 + warp] = bk[rr]; }
       }
-      if (lane == 0) { wbest[rr * 16 + warp] = best[rr]; wk[rr * 16 + warp] = bk[rr]; }
-    }
-    __syncthreads();
-    if (tid < V2_EX_ROWS && f0 + tid < nf) {
-      float b = wbest[tid * 16];
-      int k = wk[tid * 16];
-      for (int w = 1; w < V2_EX_THREADS / 32; ++w)
-        if (wbest[tid * 16 + w] < b || (wbest[tid * 16 + w] == b && wk[tid * 16 + w] < k)) { b = wbest[tid * 16 + w]; k = wk[tid * 16 + w]; }
-      p.idx[p.flist[f0 + tid]] = k;
+      __syncthreads();
+      if (tid < V2_EX_ROWS && f0 + tid < nf) {
+        float b = wbest[tid * 16];
+        int k = wk[tid * 16];
+        for (int w = 1; w < V2_EX_THREADS / 32; ++w)
+          if (wbest[tid * 16 + w] < b || (wbest[tid * 16 + w] == b && wk[tid * 16 + w] < k)) { b = wbest[tid * 16 + w]; k = wk[tid * 16 + w]; }
+        if (nblocks > 1) {  // running exact minimum over the code blocks (earlier blocks = lower indices win ties)
+          if (cb > 0 && !(b < p.fbest[f0 + tid])) { b = p.fbest[f0 + tid]; k = p.fk[f0 + tid]; }
+          p.fbest[f0 + tid] = b; p.fk[f0 + tid] = k;
+        }
+        if (cb == nblocks - 1) p.idx[p.flist[f0 + tid]] = k;
+      }
     }
   }
 }
@@ -490,7 +509,7 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
         fence_after_sync();
         if (ch == p.nchunks - 1 && has_next) stage(it + 1);  // all MMAs of this tile have completed: the x tile is free
         const uint32_t taddr = tmem + (((uint32_t)qd * 32u) << 16) + (uint32_t)(ch * VT_CHUNK + part * V2_COLS);
-        const int kbase = ch * VT_CHUNK + part * V2_COLS;
+        const int kbase = p.code0 + ch * VT_CHUNK + part * V2_COLS;
 #pragma unroll 1
         for (int c0 = 0; c0 < V2_COLS; c0 += 32) {
           float v[32];
@@ -532,10 +551,21 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
         }
         const long n = n0 + r;
         if (n < p.N) {
-          // score error <= 2^-15 |x||e| (operand pieces) + accumulation rounding of the -ee/2 term, for both scores
-          const float margin = V2_MARGIN * xn_s[(it & 1) * VT_ROWS + r] * en_max + 1e-6f * en_max * en_max;
-          p.idx[n] = i1;
-          if (!(m1 - m2 > margin)) p.flist[atomicAdd(p.fcount, 1)] = (int)n;
+          if (!p.first_pass) {  // codes of the earlier passes (lower indices: they win ties)
+            const float o1 = p.st_m1[n], o2 = p.st_m2[n];
+            const int oi = p.st_i1[n];
+            const float second = fmaxf(fminf(m1, o1), fmaxf(m2, o2));
+            const bool take = o1 >= m1;
+            m1 = take ? o1 : m1; i1 = take ? oi : i1; m2 = second;
+          }
+          if (!p.last_pass) {
+            p.st_m1[n] = m1; p.st_m2[n] = m2; p.st_i1[n] = i1;
+          } else {
+            // score error <= 2^-15 |x||e| (operand pieces) + accumulation rounding of the -ee/2 term, for both scores
+            const float margin = V2_MARGIN * xn_s[(it & 1) * VT_ROWS + r] * en_max + 1e-6f * en_max * en_max;
+            p.idx[n] = i1;
+            if (!(m1 - m2 > margin)) p.flist[atomicAdd(p.fcount, 1)] = (int)n;
+          }
         }
       }
     }
@@ -557,11 +587,13 @@ static bool vq_tc_ok(const vqb_vq_desc* d) {
 
 bool vq_search_tc_supported(const vqb_vq_desc* d) { return vq_tc_ok(d); }
 
-static bool vq2_ok(const vqb_vq_desc* d) { return d->K / VT_CHUNK <= 2; }  // the split codebook stays resident in shared memory
+static bool vq2_ok(const vqb_vq_desc* d) { return d->K / VT_CHUNK <= 16; }  // <= 2 chunks resident per pass; up to 8 passes (K <= 4096)
 
 size_t vq_search_tc_workspace_bytes(const vqb_vq_desc* d) {
   if (!vq_tc_ok(d)) return 0;
-  if (vq2_ok(d)) return (size_t)(d->K / VT_CHUNK) * V2_CHUNK_B + 256 + ((size_t)d->N + 16) * sizeof(int);  // + undecided-row list
+  if (vq2_ok(d))  // packed codebook + undecided-row list (+ exact running minima) + per-row search state of a multi-pass search
+    return (size_t)(d->K / VT_CHUNK) * V2_CHUNK_B + 256 + 3 * ((size_t)d->N + 16) * sizeof(int) +
+           (d->K / VT_CHUNK > 2 ? 3 * ((size_t)d->N + 16) * sizeof(float) : 0);
   return (size_t)(d->K / VT_CHUNK) * VT_CHUNK_BYTES + 256;
 }
 
@@ -579,28 +611,39 @@ int vq_search_tc(const vqb_vq_desc* d, const float* x, const float* E, const flo
   }
   if (vq2_ok(d)) {
     Vq2Params q{};
-    q.x = x; q.Et = Et; q.ee = ee; q.idx = idx; q.N = d->N; q.K = d->K;
-    q.nchunks = d->K / VT_CHUNK;
+    q.x = x; q.Et = Et; q.ee = ee; q.idx = idx; q.N = d->N; q.Ktot = d->K;
+    const int nchunks_tot = d->K / VT_CHUNK;
     uint8_t* Epk = (uint8_t*)ws;
-    float* ee_max = (float*)(Epk + (size_t)q.nchunks * V2_CHUNK_B);
-    q.Epk = Epk; q.ee_max_ptr = ee_max;
+    float* ee_max = (float*)(Epk + (size_t)nchunks_tot * V2_CHUNK_B);
+    q.ee_max_ptr = ee_max;
     q.fcount = reinterpret_cast<int*>(ee_max + 16);
     q.flist = q.fcount + 16;
+    q.fk = q.flist + d->N + 16;
+    q.fbest = reinterpret_cast<float*>(q.fk + d->N + 16);
+    q.st_m1 = q.fbest + d->N + 16; q.st_m2 = q.st_m1 + d->N + 16; q.st_i1 = reinterpret_cast<int*>(q.st_m2 + d->N + 16);
     VQB_REQUIRE(d->N < (1l << 31), "VQ tensor-core search: N must be below 2^31");
     VQB_CUDA(cudaMemsetAsync(q.fcount, 0, sizeof(int), st));
     q.ntiles = (d->N + VT_ROWS - 1) / VT_ROWS;
     vq2_pack_codebook_kernel<<<cdiv(d->K, 128), 128, 0, st>>>(E, d->K, ee, Epk, ee_max);
     VQB_LAUNCH_CHECK();
-    const size_t smem = vq2_smem_bytes(q.nchunks);
-    static size_t smem_set2 = 0;
-    if (smem > smem_set2) {
-      VQB_CUDA(cudaFuncSetAttribute(vq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set2 = smem;
-    }
     const long grid = q.ntiles < num_sms ? q.ntiles : num_sms;
-    vq2_kernel<<<(int)grid, V2_NSCAN + 32, smem, st>>>(q);
-    VQB_LAUNCH_CHECK();
-    const size_t esmem = ((size_t)d->K * 65 + 4 + VT_D * V2_EX_ROWS + 2 * V2_EX_ROWS * 16) * sizeof(float);
+    for (int c0 = 0; c0 < nchunks_tot; c0 += 2) {  // passes of <= 2 resident chunks (512 codes)
+      q.nchunks = nchunks_tot - c0 < 2 ? nchunks_tot - c0 : 2;
+      q.K = q.nchunks * VT_CHUNK;
+      q.code0 = c0 * VT_CHUNK;
+      q.Epk = Epk + (size_t)c0 * V2_CHUNK_B;
+      q.first_pass = c0 == 0; q.last_pass = c0 + 2 >= nchunks_tot;
+      const size_t smem = vq2_smem_bytes(q.nchunks);
+      static size_t smem_set2 = 0;
+      if (smem > smem_set2) {
+        VQB_CUDA(cudaFuncSetAttribute(vq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set2 = smem;
+      }
+      vq2_kernel<<<(int)grid, V2_NSCAN + 32, smem, st>>>(q);
+      VQB_LAUNCH_CHECK();
+    }
+    q.K = d->K < 512 ? d->K : 512;  // codes per block of the exact pass
+    const size_t esmem = ((size_t)q.K * 65 + 4 + VT_D * V2_EX_ROWS + 2 * V2_EX_ROWS * 16) * sizeof(float);
     static size_t esmem_set = 0;
     if (esmem > esmem_set) {
       VQB_CUDA(cudaFuncSetAttribute(vq2_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
