@@ -307,3 +307,33 @@ def test_strided_conv_wgrad_tc(gpu, prec, B, L):
             fn(a, b_, got_w, got_b, 2, P); fn(a, b_, want_w, want_b, 2, 0)
         assert float((got_w - want_w).abs().max() / want_w.abs().max()) < tol, fn.__name__
         assert float((got_b - want_b).abs().max() / want_b.abs().max().clamp_min(1e-6)) < tol, fn.__name__ + " bias"
+
+
+@pytest.mark.parametrize("prec", ["bf16", "bf16x2", "bf16x3", "fp16x2"])
+@pytest.mark.parametrize("cin,cout", [(32, 64), (64, 32)])
+@pytest.mark.parametrize("B,L,dil", [(2, 512, 1), (3, 1000, 1), (2, 333, 2), (1, 1, 1), (1, 127, 8), (32, 3520, 1), (2, 129, 3)])
+def test_latent_conv3_tc(gpu, prec, cin, cout, B, L, dil):
+    """Tensor-core Conv1D(64, 3, 1) on 32 channels / Conv1D(32, 3, 1) on 64 channels (encdec.py:38,60; conv3_tc.cu), forward and
+    data gradient, against the exact fp32 kernels of the same library and (small cases) the oracle's conv1d; tolerance = that of
+    the operand format (fp16x2 runs the bf16x3 kernel here)."""
+    ops, P = gpu.ops, gpu._lib.PRECISIONS[prec]
+    g = torch.Generator(device="cuda").manual_seed(L + B + cin)
+    x = torch.randn(B, L, cin, device="cuda", generator=g)
+    w = torch.randn(3, cin, cout, device="cuda", generator=g) * 0.1
+    b = torch.randn(cout, device="cuda", generator=g)
+    dy = torch.randn(B, L, cout, device="cuda", generator=g)
+    tol = TOL["bf16x3" if prec == "fp16x2" else prec]
+    d = gpu.ops._cdesc(B, L, cin, cout, 3, 1, dil, False, P)
+    assert gpu._lib.lib().vqb_conv1d_supports(gpu.ops.C.byref(d), 0) == 1 and gpu._lib.lib().vqb_conv1d_supports(gpu.ops.C.byref(d), 1) == 1
+    got_y, want_y = ops.conv1d_fwd(x, w, b, 1, dil, False, None, P), ops.conv1d_fwd(x, w, b, 1, dil, False, None, 0)
+    got_dx, want_dx = ops.conv1d_dgrad(dy, w, x.shape, None, 1, dil, False, None, P), ops.conv1d_dgrad(dy, w, x.shape, None, 1, dil, False, None, 0)
+    for got, want, what in ((got_y, want_y, "fwd"), (got_dx, want_dx, "dgrad")):
+        assert got.shape == want.shape, what
+        err = float((got - want).abs().max() / want.abs().max())
+        assert err < tol, (what, err)
+    if B * L <= 4000:
+        xo = x.cpu().requires_grad_(True)
+        yo = O.conv1d(xo, w.cpu(), b.cpu(), 1, dil)
+        (dxo,) = torch.autograd.grad(yo, xo, dy.cpu())
+        assert float((got_y.cpu() - yo.detach()).abs().max() / yo.abs().max()) < tol
+        assert float((got_dx.cpu() - dxo).abs().max() / dxo.abs().max()) < tol

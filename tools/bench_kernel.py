@@ -1,4 +1,4 @@
-"""Runs one hot kernel a few times (for `ncu --set full -k regex:...`).  Usage: python tools/bench_kernel.py resblock_fwd[_masks]|resblock_bwd[_masks]|wgrad|resblock_wgrad|vq|stack_infer|stack_train|stack_bwd [precision]
+"""Runs one hot kernel a few times (for `ncu --set full -k regex:...`).  Usage: python tools/bench_kernel.py resblock_fwd[_masks]|resblock_bwd[_masks]|wgrad|resblock_wgrad|vq|stack_infer|stack_train|stack_bwd|stack_wgrad [precision]
 stack_*: the fused DilatedResnet1D kernel (4 blocks, dilations 1,3,9,27; DILS=27,9,3,1 to reverse) — one launch per call."""
 import os
 import sys
@@ -31,6 +31,10 @@ if what.startswith("stack"):
     Bz = [torch.zeros(C, device="cuda") for _ in dils]
     _, _, sxb, shb, sws = ops.resstack_fwd(xs[0], W1, Bz, W2, Bz, dils, P, True)
 w4 = torch.randn(4, C, C, device="cuda", generator=g) * 0.1
+if what.startswith("conv3"):
+    w3u, b3u = torch.randn(3, C, 64, device="cuda", generator=g) * 0.1, torch.zeros(64, device="cuda")
+    w3d = torch.randn(3, 64, C, device="cuda", generator=g) * 0.1
+    x64 = torch.randn(B, L, 64, device="cuda", generator=g)
 dw4 = ops.empty(4, C, C)
 dyh = dy[:, :L // 2].contiguous()
 n = int(os.environ.get("N", "6"))
@@ -50,6 +54,11 @@ def one(i):
         ops.resstack_fwd(xs[i % 2], W1, Bz, W2, Bz, dils, P, True)
     elif what == "stack_bwd":
         ops.resstack_bwd_data(dy, W1, W2, sxb, shb, dils, P, fwd_ws=sws if os.environ.get("PACKED", "1") == "1" else None)
+    elif what in ("conv3_up", "conv3_down"):   # latent-rate Conv1D(64, 3, 1) on 32 channels / Conv1D(32, 3, 1) on 64 (conv3_tc_kernel)
+        if what == "conv3_up":
+            ops.conv1d_fwd(xs[i % 2], w3u, b3u, 1, 1, False, None, P)
+        else:
+            ops.conv1d_fwd(x64, w3d, b1, 1, 1, False, None, P)
     elif what == "conv_down":      # Conv1D(32, 4, strides=2) 32 -> 32 (conv_tc_kernel): the encoder's down-sampling convolution
         ops.conv1d_fwd(xs[i % 2], w4, b1, 2, 1, False, None, P)
     elif what == "conv_down_wgrad":
@@ -58,6 +67,11 @@ def one(i):
         ops.resblock_bwd_data(xs[i % 2], h, dy, w1, w2, int(os.environ.get("DIL", "1")), P)
     elif what == "resblock_wgrad":
         ops.resblock_wgrad(xs[i % 2], h, dy, xs[(i + 1) % 2], dw, db, dw2, db2, int(os.environ.get("DIL", "1")), P)
+    elif what == "stack_wgrad":    # the weight gradients of a whole DilatedResnet1D: 4 blocks = 8 problems, one launch
+        ops.reduce_begin()
+        for j, dl in enumerate((1, 3, 9, 27)):
+            ops.resblock_wgrad(xs[(i + j) % 2], h, dy, xs[(i + j + 1) % 2], dw, db, dw2, db2, dl, P)
+        ops.reduce_flush()
     elif what == "wgrad":
         ops.conv1d_wgrad(xs[i % 2], dy, dw, db, 1, 1, True, P)
     elif what == "vq":

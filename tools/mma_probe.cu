@@ -204,6 +204,181 @@ __global__ void __launch_bounds__(512, 1) probe_tmem_ld_kernel(int reps, long lo
   if (warp == 0) tmem_dealloc(tslot, 512);
 }
 
+// Round-2 follow-up: the same read with G loads in flight per wait (no wait after every instruction, no array indexing that
+// could send the registers through local memory): is 32 B/clk the pipe's rate or the latency of one load + wait?
+template <int G>
+__global__ void __launch_bounds__(512, 1) probe_tmem_ld_inflight_kernel(int reps, long long* out) {
+  __shared__ uint32_t tslot;
+  __shared__ long long t0s[16], t1s[16];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tslot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t taddr = tslot + ((uint32_t)(warp & 3) * 32u << 16) + (uint32_t)((warp >> 2) * 128);
+  uint32_t acc = 0u;
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < reps; ++i) {
+    uint32_t r[G][16];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+          : "=r"(r[g][0]), "=r"(r[g][1]), "=r"(r[g][2]), "=r"(r[g][3]), "=r"(r[g][4]), "=r"(r[g][5]), "=r"(r[g][6]), "=r"(r[g][7]),
+            "=r"(r[g][8]), "=r"(r[g][9]), "=r"(r[g][10]), "=r"(r[g][11]), "=r"(r[g][12]), "=r"(r[g][13]), "=r"(r[g][14]), "=r"(r[g][15])
+          : "r"(taddr + g * 16)
+          : "memory");
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc ^= r[g][0] ^ r[g][15];
+  }
+  const long long t1 = clock64();
+  if ((tid & 31) == 0) { t0s[warp] = t0; t1s[warp] = t1; }
+  __syncthreads();
+  if (tid == 0 && blockIdx.x == 0) {
+    long long a = t0s[0], b = t1s[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = a < t0s[w] ? a : t0s[w]; b = b > t1s[w] ? b : t1s[w]; }
+    out[0] = b - a;
+    out[1] = (long long)acc;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tslot, 512);
+}
+
+// Do tcgen05.mma and concurrent tcgen05.ld slow one another down?  Warp 0 issues `reps` MMAs (M = 128, N = 256, K-major planes of
+// the given pitches) into accumulator columns [0, 256); `nld` further warps read columns [256, 512) in a loop (2 x 32 columns per
+// wait) until the MMAs have completed.  Prints clk per MMA and the loaders' rate.
+__global__ void __launch_bounds__(544, 1) probe_mma_ld_kernel(int plane_a, int plane_b, int reps, int nld, int same_acc, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  __shared__ volatile int stop;
+  __shared__ long long nloads[16];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int e = tid; e < 200 * 1024 / 16; e += blockDim.x) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 32) tmem_alloc(&tslot, 512);
+  if (tid == 32) { mbar_init(&bar, 1); fence_mbar_init(); stop = 0; }
+  if (tid < 16) nloads[tid] = 0;
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tslot;
+  if (warp == 16) {
+    if (elect_one()) {
+      const uint64_t ad0 = smem_desc(smem_u32(smem), plane_a, 128), bd0 = smem_desc(smem_u32(smem + 100 * 1024), plane_b, 128);
+      const uint32_t idesc = instr_desc(FMT_BF16, 128, 256, false, false);
+      const long long t0 = clock64();
+#pragma unroll 1
+      for (int i = 0; i < reps; i += 4) {
+        mma<false>(tmem, ad0, bd0, idesc, 1);
+        mma<false>(tmem, ad0 + (uint64_t)((2 * plane_a) >> 4), bd0 + (uint64_t)((2 * plane_b) >> 4), idesc, 1);
+        mma<false>(tmem, ad0 + (uint64_t)((4 * plane_a) >> 4), bd0 + (uint64_t)((4 * plane_b) >> 4), idesc, 1);
+        mma<false>(tmem, ad0 + (uint64_t)((6 * plane_a) >> 4), bd0 + (uint64_t)((6 * plane_b) >> 4), idesc, 1);
+      }
+      commit(&bar);
+      mbar_wait(&bar, 0);
+      const long long t1 = clock64();
+      stop = 1;
+      if (blockIdx.x == 0) out[0] = t1 - t0;
+    }
+    __syncwarp();
+  } else if (warp < nld) {
+    const uint32_t taddr = tmem + ((uint32_t)(warp & 3) * 32u << 16) + (uint32_t)((same_acc ? 0 : 256) + (warp >> 2) * 64);
+    uint32_t acc = 0u;
+    long long n = 0;
+    while (!stop) {
+      uint32_t r[2][32];
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            : "=r"(r[g][0]), "=r"(r[g][1]), "=r"(r[g][2]), "=r"(r[g][3]), "=r"(r[g][4]), "=r"(r[g][5]), "=r"(r[g][6]), "=r"(r[g][7]), "=r"(r[g][8]),
+              "=r"(r[g][9]), "=r"(r[g][10]), "=r"(r[g][11]), "=r"(r[g][12]), "=r"(r[g][13]), "=r"(r[g][14]), "=r"(r[g][15]), "=r"(r[g][16]),
+              "=r"(r[g][17]), "=r"(r[g][18]), "=r"(r[g][19]), "=r"(r[g][20]), "=r"(r[g][21]), "=r"(r[g][22]), "=r"(r[g][23]), "=r"(r[g][24]),
+              "=r"(r[g][25]), "=r"(r[g][26]), "=r"(r[g][27]), "=r"(r[g][28]), "=r"(r[g][29]), "=r"(r[g][30]), "=r"(r[g][31])
+            : "r"(taddr + g * 32)
+            : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      acc ^= r[0][0] ^ r[1][31];
+      ++n;
+    }
+    if ((tid & 31) == 0) nloads[warp] = n + (acc == 0x12345u);
+  }
+  __syncthreads();
+  if (tid == 0 && blockIdx.x == 0) {
+    long long t = 0;
+    for (int i = 0; i < 16; ++i) t += nloads[i];
+    out[1] = t;
+  }
+  if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
+// mbarrier costs: (a) a wait on a phase that has already completed (test_wait / try_wait / the kernels' mbar_wait), (b) the wake-up
+// latency of a waiting thread after another warp's arrive, for a plain try_wait loop and for mbar_wait (try_wait with a suspend hint).
+__device__ __forceinline__ uint32_t test_wait_once(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint32_t try_wait_once(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok;
+}
+__global__ void __launch_bounds__(64, 1) probe_mbar_kernel(long long* out) {
+  __shared__ uint64_t bar[4];
+  __shared__ volatile long long t_arrive;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) { for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1); fence_mbar_init(); }
+  __syncthreads();
+  if (tid == 0) mbar_arrive(&bar[0]);  // phase 0 of bar[0] is complete from here on
+  __syncthreads();
+  if (warp == 0 && lane == 0) {
+    uint32_t acc = 0;
+    long long t0 = clock64();
+    for (int i = 0; i < 100; ++i) acc += test_wait_once(&bar[0], 0);
+    long long t1 = clock64();
+    for (int i = 0; i < 100; ++i) acc += try_wait_once(&bar[0], 0);
+    long long t2 = clock64();
+    for (int i = 0; i < 100; ++i) mbar_wait(&bar[0], 0);
+    long long t3 = clock64();
+    out[0] = t1 - t0; out[1] = t2 - t1; out[2] = t3 - t2; out[7] = acc;
+  }
+  __syncthreads();
+  // wake-up latency, 3 variants: warp 0 waits on bar[1 + v]; warp 1 arrives ~20000 clk later
+  for (int v = 0; v < 3; ++v) {
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) {
+        if (v == 0) { while (!test_wait_once(&bar[1 + v], 0)) {} }
+        else if (v == 1) { while (!try_wait_once(&bar[1 + v], 0)) {} }
+        else mbar_wait(&bar[1 + v], 0);
+        const long long t = clock64();
+        out[3 + v] = t - t_arrive;
+      }
+      __syncwarp();
+    } else {
+      if (lane == 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < 20000) {}
+        t_arrive = clock64();
+        __threadfence_block();
+        mbar_arrive(&bar[1 + v]);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 int main() {
   long long* d;
   cudaMalloc(&d, 8);
@@ -266,6 +441,47 @@ int main() {
       printf("tcgen05.ld.%s, %2d warps x 2000 loads (4 KB each)                        %8.1f B / clk / SM   (%s)\n",
              shape ? "16x256b.x8 " : "32x32b.x32 ", nw, (double)nw * 2000 * 4096 / (double)cyc, cudaGetErrorString(e));
     }
+  for (int G : {1, 2, 4, 8})
+    for (int nw : {1, 4, 8, 16}) {
+      if (G == 1) probe_tmem_ld_inflight_kernel<1><<<4, nw * 32>>>(2000, d);
+      else if (G == 2) probe_tmem_ld_inflight_kernel<2><<<4, nw * 32>>>(2000, d);
+      else if (G == 4) probe_tmem_ld_inflight_kernel<4><<<4, nw * 32>>>(2000, d);
+      else probe_tmem_ld_inflight_kernel<8><<<4, nw * 32>>>(2000, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long cyc = 0;
+      cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+      printf("tcgen05.ld.32x32b.x16, %d in flight per wait, %2d warps x 2000 rounds (%d KB each)   %8.1f B / clk / SM   (%s)\n", G, nw,
+             2 * G, (double)nw * 2000 * 2048 * G / (double)cyc, cudaGetErrorString(e));
+    }
+  cudaFuncSetAttribute(probe_mma_ld_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  {
+    long long* d2;
+    cudaMalloc(&d2, 16);
+    struct { const char* name; int pa, pb; } lay[] = {{"pitch 2048 / 4096", 2048, 4096}, {"pitch 2048+64 / 4096+64 (vq2_kernel)", 2048 + 64, 4096 + 64},
+                                                       {"pitch 2048+128 / 4096+128", 2048 + 128, 4096 + 128}};
+    for (auto& l : lay)
+      for (int same : {0, 1})
+        for (int nld : {0, 4, 8, 16}) {
+          if (same && nld == 0) continue;
+          probe_mma_ld_kernel<<<4, 544, 200 * 1024>>>(l.pa, l.pb, 400, nld, same, d2);
+          cudaError_t e = cudaDeviceSynchronize();
+          long long r[2] = {0, 0};
+          cudaMemcpy(r, d2, 16, cudaMemcpyDeviceToHost);
+          printf("MMA N=256 K-major, %-38s + %2d warps of tcgen05.ld on %s accumulator: %7.1f clk / MMA, loads %7.1f B / clk   (%s)\n", l.name, nld,
+                 same ? "the SAME " : "the other", (double)r[0] / 400, (double)r[1] * 8192 / (double)r[0], cudaGetErrorString(e));
+        }
+  }
+  {
+    long long* d3;
+    cudaMalloc(&d3, 64);
+    probe_mbar_kernel<<<1, 64>>>(d3);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long r[8];
+    cudaMemcpy(r, d3, 64, cudaMemcpyDeviceToHost);
+    printf("mbarrier, completed phase: test_wait %.1f clk, try_wait %.1f clk, mbar_wait (try_wait, then try_wait + suspend hint) %.1f clk   (%s)\n",
+           r[0] / 100.0, r[1] / 100.0, r[2] / 100.0, cudaGetErrorString(e));
+    printf("mbarrier, wake-up after another warp's arrive: test_wait spin %lld clk, try_wait loop %lld clk, mbar_wait %lld clk\n", r[3], r[4], r[5]);
+  }
   cudaFuncSetAttribute(probe_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   for (int N : {32, 64}) {
     for (int ni : {1, 2, 4}) {

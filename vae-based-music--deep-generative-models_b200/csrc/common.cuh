@@ -62,6 +62,10 @@ int resblock_wgrad_tc(const vqb_conv_desc* d, int n, const int* dilations, const
                       float* const* dw2, float* const* db2, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // tensor-core stride-2 convolutions (conv_tc.cu)
+// conv3_tc.cu: k = 3, stride-1 convolutions 32 <-> 64 channels at latent rate (forward and data gradient)
+bool conv3_tc_supported(const vqb_conv_desc* d);
+int conv3_fwd_tc(const vqb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+int conv3_dgrad_tc(const vqb_conv_desc* d, const float* dy, const float* w, float* dx, cudaStream_t st);
 bool conv_tc_supported(const vqb_conv_desc* d);
 int conv1d_fwd_tc(const vqb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
 int conv1d_dgrad_tc(const vqb_conv_desc* d, const float* dy, const float* w, float* dx, cudaStream_t st);

@@ -800,6 +800,7 @@ int vqb_conv1d_fwd(const vqb_conv_desc* d, const float* x, const float* w, const
   if (rc) return rc;
   VQB_REQUIRE(x && w && y, "vqb_conv1d_fwd: NULL pointer");
   if (d->precision != VQB_PREC_FP32) {
+    if (conv3_tc_supported(d) && !residual) return conv3_fwd_tc(d, x, w, bias, y, (cudaStream_t)stream);
     VQB_REQUIRE(conv_tc_supported(d) && !residual, "vqb_conv1d_fwd: no tensor-core kernel for this shape (k=%d stride=%d %d->%d); use VQB_PREC_FP32",
                 d->k, d->stride, d->C_in, d->C_out);
     return conv1d_fwd_tc(d, x, w, bias, y, (cudaStream_t)stream);
@@ -815,6 +816,7 @@ int vqb_conv1d_dgrad(const vqb_conv_desc* d, const float* dy, const float* w, co
   VQB_REQUIRE(dy && w && dx, "vqb_conv1d_dgrad: NULL pointer");
   VQB_REQUIRE(!d->relu_in || x, "vqb_conv1d_dgrad: relu_in needs x for the ReLU mask");
   if (d->precision != VQB_PREC_FP32) {
+    if (conv3_tc_supported(d) && !dx_add) return conv3_dgrad_tc(d, dy, w, dx, (cudaStream_t)stream);
     VQB_REQUIRE(conv_tc_supported(d) && !dx_add, "vqb_conv1d_dgrad: no tensor-core kernel for this shape (k=%d stride=%d %d->%d); use VQB_PREC_FP32",
                 d->k, d->stride, d->C_in, d->C_out);
     return conv1d_dgrad_tc(d, dy, w, dx, (cudaStream_t)stream);
@@ -826,7 +828,7 @@ int vqb_conv1d_supports(const vqb_conv_desc* d, int op) {
   if (!d || d->k < 1 || d->k > MAX_TAPS) return 0;
   if (d->precision == VQB_PREC_FP32) return 1;
   if (op == 2) return wgrad_tc_supported(d) || conv_tc_supported(d) ? 1 : 0;
-  return conv_tc_supported(d) ? 1 : 0;
+  return conv_tc_supported(d) || conv3_tc_supported(d) ? 1 : 0;
 }
 
 int vqb_conv1d_transpose_supports(const vqb_conv_desc* d, int op) {

@@ -14,6 +14,8 @@
 // the exact-fp32 argmin; typically 1-3 codes per latent are re-evaluated.
 // Persistent CTAs (2 per SM, 256 TMEM columns each): the codebook (K <= 512) stays resident in shared memory, so one
 // CTA's MMAs overlap the other's scan.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -273,7 +275,14 @@ struct Vq2Params {
   int* st_i1;
   float* fbest;         // exact pass over code blocks (vq2_exact_kernel): running exact minimum per flagged row
   int* fk;
+  long long* trace;     // TRACE build (tools/trace_vq.py): clock64 stamps of CTA 0's tiles 3 and 4, [2][16]
 };
+
+// TRACE: clock64 stamp of event `ev` (CTA 0, tiles 3 and 4, one lane)
+#define V2_TR(ev)                                                                                                   \
+  do {                                                                                                              \
+    if (TRACE && p.trace && blockIdx.x == 0 && (it == 3 || it == 4) && lane == 0) p.trace[(it - 3) * 24 + (ev)] = clock64(); \
+  } while (0)
 
 __global__ void vq2_pack_codebook_kernel(const float* __restrict__ E, int K, const float* __restrict__ ee,
                                          uint8_t* __restrict__ Epk, float* __restrict__ ee_max) {
@@ -392,6 +401,7 @@ __global__ void __launch_bounds__(V2_EX_THREADS, 1) vq2_exact_kernel(const Vq2Pa
   }
 }
 
+template <bool TRACE>
 __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* As = smem;                                 // [2 pieces][8 planes]
@@ -406,6 +416,7 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
   int* pi1 = reinterpret_cast<int*>(pm2 + 2 * (V2_PARTS - 1) * VT_ROWS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = blockIdx.x < p.ntiles ? (int)((p.ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  const bool getenv_spin = TRACE;
 
   if (warp == 0) tmem_alloc(tslot, 512);
   if (tid == 32) {
@@ -435,9 +446,11 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
       for (int it = 0; it < ntiles; ++it) {
         mbar_wait(&bar[0], it & 1);
         fence_after_sync();
+        V2_TR(0);
         for (int ch = 0; ch < p.nchunks; ++ch) {
           // accumulator `ch` was drained by the scan of the previous tile (phase it-1 of bar[3+ch])
           if (it > 0) { mbar_wait(&bar[3 + ch], (it - 1) & 1); fence_after_sync(); }
+          V2_TR(1 + 2 * ch);
           const uint64_t b_hi = smem_desc(smem_u32(Bs + (size_t)ch * V2_CHUNK_B), V2_PLANE_B, 128);
           const uint64_t b_lo = b_hi + (uint64_t)((VT_NP * V2_PLANE_B) >> 4);
           const uint64_t b_ee = b_hi + (uint64_t)((2 * VT_NP * V2_PLANE_B) >> 4);
@@ -451,6 +464,18 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
             mma<false>(d, a_hi + ka, b_hi + kb, idesc, 1);
           }
           commit(&bar[1 + ch]);
+          V2_TR(2 + 2 * ch);
+          if (TRACE && p.trace && blockIdx.x == 0 && it == 4 && getenv_spin) {  // tile 4 only: spin (test_wait, no suspend) until the chunk has completed
+            uint32_t ok = 0;
+            while (!ok)
+              asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+                           : "=r"(ok) : "r"(smem_u32(&bar[1 + ch])), "r"((uint32_t)(it & 1)) : "memory");
+            V2_TR(19 + ch);
+          }
+        }
+        if (TRACE && p.trace && blockIdx.x == 0 && (it == 3 || it == 4)) {  // when do the chunks really complete?  (perturbs the next tile slightly)
+          mbar_wait(&bar[1], it & 1); V2_TR(12);
+          mbar_wait(&bar[2], it & 1); V2_TR(15);
         }
       }
     }
@@ -500,14 +525,18 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
       const long n0 = ((long)blockIdx.x + (long)it * gridDim.x) * VT_ROWS;
       const bool has_next = it + 1 < ntiles;
       if (has_next) load(it + 1);
+      if (warp == 0) { V2_TR(5); V2_TR(16); }
       // two independent (best, second, index) trackers over the even / odd columns halve the dependency chains
       float m1 = -INFINITY, m2 = -INFINITY, n1 = -INFINITY, n2 = -INFINITY;
       int i1 = 0, j1 = 0;
 #pragma unroll 1
       for (int ch = 0; ch < p.nchunks; ++ch) {
         mbar_wait(&bar[1 + ch], it & 1);
+        if (warp == 0) V2_TR(17 + ch);
         fence_after_sync();
+        if (warp == 0) V2_TR(6 + 2 * ch);
         if (ch == p.nchunks - 1 && has_next) stage(it + 1);  // all MMAs of this tile have completed: the x tile is free
+        if (warp == 0 && ch == p.nchunks - 1) V2_TR(10);
         const uint32_t taddr = tmem + (((uint32_t)qd * 32u) << 16) + (uint32_t)(ch * VT_CHUNK + part * V2_COLS);
         const int kbase = p.code0 + ch * VT_CHUNK + part * V2_COLS;
 #pragma unroll 1
@@ -526,6 +555,8 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[3 + ch]);
+        if (warp == 0) V2_TR(7 + 2 * ch);
+        if (warp == 15) V2_TR(13 + ch);
       }
       {  // fold the odd-column tracker into the even one (ties go to the lower index; they are re-evaluated exactly anyway)
         const float second = fmaxf(fminf(m1, n1), fmaxf(m2, n2));
@@ -539,6 +570,7 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
         pm1[o] = m1; pm2[o] = m2; pi1[o] = i1;
       }
       bar_scan();
+      if (warp == 0) V2_TR(11);
       if (part == 0) {
 #pragma unroll
         for (int q = 0; q < V2_PARTS - 1; ++q) {
@@ -636,10 +668,15 @@ int vq_search_tc(const vqb_vq_desc* d, const float* x, const float* E, const flo
       const size_t smem = vq2_smem_bytes(q.nchunks);
       static size_t smem_set2 = 0;
       if (smem > smem_set2) {
-        VQB_CUDA(cudaFuncSetAttribute(vq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VQB_CUDA(cudaFuncSetAttribute(vq2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VQB_CUDA(cudaFuncSetAttribute(vq2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set2 = smem;
       }
-      vq2_kernel<<<(int)grid, V2_NSCAN + 32, smem, st>>>(q);
+      if (getenv("VQB_VQ_TRACE")) {  // profiling aid: address of a device buffer of 32 int64 (tools/trace_vq.py)
+        q.trace = reinterpret_cast<long long*>(strtoull(getenv("VQB_VQ_TRACE"), nullptr, 0));
+        vq2_kernel<true><<<(int)grid, V2_NSCAN + 32, smem, st>>>(q);
+      } else
+        vq2_kernel<false><<<(int)grid, V2_NSCAN + 32, smem, st>>>(q);
       VQB_LAUNCH_CHECK();
     }
     q.K = d->K < 512 ? d->K : 512;  // codes per block of the exact pass
