@@ -448,11 +448,10 @@ def vq_section(V, pk):
         mb, nb = ops.empty(D, K), ops.empty(K)
         for io in ("fp32", "bf16"):
             if io == "bf16" and not getattr(ops, "VQ_BF16_IO", False):
-                sweep.append({"K": K, "io": io, "unavailable": "bf16 I/O for the VectorQuantizer is not implemented (fp32 activations end to end)"})
+                sweep.append({"K": K, "io": io, "unavailable": "this build of libvqvae_b200 has no vqb_vq_fwd_bf16"})
                 continue
-            kw = {"io_bf16": True} if io == "bf16" else {}
-            xin = [x.to(torch.bfloat16) for x in xs] if io == "bf16" else xs
-            ms = device_ms(lambda i: ops.vq_fwd(xin[i % 2], E, 0.25, True, False, mb, nb, P, **kw), n=10)
+            xin = [x.to(torch.bfloat16) for x in xs] if io == "bf16" else xs   # a bfloat16 input selects vqb_vq_fwd_bf16
+            ms = device_ms(lambda i: ops.vq_fwd(xin[i % 2], E, 0.25, True, False, mb, nb, P), n=10)
             per = 264 if io == "bf16" else 520
             t_hbm, t_mma = N * per / (pk["hbm"] * 1e9), N * 2.0 * K * D / (pk["tf_sust"] * 1e12)
             bound = "hbm" if t_hbm >= t_mma else "tensor"

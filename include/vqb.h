@@ -242,6 +242,14 @@ size_t vqb_vq_fwd_workspace_bytes(const vqb_vq_desc* d);
 int vqb_vq_fwd(const vqb_vq_desc* d, const float* x, const float* E, int64_t* idx, float* q_st, float* q,
                float* loss, float* m_batch, float* n_batch, void* workspace, size_t workspace_bytes,
                void* stream);
+/* The same layer with bfloat16 ACTIVATIONS (BASELINE.json configs[3] "bf16"): x, q_st and q are [N,D] bfloat16 (raw 16-bit
+ * patterns); the codebook, the search, the loss and the batch statistics are the fp32 arithmetic of vqb_vq_fwd applied to
+ * float(x), and q_st = bf16_rn(x + (q - x)), q = bf16_rn(E[:,idx]).  The reference layer itself is fp32 end to end
+ * (VectorQuantizer.py:75-124 under Keras' default float32 policy); this entry halves the layer's HBM traffic for callers that
+ * keep bf16 latents.  Tensor-core search: K <= 4096. */
+int vqb_vq_fwd_bf16(const vqb_vq_desc* d, const uint16_t* x, const float* E, int64_t* idx, uint16_t* q_st, uint16_t* q,
+                    float* loss, float* m_batch, float* n_batch, void* workspace, size_t workspace_bytes,
+                    void* stream);
 /* straight-through + commitment gradient (VectorQuantizer.py:97-99,114):
  *   dx = dq_out + loss_scale * (2*beta/(N*D)) * (x - q)   (loss_scale: d total / d commitment loss) */
 int vqb_vq_bwd(const vqb_vq_desc* d, const float* dq_out, const float* x, const float* q, float loss_scale,

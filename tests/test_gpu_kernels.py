@@ -135,6 +135,44 @@ def check_indices(idx, x, E):
     return ref
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("N,D,K,kind", [(28160, 64, 512, "normal"), (1 << 16, 64, 2048, "normal"), (4096, 64, 512, "nearties"),
+                                        (440, 64, 512, "init"), (1000, 48, 100, "normal"), (33, 200, 9, "normal"), (5, 64, 512, "normal")])
+def test_vq_forward_bf16_activations(gpu, prec, N, D, K, kind):
+    """vqb_vq_fwd_bf16 (BASELINE configs[3] "bf16"): x, q_st, q in bfloat16, everything in between the fp32 arithmetic of the
+    fp32 entry applied to float(x).  Oracle = VectorQuantizer.py:86-124,170-186 on float(x): indices by the same near-tie rule,
+    q = bf16_rn(E[:, idx]) and q_st = bf16_rn(fl(x + fl(q - x))) bit for bit, loss / statistics as in the fp32 test.  prec = the
+    search arithmetic (exact fp32 CUDA cores / tensor cores + exact re-ranking)."""
+    ops = gpu.ops
+    rng = np.random.default_rng(N + K + 1)
+    xb = torch.tensor(rng.normal(size=(N, D)).astype(np.float32)).bfloat16()
+    x = xb.float().numpy()
+    if kind == "init":
+        E = rng.uniform(-0.05, 0.05, size=(D, K)).astype(np.float32)
+    elif kind == "nearties":
+        E = (x[rng.integers(0, N, K)] + 1e-3 * rng.normal(size=(K, D))).T.astype(np.float32).copy()
+    else:
+        E = rng.normal(size=(D, K)).astype(np.float32)
+    m_batch, n_batch = ops.empty(D, K), ops.empty(K)
+    P = gpu._lib.PRECISIONS[prec]
+    idx, q_st, q, loss = ops.vq_fwd(xb.cuda().contiguous(), dev(E), 0.25, True, True, m_batch, n_batch, P)
+    assert idx.dtype == torch.int64 and q_st.dtype == torch.bfloat16 and q.dtype == torch.bfloat16
+    check_indices(idx, x, E)
+    ic = idx.cpu()
+    qr = torch.tensor(E).t()[ic]
+    xt = torch.tensor(x)
+    assert torch.equal(q.cpu(), qr.bfloat16())
+    assert torch.equal(q_st.cpu(), (xt + (qr - xt)).bfloat16())
+    want_loss = 0.25 * ((qr.double() - xt.double()) ** 2).mean()
+    assert abs(float(loss) - float(want_loss)) <= 1e-5 * float(want_loss)
+    mb, nb = O.vq_batch_stats(xt.double(), ic, K)
+    assert torch.equal(n_batch.cpu().double(), nb)
+    close(m_batch, mb, 1e-5, "m_batch")
+    # the fp32 entry on float(x) picks the same codes
+    idx32, _, _, loss32 = ops.vq_fwd(dev(x), dev(E), 0.25, False, False, None, None, P)
+    assert torch.equal(idx32, idx) and float(loss32) == float(loss)
+
+
 @pytest.mark.parametrize("N,D,K,kind", [(28160, 64, 512, "normal"), (3520, 64, 512, "init"), (1 << 16, 64, 2048, "normal"),
                                         (4096, 64, 512, "nearties"), (3200, 2, 6, "normal"), (440, 64, 512, "normal"),
                                         (1000, 48, 100, "normal"), (33, 200, 9, "normal")])

@@ -20,11 +20,12 @@ for K in (512, 2048):
     E = torch.randn(D, K, device="cuda", generator=g)
     m_t, N_t = E.clone(), torch.ones(K, device="cuda")
     mb, nb, rows, met = ops.empty(D, K), ops.empty(K), ops.zeros(K, D), ops.zeros(3)
-    for prec in ("fp32", "bf16"):
+    for prec, io in (("fp32", "fp32"), ("bf16", "fp32"), ("bf16", "bf16")):
         P = V._lib.PRECISIONS[prec]
+        xin = [x.to(torch.bfloat16) for x in xs] if io == "bf16" else xs   # bfloat16 latents: vqb_vq_fwd_bf16
         for ema in (False, True):
             def one(i):
-                ops.vq_fwd(xs[i % 2], E, 0.25, True, False, mb, nb, P)
+                ops.vq_fwd(xin[i % 2], E, 0.25, True, False, mb, nb, P)
                 if ema:
                     ops.vq_ema_update(E.clone(), m_t, N_t, mb, nb, rows, 0.99, 1.0, met)
             for i in range(3):
@@ -39,8 +40,8 @@ for K in (512, 2048):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / n
             lat = N / (ms * 1e-3)
-            t_hbm = N * 520 / (peaks["hbm_gbs"] * 1e9)
+            t_hbm = N * (264 if io == "bf16" else 520) / (peaks["hbm_gbs"] * 1e9)
             t_mma = N * 2.0 * K * D / (peaks["bf16_tflops_sustained"] * 1e12)
-            print(json.dumps({"workload": f"VQ-only N=2^20 K={K} D=64 {'fwd+EMA' if ema else 'fwd'}", "search": "tcgen05+exact-rerank" if prec != "fp32" else "fp32 CUDA cores",
+            print(json.dumps({"workload": f"VQ-only N=2^20 K={K} D=64 {'fwd+EMA' if ema else 'fwd'}", "search": "tcgen05+exact-rerank" if prec != "fp32" else "fp32 CUDA cores", "io": io,
                               "ms": ms, "latents_per_s": lat, "roofline_ms": max(t_hbm, t_mma) * 1e3,
                               "bound": "hbm" if t_hbm > t_mma else "tensor", "frac_of_roofline": max(t_hbm, t_mma) * 1e3 / ms}))

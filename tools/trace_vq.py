@@ -22,7 +22,7 @@ torch.cuda.synchronize()
 t = buf.cpu().view(2, 24)
 names = ["iss: x staged", "iss: acc0 drained", "iss: chunk0 committed", "iss: acc1 drained", "iss: chunk1 committed",
          "scan0: iteration start", "scan0: acc0 complete", "scan0: chunk0 scanned", "scan0: acc1 complete", "scan0: chunk1 scanned",
-         "scan0: next tile staged", "scan0: rows merged", "iss: sees acc0 complete", "scan15: chunk0 scanned", "scan15: chunk1 scanned", "iss: sees acc1 complete", "scan0: iteration start (2nd stamp)", "scan0: bar acc0 passed", "scan0: bar acc1 passed", "iss: SPIN sees acc0 complete", "iss: SPIN sees acc1 complete", "-", "-", "-"]
+         "scan0: next tile staged", "scan0: rows merged", "iss: sees acc0 complete", "scan15: chunk0 scanned", "scan15: chunk1 scanned", "iss: sees acc1 complete", "scan0: iteration start (2nd stamp)", "scan0: bar acc0 passed", "scan0: bar acc1 passed", "iss: SPIN sees acc0 complete", "iss: SPIN sees acc1 complete", "scan0: partials merged", "scan0: index stored", "scan0: iteration end"]
 t0 = min(int(v) for v in t.flatten() if int(v))
 ev = sorted((int(t[i, e]) - t0, f"tile {3 + i}", names[e]) for i in range(2) for e in range(24) if int(t[i, e]))
 for c, ti, n in ev:

@@ -91,6 +91,7 @@ SIGNATURES = {
     "vqb_dec_tail_bwd": (C.c_int, [_TD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_vq_fwd_workspace_bytes": (C.c_size_t, [_VD]),
     "vqb_vq_fwd": (C.c_int, [_VD, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vqb_vq_fwd_bf16": (C.c_int, [_VD, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_vq_bwd": (C.c_int, [_VD, _P, _P, _P, C.c_float, _P, _P]),
     "vqb_vq_ema_update": (C.c_int, [C.c_int32, C.c_int32, C.c_double, C.c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vqb_gather_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),

@@ -6,15 +6,37 @@
 //                      count / sum statistics                                 (:86-99,114,123-124)
 //   vq_ema_kernel      EMA + dead-code restart, separately rounded ops        (:128-145)
 //   vq_metrics_kernel  batch usage, running usage, entropy                    (:151-159)
+#include <cuda_bf16.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vqb {
 
 // implemented in vq_tc.cu (tcgen05 search); returns VQB_ERR_UNIMPLEMENTED for unsupported shapes
-int vq_search_tc(const vqb_vq_desc* d, const float* x, const float* E, const float* Et, const float* ee,
+int vq_search_tc(const vqb_vq_desc* d, const void* x, int x_bf16, const float* E, const float* Et, const float* ee,
                  int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t vq_search_tc_workspace_bytes(const vqb_vq_desc* d);
 bool vq_search_tc_supported(const vqb_vq_desc* d);
+
+// ---- activation I/O type: fp32 (the reference's) or bf16 (BASELINE configs[3] "bf16": x, q_st, q are bfloat16, everything the
+// layer computes with them is fp32 arithmetic on float(x)) ----------------------------------------------------------------
+typedef __nv_bfloat16 bf16_t;
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ float ld1(const bf16_t* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const bf16_t* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(bf16_t* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16_t* p, const float4& v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
 
 __global__ void vq_prep_kernel(const float* __restrict__ E, int D, int K, float* __restrict__ Et,
                                float* __restrict__ ee) {
@@ -34,7 +56,8 @@ constexpr int VQ_CT = 128;  // codes per tile
 constexpr int VQ_DC = 64;   // depth chunk
 
 // 256 threads: tx = tid % 32 -> 4 codes, ty = tid / 32 -> 4 rows.
-__global__ void __launch_bounds__(256) vq_search_kernel(const float* __restrict__ x, const float* __restrict__ E,
+template <typename XT>
+__global__ void __launch_bounds__(256) vq_search_kernel(const XT* __restrict__ x, const float* __restrict__ E,
                                                         const float* __restrict__ ee, long N, int D, int K,
                                                         int64_t* __restrict__ idx) {
   __shared__ __align__(16) float Xs[VQ_DC][VQ_RT + 4];   // transposed rows (+4: fewer store conflicts)
@@ -49,7 +72,7 @@ __global__ void __launch_bounds__(256) vq_search_kernel(const float* __restrict_
     float s = 0.f;
     const long n = n0 + tid;
     if (n < N)
-      for (int d = 0; d < D; ++d) { const float v = x[n * D + d]; s = fmaf(v, v, s); }
+      for (int d = 0; d < D; ++d) { const float v = ld1(x + n * D + d); s = fmaf(v, v, s); }
     xx_s[tid] = s;
   }
   float best[4];
@@ -70,7 +93,7 @@ __global__ void __launch_bounds__(256) vq_search_kernel(const float* __restrict_
         for (int e = tid; e < VQ_RT * VQ_DC; e += 256) {
           const int r = e / VQ_DC, d = e - r * VQ_DC;  // coalesced over d
           const long n = n0 + r;
-          Xs[d][r] = (n < N && d0 + d < D) ? x[n * D + d0 + d] : 0.f;
+          Xs[d][r] = (n < N && d0 + d < D) ? ld1(x + n * D + d0 + d) : 0.f;
         }
       }
       for (int e = tid; e < VQ_DC * VQ_CT; e += 256) {
@@ -129,9 +152,10 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict__ x, const float* __restrict__ Et,
+template <typename XT>
+__global__ void __launch_bounds__(256) vq_finish_kernel(const XT* __restrict__ x, const float* __restrict__ Et,
                                                         const int64_t* __restrict__ idx, long N, int D, int K,
-                                                        float* __restrict__ q_st, float* __restrict__ q,
+                                                        XT* __restrict__ q_st, XT* __restrict__ q,
                                                         float* __restrict__ m_kd, float* __restrict__ n_batch,
                                                         float* __restrict__ loss_partial) {
   __shared__ float red[32];
@@ -144,22 +168,21 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
     const int k = (int)idx[n];
     if (vec) {
       for (int d = lane * 4; d < D; d += 128) {
-        const float4 xv = *reinterpret_cast<const float4*>(x + n * D + d);
+        const float4 xv = ld4(x + n * D + d);
         const float4 qv = *reinterpret_cast<const float4*>(Et + (size_t)k * D + d);
         const float4 df = make_float4(__fsub_rn(qv.x, xv.x), __fsub_rn(qv.y, xv.y), __fsub_rn(qv.z, xv.z), __fsub_rn(qv.w, xv.w));
-        if (q) *reinterpret_cast<float4*>(q + n * D + d) = qv;
-        if (q_st) *reinterpret_cast<float4*>(q_st + n * D + d) =
-            make_float4(__fadd_rn(xv.x, df.x), __fadd_rn(xv.y, df.y), __fadd_rn(xv.z, df.z), __fadd_rn(xv.w, df.w));
+        if (q) st4(q + n * D + d, qv);
+        if (q_st) st4(q_st + n * D + d, make_float4(__fadd_rn(xv.x, df.x), __fadd_rn(xv.y, df.y), __fadd_rn(xv.z, df.z), __fadd_rn(xv.w, df.w)));
         ls = fmaf(df.x, df.x, ls); ls = fmaf(df.y, df.y, ls); ls = fmaf(df.z, df.z, ls); ls = fmaf(df.w, df.w, ls);
         if (m_kd) red_add_v4(m_kd + (size_t)k * D + d, xv.x, xv.y, xv.z, xv.w);
       }
     } else {
       for (int d = lane; d < D; d += 32) {
-        const float xv = x[n * D + d];
+        const float xv = ld1(x + n * D + d);
         const float qv = Et[(size_t)k * D + d];
         const float diff = __fsub_rn(qv, xv);
-        if (q) q[n * D + d] = qv;
-        if (q_st) q_st[n * D + d] = __fadd_rn(xv, diff);
+        if (q) st1(q + n * D + d, qv);
+        if (q_st) st1(q_st + n * D + d, __fadd_rn(xv, diff));
         ls = fmaf(diff, diff, ls);
         if (m_kd) atomicAdd(&m_kd[(size_t)k * D + d], xv);
       }
@@ -174,9 +197,10 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
 // threads accumulate the per-code sums of their slab of rows with SHARED-memory reductions and write one [K, D] partial
 // each; the partials are reduced in a fixed order.  No global atomics at all.
 constexpr int VQ_FS_THREADS = 1024;
+template <typename XT>
 __global__ void __launch_bounds__(VQ_FS_THREADS, 1) vq_finish_smem_kernel(
-    const float* __restrict__ x, const float* __restrict__ Et, const int64_t* __restrict__ idx, long N, int D, int K,
-    float* __restrict__ q_st, float* __restrict__ q, int stats, float* __restrict__ partial_kd,
+    const XT* __restrict__ x, const float* __restrict__ Et, const int64_t* __restrict__ idx, long N, int D, int K,
+    XT* __restrict__ q_st, XT* __restrict__ q, int stats, float* __restrict__ partial_kd,
     float* __restrict__ partial_n, float* __restrict__ loss_partial) {
   extern __shared__ __align__(16) float fsm[];  // [K*D] sums, [K] counts
   __shared__ float red[32];
@@ -203,7 +227,7 @@ __global__ void __launch_bounds__(VQ_FS_THREADS, 1) vq_finish_smem_kernel(
       float4 xv[VQ_FU], qv[VQ_FU];
 #pragma unroll
       for (int u = 0; u < VQ_FU; ++u)
-        if (k[u] >= 0) xv[u] = *reinterpret_cast<const float4*>(x + (n0 + (long)u * RS) * D + d);
+        if (k[u] >= 0) xv[u] = ld4(x + (n0 + (long)u * RS) * D + d);
 #pragma unroll
       for (int u = 0; u < VQ_FU; ++u)
         if (k[u] >= 0) qv[u] = *reinterpret_cast<const float4*>(Et + (size_t)k[u] * D + d);
@@ -213,9 +237,8 @@ __global__ void __launch_bounds__(VQ_FS_THREADS, 1) vq_finish_smem_kernel(
         const long n = n0 + (long)u * RS;
         const float4 df = make_float4(__fsub_rn(qv[u].x, xv[u].x), __fsub_rn(qv[u].y, xv[u].y), __fsub_rn(qv[u].z, xv[u].z),
                                       __fsub_rn(qv[u].w, xv[u].w));
-        if (q) *reinterpret_cast<float4*>(q + n * D + d) = qv[u];
-        if (q_st) *reinterpret_cast<float4*>(q_st + n * D + d) =
-            make_float4(__fadd_rn(xv[u].x, df.x), __fadd_rn(xv[u].y, df.y), __fadd_rn(xv[u].z, df.z), __fadd_rn(xv[u].w, df.w));
+        if (q) st4(q + n * D + d, qv[u]);
+        if (q_st) st4(q_st + n * D + d, make_float4(__fadd_rn(xv[u].x, df.x), __fadd_rn(xv[u].y, df.y), __fadd_rn(xv[u].z, df.z), __fadd_rn(xv[u].w, df.w)));
         ls = fmaf(df.x, df.x, ls); ls = fmaf(df.y, df.y, ls); ls = fmaf(df.z, df.z, ls); ls = fmaf(df.w, df.w, ls);
         if (stats) {
           // channel d + c lives at word (d & ~63) + 16 * c + (d % 64) / 4 of the code's row: the 16 lanes of a half-warp hit
@@ -456,8 +479,12 @@ size_t vqb_vq_fwd_workspace_bytes(const vqb_vq_desc* d) {
   return b;
 }
 
-int vqb_vq_fwd(const vqb_vq_desc* d, const float* x, const float* E, int64_t* idx, float* q_st, float* q,
-               float* loss, float* m_batch, float* n_batch, void* workspace, size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+template <typename XT>
+static int vq_fwd_impl(const vqb_vq_desc* d, const XT* x, const float* E, int64_t* idx, XT* q_st, XT* q,
+                       float* loss, float* m_batch, float* n_batch, void* workspace, size_t workspace_bytes, void* stream) {
+  constexpr bool BF = !std::is_same<XT, float>::value;
   VQB_ARCH();
   VQB_REQUIRE(d && d->N >= 0 && d->D > 0 && d->K > 0, "vqb_vq_fwd: bad descriptor");
   VQB_REQUIRE(E && (d->N == 0 || (x && idx)), "vqb_vq_fwd: NULL pointer");
@@ -483,11 +510,11 @@ int vqb_vq_fwd(const vqb_vq_desc* d, const float* x, const float* E, int64_t* id
     return VQB_OK;
   }
   if (d->precision == VQB_PREC_FP32 || !vq_search_tc_supported(d)) {  // shapes without a tensor-core kernel: exact fp32 search
-    vq_search_kernel<<<cdiv(N, VQ_RT), 256, 0, st>>>(x, E, ee, N, D, K, idx);
+    vq_search_kernel<XT><<<cdiv(N, VQ_RT), 256, 0, st>>>(x, E, ee, N, D, K, idx);
     VQB_LAUNCH_CHECK();
   } else {
     size_t off = (vq_base_ws_floats(d) * sizeof(float) + 1023) & ~(size_t)1023;
-    int rc = vq_search_tc(d, x, E, Et, ee, idx, (char*)workspace + off, workspace_bytes - off, st);
+    int rc = vq_search_tc(d, x, BF ? 1 : 0, E, Et, ee, idx, (char*)workspace + off, workspace_bytes - off, st);
     if (rc != VQB_OK) return rc;
   }
   int nfin = cdiv(N, 8 * VQ_FR);
@@ -498,10 +525,10 @@ int vqb_vq_fwd(const vqb_vq_desc* d, const float* x, const float* E, int64_t* id
     const size_t smem = ((size_t)K * D + K) * sizeof(float);
     static size_t smem_set = 0;
     if (smem > smem_set) {
-      VQB_CUDA(cudaFuncSetAttribute(vq_finish_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VQB_CUDA(cudaFuncSetAttribute(vq_finish_smem_kernel<XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set = smem;
     }
-    vq_finish_smem_kernel<<<VQ_FS_GRID, VQ_FS_THREADS, smem, st>>>(x, Et, idx, N, D, K, q_st, q, m_batch ? 1 : 0, pkd, pn, part);
+    vq_finish_smem_kernel<XT><<<VQ_FS_GRID, VQ_FS_THREADS, smem, st>>>(x, Et, idx, N, D, K, q_st, q, m_batch ? 1 : 0, pkd, pn, part);
     VQB_LAUNCH_CHECK();
     if (m_batch) {
       reduce_chunks_strided(pkd, VQ_FS_GRID, (long)K * D, 0, K * D, m_kd, st);
@@ -510,7 +537,7 @@ int vqb_vq_fwd(const vqb_vq_desc* d, const float* x, const float* E, int64_t* id
       VQB_LAUNCH_CHECK();
     }
   } else {
-    vq_finish_kernel<<<nfin, 256, 0, st>>>(x, Et, idx, N, D, K, q_st, q, m_batch ? m_kd : nullptr, n_batch, part);
+    vq_finish_kernel<XT><<<nfin, 256, 0, st>>>(x, Et, idx, N, D, K, q_st, q, m_batch ? m_kd : nullptr, n_batch, part);
     VQB_LAUNCH_CHECK();
   }
   if (m_batch) {
@@ -522,6 +549,19 @@ int vqb_vq_fwd(const vqb_vq_desc* d, const float* x, const float* E, int64_t* id
     VQB_LAUNCH_CHECK();
   }
   return VQB_OK;
+}
+
+extern "C" {
+
+int vqb_vq_fwd(const vqb_vq_desc* d, const float* x, const float* E, int64_t* idx, float* q_st, float* q,
+               float* loss, float* m_batch, float* n_batch, void* workspace, size_t workspace_bytes, void* stream) {
+  return vq_fwd_impl<float>(d, x, E, idx, q_st, q, loss, m_batch, n_batch, workspace, workspace_bytes, stream);
+}
+
+int vqb_vq_fwd_bf16(const vqb_vq_desc* d, const uint16_t* x, const float* E, int64_t* idx, uint16_t* q_st, uint16_t* q,
+                    float* loss, float* m_batch, float* n_batch, void* workspace, size_t workspace_bytes, void* stream) {
+  return vq_fwd_impl<bf16_t>(d, reinterpret_cast<const bf16_t*>(x), E, idx, reinterpret_cast<bf16_t*>(q_st),
+                             reinterpret_cast<bf16_t*>(q), loss, m_batch, n_batch, workspace, workspace_bytes, stream);
 }
 
 int vqb_vq_bwd(const vqb_vq_desc* d, const float* dq_out, const float* x, const float* q, float loss_scale,

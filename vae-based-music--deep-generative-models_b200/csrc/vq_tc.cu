@@ -256,7 +256,7 @@ constexpr int V2_NLD = (VT_ROWS * 8) / V2_NSCAN;           // 8-channel units of
 constexpr float V2_MARGIN = 2.5f * 3.0517578125e-5f;       // 2 scores x 2^-15, x1.25 for the exact evaluation's own rounding
 
 struct Vq2Params {
-  const float* x;       // [N, 64]
+  const void* x;        // [N, 64] fp32, or bf16 in the BF instantiations (vqb_vq_fwd_bf16)
   const float* Et;      // [K, 64] fp32 (exact re-evaluation)
   const float* ee;      // [K]
   const uint8_t* Epk;   // packed codebook, V2_CHUNK_B bytes per 256-code chunk
@@ -328,6 +328,7 @@ __device__ __forceinline__ void bar_scan() { asm volatile("bar.sync 1, %0;" ::"n
 // serves four independent FMA chains), one thread per code.
 constexpr int V2_EX_THREADS = 512;
 constexpr int V2_EX_ROWS = 4;
+template <bool BF>
 __global__ void __launch_bounds__(V2_EX_THREADS, 1) vq2_exact_kernel(const Vq2Params p) {
   extern __shared__ __align__(16) float esm[];  // [KB][65] codebook block, [64][4] x rows (row-interleaved), [4][16] warp results
   const int KB = p.K;                           // codes per block staged in shared memory (<= 512); p.Ktot codes in all
@@ -346,7 +347,9 @@ __global__ void __launch_bounds__(V2_EX_THREADS, 1) vq2_exact_kernel(const Vq2Pa
       __syncthreads();  // codebook staged / previous rows' buffers consumed
       if (tid < VT_D * V2_EX_ROWS) {
         const int rr = tid >> 6, d = tid & 63;
-        xs[d * V2_EX_ROWS + rr] = f0 + rr < nf ? p.x[(long)p.flist[f0 + rr] * VT_D + d] : 0.f;
+        xs[d * V2_EX_ROWS + rr] = f0 + rr >= nf ? 0.f
+                                  : BF ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.x)[(long)p.flist[f0 + rr] * VT_D + d])
+                                       : reinterpret_cast<const float*>(p.x)[(long)p.flist[f0 + rr] * VT_D + d];
       }
       __syncthreads();
       float xx[V2_EX_ROWS] = {0.f, 0.f, 0.f, 0.f};
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(V2_EX_THREADS, 1) vq2_exact_kernel(const Vq2Pa
   }
 }
 
-template <bool TRACE>
+template <bool TRACE, bool BF>
 __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* As = smem;                                 // [2 pieces][8 planes]
@@ -493,8 +496,15 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
       for (int k = 0; k < V2_NLD; ++k) {
         const long n = n0 + ((tid + k * V2_NSCAN) >> 3);
         const bool ok = n < p.N;
-        ra[k] = ok ? *reinterpret_cast<const float4*>(p.x + n * VT_D + oct * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
-        rb[k] = ok ? *reinterpret_cast<const float4*>(p.x + n * VT_D + oct * 8 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (BF) {  // 8 bf16 channels = one 16-byte load; bf16 -> fp32 is a shift
+          const uint4 u = ok ? *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + n * VT_D + oct * 8) : make_uint4(0u, 0u, 0u, 0u);
+          ra[k] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+          rb[k] = make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u), __uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
+        } else {
+          const float* xf = reinterpret_cast<const float*>(p.x);
+          ra[k] = ok ? *reinterpret_cast<const float4*>(xf + n * VT_D + oct * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+          rb[k] = ok ? *reinterpret_cast<const float4*>(xf + n * VT_D + oct * 8 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     };
     auto stage = [&](int it) {
@@ -582,6 +592,7 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
           m1 = take ? o1 : m1; i1 = take ? oi : i1; m2 = second;
         }
         const long n = n0 + r;
+        if (warp == 0) V2_TR(21);
         if (n < p.N) {
           if (!p.first_pass) {  // codes of the earlier passes (lower indices: they win ties)
             const float o1 = p.st_m1[n], o2 = p.st_m2[n];
@@ -599,7 +610,9 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
             if (!(m1 - m2 > margin)) p.flist[atomicAdd(p.fcount, 1)] = (int)n;
           }
         }
+        if (warp == 0) V2_TR(22);
       }
+      if (warp == 0) V2_TR(23);
     }
   }
   fence_before_sync();
@@ -629,7 +642,7 @@ size_t vq_search_tc_workspace_bytes(const vqb_vq_desc* d) {
   return (size_t)(d->K / VT_CHUNK) * VT_CHUNK_BYTES + 256;
 }
 
-int vq_search_tc(const vqb_vq_desc* d, const float* x, const float* E, const float* Et, const float* ee, int64_t* idx,
+int vq_search_tc(const vqb_vq_desc* d, const void* x, int x_bf16, const float* E, const float* Et, const float* ee, int64_t* idx,
                  void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!vq_tc_ok(d))
     return set_err(VQB_ERR_UNIMPLEMENTED, "tensor-core VQ search needs D = 64 and K a multiple of 256 (got D=%d K=%d)", d->D, d->K);
@@ -668,30 +681,36 @@ int vq_search_tc(const vqb_vq_desc* d, const float* x, const float* E, const flo
       const size_t smem = vq2_smem_bytes(q.nchunks);
       static size_t smem_set2 = 0;
       if (smem > smem_set2) {
-        VQB_CUDA(cudaFuncSetAttribute(vq2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VQB_CUDA(cudaFuncSetAttribute(vq2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VQB_CUDA((cudaFuncSetAttribute(vq2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        VQB_CUDA((cudaFuncSetAttribute(vq2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        VQB_CUDA((cudaFuncSetAttribute(vq2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         smem_set2 = smem;
       }
-      if (getenv("VQB_VQ_TRACE")) {  // profiling aid: address of a device buffer of 32 int64 (tools/trace_vq.py)
+      if (getenv("VQB_VQ_TRACE") && !x_bf16) {  // profiling aid: address of a device buffer of 48 int64 (tools/trace_vq.py)
         q.trace = reinterpret_cast<long long*>(strtoull(getenv("VQB_VQ_TRACE"), nullptr, 0));
-        vq2_kernel<true><<<(int)grid, V2_NSCAN + 32, smem, st>>>(q);
-      } else
-        vq2_kernel<false><<<(int)grid, V2_NSCAN + 32, smem, st>>>(q);
+        vq2_kernel<true, false><<<(int)grid, V2_NSCAN + 32, smem, st>>>(q);
+      } else if (x_bf16)
+        vq2_kernel<false, true><<<(int)grid, V2_NSCAN + 32, smem, st>>>(q);
+      else
+        vq2_kernel<false, false><<<(int)grid, V2_NSCAN + 32, smem, st>>>(q);
       VQB_LAUNCH_CHECK();
     }
     q.K = d->K < 512 ? d->K : 512;  // codes per block of the exact pass
     const size_t esmem = ((size_t)q.K * 65 + 4 + VT_D * V2_EX_ROWS + 2 * V2_EX_ROWS * 16) * sizeof(float);
     static size_t esmem_set = 0;
     if (esmem > esmem_set) {
-      VQB_CUDA(cudaFuncSetAttribute(vq2_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+      VQB_CUDA(cudaFuncSetAttribute(vq2_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+      VQB_CUDA(cudaFuncSetAttribute(vq2_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
       esmem_set = esmem;
     }
-    vq2_exact_kernel<<<num_sms, V2_EX_THREADS, esmem, st>>>(q);
+    if (x_bf16) vq2_exact_kernel<true><<<num_sms, V2_EX_THREADS, esmem, st>>>(q);
+    else vq2_exact_kernel<false><<<num_sms, V2_EX_THREADS, esmem, st>>>(q);
     VQB_LAUNCH_CHECK();
     return VQB_OK;
   }
+  if (x_bf16) return set_err(VQB_ERR_UNIMPLEMENTED, "vqb_vq_fwd_bf16: the tensor-core search for K = %d > 4096 takes fp32 activations only", d->K);
   VqTcParams p{};
-  p.x = x; p.Et = Et; p.ee = ee; p.idx = idx; p.N = d->N; p.K = d->K;
+  p.x = reinterpret_cast<const float*>(x); p.Et = Et; p.ee = ee; p.idx = idx; p.N = d->N; p.K = d->K;
   p.nchunks = d->K / VT_CHUNK;
   p.resident = p.nchunks <= VT_MAX_RESIDENT;
   uint8_t* Epk = (uint8_t*)ws;

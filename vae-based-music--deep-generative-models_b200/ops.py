@@ -362,21 +362,31 @@ def _resblock_wgrad_now(x, h, dy, dh, dw1, db1, dw2, db2, dilation, precision=0)
          ws.numel(), _lib.stream())
 
 
+VQ_BF16_IO = True  # vq_fwd takes bfloat16 latents (vqb_vq_fwd_bf16)
+
+
 def vq_fwd(flat, E, beta, want_q_st=True, want_q=True, m_batch=None, n_batch=None, precision=0):
-    """flat [N,D], E [D,K] -> idx int64 [N], q_st, q, loss[1]"""
-    _chk(flat, "x"); _chk(E, "embeddings")
+    """flat [N,D], E [D,K] -> idx int64 [N], q_st, q, loss[1].  A bfloat16 `flat` selects vqb_vq_fwd_bf16: q_st / q come back
+    in bfloat16, codebook, loss and statistics stay fp32 (include/vqb.h)."""
+    bf = flat.dtype == torch.bfloat16
+    if bf:
+        if not flat.is_contiguous() or flat.device != _lib.device():
+            raise ValueError(f"x: expected a contiguous tensor on {_lib.device()}")
+    else:
+        _chk(flat, "x")
+    _chk(E, "embeddings")
     N, D = flat.shape
     if E.shape[0] != D:
         raise ValueError(f"VectorQuantizer: input depth {D} != embedding_dim {E.shape[0]}")
     K = E.shape[1]
     idx = empty(N, dtype=torch.int64)
-    q_st = empty(N, D) if want_q_st else None
-    q = empty(N, D) if want_q else None
+    q_st = empty(N, D, dtype=flat.dtype) if want_q_st else None
+    q = empty(N, D, dtype=flat.dtype) if want_q else None
     loss = empty(1)
     d = VQDesc(N, D, K, beta, precision)
     ws = _ws(_lib.lib().vqb_vq_fwd_workspace_bytes(C.byref(d)))
-    call("vqb_vq_fwd", C.byref(d), ptr(flat), ptr(E), ptr(idx), ptr(q_st), ptr(q), ptr(loss), ptr(m_batch),
-         ptr(n_batch), ptr(ws), ws.numel(), _lib.stream())
+    call("vqb_vq_fwd_bf16" if bf else "vqb_vq_fwd", C.byref(d), ptr(flat), ptr(E), ptr(idx), ptr(q_st), ptr(q), ptr(loss),
+         ptr(m_batch), ptr(n_batch), ptr(ws), ws.numel(), _lib.stream())
     return idx, q_st, q, loss
 
 
