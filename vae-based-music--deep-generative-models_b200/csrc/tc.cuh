@@ -176,6 +176,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// One non-blocking poll of the phase with the given parity (1 = complete).  The result arrives ~150 clk after issue whatever the
+// barrier's state (tools/mma_probe.cu, mbarrier rows): callers put independent work between this call and the first use of its result.
+__device__ __forceinline__ uint32_t mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // one arrival (release semantics: this thread's earlier shared-memory writes are visible to whoever observes the phase)
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

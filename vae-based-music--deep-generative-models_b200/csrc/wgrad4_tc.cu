@@ -129,10 +129,12 @@ __global__ void __launch_bounds__(Wg4Cfg<S>::NT + 32, 1) wgrad4_tc_kernel(const 
   } else {
     // ---------------------------------------------------------------------------------- loaders / converters
     const int o = tid & 3;  // 8-channel unit of this thread
+    // tiles are loaded strictly in order: a running (batch item, tile in item) cursor instead of a 64-bit division per tile and thread
+    int ld_b = (int)(first / p.tiles_per_b), ld_tx = (int)(first - (long)ld_b * p.tiles_per_b);
     auto load = [&](int it, Wg4Regs<NG, NO>& R) {
-      const long tile = first + it;
-      const int b = (int)(tile / p.tiles_per_b);
-      const int m0 = (int)(tile - (long)b * p.tiles_per_b) * Cfg::TK;
+      const int b = ld_b;
+      const int m0 = ld_tx * Cfg::TK;
+      if (++ld_tx == p.tiles_per_b) { ld_tx = 0; ++ld_b; }
       const float* otb = p.ot + (size_t)b * p.Lo * 32 + o * 8;
       const float* gab = p.ga + (size_t)b * p.Lg * 32 + o * 8;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -32,7 +32,13 @@ struct WgTcParams {
   float* partialq[MAXP];
   int dilq[MAXP], reluq[MAXP];
   int nprob;
+  long long* trace;  // TRACE build (tools/trace_wgrad.py): clock64 stamps of CTA 0's tiles 6..9, [4][8]
 };
+
+#define WG_TR(ev)                                                                                                        \
+  do {                                                                                                                   \
+    if (TRACE && pp.trace && blockIdx.x == 0 && it >= 6 && it < 10 && (threadIdx.x & 31) == 0) pp.trace[(it - 6) * 8 + (ev)] = clock64(); \
+  } while (0)
 
 // S = number of bf16 pieces each operand is split into (1: bf16, 2: bf16x2, 3: bf16x3 = fp32-grade products)
 template <int S_, int NT_ = 256>
@@ -70,7 +76,7 @@ struct WgRegs {
 // has arrived into bf16 pieces in one of two shared-memory operand buffers and signal full[buf]; the issuing warp waits
 // for full[buf], issues the tile's MMAs and commits them to empty[buf], which the converters wait on before they
 // overwrite that buffer two tiles later.  Nobody waits for a global load it issued less than two tiles ago.
-template <int S, int NT_>
+template <int S, int NT_, bool TRACE = false>
 __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams pp) {
   using Cfg = WgCfg<S, NT_>;
   // CTA-local view: which problem, which slice of its tiles
@@ -117,8 +123,10 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
       const uint64_t dil = (uint64_t)p.dil;  // a row is 16 bytes = one unit of the descriptor's start-address field
       for (int it = 0; it < ntiles; ++it) {
         const int buf = it & 1;
+        WG_TR(0);
         mbar_wait(&full[buf], (it >> 1) & 1);
         fence_after_sync();
+        WG_TR(1);
         const uint64_t ad0 = smem_desc(smem_u32(smem + buf * Cfg::BUF), 128, Cfg::PLANE_X);
         const uint64_t bd0 = smem_desc(smem_u32(smem + buf * Cfg::BUF + Cfg::TILE_X), 128, Cfg::PLANE_D);
         uint32_t acc = it != 0;
@@ -132,6 +140,7 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
           acc = 1;
         }
         commit(&empty[buf]);
+        WG_TR(2);
       }
       commit(&done);  // everything issued so far
     }
@@ -139,10 +148,13 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
   } else {
     // ---------------------------------------------------------------------------------- loaders / converters
     const int o = tid & 3;  // 8-channel unit of this thread (the same for all its rows: idx = tid + k*NT, NT % 4 == 0)
+    // tiles are loaded strictly in order: a running (batch item, tile in item) cursor replaces the 64-bit division per tile and
+    // thread that tools/trace_wgrad.py showed on the converters' critical path (~600 clk per tile to issue six loads)
+    int ld_b = (int)(first / p.tiles_per_b), ld_tx = (int)(first - (long)ld_b * p.tiles_per_b);
     auto load = [&](int it, WgRegs<NA, NB>& R) {
-      const long tile = first + it;
-      const int b = (int)(tile / p.tiles_per_b);
-      const int t0 = (int)(tile - (long)b * p.tiles_per_b) * Cfg::TK;
+      const int b = ld_b;
+      const int t0 = ld_tx * Cfg::TK;
+      if (++ld_tx == p.tiles_per_b) { ld_tx = 0; ++ld_b; }
       const float* otb = p.ot + (size_t)b * p.L * 32 + o * 8;
       const float* gab = p.ga + (size_t)b * p.L * 32 + o * 8;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -166,14 +178,23 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
       const int buf = it & 1;
       uint8_t* Xt = smem + buf * Cfg::BUF;
       uint8_t* Dt = Xt + Cfg::TILE_X;
-      if (it >= 2) mbar_wait(&empty[buf], ((it >> 1) - 1) & 1);  // the MMAs that read this buffer have completed
+      if (warp == 0) WG_TR(3);
+      // "the MMAs that read this buffer have completed": even a satisfied mbarrier wait returns only after ~150-400 clk (tools/mma_probe,
+      // tools/trace_wgrad.py), and all converter warps reach it together — so the poll is issued first, the dy rows are split in
+      // registers under its latency, and only the shared-memory stores wait for the answer
+      const uint32_t epar = (uint32_t)(((it >> 1) - 1) & 1);
+      const uint32_t free_now = it >= 2 ? mbar_try(&empty[buf], epar) : 1u;
+      uint4 pa[NA][S];
+#pragma unroll
+      for (int k = 0; k < NA; ++k) split8<S>(R.a[k][0], R.a[k][1], pa[k]);
+      if (!free_now) mbar_wait(&empty[buf], epar);
+      if (warp == 0) WG_TR(4);
       uint4 pc[S];
 #pragma unroll
       for (int k = 0; k < NA; ++k) {
-        split8<S>(R.a[k][0], R.a[k][1], pc);
 #pragma unroll
         for (int s = 0; s < S; ++s)
-          *reinterpret_cast<uint4*>(Dt + (s * 4 + o) * Cfg::PLANE_D + ((tid + k * NT) >> 2) * 16) = pc[s];
+          *reinterpret_cast<uint4*>(Dt + (s * 4 + o) * Cfg::PLANE_D + ((tid + k * NT) >> 2) * 16) = pa[k][s];
       }
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
@@ -189,9 +210,11 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
           for (int s = 0; s < S; ++s) *reinterpret_cast<uint4*>(Xt + (s * 4 + o) * Cfg::PLANE_X + r * 16) = pc[s];
         }
       }
+      if (warp == 0) WG_TR(5);
       fence_proxy_async();  // these generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[buf]);
+      if (warp == 0) WG_TR(6);
     };
     WgRegs<NA, NB> R[NSETS];
 #pragma unroll
@@ -204,6 +227,7 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
         const int it = base + u;
         if (it < ntiles) {
           if (it + NSETS - 1 < ntiles) load(it + NSETS - 1, R[(u + NSETS - 1) % NSETS]);
+          if (warp == 0) WG_TR(7);
           convert(it, R[u]);
         }
       }
@@ -310,6 +334,15 @@ static int launch_wg_any(int S, const WgTcParams& p, int grid, cudaStream_t st) 
   // step than 256 (8 warps, 3 sets) once the launches were batched; VQB_WGRAD_NT=256 selects the other variant
   const char* e = getenv("VQB_WGRAD_NT");
   const int nt = e ? atoi(e) : 512;
+  if (getenv("VQB_WG_TRACE") && S == 3 && nt == 512) {  // profiling aid (tools/trace_wgrad.py): device buffer of 32 int64
+    WgTcParams q = p;
+    q.trace = reinterpret_cast<long long*>(strtoull(getenv("VQB_WG_TRACE"), nullptr, 0));
+    static bool set = false;
+    if (!set) { VQB_CUDA((cudaFuncSetAttribute(wgrad_tc_kernel<3, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<3, 512>::SMEM))); set = true; }
+    VQB_CUDA((launch_pdl(wgrad_tc_kernel<3, 512, true>, dim3(grid), dim3(512 + 32), (size_t)WgCfg<3, 512>::SMEM, st, q)));
+    VQB_LAUNCH_CHECK();
+    return VQB_OK;
+  }
   return nt == 512 ? (S == 3 ? launch_wg<3, 512>(p, grid, st) : S == 2 ? launch_wg<2, 512>(p, grid, st) : launch_wg<1, 512>(p, grid, st))
                    : (S == 3 ? launch_wg<3>(p, grid, st) : S == 2 ? launch_wg<2>(p, grid, st) : launch_wg<1>(p, grid, st));
 }
