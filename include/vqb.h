@@ -296,7 +296,8 @@ int vqb_spec_diff(const float* S, const float* mag_t, int64_t B, int64_t per_exa
  * d loss / d(sum-of-squares root) factors consumed by vqb_spec_grad */
 int vqb_spec_loss(const float* dsum, const float* tsum, int32_t nscales, int32_t B, float* loss, float* coef,
                   void* stream);
-/* G [B, F, bins] complex64: irfft(G, n = n_fft) is d(upstream[0] * loss) / d frames (coef = this scale's row) */
+/* G [B, F, bins] complex64: the UNNORMALISED inverse real FFT of G (torch.fft.irfft(G, n = n_fft, norm = "forward"), cuFFT C2R)
+ * is d(upstream[0] * loss) / d frames (coef = this scale's row) */
 int vqb_spec_grad(const float* S, const float* mag_t, const float* coef, const float* upstream, int64_t B,
                   int64_t per_example, int32_t bins, int32_t n_fft, float* G, void* stream);
 /* dx [B, T] (+)= overlap-add of dframes [B, F, n_fft] * window (accumulate != 0: add to dx) */

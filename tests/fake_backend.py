@@ -207,7 +207,7 @@ class FakeBackend:
         s = _t(S, (B, per, 2)); mt = _t(mag_t, (B, per))
         m = torch.sqrt(s[..., 0] ** 2 + s[..., 1] ** 2)
         k = torch.arange(per) % bins
-        w = torch.where((k == 0) | (k == bins - 1), float(n_fft), 0.5 * n_fft)
+        w = torch.where((k == 0) | (k == bins - 1), 1.0, 0.5)  # for the unnormalised inverse FFT (include/vqb.h)
         c = _t(upstream, (1,))[0] * _t(coef, (B,))[:, None] * (m - mt) / torch.where(m > 0, m, torch.ones_like(m)) * w
         c = torch.where(m > 0, c, torch.zeros_like(c))
         _t(G, (B, per, 2)).copy_(c[..., None] * s)

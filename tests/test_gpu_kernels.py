@@ -28,6 +28,7 @@ def close(got, want, tol=1e-4, what=""):
 
 CONV_CASES = [  # B, L, cin, cout, k, s, d, relu
     (2, 28160 // 16, 1, 32, 4, 2, 1, 0),   # first stage (Cin = 1)
+    (1, 7, 1, 32, 4, 2, 1, 0), (3, 1001, 1, 32, 4, 2, 1, 0), (2, 333, 1, 16, 6, 2, 1, 0), (2, 64, 1, 8, 3, 1, 1, 0),  # ... ragged / other taps
     (3, 500, 32, 32, 3, 1, 1, 1), (3, 500, 32, 32, 3, 1, 3, 1), (2, 500, 32, 32, 3, 1, 9, 1),
     (2, 501, 32, 32, 3, 1, 27, 1),         # res-block convs, odd length
     (2, 40, 32, 32, 3, 1, 27, 1),          # window shorter than the receptive field

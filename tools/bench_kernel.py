@@ -31,6 +31,9 @@ if what.startswith("stack"):
     Bz = [torch.zeros(C, device="cuda") for _ in dils]
     _, _, sxb, shb, sws = ops.resstack_fwd(xs[0], W1, Bz, W2, Bz, dils, P, True)
 w4 = torch.randn(4, C, C, device="cuda", generator=g) * 0.1
+if what == "conv_in1_wgrad":
+    xa = torch.randn(B, 2 * L, 1, device="cuda", generator=g)
+    dw1c = ops.empty(4, 1, C)
 if what.startswith("conv3"):
     w3u, b3u = torch.randn(3, C, 64, device="cuda", generator=g) * 0.1, torch.zeros(64, device="cuda")
     w3d = torch.randn(3, 64, C, device="cuda", generator=g) * 0.1
@@ -59,6 +62,8 @@ def one(i):
             ops.conv1d_fwd(xs[i % 2], w3u, b3u, 1, 1, False, None, P)
         else:
             ops.conv1d_fwd(x64, w3d, b1, 1, 1, False, None, P)
+    elif what == "conv_in1_wgrad":   # weight gradient of the C_in = 1 first convolution (exact fp32)
+        ops.conv1d_wgrad(xa, dy, dw1c, db, 2, 1, False, 0)
     elif what == "conv_down":      # Conv1D(32, 4, strides=2) 32 -> 32 (conv_tc_kernel): the encoder's down-sampling convolution
         ops.conv1d_fwd(xs[i % 2], w4, b1, 2, 1, False, None, P)
     elif what == "conv_down_wgrad":

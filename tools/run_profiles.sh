@@ -28,9 +28,13 @@ full rs_bwd rs_kernel 3 python tools/bench_kernel.py stack_bwd $P
 DILS=27,9,3,1 full rs_train_rev rs_kernel 4 python tools/bench_kernel.py stack_train $P
 full wgrad_$P wgrad_tc_kernel 4 python tools/bench_kernel.py resblock_wgrad $P
 full conv_tc conv_tc_kernel 2 python tools/bench_kernel.py conv_down $P
+L=3520 full conv3_tc conv3_tc_kernel 2 python tools/bench_kernel.py conv3_up $P
 full wgrad4_tc wgrad4_tc_kernel 2 python tools/bench_kernel.py conv_down_wgrad $P
 full rb_fwd_masks_$P rb_tc_kernel 5 python tools/bench_kernel.py resblock_fwd_masks $P
 full vq_search vq2_kernel 2 python tools/profile_vq.py
 full vq_finish vq_finish_smem_kernel 2 python tools/profile_vq.py
+python tools/trace_vq.py > $O/trace_vq.txt 2>&1
+python tools/trace_wgrad.py > $O/trace_wgrad.txt 2>&1
+./tools/mma_probe > $O/mma_probe.txt 2>&1
 ls -la $O/prof_*.ncu-rep 2>/dev/null | awk '{print $5, $9}'
 cut -c1-300 $O/bench_final.json

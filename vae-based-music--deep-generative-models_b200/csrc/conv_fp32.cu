@@ -671,30 +671,54 @@ __global__ void __launch_bounds__(256) conv_in1_fwd_kernel(const float* __restri
 }
 
 constexpr int IN1_PART = (IN1_MAXK + 1) * 32;  // per-CTA partial: k tap rows + the bias row, 32 channels each
+template <int KT>  // taps handled (>= k): 4 for the encoders' Conv1D(32, 4, strides=2), else IN1_MAXK
 __global__ void __launch_bounds__(256) conv_in1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                              float* __restrict__ partial, long rows, int L, int Lo, int Co, int k,
                                                              int stride, int padL, long rpw) {
+  // A warp walks its rows four at a time: lane = (row in group, channel quad), so one warp instruction fetches 4 x 128 B of dy,
+  // and four groups are in flight per warp (unroll): the kernel is a pure stream over dy, its speed is the number of bytes in
+  // flight per SM (the one-row-per-instruction form of round 1 had 16 KB in flight per SM and ran at a fifth of the HBM rate).
   __shared__ float red[8][IN1_PART];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float acc[IN1_MAXK + 1];
+  const int rs = lane >> 3, q = lane & 7;
+  float acc[KT + 1][4];
 #pragma unroll
-  for (int j = 0; j <= IN1_MAXK; ++j) acc[j] = 0.f;
+  for (int j = 0; j <= KT; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
   const long r0 = ((long)blockIdx.x * 8 + warp) * rpw;
   const long r1 = r0 + rpw < rows ? r0 + rpw : rows;
-  long b = r0 / Lo;                  // one 64-bit division per warp, not per row
-  int t = (int)(r0 - b * Lo) - 1;
+  const bool qok = q * 4 < Co;
+  long b = (r0 + rs) / Lo;           // one 64-bit division per thread, not per row
+  int t = (int)(r0 + rs - b * Lo);
 #pragma unroll 4
-  for (long row = r0; row < r1; ++row) {
-    if (++t == Lo) { t = 0; ++b; }
-    const int g = t * stride + lane - padL;
-    const float xv = (lane < k && g >= 0 && g < L) ? x[b * L + g] : 0.f;
-    const float d = lane < Co ? dy[row * Co + lane] : 0.f;
+  for (long row = r0 + rs; row < r1; row += 4) {
+    const float4 d = qok ? *reinterpret_cast<const float4*>(dy + row * Co + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* xb = x + b * L;
+    const int g0 = t * stride - padL;
 #pragma unroll
-    for (int j = 0; j < IN1_MAXK; ++j) acc[j] = fmaf(__shfl_sync(0xffffffffu, xv, j), d, acc[j]);
-    acc[IN1_MAXK] += d;
+    for (int j = 0; j < KT; ++j) {
+      const int g = g0 + j;
+      const float xv = (j < k && g >= 0 && g < L) ? xb[g] : 0.f;
+      acc[j][0] = fmaf(xv, d.x, acc[j][0]); acc[j][1] = fmaf(xv, d.y, acc[j][1]);
+      acc[j][2] = fmaf(xv, d.z, acc[j][2]); acc[j][3] = fmaf(xv, d.w, acc[j][3]);
+    }
+    acc[KT][0] += d.x; acc[KT][1] += d.y; acc[KT][2] += d.z; acc[KT][3] += d.w;
+    t += 4;
+    while (t >= Lo) { t -= Lo; ++b; }
   }
+  // the four row groups of a warp (lanes q, q + 8, q + 16, q + 24), fixed order
+  for (int e = lane; e < IN1_PART; e += 32) red[warp][e] = 0.f;  // tap rows KT .. IN1_MAXK - 1 stay zero
+  __syncwarp();
 #pragma unroll
-  for (int j = 0; j <= IN1_MAXK; ++j) red[warp][j * 32 + lane] = acc[j];
+  for (int j = 0; j <= KT; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v = acc[j][c];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (rs == 0) red[warp][(j < KT ? j : IN1_MAXK) * 32 + q * 4 + c] = v;  // the bias row keeps its place behind IN1_MAXK tap rows
+    }
   __syncthreads();
   for (int e = tid; e < IN1_PART; e += 256) {
     float s_ = red[0][e];
@@ -877,7 +901,8 @@ int vqb_conv1d_wgrad(const vqb_conv_desc* d, const float* x, const float* dy, fl
     const long rows = (long)d->B * Lo;
     const int grid = conv_in1_grid(rows, &rpw);
     float* partial = (float*)workspace;
-    conv_in1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, dy, partial, rows, d->L, Lo, d->C_out, d->k, d->stride, padL, rpw);
+    if (d->k <= 4) conv_in1_wgrad_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, dy, partial, rows, d->L, Lo, d->C_out, d->k, d->stride, padL, rpw);
+    else conv_in1_wgrad_kernel<IN1_MAXK><<<grid, 256, 0, (cudaStream_t)stream>>>(x, dy, partial, rows, d->L, Lo, d->C_out, d->k, d->stride, padL, rpw);
     VQB_LAUNCH_CHECK();
     for (int j = 0; j < d->k; ++j) {  // dw [k, 1, C_out]: one fixed-order reduction per tap row (32-float rows in the partials)
       reduce_chunks_strided(partial, grid, IN1_PART, j * 32, d->C_out, dw + (size_t)j * d->C_out, (cudaStream_t)stream);

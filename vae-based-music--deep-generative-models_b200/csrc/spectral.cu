@@ -199,8 +199,11 @@ int vqb_spec_grad(const float* S, const float* mag_t, const float* coef, const f
   VQB_REQUIRE(S && mag_t && coef && upstream && G && bins >= 2, "vqb_spec_grad: bad arguments");
   const long total = B * per_example;
   if (total == 0) return VQB_OK;
+  // scale 1: the caller's inverse FFT is the UNNORMALISED one (irfft(..., norm="forward")), which saves the library's 1/n pass
+  // over the frames; n_fft is a power of two in every STFT scale of the reference, so the values are bit-identical to scaling
+  // by n here and by 1/n there
   spec_grad_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)S, mag_t, coef, upstream, per_example, bins,
-                                                                        (float)n_fft, (float2*)G, total);
+                                                                        1.0f, (float2*)G, total);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

@@ -90,7 +90,7 @@ class MultiSpectralLoss:
             dr = ops.empty(B, T)
             for s, (n_fft, hop, win) in enumerate(scales):
                 G = ops.spec_grad(specs[s], mags[s], coef[s], up, n_fft)
-                dfr = torch.fft.irfft(G, n=n_fft, dim=-1).contiguous()
+                dfr = torch.fft.irfft(G, n=n_fft, dim=-1, norm="forward").contiguous()  # unnormalised C2R: no 1/n pass
                 ops.stft_frames_bwd(dfr, T, hop, win, dr, s > 0)
             return [dr.reshape(r.shape)]
 
