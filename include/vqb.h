@@ -322,6 +322,12 @@ int vqb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
 int vqb_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float b1, float b2,
                       float eps, float grad_scale, const int64_t* step_counter, void* stream);
 int vqb_increment(int64_t* counter, void* stream);
+/* out[i] = sum_{j in [term_start[i], term_start[i+1])} term_coef[j] * term_ptr[j][0],  i < n_out <= 32, <= 96 terms: the loss
+ * bookkeeping of train_step (vqvae.py:127-146: level_loss = recon + commit + spectral, the sums over levels, the metric
+ * increments) as ONE launch instead of one library kernel per `+`.  term_start / term_ptr / term_coef are HOST arrays (term_ptr
+ * holds device pointers); the terms of an output are added in order. */
+int vqb_lincomb(int32_t n_out, const int32_t* term_start, const float* const* term_ptr, const float* term_coef, float* out,
+                void* stream);
 
 #ifdef __cplusplus
 }

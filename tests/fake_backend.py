@@ -407,6 +407,19 @@ class FakeBackend:
     def vqb_adam_step_dev(self, p, g, m, v, n, lr_dev, b1, b2, eps, gs, step, stream):
         return self.vqb_adam_step(p, g, m, v, n, float(_t(lr_dev, (1,))[0]), b1, b2, eps, gs, step, stream)
 
+    def vqb_lincomb(self, n_out, term_start, term_ptr, term_coef, out, stream):
+        st = _t(term_start, (n_out + 1,), np.int32)
+        n = int(st[n_out])
+        ptrs = np.frombuffer((C.c_void_p * max(n, 1)).from_address(int(term_ptr)), dtype=np.uint64)[:n]
+        cf = _t(term_coef, (max(n, 1),))
+        o = _t(out, (n_out,))
+        for i in range(n_out):
+            s_ = torch.zeros((), dtype=torch.float32)
+            for j in range(int(st[i]), int(st[i + 1])):
+                s_ = s_ + cf[j] * _t(int(ptrs[j]), (1,))[0]
+            o[i] = s_
+        return 0
+
     def vqb_increment(self, c, stream):
         _t(c, (1,), np.int64).add_(1)
         return 0

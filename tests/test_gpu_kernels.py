@@ -383,3 +383,20 @@ def test_multispectral_loss_kernels_match_oracle(gpu, B, T):
     # the public helpers keep the reference's semantics (data_utils.py:25-40)
     s = V.data_utils.spectral(dev(x).squeeze(-1), 512, 50, 240)
     close(s, O.spectral(torch.tensor(x).squeeze(-1), 512, 50, 240), tol=2e-5, what="spectral")
+
+
+def test_lincomb_one_launch(gpu):
+    """vqb_lincomb: the loss bookkeeping of train_step (vqvae.py:127-146) as one launch; terms are added in order, in fp32."""
+    ops = gpu.ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    leaves = [torch.randn(3, device="cuda", generator=g) for _ in range(7)]
+    outs = [[(leaves[0][0:1], 1.0), (leaves[1][1:2], 1.0), (leaves[2][2:3], 1.0)], [], [(leaves[3][0:1], 0.25)],
+            [(leaves[i][0:1], float(i)) for i in range(7)]]
+    got = ops.lincomb(outs).cpu()
+    want = []
+    for terms in outs:
+        acc = torch.zeros((), dtype=torch.float32)
+        for t, c in terms:
+            acc = acc + torch.tensor(c, dtype=torch.float32) * t.cpu()[0]
+        want.append(acc)
+    assert torch.equal(got, torch.stack(want))

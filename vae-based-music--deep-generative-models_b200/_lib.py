@@ -110,6 +110,7 @@ SIGNATURES = {
                                 C.c_float, _P, _P]),
     "vqb_adam_step_dev": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
     "vqb_increment": (C.c_int, [_P, _P]),
+    "vqb_lincomb": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P]),
 }
 
 _BACKEND = None  # ctypes.CDLL, or an injected test double

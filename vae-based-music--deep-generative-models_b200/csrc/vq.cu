@@ -452,6 +452,20 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 __global__ void increment_kernel(int64_t* c) { c[0] += 1; }
 
+struct LincombParams {
+  const float* ptr[96];
+  float coef[96];
+  int start[33];
+  int n_out;
+};
+__global__ void lincomb_kernel(const LincombParams p, float* __restrict__ out) {
+  const int i = threadIdx.x;
+  if (i >= p.n_out) return;
+  float s = 0.f;
+  for (int j = p.start[i]; j < p.start[i + 1]; ++j) s = __fadd_rn(s, __fmul_rn(p.coef[j], p.ptr[j][0]));
+  out[i] = s;
+}
+
 }  // namespace vqb
 
 using namespace vqb;
@@ -657,6 +671,27 @@ int vqb_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, c
   int nb = cdiv(n, 256);
   if (nb > 148 * 16) nb = 148 * 16;
   adam_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, lr_dev, b1, b2, eps, grad_scale, step_counter);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+int vqb_lincomb(int32_t n_out, const int32_t* term_start, const float* const* term_ptr, const float* term_coef, float* out,
+                void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(n_out >= 0 && n_out <= 32 && (n_out == 0 || (term_start && term_ptr && term_coef && out)), "vqb_lincomb: bad argument");
+  if (n_out == 0) return VQB_OK;
+  VQB_REQUIRE(term_start[0] == 0 && term_start[n_out] <= 96, "vqb_lincomb: at most 96 terms (got %d)", term_start[n_out]);
+  LincombParams p{};
+  p.n_out = n_out;
+  for (int i = 0; i <= n_out; ++i) {
+    VQB_REQUIRE(i == 0 || term_start[i] >= term_start[i - 1], "vqb_lincomb: term_start must be non-decreasing");
+    p.start[i] = term_start[i];
+  }
+  for (int j = 0; j < term_start[n_out]; ++j) {
+    VQB_REQUIRE(term_ptr[j] != nullptr, "vqb_lincomb: NULL term %d", j);
+    p.ptr[j] = term_ptr[j]; p.coef[j] = term_coef[j];
+  }
+  lincomb_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, out);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

@@ -452,6 +452,23 @@ def adam_step_dev(p, g, m, v, lr_dev, b1, b2, eps, grad_scale, step_counter):
          float(grad_scale), ptr(step_counter), _lib.stream())
 
 
+def lincomb(outputs):
+    """outputs: list of term lists [(tensor with >= 1 element, coefficient), ...] -> float32 vector [len(outputs)] of the
+    weighted sums of the tensors' first elements, ONE launch (vqb_lincomb)."""
+    starts, ptrs, coefs, keep = [0], [], [], []
+    for terms in outputs:
+        for t, c in terms:
+            _chk(t, "term")
+            ptrs.append(ptr(t)); coefs.append(float(c)); keep.append(t)
+        starts.append(len(ptrs))
+    out = empty(len(outputs))
+    n = len(ptrs)
+    call("vqb_lincomb", len(outputs), C.cast((C.c_int32 * len(starts))(*starts), C.c_void_p),
+         C.cast((C.c_void_p * max(n, 1))(*ptrs), C.c_void_p), C.cast((C.c_float * max(n, 1))(*coefs), C.c_void_p), ptr(out),
+         _lib.stream())
+    return out
+
+
 def increment(counter):
     call("vqb_increment", ptr(counter), _lib.stream())
 

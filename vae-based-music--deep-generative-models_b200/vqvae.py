@@ -266,10 +266,11 @@ class VQVAE(Model):
         level_losses, recon_losses, commit_losses, spectral_losses = losses
         parts = [sum(level_losses), sum(recon_losses), sum(commit_losses), sum(spectral_losses),
                  *level_losses, *recon_losses, *commit_losses, *spectral_losses]
-        vec = [p.tensor().reshape(1) for p in parts]
-        for vq in self.vqs:
-            vec.append(vq._metrics_buf if (vq._metrics_buf is not None and self.train_step_training) else ops.zeros(3))
-        return torch.cat(vec)
+        outs = [list(p.terms) for p in parts]   # every entry is a linear combination of the loss kernels' scalars ...
+        for vq in self.vqs:                     # ... or one of a VQ layer's three usage / entropy metrics
+            buf = vq._metrics_buf if (vq._metrics_buf is not None and self.train_step_training) else None
+            outs.extend([[(buf[i:i + 1], 1.0)] if buf is not None else [] for i in range(3)])
+        return ops.lincomb(outs)                # one launch (vqb_lincomb) instead of a library kernel per `+` and a concatenation
 
     def _graph_train_step(self, raw):
         key = (tuple(raw.shape), vdist.world_size(), self.train_step_training, self.spectral_weight,
