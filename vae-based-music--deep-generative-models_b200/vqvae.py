@@ -331,19 +331,30 @@ class VQVAE(Model):
 
     def _capture(self, st, world):
         """Captures train_step for st["x"].  One process: ONE graph (forward + backward of every level, EMA + Adam + metric
-        vector).  Data parallel: graph A (forward + backward), the NCCL all-reduce of [gradients | EMA statistics | loss scalars]
-        issued by torch.distributed between the replays, graph B (EMA + Adam + metrics).  (Capturing the collective into the
-        step graph was tried in round 2 and hung at the first replay on 2 GPUs — ProcessGroupNCCL's side-stream / watchdog
-        interplay under capture with the level streams — so it stays outside; it costs two graph launches and one host-side
-        enqueue per step, 0.1 ms of a 7.9 ms step at 8 GPUs.)"""
+        vector).  Data parallel, default: graph A (forward + backward), torch.distributed.all_reduce of [gradients | EMA
+        statistics | loss scalars] between the replays, graph B (EMA + Adam + metrics).  With VQB_DP_INGRAPH=1 the collective is
+        captured too — ONE graph per step — through dist.GraphComm (a communicator of our own on the loaded NCCL library:
+        ncclAllReduce on the capture stream; capturing torch.distributed.all_reduce itself hung at the first replay).  Verified on
+        2 and 8 B200 (bit-identical ranks), but measured 0.4-0.8 % slower than the two-graph form, hence opt-in."""
         torch.cuda.synchronize()
         self.optimizer.refresh_lr()
         pool = torch.cuda.graph_pool_handle()
         st["gone"] = None
-        if world == 1:
+        gc = vdist.graph_comm() if world > 1 else None   # a communicator whose all-reduce can be captured (dist.GraphComm)
+        if world == 1 or gc is not None:
+            kw = {}
+            if gc is not None:
+                # NCCL sets up channels / protocols lazily per message size: once at full size outside the capture; its proxy thread
+                # may touch the CUDA API while we capture, hence the thread-local capture mode
+                tmp = torch.zeros_like(self._packed.comm)
+                gc.all_reduce_sum(tmp)
+                torch.cuda.synchronize()
+                kw["capture_error_mode"] = "thread_local"
             g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1, pool=pool):
+            with torch.cuda.graph(g1, pool=pool, **kw):
                 grads, tvars, losses = self._head(st["x"], world)
+                if gc is not None:
+                    gc.all_reduce_sum(self._packed.comm)   # [gradients | EMA statistics + restart rows | loss scalars], inside the graph
                 st["vec"] = self._tail(grads, tvars, losses, world)
             st["gone"] = g1
             st["graph"] = True
