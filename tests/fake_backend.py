@@ -408,15 +408,14 @@ class FakeBackend:
         return self.vqb_adam_step(p, g, m, v, n, float(_t(lr_dev, (1,))[0]), b1, b2, eps, gs, step, stream)
 
     def vqb_lincomb(self, n_out, term_start, term_ptr, term_coef, out, stream):
-        st = _t(term_start, (n_out + 1,), np.int32)
-        n = int(st[n_out])
-        ptrs = np.frombuffer((C.c_void_p * max(n, 1)).from_address(int(term_ptr)), dtype=np.uint64)[:n]
-        cf = _t(term_coef, (max(n, 1),))
+        st = C.cast(term_start, C.POINTER(C.c_int32))
+        ptrs = C.cast(term_ptr, C.POINTER(C.c_void_p))
+        cf = C.cast(term_coef, C.POINTER(C.c_float))
         o = _t(out, (n_out,))
         for i in range(n_out):
             s_ = torch.zeros((), dtype=torch.float32)
-            for j in range(int(st[i]), int(st[i + 1])):
-                s_ = s_ + cf[j] * _t(int(ptrs[j]), (1,))[0]
+            for j in range(st[i], st[i + 1]):
+                s_ = s_ + torch.tensor(cf[j], dtype=torch.float32) * _t(ptrs[j], (1,))[0]
             o[i] = s_
         return 0
 

@@ -403,3 +403,34 @@ def test_checkpoint_carries_optimizer_and_restart_state(cpu_backend, tmp_path):
                                      "down_depth": [3], "strides": [2]})
     with pytest.raises(ValueError):
         m3.load_weights(str(tmp_path / "ck"))
+
+
+def test_step_vector_is_one_lincomb_call(cpu_backend):
+    """The metric increments of a captured step (`VQVAE._step_vector`: total / per-kind / per-level losses in `_all_trackers()`
+    order + the VQ layers' usage / entropy metrics) come from ONE vqb_lincomb call and equal the sums formed term by term."""
+    V = cpu_backend
+    m, spec, weights, vq, x = build_tiny(V)
+    m.compile(optimizer=V.keras.optimizers.Adam())
+    grads, tvars, losses = m._forward_backward(V.keras_compat.convert_to_tensor(x))
+    n0 = V._lib.launches()
+    vec = m._step_vector(losses)
+    assert V._lib.launches() - n0 == 1
+    level, recon, commit, spectral = losses
+    L = len(level)
+    want = [sum(float(v) for v in level), sum(float(v) for v in recon), sum(float(v) for v in commit), sum(float(v) for v in spectral)]
+    want += [float(v) for v in (*level, *recon, *commit, *spectral)]
+    got = vec.cpu().numpy()
+    assert got.shape == (4 + 4 * L + 3 * L,)
+    np.testing.assert_allclose(got[:4 + 4 * L], np.array(want, dtype=np.float32), rtol=1e-6)
+
+
+def test_in_graph_collective_is_opt_in_and_nccl_only(cpu_backend, monkeypatch):
+    """dist.graph_comm(): None unless VQB_DP_INGRAPH=1 AND torch.distributed runs on NCCL (the CPU tests' gloo group never gets one)."""
+    V = cpu_backend
+    monkeypatch.setattr(V.dist, "_graph_comm", None)
+    monkeypatch.delenv("VQB_DP_INGRAPH", raising=False)
+    assert V.dist.graph_comm() is None
+    monkeypatch.setattr(V.dist, "_graph_comm", None)
+    monkeypatch.setenv("VQB_DP_INGRAPH", "1")
+    assert V.dist.graph_comm() is None   # no process group at all in this test
+    monkeypatch.setattr(V.dist, "_graph_comm", None)
