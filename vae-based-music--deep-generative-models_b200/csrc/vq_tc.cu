@@ -419,7 +419,6 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
   int* pi1 = reinterpret_cast<int*>(pm2 + 2 * (V2_PARTS - 1) * VT_ROWS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = blockIdx.x < p.ntiles ? (int)((p.ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
-  const bool getenv_spin = TRACE;
 
   if (warp == 0) tmem_alloc(tslot, 512);
   if (tid == 32) {
@@ -468,7 +467,7 @@ __global__ void __launch_bounds__(V2_NSCAN + 32, 1) vq2_kernel(const Vq2Params p
           }
           commit(&bar[1 + ch]);
           V2_TR(2 + 2 * ch);
-          if (TRACE && p.trace && blockIdx.x == 0 && it == 4 && getenv_spin) {  // tile 4 only: spin (test_wait, no suspend) until the chunk has completed
+          if (TRACE && p.trace && blockIdx.x == 0 && it == 4) {  // tile 4 only: spin (test_wait, no suspend) until the chunk has completed
             uint32_t ok = 0;
             while (!ok)
               asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
