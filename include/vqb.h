@@ -98,7 +98,8 @@ int vqb_conv1d_wgrad(const vqb_conv_desc* d, const float* x, const float* dy, fl
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Optional batching of the weight-gradient reductions: between vqb_reduce_begin() and vqb_reduce_flush(stream) (same host
- * thread) the *_wgrad calls only enqueue their partial-sum kernels and leave dw / dbias UNWRITTEN; vqb_reduce_flush launches
+ * thread) the *_wgrad calls only enqueue their partial-sum kernels and MAY leave dw / dbias unwritten (the tensor-core kernels of
+ * the k = 3, 32 -> 32 convolutions reduce inside their own launch and write at once); vqb_reduce_flush launches
  * all pending fixed-order reductions as a few batched kernels.  Workspaces passed to those calls must stay alive until the
  * flush.  Without begin/flush every *_wgrad call is self-contained. */
 int vqb_reduce_begin(void);

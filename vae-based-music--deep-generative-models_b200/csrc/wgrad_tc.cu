@@ -32,6 +32,12 @@ struct WgTcParams {
   float* partialq[MAXP];
   int dilq[MAXP], reluq[MAXP];
   int nprob;
+  // The fixed-order sum over a problem's per-CTA partials happens inside the launch: the CTA that finishes a problem last
+  // (counter in the workspace, zeroed by a memset node before the launch) adds the partials in the order of reduce_chunks_kernel
+  // and writes dw / dbias — no separate reduction launches (they were 1.2 % of a training step).
+  float* dwq[MAXP];
+  float* dbq[MAXP];
+  unsigned* counters;
   long long* trace;  // TRACE build (tools/trace_wgrad.py): clock64 stamps of CTA 0's tiles 6..9, [4][8]
 };
 
@@ -286,6 +292,54 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
       out[e] = t;
     }
   }
+  if (pp.counters) {
+    __shared__ int is_last;
+    __threadfence();  // this CTA's partial is visible device-wide before it is counted
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(&pp.counters[prob], 1u) == (unsigned)(nblk - 1);
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const float* base = p.partial;  // [nblk][PART]
+      float* dw = pp.dwq[prob];
+      float* db = pp.dbq[prob];
+      // three elements x eight chains = 24 independent loads per step: a single CTA has to pull nblk x 12 KB out of L2, and
+      // with one load in flight per thread that took longer than the separate reduction kernels it replaces
+      constexpr int EB = 3;
+      for (int e0 = tid; e0 < Cfg::PART; e0 += EB * (NT + 32)) {
+        float sl[EB][8];
+#pragma unroll
+        for (int k = 0; k < EB; ++k)
+#pragma unroll
+          for (int l = 0; l < 8; ++l) sl[k][l] = 0.f;
+        for (int c0 = 0; c0 < nblk; c0 += 8) {
+          float v[EB][8];
+#pragma unroll
+          for (int k = 0; k < EB; ++k)
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+              const int e = e0 + k * (NT + 32);
+              v[k][l] = (c0 + l < nblk && e < Cfg::PART) ? __ldcg(base + (size_t)(c0 + l) * Cfg::PART + e) : 0.f;
+            }
+#pragma unroll
+          for (int k = 0; k < EB; ++k)
+#pragma unroll
+            for (int l = 0; l < 8; ++l) sl[k][l] += v[k][l];  // chain l: chunks l, l + 8, ... in order (+ 0.f past the end: exact)
+        }
+#pragma unroll
+        for (int k = 0; k < EB; ++k) {
+          const int e = e0 + k * (NT + 32);
+          if (e < Cfg::PART) {
+            float t = 0.f;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) t += sl[k][l];  // the summation tree of reduce_chunks_kernel
+            if (e < 3 * 32 * 32) dw[e] = t;
+            else if (db) db[e - 3 * 32 * 32] = t;
+          }
+        }
+      }
+    }
+  }
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
@@ -373,19 +427,13 @@ int resblock_wgrad_tc(const vqb_conv_desc* d, int n, const int* dilations, const
     p.partialq[q] = (float*)ws + (size_t)q * g * PART;
   }
   p.ga = p.gaq[0]; p.ot = p.otq[0]; p.dil = p.dilq[0]; p.relu_ga = 1; p.partial = p.partialq[0];
-  int rc = launch_wg_any(wg_split(d->precision), p, np * g, st);
-  if (rc) return rc;
   for (int q = 0; q < np; ++q) {
-    float* dw = (q & 1) ? dw2[q >> 1] : dw1[q >> 1];
-    float* db = (q & 1) ? db2[q >> 1] : db1[q >> 1];
-    reduce_chunks_strided(p.partialq[q], g, PART, 0, 3 * 32 * 32, dw, st);
-    VQB_LAUNCH_CHECK();
-    if (db) {
-      reduce_chunks_strided(p.partialq[q], g, PART, 3 * 32 * 32, 32, db, st);
-      VQB_LAUNCH_CHECK();
-    }
+    p.dwq[q] = (q & 1) ? dw2[q >> 1] : dw1[q >> 1];
+    p.dbq[q] = (q & 1) ? db2[q >> 1] : db1[q >> 1];
   }
-  return VQB_OK;
+  p.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + need - 64);  // the spare tail of the workspace
+  VQB_CUDA(cudaMemsetAsync(p.counters, 0, WgTcParams::MAXP * sizeof(unsigned), st));
+  return launch_wg_any(wg_split(d->precision), p, np * g, st);
 }
 
 int conv1d_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, void* ws,
@@ -399,17 +447,10 @@ int conv1d_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* dy, flo
   p.total_tiles = d->B * p.tiles_per_b;
   const int S = wg_split(d->precision);
   p.nprob = 1;
-  int rc = launch_wg_any(S, p, grid, st);
-  if (rc) return rc;
-  constexpr int PART = WgCfg<1>::PART;
-  // dw and dbias are separate buffers: two fixed-order reductions over the per-CTA partials
-  reduce_chunks_strided(p.partial, grid, PART, 0, 3 * 32 * 32, dw, st);
-  VQB_LAUNCH_CHECK();
-  if (dbias) {
-    reduce_chunks_strided(p.partial, grid, PART, 3 * 32 * 32, 32, dbias, st);
-    VQB_LAUNCH_CHECK();
-  }
-  return VQB_OK;
+  p.dwq[0] = dw; p.dbq[0] = dbias;
+  p.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + need - 64);
+  VQB_CUDA(cudaMemsetAsync(p.counters, 0, WgTcParams::MAXP * sizeof(unsigned), st));
+  return launch_wg_any(S, p, grid, st);
 }
 
 }  // namespace vqb
