@@ -171,6 +171,14 @@ size_t vqb_resstack_workspace_bytes(const vqb_resstack_desc* d);
 int vqb_resstack_fwd(const vqb_resstack_desc* d, const float* x, const float* const* w1, const float* const* b1,
                      const float* const* w2, const float* const* b2, float* const* h, float* const* y,
                      uint32_t* const* xbits, uint32_t* const* hbits, void* workspace, size_t workspace_bytes, void* stream);
+/* vqb_resstack_fwd for callers that OWN the workspace (one buffer per DilatedResnet1D, never handed to anything else, e.g. a
+ * member of the layer object): no earlier kernel of the stream can be using that memory, so the weight-packing launch MAY run
+ * under programmatic dependent launch next to the previous kernel (VQB_RS_EARLY_PACK=1; measured slower on B200, off by
+ * default).  Same results as vqb_resstack_fwd. */
+int vqb_resstack_fwd_private_ws(const vqb_resstack_desc* d, const float* x, const float* const* w1, const float* const* b1,
+                                const float* const* w2, const float* const* b2, float* const* h, float* const* y,
+                                uint32_t* const* xbits, uint32_t* const* hbits, void* workspace, size_t workspace_bytes,
+                                void* stream);
 int vqb_resstack_bwd_data(const vqb_resstack_desc* d, const float* dy, const float* const* w1, const float* const* w2,
                           const uint32_t* const* xbits, const uint32_t* const* hbits, float* const* dh, float* const* dx,
                           void* workspace, size_t workspace_bytes, void* stream);

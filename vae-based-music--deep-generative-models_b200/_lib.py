@@ -83,6 +83,7 @@ SIGNATURES = {
     "vqb_resstack_supports": (C.c_int, [_SD]),
     "vqb_resstack_workspace_bytes": (C.c_size_t, [_SD]),
     "vqb_resstack_fwd": (C.c_int, [_SD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vqb_resstack_fwd_private_ws": (C.c_int, [_SD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_resstack_bwd_data": (C.c_int, [_SD, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_resstack_bwd_data_packed": (C.c_int, [_SD, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vqb_dec_tail_supports": (C.c_int, [_TD]),

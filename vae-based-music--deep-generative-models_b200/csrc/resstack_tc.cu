@@ -74,6 +74,8 @@ struct RsPackParams {  // up to 2 * RS_MAXC records: a training forward also pac
   const float* bias[2 * RS_MAXC];
   int sj[2 * RS_MAXC], si[2 * RS_MAXC], so[2 * RS_MAXC], flip[2 * RS_MAXC];
   uint8_t* out;
+  int early;  // launched with the programmatic-serialization attribute: `out` is private to the stack (nobody else touches it), so
+              // the whole kernel may run before the previous kernel of the stream has completed (vqb_resstack_fwd_private_ws)
 };
 
 // One block per convolution: element (tap j, in-channel k, out-channel n) at w[jj*sj + k*si + n*so] (jj = flip ? 2-j : j) ->
@@ -81,6 +83,7 @@ struct RsPackParams {  // up to 2 * RS_MAXC records: a training forward also pac
 // gain  max_n sum_{j,k} |w|  (L1 bound) and the bias.
 __global__ void __launch_bounds__(256) rs_pack_kernel(const RsPackParams p) {
   const int c = blockIdx.x, tid = threadIdx.x;
+  if (p.early) pdl_launch_dependents();
   __shared__ float l1p[8][32];
   __shared__ uint32_t mx;
   if (tid == 0) mx = 0u;
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(256) rs_pack_kernel(const RsPackParams p) {
     meta[4 + tid] = b;
     if (tid == 0) { meta[0] = sw; meta[1] = l * 1.0001f; meta[2] = __uint_as_float(bm); meta[3] = 0.f; }
   }
+  if (p.early) pdl_wait();  // completion stays transitive: whoever waits for this kernel has waited for its predecessors too
 }
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -566,7 +570,7 @@ static int pick_mb(const vqb_resstack_desc* d, int H) {
 // run from the same workspace without a packing launch of its own (`prepacked`).
 int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const float* const* w1, const float* const* b1,
                 const float* const* w2, const float* const* b2, float* const* o1, float* const* o2, uint32_t* const* xbits,
-                uint32_t* const* hbits, void* ws, size_t ws_bytes, cudaStream_t st, bool prepacked = false) {
+                uint32_t* const* hbits, void* ws, size_t ws_bytes, cudaStream_t st, bool prepacked = false, bool private_ws = false) {
   if (!resstack_tc_supported(d))
     return set_err(VQB_ERR_UNIMPLEMENTED, "fused residual stack: C = 32, 1..%d blocks, dilations < %d, fp16x2 only", VQB_RESSTACK_MAX_BLOCKS, RsCfg4::G);
   if (d->B == 0 || d->L == 0) return VQB_OK;
@@ -630,7 +634,16 @@ int resstack_tc(int kind, const vqb_resstack_desc* d, const float* in, const flo
     npack = 2 * nconv;
   }
   if (!(kind == 2 && prepacked)) {
-    rs_pack_kernel<<<npack, 256, 0, st>>>(pk);
+    // Measured (three A/B pairs on one B200): launching the packing kernel early costs time instead of saving it (7.31-7.38 ms
+    // per training step against 7.23-7.25 with the plain launch) — its CTAs land in the middle of the persistent kernel before
+    // it.  So the early launch stays behind VQB_RS_EARLY_PACK=1; the private workspace itself (no allocation per call) is kept.
+    static const bool early_ok = getenv("VQB_RS_EARLY_PACK") && atoi(getenv("VQB_RS_EARLY_PACK")) == 1;
+    if (private_ws && early_ok) {  // the images go to memory no earlier kernel can be using: packing overlaps the predecessor's run
+      pk.early = 1;
+      VQB_CUDA(launch_pdl(rs_pack_kernel, dim3(npack), dim3(256), (size_t)0, st, pk));
+    } else {
+      rs_pack_kernel<<<npack, 256, 0, st>>>(pk);
+    }
     VQB_LAUNCH_CHECK();
   }
   if (kind == 0 && mbsel == 4 && getenv("VQB_RS_TRACE")) {  // profiling aid: address of a device buffer of 5 * 9 * 8 int64 (tools/trace_stack.py)
@@ -674,6 +687,21 @@ int vqb_resstack_fwd(const vqb_resstack_desc* d, const float* x, const float* co
       VQB_REQUIRE(h[i] && y[i] && xbits[i] && hbits[i], "vqb_resstack_fwd: training forward needs h, y, xbits, hbits of block %d", i);
   }
   return resstack_tc(train ? 1 : 0, d, x, w1, b1, w2, b2, h, y, xbits, hbits, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int vqb_resstack_fwd_private_ws(const vqb_resstack_desc* d, const float* x, const float* const* w1, const float* const* b1,
+                                const float* const* w2, const float* const* b2, float* const* h, float* const* y,
+                                uint32_t* const* xbits, uint32_t* const* hbits, void* workspace, size_t workspace_bytes, void* stream) {
+  VQB_ARCH();
+  VQB_REQUIRE(d && x && w1 && w2 && y, "vqb_resstack_fwd_private_ws: NULL pointer");
+  VQB_REQUIRE(d->B >= 0 && d->L >= 0, "vqb_resstack_fwd_private_ws: bad shape B=%d L=%d", d->B, d->L);
+  const bool train = h != nullptr;
+  if (train) {
+    VQB_REQUIRE(xbits && hbits, "vqb_resstack_fwd_private_ws: h given without xbits / hbits (training forward stores all of them)");
+    for (int i = 0; i < d->n_blocks && i < VQB_RESSTACK_MAX_BLOCKS; ++i)
+      VQB_REQUIRE(h[i] && y[i] && xbits[i] && hbits[i], "vqb_resstack_fwd_private_ws: training forward needs h, y, xbits, hbits of block %d", i);
+  }
+  return resstack_tc(train ? 1 : 0, d, x, w1, b1, w2, b2, h, y, xbits, hbits, workspace, workspace_bytes, (cudaStream_t)stream, false, true);
 }
 
 int vqb_resstack_bwd_data(const vqb_resstack_desc* d, const float* dy, const float* const* w1, const float* const* w2,

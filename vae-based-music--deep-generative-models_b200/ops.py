@@ -257,7 +257,13 @@ def _parr(ts):
     return C.cast((C.c_void_p * len(ts))(*[ptr(t) for t in ts]), C.c_void_p)
 
 
-def resstack_fwd(x, w1s, b1s, w2s, b2s, dilations, precision, train):
+def resstack_workspace(Cc, dilations, precision):
+    """A workspace for resstack_fwd(..., ws=...) that the caller keeps for itself (one per DilatedResnet1D)."""
+    d = _sdesc(1, 1, Cc, list(dilations), precision)
+    return torch.empty(max(int(_lib.lib().vqb_resstack_workspace_bytes(C.byref(d))), 16), dtype=torch.uint8, device=_lib.device())
+
+
+def resstack_fwd(x, w1s, b1s, w2s, b2s, dilations, precision, train, ws=None):
     """A chain of len(dilations) residual blocks in one launch (vqb_resstack_fwd).  Returns (ys, hs, xbits, hbits, ws): under a
     tape (`train`) every block's h, output and sign masks (lists of n tensors) and the workspace with the packed operand
     images of both directions (hand it to resstack_bwd_data), else ys = [None, ..., y_last] and hs, xbits, hbits, ws = None
@@ -268,17 +274,20 @@ def resstack_fwd(x, w1s, b1s, w2s, b2s, dilations, precision, train):
     B, L, Cc = x.shape
     n = len(dilations)
     d = _sdesc(B, L, Cc, list(dilations), precision)
-    ws = _ws(_lib.lib().vqb_resstack_workspace_bytes(C.byref(d)))
+    # ws given: the caller's own buffer (nothing else ever uses it), which lets the packing launch overlap the previous kernel
+    entry = "vqb_resstack_fwd_private_ws" if ws is not None else "vqb_resstack_fwd"
+    if ws is None:
+        ws = _ws(_lib.lib().vqb_resstack_workspace_bytes(C.byref(d)))
     if train:
         ys = [empty(B, L, Cc) for _ in range(n)]
         hs = [empty(B, L, Cc) for _ in range(n)]
         xb = [torch.empty(B, L, dtype=torch.int32, device=_lib.device()) for _ in range(n)]
         hb = [torch.empty(B, L, dtype=torch.int32, device=_lib.device()) for _ in range(n)]
-        call("vqb_resstack_fwd", C.byref(d), ptr(x), _parr(w1s), _parr(b1s), _parr(w2s), _parr(b2s), _parr(hs), _parr(ys),
+        call(entry, C.byref(d), ptr(x), _parr(w1s), _parr(b1s), _parr(w2s), _parr(b2s), _parr(hs), _parr(ys),
              _parr(xb), _parr(hb), ptr(ws), ws.numel(), _lib.stream())
         return ys, hs, xb, hb, ws
     ys = [None] * (n - 1) + [empty(B, L, Cc)]
-    call("vqb_resstack_fwd", C.byref(d), ptr(x), _parr(w1s), _parr(b1s), _parr(w2s), _parr(b2s), None, _parr(ys), None, None,
+    call(entry, C.byref(d), ptr(x), _parr(w1s), _parr(b1s), _parr(w2s), _parr(b2s), None, _parr(ys), None, None,
          ptr(ws), ws.numel(), _lib.stream())
     return ys, None, None, None, None
 

@@ -130,7 +130,13 @@ class DilatedResnet1D(layers.Layer):
         w2 = [c2.kernel.value for _, c2 in convs]; b2 = [c2.bias.value for _, c2 in convs]
         dils = [b.dilation for b in chunk]
         taping = GradientTape.current() is not None
-        ys, hs, xbits, hbits, ws = ops.resstack_fwd(x, w1, b1, w2, b2, dils, prec, train=taping)
+        # the chain's own workspace (packed operand images of its weights), kept on its first block: memory nothing else uses, so
+        # the packing launch may overlap the previous kernel (vqb_resstack_fwd_private_ws)
+        own = getattr(chunk[0], "_stack_ws", None)
+        if own is None or own.device != x.device or getattr(chunk[0], "_stack_ws_key", None) != (tuple(dils), prec):
+            own = ops.resstack_workspace(x.shape[-1], dils, prec)
+            chunk[0]._stack_ws, chunk[0]._stack_ws_key = own, (tuple(dils), prec)
+        ys, hs, xbits, hbits, ws = ops.resstack_fwd(x, w1, b1, w2, b2, dils, prec, train=taping, ws=own)
         y = ys[-1]
         if not taping:
             return y
