@@ -445,5 +445,7 @@ def test_checkpoint_round_trip_on_device(gpu, tmp_path):
     for a, b in zip(m.variables, m2.variables):
         if a.trainable:
             assert np.array_equal(a.numpy(), b.numpy()), a.name
-        else:  # VQ state: the per-code sums are accumulated with shared-memory atomics (order, hence the last bit, varies per run)
-            np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=2e-6, atol=1e-7, err_msg=a.name)
+        else:  # VQ state: the per-code sums are accumulated with shared-memory atomics, so the summation order — and with it the
+            # last bits of a sum, relative to its largest ADDEND, not to a result that may be a near-cancellation — varies per run
+            an = a.numpy()
+            np.testing.assert_allclose(an, b.numpy(), rtol=2e-6, atol=2e-6 * float(np.abs(an).max()), err_msg=a.name)

@@ -345,6 +345,10 @@ __global__ void __launch_bounds__(NT_ + 32, 1) wgrad_tc_kernel(const WgTcParams 
   if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
+// in-kernel reduction (last CTA of a problem) only up to this many partials per problem: one CTA pulling 12 KB per partial out of
+// L2 is quicker than the separate reduction launches for the 18 partials of a batched launch, not for the 74-148 of a small one
+constexpr int WG_INKERNEL_MAX = 32;
+
 static int wg_split(int precision) { return (precision == VQB_PREC_BF16X3 || precision == VQB_PREC_FP16X2) ? 3 : precision == VQB_PREC_BF16X2 ? 2 : 1; }
 
 bool wgrad_tc_supported(const vqb_conv_desc* d) {
@@ -431,9 +435,22 @@ int resblock_wgrad_tc(const vqb_conv_desc* d, int n, const int* dilations, const
     p.dwq[q] = (q & 1) ? dw2[q >> 1] : dw1[q >> 1];
     p.dbq[q] = (q & 1) ? db2[q >> 1] : db1[q >> 1];
   }
-  p.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + need - 64);  // the spare tail of the workspace
-  VQB_CUDA(cudaMemsetAsync(p.counters, 0, WgTcParams::MAXP * sizeof(unsigned), st));
-  return launch_wg_any(wg_split(d->precision), p, np * g, st);
+  if (g <= WG_INKERNEL_MAX) {  // few partials per problem (a batched launch): the last CTA of each problem adds them up
+    p.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + need - 64);  // the spare tail of the workspace
+    VQB_CUDA(cudaMemsetAsync(p.counters, 0, WgTcParams::MAXP * sizeof(unsigned), st));
+    return launch_wg_any(wg_split(d->precision), p, np * g, st);
+  }
+  int rc = launch_wg_any(wg_split(d->precision), p, np * g, st);  // many partials: the parallel reduction kernels are faster than one CTA
+  if (rc) return rc;
+  for (int q = 0; q < np; ++q) {
+    reduce_chunks_strided(p.partialq[q], g, PART, 0, 3 * 32 * 32, p.dwq[q], st);
+    VQB_LAUNCH_CHECK();
+    if (p.dbq[q]) {
+      reduce_chunks_strided(p.partialq[q], g, PART, 3 * 32 * 32, 32, p.dbq[q], st);
+      VQB_LAUNCH_CHECK();
+    }
+  }
+  return VQB_OK;
 }
 
 int conv1d_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, void* ws,
@@ -448,9 +465,21 @@ int conv1d_wgrad_tc(const vqb_conv_desc* d, const float* x, const float* dy, flo
   const int S = wg_split(d->precision);
   p.nprob = 1;
   p.dwq[0] = dw; p.dbq[0] = dbias;
-  p.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + need - 64);
-  VQB_CUDA(cudaMemsetAsync(p.counters, 0, WgTcParams::MAXP * sizeof(unsigned), st));
-  return launch_wg_any(S, p, grid, st);
+  if (grid <= WG_INKERNEL_MAX) {
+    p.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + need - 64);
+    VQB_CUDA(cudaMemsetAsync(p.counters, 0, WgTcParams::MAXP * sizeof(unsigned), st));
+    return launch_wg_any(S, p, grid, st);
+  }
+  int rc = launch_wg_any(S, p, grid, st);
+  if (rc) return rc;
+  constexpr int PART = WgCfg<1>::PART;
+  reduce_chunks_strided(p.partial, grid, PART, 0, 3 * 32 * 32, dw, st);
+  VQB_LAUNCH_CHECK();
+  if (dbias) {
+    reduce_chunks_strided(p.partial, grid, PART, 3 * 32 * 32, 32, dbias, st);
+    VQB_LAUNCH_CHECK();
+  }
+  return VQB_OK;
 }
 
 }  // namespace vqb
