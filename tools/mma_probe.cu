@@ -1,7 +1,7 @@
 // mma_probe.cu — issue-throughput probe for tcgen05.mma (kind::f16, M = 128, K = 16) with both operands in shared memory
 // in the no-swizzle "plane layout" of csrc/tc.cuh: how many SM clocks does one MMA cost as a function of N, of the operand
 // majors (K-major as in resblock_tc.cu / conv_tc.cu, MN-major as in wgrad_tc.cu) and of the plane pitch?  The numbers
-// feed the kernel cost models in DESIGN.md.  Build + run: tools/run_mma_probe.sh (nvcc here, gpurun for the run).
+// feed the kernel cost models in DESIGN.md.  Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I<package>/csrc -Iinclude -o tools/mma_probe tools/mma_probe.cu; tools/run_profiles.sh builds it when missing and runs it on the GPU box.
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>

@@ -35,6 +35,7 @@ full vq_search vq2_kernel 2 python tools/profile_vq.py
 full vq_finish vq_finish_smem_kernel 2 python tools/profile_vq.py
 python tools/trace_vq.py > $O/trace_vq.txt 2>&1
 python tools/trace_wgrad.py > $O/trace_wgrad.txt 2>&1
+[ -x tools/mma_probe ] || nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I"vae-based-music--deep-generative-models_b200/csrc" -Iinclude -o tools/mma_probe tools/mma_probe.cu
 ./tools/mma_probe > $O/mma_probe.txt 2>&1
 ls -la $O/prof_*.ncu-rep 2>/dev/null | awk '{print $5, $9}'
 cut -c1-300 $O/bench_final.json
